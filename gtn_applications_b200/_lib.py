@@ -1,0 +1,89 @@
+"""ctypes binding of libwfst_b200.so (C ABI: include/wfst_b200.h).
+
+The library is built in-tree (gtn_applications_b200/lib/) by
+``__graft_entry__.build()`` / ``make -C gtn_applications_b200/csrc``.  Loading
+fails loudly: there is no fallback implementation."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libwfst_b200.so")
+
+c_float_p = ctypes.c_void_p
+c_int_p = ctypes.c_void_p
+
+
+class AcceptorBatch(ctypes.Structure):
+    """wfst_acceptor_batch_t"""
+    _fields_ = [
+        ("B", ctypes.c_int32), ("max_nodes", ctypes.c_int32), ("max_arcs", ctypes.c_int32),
+        ("node_offsets", ctypes.c_void_p), ("arc_offsets", ctypes.c_void_p),
+        ("node_flags", ctypes.c_void_p),
+        ("in_ptr", ctypes.c_void_p), ("in_src", ctypes.c_void_p), ("in_label", ctypes.c_void_p),
+        ("in_arc", ctypes.c_void_p),
+        ("out_ptr", ctypes.c_void_p), ("out_dst", ctypes.c_void_p), ("out_label", ctypes.c_void_p),
+        ("out_arc", ctypes.c_void_p),
+        ("weights", ctypes.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); the single source of truth for the symbols the
+# library must export (tests/test_capi_symbols.py checks it against the header)
+_I, _Z, _P = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p
+SIGNATURES = {
+    "wfst_last_error": (ctypes.c_char_p, []),
+    "wfst_abi_version": (_I, []),
+    "wfst_launch_count": (ctypes.c_ulonglong, []),
+    "wfst_ctc_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "wfst_ctc_forward_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "wfst_ctc_forward_backward_host": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "wfst_lattice_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "wfst_lattice_forward_backward": (_I, [_P, _I, _I, _I, ctypes.POINTER(AcceptorBatch), _I, _P, _P,
+                                           _P, _I, _P, _P, _Z, _P]),
+    "wfst_asg_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "wfst_asg_forward_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "wfst_scale_inplace": (_I, [_P, _Z, _P, _P]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class WfstError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise WfstError(
+                    "libwfst_b200.so is not built (%s). Build it with "
+                    "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                    "`make -C gtn_applications_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+            handle = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)  # AttributeError if the symbol is missing
+                fn.restype = res
+                fn.argtypes = args
+            if handle.wfst_abi_version() != 1:
+                raise WfstError("libwfst_b200.so ABI version mismatch")
+            _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().wfst_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(msg)
+        raise WfstError("libwfst_b200 error %d: %s" % (rc, msg))
+
+
+def launch_count():
+    return int(lib().wfst_launch_count())

@@ -1,0 +1,200 @@
+// extern "C" entry points of libwfst_b200.so (contract: include/wfst_b200.h).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "launchers.h"
+
+namespace wfst {
+
+static thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// grow-only device scratch used by the *_host entry points
+struct HostPathBuffers {
+  std::mutex mu;
+  void* dev = nullptr;
+  size_t bytes = 0;
+  cudaStream_t stream = nullptr;
+  int ensure(size_t need) {
+    if (!stream) WFST_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (need <= bytes) return WFST_OK;
+    if (dev) WFST_CUDA_CHECK(cudaFree(dev));
+    dev = nullptr;
+    bytes = 0;
+    WFST_CUDA_CHECK(cudaMalloc(&dev, need));
+    bytes = need;
+    return WFST_OK;
+  }
+};
+static HostPathBuffers g_host;
+
+}  // namespace wfst
+
+using namespace wfst;
+
+extern "C" {
+
+const char* wfst_last_error(void) { return g_err; }
+int wfst_abi_version(void) { return WFST_ABI_VERSION; }
+unsigned long long wfst_launch_count(void) { return g_launches.load(); }
+
+// --------------------------------------------------------------------- CTC
+size_t wfst_ctc_workspace_bytes(int B, int T, int C, int max_target_len) {
+  (void)C;
+  return lattice_hist_bytes(B, T, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
+}
+
+int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
+                              const int32_t* target_offsets, int B, int T, int C, int blank,
+                              int max_target_len, const float* grad_scale, float* loss,
+                              float* mean_loss, float* grad, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  WFST_REQUIRE(emissions && target_offsets && workspace, "null pointer argument");
+  WFST_REQUIRE(targets || max_target_len == 0, "null targets");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0 && max_target_len >= 0, "bad shape B=%d T=%d C=%d L=%d",
+               B, T, C, max_target_len);
+  WFST_REQUIRE(blank >= 0 && blank < C, "blank %d outside [0,%d)", blank, C);
+  if (workspace_bytes < wfst_ctc_workspace_bytes(B, T, C, max_target_len)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes,
+              wfst_ctc_workspace_bytes(B, T, C, max_target_len));
+    return WFST_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* hist = (float*)workspace;
+  float* z = (float*)((char*)workspace + lattice_hist_bytes(B, T, 2 * max_target_len + 1));
+  int rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+                      grad_scale, z, grad, hist, st);
+  if (rc != WFST_OK) return rc;
+  return launch_finalize(z, nullptr, -1.f, B, grad_scale, loss, mean_loss, st);
+}
+
+int wfst_ctc_forward_backward_host(const float* emissions, const int32_t* targets,
+                                   const int32_t* target_offsets, int B, int T, int C,
+                                   int blank, const float* grad_scale, float* loss,
+                                   float* mean_loss, float* grad) {
+  WFST_REQUIRE(emissions && target_offsets, "null pointer argument");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0, "bad shape B=%d T=%d C=%d", B, T, C);
+  int total = target_offsets[B], maxL = 0;
+  for (int b = 0; b < B; ++b) {
+    int L = target_offsets[b + 1] - target_offsets[b];
+    WFST_REQUIRE(L >= 0, "target_offsets must be non-decreasing");
+    if (L > maxL) maxL = L;
+  }
+  for (int k = 0; k < total; ++k)
+    WFST_REQUIRE(targets[k] >= 0 && targets[k] < C, "target label %d outside [0,%d)", targets[k], C);
+  std::lock_guard<std::mutex> lk(g_host.mu);
+  size_t nE = align_up((size_t)B * T * C * 4, 256), nT = align_up((size_t)(total + 1) * 4, 256),
+         nO = align_up((size_t)(B + 1) * 4, 256), nS = align_up((size_t)B * 4, 256);
+  size_t ws = wfst_ctc_workspace_bytes(B, T, C, maxL);
+  size_t need = nE * 2 + nT + nO + nS * 2 + 256 + ws;
+  int rc = g_host.ensure(need);
+  if (rc != WFST_OK) return rc;
+  char* p = (char*)g_host.dev;
+  float* dE = (float*)p; p += nE;
+  float* dG = (float*)p; p += nE;
+  int32_t* dT = (int32_t*)p; p += nT;
+  int32_t* dO = (int32_t*)p; p += nO;
+  float* dS = (float*)p; p += nS;
+  float* dL = (float*)p; p += nS;
+  float* dM = (float*)p; p += 256;
+  void* dW = p;
+  cudaStream_t st = g_host.stream;
+  WFST_CUDA_CHECK(cudaMemcpyAsync(dE, emissions, (size_t)B * T * C * 4, cudaMemcpyHostToDevice, st));
+  if (total > 0)
+    WFST_CUDA_CHECK(cudaMemcpyAsync(dT, targets, (size_t)total * 4, cudaMemcpyHostToDevice, st));
+  WFST_CUDA_CHECK(cudaMemcpyAsync(dO, target_offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (grad_scale)
+    WFST_CUDA_CHECK(cudaMemcpyAsync(dS, grad_scale, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  rc = wfst_ctc_forward_backward(dE, dT, dO, B, T, C, blank, maxL, grad_scale ? dS : nullptr, dL, dM,
+                                 grad ? dG : nullptr, dW, ws, st);
+  if (rc != WFST_OK) return rc;
+  if (loss) WFST_CUDA_CHECK(cudaMemcpyAsync(loss, dL, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (mean_loss) WFST_CUDA_CHECK(cudaMemcpyAsync(mean_loss, dM, 4, cudaMemcpyDeviceToHost, st));
+  if (grad) WFST_CUDA_CHECK(cudaMemcpyAsync(grad, dG, (size_t)B * T * C * 4, cudaMemcpyDeviceToHost, st));
+  WFST_CUDA_CHECK(cudaStreamSynchronize(st));
+  return WFST_OK;
+}
+
+// ----------------------------------------------------------------- lattice
+size_t wfst_lattice_workspace_bytes(int B, int T, int C, int total_nodes, int max_nodes) {
+  (void)C; (void)total_nodes;
+  return lattice_hist_bytes(B, T, max_nodes);
+}
+
+int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
+                                  const wfst_acceptor_batch_t* graphs, int shared_graph,
+                                  const float* grad_scale, float* scores, float* grad_emissions,
+                                  int accumulate, float* grad_weights, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  WFST_REQUIRE(emissions && graphs && scores && workspace, "null pointer argument");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0, "bad shape B=%d T=%d C=%d", B, T, C);
+  WFST_REQUIRE(shared_graph ? graphs->B == 1 : graphs->B == B,
+               "graph batch %d does not match B=%d (shared=%d)", graphs->B, B, shared_graph);
+  WFST_REQUIRE(graphs->max_nodes > 0, "empty acceptor");
+  if (workspace_bytes < lattice_hist_bytes(B, T, graphs->max_nodes)) {
+    set_error("workspace too small");
+    return WFST_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  wfst_acceptor_batch_t g = *graphs;
+  g.B = B;
+  if (shared_graph && grad_weights)
+    WFST_CUDA_CHECK(cudaMemsetAsync(grad_weights, 0, (size_t)graphs->max_arcs * 4, st));
+  return launch_csr(emissions, T, C, g, shared_graph, grad_scale, 1.f, scores, grad_emissions,
+                    accumulate, grad_weights, (float*)workspace, st);
+}
+
+// --------------------------------------------------------------------- ASG
+size_t wfst_asg_workspace_bytes(int B, int T, int C, int max_target_len) {
+  int n = max_target_len + 1 > C + 1 ? max_target_len + 1 : C + 1;
+  return lattice_hist_bytes(B, T, n) + 2 * align_up((size_t)B * sizeof(float), 256);
+}
+
+int wfst_asg_forward_backward(const float* emissions, const float* transitions,
+                              const int32_t* targets, const int32_t* target_offsets, int B,
+                              int T, int C, int max_target_len, const float* grad_scale,
+                              float* loss, float* mean_loss, float* grad_emissions,
+                              float* grad_transitions, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  WFST_REQUIRE(emissions && transitions && target_offsets && workspace, "null pointer argument");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0 && max_target_len >= 0, "bad shape");
+  if (workspace_bytes < wfst_asg_workspace_bytes(B, T, C, max_target_len)) {
+    set_error("workspace too small");
+    return WFST_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int n = max_target_len + 1 > C + 1 ? max_target_len + 1 : C + 1;
+  size_t hb = lattice_hist_bytes(B, T, n), zb = align_up((size_t)B * sizeof(float), 256);
+  float* hist = (float*)workspace;
+  float* zfcc = (float*)((char*)workspace + hb);
+  float* zfal = (float*)((char*)workspace + hb + zb);
+  if (grad_transitions)
+    WFST_CUDA_CHECK(cudaMemsetAsync(grad_transitions, 0, (size_t)(C + 1) * C * 4, st));
+  // loss = Z_fcc - Z_fal (asg.py:111-115): full-connect writes, force-align subtracts
+  int rc = launch_asg_fcc(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
+                          grad_transitions, hist, st);
+  if (rc != WFST_OK) return rc;
+  rc = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
+                      grad_scale, -1.f, zfal, grad_emissions, 1, grad_transitions, hist, st);
+  if (rc != WFST_OK) return rc;
+  return launch_finalize(zfcc, zfal, 1.f, B, grad_scale, loss, mean_loss, st);
+}
+
+int wfst_scale_inplace(float* x, size_t n, const float* scale, void* stream) {
+  WFST_REQUIRE(x && scale, "null pointer argument");
+  return launch_scale(x, n, scale, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+// Time-synchronous log-semiring forward/backward over (emissions x acceptor),
+// one thread block per utterance.  This is the generic skeleton: what varies
+// between criteria is only the acceptor ("Topo" policy) — a packed CSR graph, the
+// closed-form CTC chain, the ASG force-alignment chain or the ASG full-connect
+// graph.  It computes what the reference gets from
+//   forward_score(intersect(linear_graph(T,C) with weights E_b, A_b))  + gtn.backward
+// (criterions/ctc.py:49-51,78; asg.py:111-115,158; stc.py:85-86,113;
+// transducer.py:283-290,321) without materialising the composed lattice:
+//   alpha_0[q] = 0 (start) / -inf;  alpha_{t+1}[v] = LSE_{u->v} alpha_t[u] + E[t,c] + w
+//   Z = LSE_{accept} alpha_T;  beta symmetric;
+//   dZ/dE[t,c] = sum_{arcs labelled c} exp(alpha_t[u] + E[t,c] + w + beta_{t+1}[v] - Z)
+//
+// Data movement: the [T,C] emissions of the utterance are streamed HBM -> shared
+// memory in tiles of Kt frames with 1-D bulk async copies (TMA engine, mbarrier
+// completion), double buffered; alpha_t is kept in shared memory and spilled to a
+// [T+1, N] history in HBM for the backward sweep; gradient rows are accumulated in a
+// shared-memory tile and written back with a bulk async store (or coalesced
+// stores when the tile is not 16-byte aligned / in accumulate mode).
+#pragma once
+
+#include "common.cuh"
+
+namespace wfst {
+
+struct LatticeArgs {
+  const float* E;        // [B, T, C]
+  int T, C;
+  const float* grad_scale;  // [B] or null
+  float sign;            // multiplies grad_scale (e.g. -1 for loss = -Z)
+  float* scores;         // [B] Z_b
+  float* gradE;          // [B, T, C] or null
+  int accumulate;        // add into gradE instead of overwriting
+  float* hist;           // [B, T+1, hist_stride] alpha history
+  int hist_stride;       // >= max nodes
+  int Kt;                // frames per tile (multiple of 4)
+  int npad;              // smem floats reserved per alpha buffer
+  int extra_floats;      // policy-owned smem floats (after the fixed regions)
+};
+
+// shared memory carve-up (all float-sized slots; base is 16B aligned)
+struct SmemLayout {
+  float* alpha0;
+  float* alpha1;
+  float* tile0;
+  float* tile1;
+  float* gtile;
+  float* extra;
+  uint64_t* bars;
+  float* red;
+};
+
+__device__ __forceinline__ SmemLayout carve(float* base, const LatticeArgs& a) {
+  SmemLayout s;
+  size_t tile = (size_t)a.Kt * a.C;
+  tile = (tile + 3) & ~(size_t)3;
+  s.bars = reinterpret_cast<uint64_t*>(base);  // 2 barriers = 4 floats
+  s.red = base + 4;                            // 36 floats (warp partials + broadcast)
+  s.tile0 = base + 40;
+  s.tile1 = s.tile0 + tile;
+  s.gtile = s.tile1 + tile;
+  s.alpha0 = s.gtile + tile;
+  s.alpha1 = s.alpha0 + a.npad;
+  s.extra = s.alpha1 + a.npad;
+  return s;
+}
+
+inline size_t lattice_smem_bytes(int Kt, int C, int npad, int extra_floats) {
+  size_t tile = ((size_t)Kt * C + 3) & ~(size_t)3;
+  return sizeof(float) * (40 + 3 * tile + 2 * (size_t)npad + (size_t)extra_floats);
+}
+
+// block-wide LSE of per-thread partial (m, s) pairs
+__device__ __forceinline__ float block_lse(float v, float* red) {
+  // v is a per-thread log value (-inf allowed)
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  float m = warp_max(v);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  float bm = (lane < nw) ? red[lane] : kNegInf;
+  bm = warp_max(bm);
+  __syncthreads();
+  float e = (bm == kNegInf || v == kNegInf) ? 0.f : __expf(v - bm);
+  e = warp_sum(e);
+  if (lane == 0) red[w] = e;
+  __syncthreads();
+  float bs = (lane < nw) ? red[lane] : 0.f;
+  bs = warp_sum(bs);
+  __syncthreads();
+  return (bm == kNegInf) ? kNegInf : bm + __logf(bs);
+}
+
+template <class Topo>
+__global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a, typename Topo::Params tp) {
+  extern __shared__ __align__(16) float smem_raw[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  SmemLayout sm = carve(smem_raw, a);
+  Topo topo;
+  topo.init(tp, b, sm.extra);  // may use all threads; ends with __syncthreads
+  const int N = topo.num_nodes();
+  const int T = a.T, C = a.C, Kt = a.Kt;
+  const float* Eb = a.E + (size_t)b * T * C;
+  float* hist = a.hist + (size_t)b * (T + 1) * a.hist_stride;
+  const int ntiles = (T + Kt - 1) / Kt;
+
+  if (tid == 0) {
+    mbar_init(&sm.bars[0], 1);
+    mbar_init(&sm.bars[1], 1);
+    fence_barrier_init();
+  }
+  uint32_t phase[2] = {0u, 0u};
+  float* tiles[2] = {sm.tile0, sm.tile1};
+  __syncthreads();
+
+  auto tile_rows = [&](int i) { return min(Kt, T - i * Kt); };
+  auto tile_tma_ok = [&](int i) {
+    const float* src = Eb + (size_t)i * Kt * C;
+    uint32_t bytes = (uint32_t)tile_rows(i) * C * 4u;
+    return ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15u) == 0);
+  };
+  // all threads call; returns whether the consumer must wait on the mbarrier
+  auto issue_tile = [&](int i, int buf) {
+    const float* src = Eb + (size_t)i * Kt * C;
+    int n = tile_rows(i) * C;
+    if (tile_tma_ok(i)) {
+      if (tid == 0) {
+        mbar_expect_tx(&sm.bars[buf], (uint32_t)n * 4u);
+        bulk_g2s(tiles[buf], src, (uint32_t)n * 4u, &sm.bars[buf]);
+      }
+    } else {
+      for (int k = tid; k < n; k += NT) tiles[buf][k] = __ldg(src + k);
+    }
+  };
+  auto wait_tile = [&](int i, int buf) {
+    if (tile_tma_ok(i)) {
+      mbar_wait(&sm.bars[buf], phase[buf]);
+      phase[buf] ^= 1u;
+    }
+  };
+
+  // ------------------------------------------------------------- forward
+  float* cur = sm.alpha0;
+  float* nxt = sm.alpha1;
+  for (int v = tid; v < N; v += NT) {
+    float x = topo.is_start(v) ? 0.f : kNegInf;
+    cur[v] = x;
+    hist[v] = x;
+  }
+  if (ntiles > 0) issue_tile(0, 0);
+  __syncthreads();
+  for (int i = 0; i < ntiles; ++i) {
+    const int buf = i & 1;
+    wait_tile(i, buf);
+    if (i + 1 < ntiles) issue_tile(i + 1, buf ^ 1);
+    const int rows = tile_rows(i);
+    for (int tt = 0; tt < rows; ++tt) {
+      const float* Et = tiles[buf] + tt * C;
+      const int t = i * Kt + tt;
+      float* hrow = hist + (size_t)(t + 1) * a.hist_stride;
+      for (int v = tid; v < N; v += NT) {
+        float m = kNegInf;
+        topo.in_arcs(v, [&](int u, int lab, float w, int) {
+          m = fmaxf(m, cur[u] + Et[lab] + w);
+        });
+        float r = kNegInf;
+        if (m != kNegInf) {
+          float s = 0.f;
+          topo.in_arcs(v, [&](int u, int lab, float w, int) {
+            s += __expf(cur[u] + Et[lab] + w - m);
+          });
+          r = m + __logf(s);
+        }
+        nxt[v] = r;
+        hrow[v] = r;
+      }
+      __syncthreads();
+      float* tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+  }
+
+  // ------------------------------------------------------------- Z
+  float part = kNegInf;
+  for (int v = tid; v < N; v += NT)
+    if (topo.is_accept(v)) part = log_add(part, cur[v]);
+  const float Z = block_lse(part, sm.red);
+  if (tid == 0) a.scores[b] = Z;
+  const bool want_gE = a.gradE != nullptr;
+  const bool want_gW = topo.wants_weight_grad();
+  if (!want_gE && !want_gW) return;
+  const float gs = a.sign * (a.grad_scale ? a.grad_scale[b] : 1.f);
+  float* gEb = want_gE ? a.gradE + (size_t)b * T * C : nullptr;
+  const bool feasible = (Z != kNegInf) && (Z == Z) && (Z != -kNegInf);
+  if (!feasible) {
+    // no accepting path: gradient defined as zero (documented deviation: GTN yields NaNs)
+    if (want_gE && !a.accumulate)
+      for (size_t k = tid; k < (size_t)T * C; k += NT) gEb[k] = 0.f;
+    topo.finish_weight_grad(0.f);
+    return;
+  }
+
+  // ------------------------------------------------------------- backward
+  // beta_{t+1} lives in `nxt`, beta_t is written to `cur`
+  __syncthreads();
+  for (int v = tid; v < N; v += NT) nxt[v] = topo.is_accept(v) ? 0.f : kNegInf;
+  if (ntiles > 0) issue_tile(ntiles - 1, (ntiles - 1) & 1);
+  __syncthreads();
+  for (int i = ntiles - 1; i >= 0; --i) {
+    const int buf = i & 1;
+    wait_tile(i, buf);
+    if (i > 0) issue_tile(i - 1, buf ^ 1);
+    const int rows = tile_rows(i);
+    float* gt = sm.gtile;
+    if (want_gE) {
+      for (int k = tid; k < rows * C; k += NT) gt[k] = 0.f;
+      __syncthreads();
+    }
+    for (int tt = rows - 1; tt >= 0; --tt) {
+      const float* Et = tiles[buf] + tt * C;
+      const int t = i * Kt + tt;
+      const float* hrow = hist + (size_t)t * a.hist_stride;
+      float* grow = gt + tt * C;
+      for (int u = tid; u < N; u += NT) {
+        const float au = hrow[u];
+        float m = kNegInf;
+        topo.out_arcs(u, [&](int v, int lab, float w, int) {
+          m = fmaxf(m, Et[lab] + w + nxt[v]);
+        });
+        float r = kNegInf;
+        if (m != kNegInf) {
+          float s = 0.f;
+          const bool live = au != kNegInf;
+          const float off = au - Z;
+          topo.out_arcs(u, [&](int v, int lab, float w, int arc) {
+            float x = Et[lab] + w + nxt[v];
+            s += __expf(x - m);
+            if (live && x != kNegInf) {
+              float p = __expf(x + off);
+              if (want_gE) atomicAdd(&grow[lab], p * gs);
+              topo.add_weight_grad(arc, p);
+            }
+          });
+          r = m + __logf(s);
+        }
+        cur[u] = r;
+      }
+      __syncthreads();
+      float* tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+    if (want_gE) {
+      float* dst = gEb + (size_t)i * Kt * C;
+      const int n = rows * C;
+      const bool tma = !a.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
+      if (tma) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          bulk_s2g(dst, gt, (uint32_t)n * 4u);
+          bulk_commit();
+          bulk_wait_read<0>();  // gtile is re-zeroed by the next tile
+        }
+      } else if (a.accumulate) {
+        for (int k = tid; k < n; k += NT) dst[k] += gt[k];
+      } else {
+        for (int k = tid; k < n; k += NT) dst[k] = gt[k];
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) bulk_wait_all<0>();
+  topo.finish_weight_grad(gs);
+}
+
+}  // namespace wfst

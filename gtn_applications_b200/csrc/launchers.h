@@ -1,0 +1,25 @@
+// Internal host-side launchers (lattice.cu) used by the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/wfst_b200.h"
+
+namespace wfst {
+size_t lattice_hist_bytes(int B, int T, int max_nodes);
+int launch_ctc(const float* E, const int* targets, const int* offsets, int B, int T, int C,
+               int blank, int max_target_len, const float* grad_scale, float* scores,
+               float* gradE, float* hist, cudaStream_t st);
+int launch_csr(const float* E, int T, int C, const wfst_acceptor_batch_t& g, int shared,
+               const float* grad_scale, float sign, float* scores, float* gradE, int accumulate,
+               float* gradW, float* hist, cudaStream_t st);
+int launch_asg_fal(const float* E, const float* tr, const int* targets, const int* offsets, int B,
+                   int T, int C, int max_target_len, const float* grad_scale, float sign,
+                   float* scores, float* gradE, int accumulate, float* gradTr, float* hist,
+                   cudaStream_t st);
+int launch_asg_fcc(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
+                   float sign, float* scores, float* gradE, int accumulate, float* gradTr,
+                   float* hist, cudaStream_t st);
+int launch_finalize(const float* za, const float* zb, float sign, int B, const float* grad_scale,
+                    float* loss, float* mean_loss, cudaStream_t st);
+int launch_scale(float* x, size_t n, const float* scale, cudaStream_t st);
+}  // namespace wfst

@@ -1,0 +1,161 @@
+/*
+ * wfst_b200.h — C ABI of libwfst_b200.so, the B200 (sm_100a) implementation of the
+ * WFST sequence-criterion hot path of facebookresearch/gtn_applications.
+ *
+ * What it replaces.  In the reference every criterion computes, per utterance b,
+ *     Z_b = forward_score(intersect(linear_graph(T, C) with weights E[b], A_b))
+ * on the CPU inside the external GTN library and then calls gtn.backward to get
+ * dZ_b/dE[b] (and dZ_b/d arc weights of A_b):
+ *     criterions/ctc.py:40-51,78-81        (CTC: A_b = create_ctc_graph, ctc.py:15-29)
+ *     criterions/asg.py:96-115,158-168     (ASG: force-align o transitions, and transitions)
+ *     criterions/stc.py:74-86,113-115      (STC: create_stc_graph, stc.py:22-64)
+ *     criterions/transducer.py:262-290,320-336 (alignment graph, optional transitions)
+ * The entry points below are what a binding of that path would call instead of
+ * gtn.linear_graph / set_weights / intersect / forward_score / backward: the
+ * composed lattice is never materialised, the time-synchronous recursion
+ *     alpha_{t+1}[v] = LSE_{(u->v, c, w) in A_b} alpha_t[u] + E[b,t,c] + w
+ * and its reverse are run on the GPU, one thread block per utterance.
+ *
+ * Conventions.  Plain pointers and sizes only; no torch / C++ types.  Unless a
+ * function name ends in _host, every pointer is a DEVICE pointer on the current
+ * CUDA device and `stream` is a cudaStream_t passed as void* (NULL = the legacy
+ * default stream); calls are asynchronous with respect to the host.  All scores
+ * are float32, all indices int32, epsilon is not allowed in acceptors handed to
+ * the lattice kernels.  Every function returns WFST_OK (0) or a negative error
+ * code; wfst_last_error() returns a thread-local message for the last failure.
+ * There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef WFST_B200_H
+#define WFST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFST_OK 0
+#define WFST_ERR_INVALID (-1)     /* bad argument (shape, null pointer, label out of range) */
+#define WFST_ERR_CUDA (-2)        /* a CUDA runtime call failed */
+#define WFST_ERR_UNSUPPORTED (-3) /* shape outside what the kernels handle */
+#define WFST_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define WFST_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define WFST_API __attribute__((visibility("default")))
+#else
+#define WFST_API
+#endif
+
+/* thread-local message of the last error returned on this thread ("" if none) */
+WFST_API const char* wfst_last_error(void);
+WFST_API int wfst_abi_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+WFST_API unsigned long long wfst_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * CTC — replaces CTCLossFunction.forward + .backward (criterions/ctc.py:31-94):
+ * per-utterance create_ctc_graph (built on the device from the target), the
+ * intersect with the emissions graph, forward_score, negate, and gtn.backward.
+ *
+ *   emissions       [B, T, C] float32 row-major (ctc.py:33,43-44: log_probs[b])
+ *   targets         concatenated int32 labels; target_offsets [B+1]
+ *   blank           blank label (ctc.py:32 blank_idx)
+ *   max_target_len  max_b (target_offsets[b+1] - target_offsets[b]); sizes the
+ *                   workspace and shared memory (labels must lie in [0, C))
+ *   grad_scale      [B] or NULL(=1): multiplies utterance b's gradient; the
+ *                   Function passes scale_b / B (ctc.py:53-56,81,87)
+ *   loss            [B] out: -Z_b (unscaled; ctc.py:49-51).  +inf if no alignment.
+ *   mean_loss       [1] out or NULL: sum_b loss_b * grad_scale[b]  (= ctc.py:68-69
+ *                   when grad_scale = scale_b / B); deterministic order
+ *   grad            [B, T, C] out or NULL: grad_scale[b] * d(-Z_b)/dE[b]
+ *                   (= -grad_scale[b] * posterior; all zero for an infeasible b)
+ * ---------------------------------------------------------------------- */
+WFST_API size_t wfst_ctc_workspace_bytes(int B, int T, int C, int max_target_len);
+
+WFST_API int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
+                              const int32_t* target_offsets, int B, int T, int C, int blank,
+                              int max_target_len, const float* grad_scale, float* loss,
+                              float* mean_loss, float* grad, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* Same computation with HOST buffers: copies inputs to the device, runs the
+ * kernels and copies loss / mean_loss (and grad when not NULL) back, then
+ * synchronises.  This is the call a binding that owns host memory would make
+ * (the reference hands GTN a host pointer, ctc.py:43-44). */
+WFST_API int wfst_ctc_forward_backward_host(const float* emissions, const int32_t* targets,
+                                   const int32_t* target_offsets, int B, int T, int C,
+                                   int blank, const float* grad_scale, float* loss,
+                                   float* mean_loss, float* grad);
+
+/* ------------------------------------------------------------------------
+ * Generic acceptor lattice — replaces forward_score(intersect(emissions, A_b))
+ * + gtn.backward for arbitrary epsilon-free acceptors A_b (STC stc.py:85-86;
+ * transducer alignments transducer.py:283; ASG force-align asg.py:111-113).
+ * A batch of acceptors is passed packed: nodes and arcs of all utterances are
+ * concatenated; arcs are listed twice, grouped by destination (in_*) and by
+ * source (out_*), each entry carrying the ORIGINAL arc index (position in
+ * `weights` / `grad_weights`, relative to arc_offsets[b]).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t B;
+  int32_t max_nodes;            /* max over b of nodes in A_b */
+  int32_t max_arcs;             /* max over b of arcs in A_b  */
+  const int32_t* node_offsets;  /* [B+1] */
+  const int32_t* arc_offsets;   /* [B+1] */
+  const uint8_t* node_flags;    /* [nodes] bit0 = start, bit1 = accept */
+  const int32_t* in_ptr;        /* [nodes + B] per-utterance CSR (N_b+1 entries at node_offsets[b]+b) */
+  const int32_t* in_src;        /* [arcs] local source node, grouped by destination */
+  const int32_t* in_label;      /* [arcs] */
+  const int32_t* in_arc;        /* [arcs] original (local) arc index */
+  const int32_t* out_ptr;       /* [nodes + B] */
+  const int32_t* out_dst;       /* [arcs] local destination node, grouped by source */
+  const int32_t* out_label;     /* [arcs] */
+  const int32_t* out_arc;       /* [arcs] */
+  const float* weights;         /* [arcs] original order, or NULL (= 0) */
+} wfst_acceptor_batch_t;
+
+WFST_API size_t wfst_lattice_workspace_bytes(int B, int T, int C, int total_nodes, int max_nodes);
+
+/*   shared_graph  0: graphs->B == B, utterance b is scored against graph b;
+ *                 1: graphs->B == 1 and every utterance is scored against graph 0
+ *                    (transducer.py:287 em o transitions); grad_weights is then
+ *                    the sum over b
+ *   scores        [B] out: Z_b (-inf if no accepting path)
+ *   grad_emissions[B, T, C] out or NULL: grad_scale[b] * dZ_b/dE[b]; when
+ *                 `accumulate` != 0 it is added to what the buffer holds
+ *   grad_weights  [arcs] out or NULL: grad_scale[b] * dZ_b/dw_a (original order) */
+WFST_API int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
+                                  const wfst_acceptor_batch_t* graphs, int shared_graph,
+                                  const float* grad_scale, float* scores, float* grad_emissions,
+                                  int accumulate, float* grad_weights, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * ASG — replaces ASGLossFunction.forward + .backward (criterions/asg.py:83-185):
+ *   loss_b = Z(E_b o transitions) - Z((force_align(y_b) o transitions) o E_b)
+ *   transitions [(C+1), C]: row 0 = start scores, transitions[1+i, j] = i after j
+ *   (layout of create_transitions_graph, asg.py:53-69).
+ *   grad_transitions [(C+1), C] out or NULL: sum_b grad_scale[b] * dloss_b/dtransitions
+ *   (asg.py:175-179 with grad_scale = scale_b / B).
+ * ---------------------------------------------------------------------- */
+WFST_API size_t wfst_asg_workspace_bytes(int B, int T, int C, int max_target_len);
+
+WFST_API int wfst_asg_forward_backward(const float* emissions, const float* transitions,
+                              const int32_t* targets, const int32_t* target_offsets, int B,
+                              int T, int C, int max_target_len, const float* grad_scale,
+                              float* loss, float* mean_loss, float* grad_emissions,
+                              float* grad_transitions, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
+/* Multiplies x[0..n) in place by *scale (a device scalar); returns immediately on
+ * the device when *scale == 1 (the common loss.backward() case), so autograd's
+ * grad_output costs no pass over the [B,T,C] gradient (ctc.py:87, asg.py:174). */
+WFST_API int wfst_scale_inplace(float* x, size_t n, const float* scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFST_B200_H */

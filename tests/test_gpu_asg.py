@@ -1,0 +1,74 @@
+"""GPU parity: the CUDA ASG path (ASGLossFunction -> wfst_asg_forward_backward)
+against the float64 oracle, the reference's known-answer vector and the committed
+fixtures.  Tolerance 1e-4 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import _golden as G
+from test_gpu_ctc import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def run(e_np, tr_np, targets, reduction):
+    from gtn_applications_b200.criterions.asg import ASGLoss
+    e = torch.tensor(e_np, dtype=torch.float32, device="cuda").requires_grad_(True)
+    tr = torch.tensor(tr_np, dtype=torch.float32, device="cuda").requires_grad_(True)
+    loss = ASGLoss(e, tr, targets, reduction)
+    loss.backward()
+    return loss.item(), e.grad.cpu().numpy(), tr.grad.cpu().numpy()
+
+
+def test_known_answer():
+    import test_oracle_golden as lit
+    loss, ge, gt = run(lit.ASG_EMISSIONS, np.zeros((7, 6)), lit.ASG_LABELS, "none")
+    assert abs(loss - 7.47995) < 5e-5
+    np.testing.assert_allclose(ge, lit.ASG_GRAD, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(gt[1:], lit.ASG_TRANS_GRAD, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["small_none", "small_mean", "mid_mean"])
+def test_fixtures_from_reference(case):
+    z = G.load("asg")
+    tg = G.unpack(z[case + "_targets"], z[case + "_offsets"])
+    loss, ge, gt = run(z[case + "_emissions"], z[case + "_transitions"], tg, str(z[case + "_reduction"]))
+    want = float(z[case + "_loss"])
+    assert abs(loss - want) <= 1e-4 * max(1.0, abs(want))
+    assert_close(ge, z[case + "_grad"], rel=1e-3)
+    assert_close(gt, z[case + "_grad_transitions"], rel=1e-3)
+
+
+@pytest.mark.parametrize("B,T,C,lens,reduction", [
+    (3, 10, 5, [3, 5, 1], "none"),
+    (4, 40, 12, [9, 14, 2, 20], "mean"),
+    (2, 120, 30, [40, 60], "mean"),
+    (3, 64, 80, [10, 31, 5], "none"),     # reference benchmark's N=80 (asg_benchmark.py:19)
+])
+def test_against_float64_oracle(gtn64, B, T, C, lens, reduction):
+    import ref_criterions as rc
+    rng = np.random.default_rng(B * 100 + T)
+    e = rng.standard_normal((B, T, C)).astype(np.float32)
+    tr = rng.standard_normal((C + 1, C)).astype(np.float32)
+    tg = [rng.integers(0, C, size=n).tolist() for n in lens]
+    ref = rc.asg(gtn64, e, tr, tg, reduction)
+    loss, ge, gt = run(e, tr, tg, reduction)
+    assert abs(loss - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert_close(ge, ref["grad"])
+    assert_close(gt, ref["grad_transitions"])
+
+
+def test_module_replabels_garbage_and_checkpoint_names():
+    from gtn_applications_b200.criterions.asg import ASG
+    z = G.load("asg")
+    crit = ASG(4, num_replabels=2, use_garbage=True).cuda()
+    assert list(crit.state_dict().keys()) == ["transitions"]
+    assert tuple(crit.transitions.shape) == (crit.N + 1, crit.N)
+    crit.transitions.data = torch.tensor(z["module_transitions"], device="cuda")
+    x = torch.tensor(z["module_emissions"], device="cuda", requires_grad=True)
+    tg = [torch.tensor(t) for t in G.unpack(z["module_targets"], z["module_offsets"])]
+    loss = crit(x, tg)
+    loss.backward()
+    assert abs(loss.item() - float(z["module_loss"])) <= 1e-4 * abs(float(z["module_loss"]))
+    assert_close(x.grad.cpu().numpy(), z["module_grad"], rel=1e-3)
+    assert_close(crit.transitions.grad.cpu().numpy(), z["module_grad_transitions"], rel=1e-3)

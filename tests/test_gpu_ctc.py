@@ -1,0 +1,138 @@
+"""GPU parity: the CUDA CTC path (through CTCLossFunction -> C ABI) against the
+float64 oracle on the same seeded inputs, the reference's literal vectors, the
+committed fixtures, and size-independent properties at BASELINE.json's sizes.
+Tolerance: loss and gradient within 1e-4 relative (north_star), written as
+|a-b| <= 1e-4 * max(|b|, 1e-3 * max|b|) elementwise."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import _golden as G
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_close(got, want, rel=1e-4, floor=1e-3):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    scale = np.abs(want).max() if want.size else 0.0
+    tol = rel * np.maximum(np.abs(want), floor * scale) + 1e-12
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), "max abs err %.3e (scale %.3e), %d bad" % (
+        np.abs(got - want).max(), scale, int(bad.sum()))
+
+
+def run(lp_np, targets, blank, reduction):
+    from gtn_applications_b200.criterions.ctc import CTCLoss
+    lp = torch.tensor(lp_np, dtype=torch.float32, device="cuda").requires_grad_(True)
+    loss = CTCLoss(lp, targets, blank, reduction)
+    loss.backward()
+    return loss.item(), lp.grad.cpu().numpy()
+
+
+def test_trivial_and_uniform():
+    with np.errstate(divide="ignore"):
+        lp = np.log(np.array([1.0, 0.0, 0.0, 1.0, 1.0, 0.0]).reshape(1, 3, 2))
+    loss, _ = run(lp, [[0, 0]], 1, "none")
+    assert abs(loss) < 1e-6
+    loss, _ = run(G.log_softmax(np.zeros((1, 3, 4))), [[1, 2]], 3, "none")
+    assert abs(loss + math.log(0.25 ** 3 * 5)) < 1e-5
+
+
+def test_warpctc_vectors():
+    import test_oracle_golden as lit
+    for probs, labels, want, want_grad in ((lit.WARP_CTC_1, [[0, 1, 2, 1, 0]], 3.34211, lit.WARP_CTC_1_GRAD),
+                                           (lit.WARP_CTC_2, [[0, 1, 1, 0]], 5.42262, lit.WARP_CTC_2_GRAD)):
+        logits = np.log(probs)
+        loss, grad = run(G.log_softmax(logits), labels, 5, "none")
+        assert abs(loss - want) < 5e-5
+        np.testing.assert_allclose(G.through_log_softmax(logits, grad), want_grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["small_none", "small_mean", "raw_mean", "repeats", "cfg1_raw", "cfg1_lsm"])
+def test_fixtures_from_reference(case):
+    z = G.load("ctc")
+    tg = G.unpack(z[case + "_targets"], z[case + "_offsets"])
+    loss, grad = run(z[case + "_emissions"], tg, int(z[case + "_blank"]), str(z[case + "_reduction"]))
+    want = float(z[case + "_loss"])
+    assert abs(loss - want) <= 1e-4 * max(1.0, abs(want))
+    # the fixture itself is float32 GTN arithmetic: compare at 1e-3 here, 1e-4 vs float64 below
+    assert_close(grad, z[case + "_grad"], rel=1e-3)
+
+
+@pytest.mark.parametrize("B,T,C,lens,lsm,reduction", [
+    (3, 12, 6, [4, 0, 6], True, "none"),
+    (5, 33, 9, [1, 16, 7, 0, 11], True, "mean"),
+    (4, 150, 28, [20, 20, 20, 20], False, "none"),     # BASELINE configs[0]
+    (2, 64, 5, [30, 32], False, "mean"),                # T barely enough (repeats may make it infeasible)
+    (6, 257, 31, [40, 3, 77, 128, 0, 64], True, "mean"),
+])
+def test_against_float64_oracle(gtn64, B, T, C, lens, lsm, reduction):
+    import ref_criterions as rc
+    rng = np.random.default_rng(B * 1000 + T)
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    lp = G.log_softmax(x).astype(np.float32) if lsm else x
+    tg = [rng.integers(0, C - 1, size=n).tolist() for n in lens]
+    ref = rc.ctc(gtn64, lp, tg, C - 1, reduction)
+    loss, grad = run(lp, tg, C - 1, reduction)
+    if math.isinf(ref["loss"]):
+        assert math.isinf(loss)
+        return
+    assert abs(loss - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert_close(grad, ref["grad"])
+
+
+def test_infeasible_alignment_gives_inf_loss_and_zero_grad():
+    lp = G.log_softmax(np.random.default_rng(0).standard_normal((2, 3, 4))).astype(np.float32)
+    loss, grad = run(lp, [[0, 1, 2, 0, 1], [1]], 3, "none")
+    assert math.isinf(loss) and loss > 0
+    assert np.all(grad[0] == 0) and np.isfinite(grad).all() and np.abs(grad[1]).sum() > 0
+
+
+def test_errors_match_reference():
+    from gtn_applications_b200.criterions.ctc import CTCLoss
+    lp = torch.zeros(1, 4, 3, device="cuda")
+    with pytest.raises(ValueError, match="invalid value for reduction"):
+        CTCLoss(lp, [[0]], 2, "sum")
+    with pytest.raises(TypeError):
+        CTCLoss(lp.double(), [[0]], 2, "none")
+    with pytest.raises(ValueError):
+        CTCLoss(lp, [[7]], 2, "none")
+
+
+def test_grad_output_scaling_and_cpu_input():
+    from gtn_applications_b200.criterions.ctc import CTCLoss
+    rng = np.random.default_rng(3)
+    lp0 = torch.tensor(G.log_softmax(rng.standard_normal((2, 20, 5))), dtype=torch.float32)
+    tg = [[0, 1, 2], [3, 3]]
+    a = lp0.clone().cuda().requires_grad_(True)
+    CTCLoss(a, tg, 4, "mean").backward()
+    b = lp0.clone().cuda().requires_grad_(True)
+    (CTCLoss(b, tg, 4, "mean") * 2.5).backward()
+    torch.testing.assert_close(b.grad, a.grad * 2.5)
+    c = lp0.clone().requires_grad_(True)  # host tensor: result and grad come back on the host
+    out = CTCLoss(c, tg, 4, "mean")
+    out.backward()
+    assert not out.is_cuda and not c.grad.is_cuda
+    torch.testing.assert_close(c.grad, a.grad.cpu())
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] (B=256, T=1000, C=30, L=176): size-independent checks —
+    every frame's posteriors sum to one (so grad rows sum to -scale/B), the
+    gradient is non-positive, and loss equals torch's own ctc_loss."""
+    from gtn_applications_b200.criterions.ctc import CTCLoss
+    torch.manual_seed(0)
+    B, T, C, L = 256, 1000, 30, 176
+    lp = torch.log_softmax(torch.randn(B, T, C, device="cuda"), 2).requires_grad_(True)
+    tg = torch.randint(C - 2, (B, L))
+    loss = CTCLoss(lp, tg.tolist(), C - 1, "none")
+    loss.backward()
+    rows = lp.grad.sum(2)
+    assert torch.all(lp.grad <= 1e-7)
+    torch.testing.assert_close(rows, torch.full_like(rows, -1.0 / B), rtol=2e-4, atol=0)
+    ref = torch.nn.functional.ctc_loss(lp.detach().permute(1, 0, 2), tg.cuda(), [T] * B, [L] * B,
+                                       blank=C - 1, reduction="none").mean()
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())

@@ -1,0 +1,86 @@
+"""GPU parity: the generic acceptor lattice kernel (wfst_lattice_forward_backward,
+packed CSR acceptors) against the float64 closed-form DP oracle on random
+acceptors — scores, emission gradients and arc-weight gradients."""
+import numpy as np
+import pytest
+import torch
+
+import dp_numpy
+from test_gpu_ctc import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def random_acceptor(rng, N, A, C, weights=True):
+    g = {"start": np.zeros(N, dtype=bool), "accept": np.zeros(N, dtype=bool),
+         "src": rng.integers(0, N, A), "dst": rng.integers(0, N, A), "label": rng.integers(0, C, A)}
+    g["start"][rng.integers(0, N, 2)] = True
+    g["accept"][rng.integers(0, N, 3)] = True
+    g["weight"] = rng.standard_normal(A).astype(np.float32) if weights else None
+    return g
+
+
+@pytest.mark.parametrize("B,T,C,N,A", [(3, 9, 5, 6, 20), (4, 33, 17, 40, 160), (2, 70, 1001, 300, 900),
+                                       (5, 16, 8, 1, 3)])
+def test_random_acceptors(B, T, C, N, A):
+    from gtn_applications_b200.packing import PackedAcceptors
+    from gtn_applications_b200.lattice import lattice_forward_backward
+    rng = np.random.default_rng(B + T + C)
+    graphs = [random_acceptor(rng, max(1, N - b), max(1, A - 3 * b), C) for b in range(B)]
+    E = rng.standard_normal((B, T, C)).astype(np.float32)
+    gs = rng.uniform(0.5, 2.0, B).astype(np.float32)
+    packed = PackedAcceptors(graphs, "cuda")
+    scores, gE, gW = lattice_forward_backward(torch.tensor(E, device="cuda"), packed,
+                                              grad_scale=torch.tensor(gs, device="cuda"),
+                                              want_grad_weights=True)
+    scores, gE, gW = scores.cpu().numpy(), gE.cpu().numpy(), gW.cpu().numpy()
+    for b, g in enumerate(graphs):
+        Z, rE, rW = dp_numpy.acceptor_forward_backward(E[b], g["start"], g["accept"], g["src"], g["dst"],
+                                                       g["label"], g["weight"])
+        if not np.isfinite(Z):
+            assert scores[b] == -np.inf and np.all(gE[b] == 0)
+            continue
+        assert abs(scores[b] - Z) <= 1e-4 * max(1.0, abs(Z))
+        assert_close(gE[b], rE * gs[b])
+        a0, a1 = packed.arc_offsets_host[b], packed.arc_offsets_host[b + 1]
+        assert_close(gW[a0:a1], rW * gs[b])
+
+
+def test_ctc_chain_through_csr_matches_closed_form_kernel():
+    from gtn_applications_b200.packing import PackedAcceptors
+    from gtn_applications_b200.lattice import lattice_forward_backward
+    from gtn_applications_b200.criterions.ctc import CTCLoss
+    rng = np.random.default_rng(5)
+    B, T, C = 4, 60, 11
+    tg = [rng.integers(0, C - 1, size=n).tolist() for n in (9, 0, 25, 14)]
+    graphs = []
+    for y in tg:
+        st, ac, src, dst, lab, w = dp_numpy.ctc_acceptor(y, C - 1)
+        graphs.append({"start": st, "accept": ac, "src": src, "dst": dst, "label": lab, "weight": None})
+    E = torch.tensor(rng.standard_normal((B, T, C)), dtype=torch.float32, device="cuda")
+    scores, gE, _ = lattice_forward_backward(E, PackedAcceptors(graphs, "cuda"))
+    lp = E.clone().requires_grad_(True)
+    loss = CTCLoss(lp, tg, C - 1, "none")
+    loss.backward()
+    assert abs(loss.item() + scores.mean().item()) <= 1e-5 * abs(loss.item())
+    torch.testing.assert_close(-gE / B, lp.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_shared_graph_accumulates_weight_gradient():
+    from gtn_applications_b200.packing import PackedAcceptors
+    from gtn_applications_b200.lattice import lattice_forward_backward
+    rng = np.random.default_rng(11)
+    B, T, C = 6, 12, 7
+    g = random_acceptor(rng, 9, 40, C)
+    E = rng.standard_normal((B, T, C)).astype(np.float32)
+    packed = PackedAcceptors([g], "cuda")
+    scores, gE, gW = lattice_forward_backward(torch.tensor(E, device="cuda"), packed,
+                                              want_grad_weights=True, shared=True)
+    want = np.zeros(40)
+    for b in range(B):
+        Z, rE, rW = dp_numpy.acceptor_forward_backward(E[b], g["start"], g["accept"], g["src"], g["dst"],
+                                                       g["label"], g["weight"])
+        assert abs(scores[b].item() - Z) <= 1e-4 * max(1.0, abs(Z))
+        assert_close(gE[b].cpu().numpy(), rE)
+        want += rW
+    assert_close(gW.cpu().numpy(), want)

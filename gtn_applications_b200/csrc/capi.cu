@@ -53,7 +53,7 @@ unsigned long long wfst_launch_count(void) { return g_launches.load(); }
 // --------------------------------------------------------------------- CTC
 size_t wfst_ctc_workspace_bytes(int B, int T, int C, int max_target_len) {
   (void)C;
-  return lattice_hist_bytes(B, T, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
+  return lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
 }
 
 int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
@@ -73,7 +73,7 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* hist = (float*)workspace;
-  float* z = (float*)((char*)workspace + lattice_hist_bytes(B, T, 2 * max_target_len + 1));
+  float* z = (float*)((char*)workspace + lattice_hist_bytes(B, T, C, 2 * max_target_len + 1));
   int rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
                       grad_scale, z, grad, hist, st);
   if (rc != WFST_OK) return rc;
@@ -130,7 +130,7 @@ int wfst_ctc_forward_backward_host(const float* emissions, const int32_t* target
 // ----------------------------------------------------------------- lattice
 size_t wfst_lattice_workspace_bytes(int B, int T, int C, int total_nodes, int max_nodes) {
   (void)C; (void)total_nodes;
-  return lattice_hist_bytes(B, T, max_nodes);
+  return lattice_hist_bytes(B, T, C, max_nodes);
 }
 
 int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
@@ -143,7 +143,7 @@ int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
   WFST_REQUIRE(shared_graph ? graphs->B == 1 : graphs->B == B,
                "graph batch %d does not match B=%d (shared=%d)", graphs->B, B, shared_graph);
   WFST_REQUIRE(graphs->max_nodes > 0, "empty acceptor");
-  if (workspace_bytes < lattice_hist_bytes(B, T, graphs->max_nodes)) {
+  if (workspace_bytes < lattice_hist_bytes(B, T, C, graphs->max_nodes)) {
     set_error("workspace too small");
     return WFST_ERR_WORKSPACE;
   }
@@ -159,7 +159,7 @@ int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
 // --------------------------------------------------------------------- ASG
 size_t wfst_asg_workspace_bytes(int B, int T, int C, int max_target_len) {
   int n = max_target_len + 1 > C + 1 ? max_target_len + 1 : C + 1;
-  return lattice_hist_bytes(B, T, n) + 2 * align_up((size_t)B * sizeof(float), 256);
+  return lattice_hist_bytes(B, T, C, n) + 2 * align_up((size_t)B * sizeof(float), 256);
 }
 
 int wfst_asg_forward_backward(const float* emissions, const float* transitions,
@@ -176,7 +176,7 @@ int wfst_asg_forward_backward(const float* emissions, const float* transitions,
   }
   cudaStream_t st = (cudaStream_t)stream;
   int n = max_target_len + 1 > C + 1 ? max_target_len + 1 : C + 1;
-  size_t hb = lattice_hist_bytes(B, T, n), zb = align_up((size_t)B * sizeof(float), 256);
+  size_t hb = lattice_hist_bytes(B, T, C, n), zb = align_up((size_t)B * sizeof(float), 256);
   float* hist = (float*)workspace;
   float* zfcc = (float*)((char*)workspace + hb);
   float* zfal = (float*)((char*)workspace + hb + zb);

@@ -279,7 +279,9 @@ static size_t hist_bytes(int B, int T, int stride) {
 // ---------------------------------------------------------------------------
 // internal launchers used by capi.cu
 // ---------------------------------------------------------------------------
-static LatticeArgs base_args(const float* E, int T, int C, const float* grad_scale, float sign,
+static int num_tiles(int T, int C) { int kt = pick_kt(C); return 2 * ((T + kt - 1) / kt + 1); }
+
+static LatticeArgs base_args(const float* E, int B, int T, int C, const float* grad_scale, float sign,
                              float* scores, float* gradE, int accumulate, float* hist,
                              int max_nodes, int extra_floats) {
   LatticeArgs a{};
@@ -287,16 +289,23 @@ static LatticeArgs base_args(const float* E, int T, int C, const float* grad_sca
   a.scores = scores; a.gradE = gradE; a.accumulate = accumulate;
   a.hist = hist; a.hist_stride = (max_nodes + 3) & ~3;
   a.Kt = pick_kt(C); a.npad = (max_nodes + 3) & ~3; a.extra_floats = extra_floats;
+  // the per-tile offsets live right after the history
+  a.offs = reinterpret_cast<double*>(reinterpret_cast<char*>(hist) +
+                                     hist_bytes(B, T, (max_nodes + 3) & ~3));
+  a.offs_stride = num_tiles(T, C);
+  a.renorm_every = (16 + a.Kt - 1) / a.Kt;
   return a;
 }
 
-size_t lattice_hist_bytes(int B, int T, int max_nodes) { return hist_bytes(B, T, (max_nodes + 3) & ~3); }
+size_t lattice_hist_bytes(int B, int T, int C, int max_nodes) {
+  return hist_bytes(B, T, (max_nodes + 3) & ~3) + align_up((size_t)B * num_tiles(T, C) * sizeof(double), 256);
+}
 
 int launch_ctc(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                int blank, int max_target_len, const float* grad_scale, float* scores,
                float* gradE, float* hist, cudaStream_t st) {
   int S = 2 * max_target_len + 1;
-  LatticeArgs a = base_args(E, T, C, grad_scale, -1.f, scores, gradE, 0, hist, S, 2 * S + 2);
+  LatticeArgs a = base_args(E, B, T, C, grad_scale, -1.f, scores, gradE, 0, hist, S, 2 * S + 2);
   CtcTopo::Params tp{targets, offsets, blank, C};
   return launch_lattice<CtcTopo>(a, tp, B, S, st);
 }
@@ -304,7 +313,7 @@ int launch_ctc(const float* E, const int* targets, const int* offsets, int B, in
 int launch_csr(const float* E, int T, int C, const wfst_acceptor_batch_t& g, int shared,
                const float* grad_scale, float sign, float* scores, float* gradE, int accumulate,
                float* gradW, float* hist, cudaStream_t st) {
-  LatticeArgs a = base_args(E, T, C, grad_scale, sign, scores, gradE, accumulate, hist,
+  LatticeArgs a = base_args(E, g.B, T, C, grad_scale, sign, scores, gradE, accumulate, hist,
                             g.max_nodes, gradW ? g.max_arcs : 0);
   CsrTopo::Params tp{g, gradW, shared};
   return launch_lattice<CsrTopo>(a, tp, g.B, g.max_nodes, st);
@@ -314,7 +323,7 @@ int launch_asg_fal(const float* E, const float* tr, const int* targets, const in
                    int T, int C, int max_target_len, const float* grad_scale, float sign,
                    float* scores, float* gradE, int accumulate, float* gradTr, float* hist,
                    cudaStream_t st) {
-  LatticeArgs a = base_args(E, T, C, grad_scale, sign, scores, gradE, accumulate, hist,
+  LatticeArgs a = base_args(E, B, T, C, grad_scale, sign, scores, gradE, accumulate, hist,
                             max_target_len + 1, gradTr ? (C + 1) * C : 0);
   AsgFalTopo::Params tp{targets, offsets, tr, gradTr, C};
   return launch_lattice<AsgFalTopo>(a, tp, B, max_target_len + 1, st);
@@ -323,7 +332,7 @@ int launch_asg_fal(const float* E, const float* tr, const int* targets, const in
 int launch_asg_fcc(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
                    float sign, float* scores, float* gradE, int accumulate, float* gradTr,
                    float* hist, cudaStream_t st) {
-  LatticeArgs a = base_args(E, T, C, grad_scale, sign, scores, gradE, accumulate, hist, C + 1,
+  LatticeArgs a = base_args(E, B, T, C, grad_scale, sign, scores, gradE, accumulate, hist, C + 1,
                             gradTr ? (C + 1) * C : 0);
   AsgFccTopo::Params tp{tr, gradTr, C};
   return launch_lattice<AsgFccTopo>(a, tp, B, C + 1, st);

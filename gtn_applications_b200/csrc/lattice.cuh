@@ -32,6 +32,9 @@ struct LatticeArgs {
   int accumulate;        // add into gradE instead of overwriting
   float* hist;           // [B, T+1, hist_stride] alpha history
   int hist_stride;       // >= max nodes
+  double* offs;          // [B, offs_stride] per tile: {cumulative alpha offset, per-frame drift}
+  int offs_stride;       // >= 2 * number of tiles
+  int renorm_every;      // renormalise alpha/beta every this many tiles
   int Kt;                // frames per tile (multiple of 4)
   int npad;              // smem floats reserved per alpha buffer
   int extra_floats;      // policy-owned smem floats (after the fixed regions)
@@ -89,6 +92,18 @@ __device__ __forceinline__ float block_lse(float v, float* red) {
   return (bm == kNegInf) ? kNegInf : bm + __logf(bs);
 }
 
+// block-wide max (all threads get the result)
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  float m = warp_max(v);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  float bm = (lane < nw) ? red[lane] : kNegInf;
+  bm = warp_max(bm);
+  __syncthreads();
+  return bm;
+}
+
 template <class Topo>
 __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a, typename Topo::Params tp) {
   extern __shared__ __align__(16) float smem_raw[];
@@ -101,6 +116,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
   const int T = a.T, C = a.C, Kt = a.Kt;
   const float* Eb = a.E + (size_t)b * T * C;
   float* hist = a.hist + (size_t)b * (T + 1) * a.hist_stride;
+  double* offA = a.offs + (size_t)b * a.offs_stride;
   const int ntiles = (T + Kt - 1) / Kt;
 
   if (tid == 0) {
@@ -141,6 +157,8 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
   // ------------------------------------------------------------- forward
   float* cur = sm.alpha0;
   float* nxt = sm.alpha1;
+  double cumA = 0.0;  // identical in every thread
+  float dA = 0.f;     // per-frame drift compensation, re-estimated at every renormalisation
   for (int v = tid; v < N; v += NT) {
     float x = topo.is_start(v) ? 0.f : kNegInf;
     cur[v] = x;
@@ -153,6 +171,22 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
     wait_tile(i, buf);
     if (i + 1 < ntiles) issue_tile(i + 1, buf ^ 1);
     const int rows = tile_rows(i);
+    // Renormalisation keeps |alpha| bounded for any T: every `renorm_every` tiles alpha
+    // is re-centred on its maximum; the removed offset is carried in float64.  (dA/dB are
+    // a per-frame drift term, currently always 0: measured on B200 it did not improve
+    // accuracy because the posterior-relevant states are not the ones near the maximum.)  Hist row t (t >= 1), written at in-tile step k of tile i, is relative to
+    // offA[2i] + (k+1) * offA[2i+1].
+    if (i % a.renorm_every == 0) {
+      float pm = kNegInf;
+      for (int v = tid; v < N; v += NT) pm = fmaxf(pm, cur[v]);
+      const float mx = block_max(pm, sm.red);
+      if (mx != kNegInf && mx != -kNegInf && mx == mx) {
+        for (int v = tid; v < N; v += NT) cur[v] -= mx;
+        cumA += (double)mx;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) { offA[2 * i] = cumA; offA[2 * i + 1] = (double)dA; }
     for (int tt = 0; tt < rows; ++tt) {
       const float* Et = tiles[buf] + tt * C;
       const int t = i * Kt + tt;
@@ -168,11 +202,12 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
           topo.in_arcs(v, [&](int u, int lab, float w, int) {
             s += __expf(cur[u] + Et[lab] + w - m);
           });
-          r = m + __logf(s);
+          r = m + __logf(s) - dA;
         }
         nxt[v] = r;
         hrow[v] = r;
       }
+      cumA += (double)dA;
       __syncthreads();
       float* tmp = cur;
       cur = nxt;
@@ -184,7 +219,9 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
   float part = kNegInf;
   for (int v = tid; v < N; v += NT)
     if (topo.is_accept(v)) part = log_add(part, cur[v]);
-  const float Z = block_lse(part, sm.red);
+  const float Zn = block_lse(part, sm.red);   // relative to cumA
+  const double Zd = (double)Zn + cumA;
+  const float Z = (float)Zd;
   if (tid == 0) a.scores[b] = Z;
   const bool want_gE = a.gradE != nullptr;
   const bool want_gW = topo.wants_weight_grad();
@@ -204,6 +241,8 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
   // beta_{t+1} lives in `nxt`, beta_t is written to `cur`
   __syncthreads();
   for (int v = tid; v < N; v += NT) nxt[v] = topo.is_accept(v) ? 0.f : kNegInf;
+  double cumB = 0.0;
+  float dB = 0.f;
   if (ntiles > 0) issue_tile(ntiles - 1, (ntiles - 1) & 1);
   __syncthreads();
   for (int i = ntiles - 1; i >= 0; --i) {
@@ -214,13 +253,27 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
     float* gt = sm.gtile;
     if (want_gE) {
       for (int k = tid; k < rows * C; k += NT) gt[k] = 0.f;
-      __syncthreads();
     }
+    if ((ntiles - 1 - i) % a.renorm_every == 0) {
+      float pm = kNegInf;
+      for (int v = tid; v < N; v += NT) pm = fmaxf(pm, nxt[v]);
+      const float mx = block_max(pm, sm.red);
+      if (mx != kNegInf && mx != -kNegInf && mx == mx) {
+        for (int v = tid; v < N; v += NT) nxt[v] -= mx;
+        cumB += (double)mx;
+      }
+    }
+    __syncthreads();
+    // offset of alpha row t = i*Kt + tt: row i*Kt is the last row of tile i-1
+    const double oa_first = (i > 0) ? offA[2 * (i - 1)] + (double)Kt * offA[2 * (i - 1) + 1] : 0.0;
+    const double oa_base = offA[2 * i], oa_step = offA[2 * i + 1];
     for (int tt = rows - 1; tt >= 0; --tt) {
       const float* Et = tiles[buf] + tt * C;
       const int t = i * Kt + tt;
       const float* hrow = hist + (size_t)t * a.hist_stride;
       float* grow = gt + tt * C;
+      // log-normaliser of this frame's posteriors, exact in float64
+      const float dlt = (float)(((tt == 0) ? oa_first : oa_base + (double)tt * oa_step) + cumB - Zd);
       for (int u = tid; u < N; u += NT) {
         const float au = hrow[u];
         float m = kNegInf;
@@ -231,26 +284,40 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
         if (m != kNegInf) {
           float s = 0.f;
           const bool live = au != kNegInf;
-          const float off = au - Z;
+          const float off = au + dlt;
           topo.out_arcs(u, [&](int v, int lab, float w, int arc) {
             float x = Et[lab] + w + nxt[v];
             s += __expf(x - m);
             if (live && x != kNegInf) {
               float p = __expf(x + off);
-              if (want_gE) atomicAdd(&grow[lab], p * gs);
+              if (want_gE) atomicAdd(&grow[lab], p);
               topo.add_weight_grad(arc, p);
             }
           });
-          r = m + __logf(s);
+          r = m + __logf(s) - dB;
         }
         cur[u] = r;
       }
+      cumB += (double)dB;
       __syncthreads();
       float* tmp = cur;
       cur = nxt;
       nxt = tmp;
     }
     if (want_gE) {
+      // Every accepting path crosses each frame exactly once, so the posteriors of a
+      // frame sum to one.  Normalising each row by its own sum removes the common-mode
+      // rounding error that alpha_t + beta_t - Z has picked up over the T steps.
+      const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
+      for (int r = wid; r < rows; r += nw) {
+        float* row = gt + r * C;
+        float rs = 0.f;
+        for (int c = lane; c < C; c += 32) rs += row[c];
+        rs = warp_sum(rs);
+        const float f = (rs > 0.f) ? gs / rs : 0.f;
+        for (int c = lane; c < C; c += 32) row[c] *= f;
+      }
+      __syncthreads();
       float* dst = gEb + (size_t)i * Kt * C;
       const int n = rows * C;
       const bool tma = !a.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);

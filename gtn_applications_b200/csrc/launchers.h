@@ -5,7 +5,7 @@
 #include "../../include/wfst_b200.h"
 
 namespace wfst {
-size_t lattice_hist_bytes(int B, int T, int max_nodes);
+size_t lattice_hist_bytes(int B, int T, int C, int max_nodes);
 int launch_ctc(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                int blank, int max_target_len, const float* grad_scale, float* scores,
                float* gradE, float* hist, cudaStream_t st);

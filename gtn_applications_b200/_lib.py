@@ -35,6 +35,8 @@ SIGNATURES = {
     "wfst_last_error": (ctypes.c_char_p, []),
     "wfst_abi_version": (_I, []),
     "wfst_launch_count": (ctypes.c_ulonglong, []),
+    "wfst_debug_force_generic_ctc": (_I, [_I]),
+    "wfst_debug_ctc_hazards": (_I, [_P, _I, _I, _I, _I, _P]),
     "wfst_ctc_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "wfst_ctc_forward_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "wfst_ctc_forward_backward_host": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),

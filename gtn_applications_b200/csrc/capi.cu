@@ -39,6 +39,8 @@ struct HostPathBuffers {
   }
 };
 static HostPathBuffers g_host;
+// test hook: route CTC through the log-semiring kernel only
+static int g_force_generic = 0;
 
 }  // namespace wfst
 
@@ -48,12 +50,15 @@ extern "C" {
 
 const char* wfst_last_error(void) { return g_err; }
 int wfst_abi_version(void) { return WFST_ABI_VERSION; }
+int wfst_debug_force_generic_ctc(int on) { int old = g_force_generic; g_force_generic = on; return old; }
 unsigned long long wfst_launch_count(void) { return g_launches.load(); }
 
 // --------------------------------------------------------------------- CTC
+// workspace: [alpha history of the log-semiring kernel][scores B][fast-path checkpoints + hazard]
 size_t wfst_ctc_workspace_bytes(int B, int T, int C, int max_target_len) {
-  (void)C;
-  return lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
+  size_t n = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
+  if (ctc_fast_eligible(T, C, max_target_len)) n += ctc_fast_workspace_bytes(B, T, max_target_len);
+  return n;
 }
 
 int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
@@ -73,11 +78,37 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* hist = (float*)workspace;
-  float* z = (float*)((char*)workspace + lattice_hist_bytes(B, T, C, 2 * max_target_len + 1));
-  int rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
-                      grad_scale, z, grad, hist, st);
+  size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1);
+  float* z = (float*)((char*)workspace + hb);
+  int rc;
+  if (ctc_fast_eligible(T, C, max_target_len) && !g_force_generic) {
+    // scaled-probability kernel; utterances it flags are redone by the log-semiring kernel
+    int* hazard = nullptr;
+    void* fws = (char*)workspace + hb + align_up((size_t)B * sizeof(float), 256);
+    rc = launch_ctc_fast(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+                         grad_scale, z, grad, fws, &hazard, st);
+    if (rc != WFST_OK) return rc;
+    rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
+                    z, grad, hist, hazard, st);
+  } else {
+    rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
+                    z, grad, hist, nullptr, st);
+  }
   if (rc != WFST_OK) return rc;
   return launch_finalize(z, nullptr, -1.f, B, grad_scale, loss, mean_loss, st);
+}
+
+int wfst_debug_ctc_hazards(const void* workspace, int B, int T, int C, int max_target_len,
+                            int32_t* host_flags) {
+  WFST_REQUIRE(workspace && host_flags, "null pointer argument");
+  for (int b = 0; b < B; ++b) host_flags[b] = -1;
+  if (!ctc_fast_eligible(T, C, max_target_len)) return WFST_OK;
+  size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
+  size_t fb = ctc_fast_workspace_bytes(B, T, max_target_len);
+  const char* hz = (const char*)workspace + hb + fb - align_up((size_t)B * sizeof(int), 256);
+  WFST_CUDA_CHECK(cudaDeviceSynchronize());
+  WFST_CUDA_CHECK(cudaMemcpy(host_flags, hz, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost));
+  return WFST_OK;
 }
 
 int wfst_ctc_forward_backward_host(const float* emissions, const int32_t* targets,

@@ -303,9 +303,10 @@ size_t lattice_hist_bytes(int B, int T, int C, int max_nodes) {
 
 int launch_ctc(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                int blank, int max_target_len, const float* grad_scale, float* scores,
-               float* gradE, float* hist, cudaStream_t st) {
+               float* gradE, float* hist, const int* active, cudaStream_t st) {
   int S = 2 * max_target_len + 1;
   LatticeArgs a = base_args(E, B, T, C, grad_scale, -1.f, scores, gradE, 0, hist, S, 2 * S + 2);
+  a.active = active;
   CtcTopo::Params tp{targets, offsets, blank, C};
   return launch_lattice<CtcTopo>(a, tp, B, S, st);
 }

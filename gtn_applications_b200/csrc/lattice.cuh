@@ -38,6 +38,7 @@ struct LatticeArgs {
   int Kt;                // frames per tile (multiple of 4)
   int npad;              // smem floats reserved per alpha buffer
   int extra_floats;      // policy-owned smem floats (after the fixed regions)
+  const int* active;     // optional [B]: blocks with active[b] == 0 return at once
 };
 
 // shared memory carve-up (all float-sized slots; base is 16B aligned)
@@ -108,6 +109,7 @@ template <class Topo>
 __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a, typename Topo::Params tp) {
   extern __shared__ __align__(16) float smem_raw[];
   const int b = blockIdx.x;
+  if (a.active && a.active[b] == 0) return;
   const int tid = threadIdx.x, NT = blockDim.x;
   SmemLayout sm = carve(smem_raw, a);
   Topo topo;

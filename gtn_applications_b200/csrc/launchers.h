@@ -8,7 +8,7 @@ namespace wfst {
 size_t lattice_hist_bytes(int B, int T, int C, int max_nodes);
 int launch_ctc(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                int blank, int max_target_len, const float* grad_scale, float* scores,
-               float* gradE, float* hist, cudaStream_t st);
+               float* gradE, float* hist, const int* active, cudaStream_t st);
 int launch_csr(const float* E, int T, int C, const wfst_acceptor_batch_t& g, int shared,
                const float* grad_scale, float sign, float* scores, float* gradE, int accumulate,
                float* gradW, float* hist, cudaStream_t st);
@@ -22,4 +22,10 @@ int launch_asg_fcc(const float* E, const float* tr, int B, int T, int C, const f
 int launch_finalize(const float* za, const float* zb, float sign, int B, const float* grad_scale,
                     float* loss, float* mean_loss, cudaStream_t st);
 int launch_scale(float* x, size_t n, const float* scale, cudaStream_t st);
+// fast CTC (ctc_fast.cu)
+bool ctc_fast_eligible(int T, int C, int max_target_len);
+size_t ctc_fast_workspace_bytes(int B, int T, int max_target_len);
+int launch_ctc_fast(const float* E, const int* targets, const int* offsets, int B, int T, int C,
+                    int blank, int max_target_len, const float* grad_scale, float* z_out,
+                    float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
 }  // namespace wfst

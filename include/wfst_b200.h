@@ -52,6 +52,12 @@ extern "C" {
 /* thread-local message of the last error returned on this thread ("" if none) */
 WFST_API const char* wfst_last_error(void);
 WFST_API int wfst_abi_version(void);
+/* test hook: 1 = run CTC on the log-semiring lattice kernel only (returns the old value) */
+WFST_API int wfst_debug_force_generic_ctc(int on);
+/* test hook: copies the per-utterance fallback flags of the last CTC call that used
+ * `workspace` to the host (1 = recomputed by the log-semiring kernel, -1 = fast path not used) */
+WFST_API int wfst_debug_ctc_hazards(const void* workspace, int B, int T, int C, int max_target_len,
+                                    int32_t* host_flags);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 WFST_API unsigned long long wfst_launch_count(void);
 

@@ -36,10 +36,20 @@
 
 namespace wfst {
 
+#ifdef WFST_PROFILE
+#define PROF_DECL long long pf_t0 = clock64(), pf_acc[8] = {0,0,0,0,0,0,0,0}
+#define PROF_MARK(i) do { long long pf_t1 = clock64(); pf_acc[i] += pf_t1 - pf_t0; pf_t0 = pf_t1; } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#endif
+
 constexpr int kSeg = 16;              // frames per segment / tile
-constexpr int kUndef = -(1 << 20);    // "no exponent": lane holds only zeros
+constexpr int kUndef = -(1 << 19);    // "no exponent": lane holds only zeros
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNB = 2;                // p-tile ring depth per direction
+constexpr int kNR = 4;                // raw (TMA) staging slots of the producer
+constexpr int kMaxPass = 4;           // transposed pass: up to 4 x 32 chunk slots per gamma row
 
 struct CtcFastArgs {
   const float* E;
@@ -56,6 +66,30 @@ struct CtcFastArgs {
   int RS;           // row stride of the stored/gamma buffer (= 4 mod 32, >= Sp and >= gamma columns)
 };
 
+// Explicit shared-state-space accesses on 32-bit addresses: generic pointers made the
+// compiler emit LD.E with 64-bit address arithmetic (5 instructions per load).
+__device__ __forceinline__ float lds(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ int2 lds64i(uint32_t a) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+
 __device__ __forceinline__ bool defined_exp(int e) { return e > kUndef / 2; }
 __device__ __forceinline__ float pow2i(int d) {  // 2^d for d in [-126, 127]
   return __uint_as_float((uint32_t)(d + 127) << 23);
@@ -66,9 +100,10 @@ __device__ __forceinline__ float pow2i(int d) {  // 2^d for d in [-126, 127]
 // ---------------------------------------------------------------------------
 template <int K>
 struct LaneTopo {
-  int labcol[K / 2];   // p-tile column of each label-type slot (C = zero column for padding)
-  float skipm[K / 2];  // 1 if the skip arc into the label-type slot exists
-  int gcol[K / 2];     // column of the slot's posterior in the sorted gamma row
+  uint32_t labofs[K / 2];  // byte offset in a p-tile row of each label-type slot's label
+                           // (column C, always zero, for padding slots)
+  float skipm[K / 2];      // 1 if the skip arc into the label-type slot exists
+  uint32_t gofs[K / 2];    // byte offset of the slot's posterior in the sorted gamma row
 };
 
 // ODD: label-type states sit at odd slots (orientation 0) or even slots (orientation 1)
@@ -93,29 +128,40 @@ __device__ __forceinline__ void build_topo(LaneTopo<K>& tp, int lane, const int*
       const int n2 = ODD ? n - 1 : n + 1;
       if (n2 >= 0 && n2 < L && y[n2] != y[n]) sk = 1.f;
     }
-    tp.labcol[q] = col;
+    tp.labofs[q] = 4u * (uint32_t)col;
     tp.skipm[q] = sk;
-    tp.gcol[q] = gc;
+    tp.gofs[q] = 4u * (uint32_t)gc;
   }
+}
+
+// The p values one frame needs: the label-type slots' labels and the blank.
+template <int K>
+struct PRow {
+  float pl[K / 2];
+  float pb;
+};
+template <int K>
+__device__ __forceinline__ PRow<K> load_prow(const LaneTopo<K>& tp, uint32_t prow, uint32_t blank_ofs) {
+  PRow<K> p;
+#pragma unroll
+  for (int q = 0; q < K / 2; ++q) p.pl[q] = lds(prow + tp.labofs[q]);
+  p.pb = lds(prow + blank_ofs);
+  return p;
 }
 
 // One frame of the recursion. v: with-emission values of the previous frame (own scale).
 // On return v holds this frame's with-emission values and, if WANT_ABAR, abar the
 // pre-emission sums.  f converts the left neighbour's scale to ours (0 in lane 0).
+// The p values are loaded by the caller one frame ahead (the shared-memory accessors are
+// volatile asm, so the software pipelining has to be explicit).
 template <int K, bool ODD, bool WANT_ABAR>
 __device__ __forceinline__ void step(float (&v)[K], float (&abar)[K], const LaneTopo<K>& tp,
-                                     const float* __restrict__ prow, int blank, float f) {
-  float pl[K / 2];
-#pragma unroll
-  for (int q = 0; q < K / 2; ++q) pl[q] = prow[tp.labcol[q]];
-  const float pb = prow[blank];
+                                     const PRow<K>& p, float f) {
   const float in1 = __shfl_up_sync(kFull, v[K - 1], 1) * f;
   float in2 = 0.f;
   if (!ODD) in2 = __shfl_up_sync(kFull, v[K - 2], 1) * f;
 #pragma unroll
   for (int i = K - 1; i >= 0; --i) {
-    constexpr bool dummy = false;
-    (void)dummy;
     const bool lab = ((i & 1) == 1) == ODD;
     const float a1 = (i >= 1) ? v[i - 1] : in1;
     float s = v[i] + a1;
@@ -124,10 +170,10 @@ __device__ __forceinline__ void step(float (&v)[K], float (&abar)[K], const Lane
       const float a2 = (i >= 2) ? v[i - 2] : (i == 1 ? in1 : in2);
       s = fmaf(tp.skipm[q], a2, s);
       if (WANT_ABAR) abar[i] = s;
-      v[i] = s * pl[q];
+      v[i] = s * p.pl[q];
     } else {
       if (WANT_ABAR) abar[i] = s;
-      v[i] = s * pb;
+      v[i] = s * p.pb;
     }
   }
 }
@@ -157,11 +203,13 @@ __device__ __forceinline__ void event(float (&v)[K], int& e, float& f, int lane)
     for (int i = 0; i < K; ++i) v[i] *= sc;
     eown = (defined_exp(e) ? e : 0) + ex;
   }
+  // (c, d) packed in one int: c * 2048 + d, d < 2048
   int c = eown, d = defined_exp(eown) ? D : 0;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int pc = __shfl_up_sync(kFull, c, o);
-    const int pd = __shfl_up_sync(kFull, d, o);
+    const int packed = __shfl_up_sync(kFull, c * 2048 + d, o);
+    const int pd = packed & 2047;
+    const int pc = (packed - pd) / 2048;
     if (lane >= o) {
       if (defined_exp(pc)) c = defined_exp(c) ? max(c, pc - d) : pc - d;
       d += pd;
@@ -205,16 +253,22 @@ template <int K>
 struct FastSmem {
   static constexpr int Sp = 32 * K;
   // per direction
-  float* stored[2];   // [kSeg][RS] recomputed opposite-direction values; row r is re-used
-                      // for the sorted per-state posteriors ("gamma") once it has been read
-  float* pbk[2];      // [kSeg][33] blank partials
-  float* out[2];      // [2][kSeg*C] output tiles (double buffered)
-  float* ptile[2];    // [kNB][kSeg][Cp]
+  // (two explicit members instead of arrays: indexing an array of pointers with the
+  // runtime direction would push the whole struct into local memory)
+  float *stored0, *stored1;   // [kSeg][RS] recomputed opposite-direction values; row r is re-used
+                              // for the sorted per-state posteriors ("gamma") once it has been read
+  float *pbk0, *pbk1;         // [kSeg][33] blank partials
+  float *out0, *out1;         // [2][kSeg*C] output tiles (double buffered)
+  float *ptile0, *ptile1;     // [kNB][kSeg][Cp]
+  __device__ __forceinline__ float* stored(int d) const { return d ? stored1 : stored0; }
+  __device__ __forceinline__ float* pbk(int d) const { return d ? pbk1 : pbk0; }
+  __device__ __forceinline__ float* out(int d) const { return d ? out1 : out0; }
+  __device__ __forceinline__ float* ptile(int d) const { return d ? ptile1 : ptile0; }
   // shared
-  float* raw;         // [2][kSeg*C] TMA staging (16B aligned)
+  float* raw;         // [kNR][kSeg*C] TMA staging (16B aligned)
   int* gcolpos;       // [Sp/2] gamma column of target position n
-  int* runs;          // [2][C+1][2] per half: (label, end column); terminated by label -1
-  int* hist;          // [C + 2] scratch for the counting sort
+  int* slotlab;       // [32*kMaxPass + 8] label of each 4-column chunk slot of the gamma row (-1: unused)
+  int* hist;          // [C + 4] scratch for the counting sort; [C]: #slots, [C+1]: max chunks per label
   uint64_t* bars;     // full[2][kNB], empty[2][kNB], tma[2], zready
   float* zx;          // Zm, eZ (as int bits), valid flag
   double* msum;       // sum of per-frame maxima (phase-1 frames)
@@ -225,7 +279,7 @@ __host__ __device__ inline size_t fast_smem_floats(int K, int C, int Cp, int RS)
   size_t per_dir = (size_t)kSeg * RS + kSeg * 33 + 2 * (((size_t)kSeg * C + 3) & ~3) +
                    (size_t)kNB * kSeg * Cp;
   per_dir = (per_dir + 3) & ~(size_t)3;
-  size_t shared = 2 * (((size_t)kSeg * C + 3) & ~3) + Sp / 2 + 4 * (C + 1) + (C + 2) + 2 * 16 + 8 + 4;
+  size_t shared = kNR * (((size_t)kSeg * C + 3) & ~3) + Sp / 2 + (32 * kMaxPass + 8) + (C + 4) + 2 * 16 + 8 + 4;
   return 2 * per_dir + shared + 16;
 }
 
@@ -235,25 +289,29 @@ __device__ __forceinline__ FastSmem<K> carve_fast(float* base, int C, int Cp, in
   FastSmem<K> s;
   float* p = base;
   const size_t outsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
-  s.raw = p; p += 2 * outsz;                       // 16B aligned (base is)
-  for (int d = 0; d < 2; ++d) { s.out[d] = p; p += 2 * outsz; }
-  for (int d = 0; d < 2; ++d) { s.stored[d] = p; p += (size_t)kSeg * RS; }
+  s.raw = p; p += kNR * outsz;                     // 16B aligned (base is)
+  s.out0 = p; p += 2 * outsz;
+  s.out1 = p; p += 2 * outsz;
+  s.stored0 = p; p += (size_t)kSeg * RS;
+  s.stored1 = p; p += (size_t)kSeg * RS;
   s.bars = reinterpret_cast<uint64_t*>(p); p += 2 * 16;      // up to 16 barriers
   s.msum = reinterpret_cast<double*>(p); p += 4;
   s.zx = p; p += 4;
-  for (int d = 0; d < 2; ++d) { s.pbk[d] = p; p += kSeg * 33; }
-  for (int d = 0; d < 2; ++d) { s.ptile[d] = p; p += (size_t)kNB * kSeg * Cp; }
+  s.pbk0 = p; p += kSeg * 33;
+  s.pbk1 = p; p += kSeg * 33;
+  s.ptile0 = p; p += (size_t)kNB * kSeg * Cp;
+  s.ptile1 = p; p += (size_t)kNB * kSeg * Cp;
   s.gcolpos = reinterpret_cast<int*>(p); p += Sp / 2;
-  s.runs = reinterpret_cast<int*>(p); p += 4 * (C + 1);
-  s.hist = reinterpret_cast<int*>(p); p += C + 2;
+  s.slotlab = reinterpret_cast<int*>(p); p += 32 * kMaxPass + 8;
+  s.hist = reinterpret_cast<int*>(p); p += C + 4;
   return s;
 }
 
 // barrier indices
 __device__ __forceinline__ int bar_full(int d, int i) { return d * kNB + i; }
 __device__ __forceinline__ int bar_empty(int d, int i) { return 2 * kNB + d * kNB + i; }
-constexpr int kBarTma = 4 * kNB;      // +0, +1
-constexpr int kBarZ = 4 * kNB + 2;
+constexpr int kBarTma = 4 * kNB;      // + raw slot
+constexpr int kBarZ = 4 * kNB + kNR;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -263,184 +321,19 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 }
 
 // ---------------------------------------------------------------------------
-// the kernel
+// One direction of one utterance (a whole warp).  DIR 0: alpha, time ascending, states
+// j = s.  DIR 1: beta, time descending, mirrored states j = Sp-1-s.
 // ---------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
+template <int K, int DIR>
+__device__ __forceinline__ void run_direction(const CtcFastArgs& a, const FastSmem<K>& sm, int b, int lane) {
   constexpr int Sp = 32 * K;
-  extern __shared__ __align__(16) float smem_raw[];
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int dir = DIR;
   const int T = a.T, C = a.C, Cp = a.Cp, RS = a.RS;
-  FastSmem<K> sm = carve_fast<K>(smem_raw, C, Cp, RS);
   const int* y = a.targets + a.offsets[b];
   const int L = a.offsets[b + 1] - a.offsets[b];
   const int nseg = a.nseg, nA = a.nA;
   const bool want_grad = a.gradE != nullptr;
-  const float* Eb = a.E + (size_t)b * T * C;
   const int dump_col = RS - 1;
-
-  // ------------------------------------------------------------------ setup
-  if (threadIdx.x == 0) {
-    for (int d = 0; d < 2; ++d)
-      for (int i = 0; i < kNB; ++i) {
-        mbar_init(&sm.bars[bar_full(d, i)], 1);
-        mbar_init(&sm.bars[bar_empty(d, i)], 1);
-      }
-    mbar_init(&sm.bars[kBarTma], 1);
-    mbar_init(&sm.bars[kBarTma + 1], 1);
-    mbar_init(&sm.bars[kBarZ], 1);
-    fence_barrier_init();
-  }
-  // zero the regions that rely on it: p-tile padding columns, output tiles (labels that
-  // do not occur in the target keep a zero gradient), blank partials
-  for (int d = 0; d < 2; ++d) {
-    for (int k = threadIdx.x; k < kNB * kSeg * Cp; k += 96) sm.ptile[d][k] = 0.f;
-    for (int k = threadIdx.x; k < 2 * (int)(((size_t)kSeg * C + 3) & ~(size_t)3); k += 96) sm.out[d][k] = 0.f;
-    for (int k = threadIdx.x; k < kSeg * 33; k += 96) sm.pbk[d][k] = 0.f;
-    for (int k = threadIdx.x; k < kSeg * RS; k += 96) sm.stored[d][k] = 0.f;
-  }
-  // counting sort of the target positions by label -> gamma columns; each label's run is
-  // padded to a multiple of 4 columns; labels are split into two halves (one per
-  // half-warp of the transposed pass), the second half starting at a column = 16 mod 32
-  for (int k = threadIdx.x; k < C + 2; k += 96) sm.hist[k] = 0;
-  __syncthreads();
-  int has_blank = 0;
-  for (int n = threadIdx.x; n < L; n += 96) {
-    atomicAdd(&sm.hist[y[n]], 1);
-    has_blank |= (y[n] == a.blank);
-  }
-  if (__syncthreads_or(has_blank)) {
-    // a target that contains the blank label shares a gradient column between a label
-    // state and the blank states: leave it to the log-semiring kernel
-    if (threadIdx.x == 0) a.hazard[b] = 1;   // reason 1: blank label inside the target
-    return;
-  }
-  if (threadIdx.x == 0) {
-    // serial over C labels (C is small); runs[h][r] = (label, end column)
-    int half_target = (L + 1) / 2, seen = 0, col = 0, h = 0, r = 0;
-    int* runs = sm.runs;
-    for (int c = 0; c < C; ++c) {
-      const int cnt = sm.hist[c];
-      sm.hist[c] = col;                 // becomes the write cursor of label c
-      if (cnt == 0) continue;
-      const int width = (cnt + 3) & ~3;
-      runs[(h * (C + 1) + r) * 2 + 0] = c;
-      runs[(h * (C + 1) + r) * 2 + 1] = col + width;
-      ++r;
-      col += width;
-      seen += cnt;
-      if (h == 0 && seen >= half_target) {
-        runs[(0 * (C + 1) + r) * 2 + 0] = -1;
-        h = 1; r = 0;
-        col = ((col + 15) & ~31) + 16;  // next column = 16 mod 32, >= col
-        sm.hist[C] = col;               // first column of the second half
-      }
-    }
-    if (h == 0) { runs[(0 * (C + 1) + r) * 2 + 0] = -1; h = 1; r = 0; sm.hist[C] = col; }
-    runs[(1 * (C + 1) + r) * 2 + 0] = -1;
-    sm.hist[C + 1] = col;               // first unused column (must be < RS - 1)
-  }
-  __syncthreads();
-  // second-half start column is recomputed by each reader from runs; assign columns
-  for (int n = threadIdx.x; n < L; n += 96) sm.gcolpos[n] = atomicAdd(&sm.hist[y[n]], 1);
-  __syncthreads();
-
-  // ===================================================================== producer
-  if (warp == 2) {
-    // Direction 0 consumes tiles 0,1,...; direction 1 consumes nseg-1, nseg-2, ...
-    // Without a gradient only the phase-1 tiles are needed.
-    const int ntile[2] = {want_grad ? nseg : nA, want_grad ? nseg : (nseg - nA)};
-    const int total = max(ntile[0], ntile[1]);
-    const int fr = lane & 15, hh = lane >> 4;
-    const int c0 = hh ? (C + 1) / 2 : 0, c1 = hh ? C : (C + 1) / 2;
-    const size_t rawsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
-    double msum = 0.0;
-    uint32_t tma_phase[2] = {0u, 0u};
-    uint32_t empty_phase[2][kNB] = {{0u, 0u}, {0u, 0u}};
-    auto tile_of = [&](int d, int k) { return d == 0 ? k : nseg - 1 - k; };
-    // the schedule is the sequence (k, d), k = 0.., d = 0, 1, restricted to k < ntile[d]
-    auto next_entry = [&](int& k, int& d) {
-      do {
-        if (d == 0) d = 1; else { d = 0; ++k; }
-      } while (k < total && k >= ntile[d]);
-    };
-    auto issue_raw = [&](int tile, int slot) -> bool {
-      const int rows = min(kSeg, T - tile * kSeg);
-      const float* src = Eb + (size_t)tile * kSeg * C;
-      const uint32_t bytes = (uint32_t)rows * C * 4u;
-      float* dst = sm.raw + (size_t)slot * rawsz;
-      const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15u) == 0);
-      if (tma) {
-        if (lane == 0) {
-          mbar_expect_tx(&sm.bars[kBarTma + slot], bytes);
-          bulk_g2s(dst, src, bytes, &sm.bars[kBarTma + slot]);
-        }
-      } else {
-        for (int q = lane; q < rows * C; q += 32) dst[q] = __ldg(src + q);
-        __syncwarp();
-      }
-      return tma;
-    };
-    int k = 0, d = -1;
-    {  // first entry
-      int kk = 0, dd = 1; --kk;  // so that next_entry lands on (0, 0) if valid
-      kk = -1; dd = 1;
-      next_entry(kk, dd);
-      k = kk; d = dd;
-    }
-    int slot = 0;
-    bool cur_tma = false;
-    if (k < total) cur_tma = issue_raw(tile_of(d, k), slot);
-    while (k < total) {
-      int nk = k, nd = d;
-      next_entry(nk, nd);
-      bool next_tma = false;
-      if (nk < total) next_tma = issue_raw(tile_of(nd, nk), slot ^ 1);   // prefetch
-      const int tile = tile_of(d, k);
-      const int rows = min(kSeg, T - tile * kSeg);
-      const int buf = k % kNB;
-      if (k >= kNB) {  // wait until the consumer has released this p-tile buffer
-        mbar_wait(&sm.bars[bar_empty(d, buf)], empty_phase[d][buf]);
-        empty_phase[d][buf] ^= 1u;
-      }
-      if (cur_tma) {
-        mbar_wait(&sm.bars[kBarTma + slot], tma_phase[slot]);
-        tma_phase[slot] ^= 1u;
-      }
-      const float* er = sm.raw + (size_t)slot * rawsz + fr * C;
-      float* pt = sm.ptile[d] + (size_t)buf * kSeg * Cp + fr * Cp;
-      float mx = kNegInf;
-      if (fr < rows)
-        for (int c = c0; c < c1; ++c) mx = fmaxf(mx, er[c]);
-      mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 16));
-      if (fr < rows) {
-        // a row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface
-        // through the row-sum certificate
-        const float base = (mx == kNegInf) ? 0.f : mx;
-        for (int c = c0; c < c1; ++c) pt[c] = __expf(er[c] - base);
-        const bool phase1 = (d == 0) ? (tile < nA) : (tile >= nA);
-        if (hh == 0 && phase1) msum += (double)base;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.bars[bar_full(d, buf)]);
-      k = nk; d = nd; slot ^= 1; cur_tma = next_tma;
-    }
-    // loss: log Z = log(Zm) + eZ ln2 + sum_t max_t
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(kFull, msum, o);
-    mbar_wait(&sm.bars[kBarZ], 0u);
-    if (lane == 0) {
-      const float Zm = sm.zx[0];
-      const int eZ = __float_as_int(sm.zx[1]);
-      const bool ok = sm.zx[2] != 0.f;
-      a.z_out[b] = ok ? (float)(log((double)Zm) + (double)eZ * 0.6931471805599453 + msum) : kNegInf;
-    }
-    return;
-  }
-
-  // ===================================================================== A / B
-  const int dir = warp;  // 0: alpha (ascending), 1: beta (descending, mirrored)
   float* ck_own = a.ckpt + ((size_t)b * 2 + dir) * (size_t)(nseg + 1) * (K + 1) * 32;
   const float* ck_other = a.ckpt + ((size_t)b * 2 + (1 - dir)) * (size_t)(nseg + 1) * (K + 1) * 32;
   const int blank = a.blank;
@@ -463,21 +356,25 @@ __global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
     // virtual pre-frame state: all mass on the start state of this orientation
     const int S = 2 * L + 1;
     const int jstart = (dir == 0) ? 0 : Sp - S;
-    if (jstart / K == lane) {
+    const bool mine = (jstart / K == lane);
+    const int jm = jstart % K;
 #pragma unroll
-      for (int i = 0; i < K; ++i)
-        if (i == jstart % K) v[i] = 1.f;
-      e = 0;
-    }
+    for (int i = 0; i < K; ++i) v[i] = (mine && jm == i) ? 1.f : 0.f;   // selects, no dynamic index
+    if (mine) e = 0;
   }
 
-  uint32_t full_phase[kNB] = {0u, 0u};
+  PROF_DECL;
+  uint32_t full_phase = 0u;   // bit per p-tile buffer
   auto seg_of = [&](int k) { return dir == 0 ? k : nseg - 1 - k; };
-  auto wait_ptile = [&](int k) -> const float* {
+  const uint32_t ptile_u32 = smem_u32(sm.ptile(dir));
+  const uint32_t row_bytes = 4u * (uint32_t)Cp;
+  const uint32_t blank_ofs = 4u * (uint32_t)a.blank;
+  // returns the shared address of the tile's first row
+  auto wait_ptile = [&](int k) -> uint32_t {
     const int buf = k % kNB;
-    mbar_wait(&sm.bars[bar_full(dir, buf)], full_phase[buf]);
-    full_phase[buf] ^= 1u;
-    return sm.ptile[dir] + (size_t)buf * kSeg * Cp;
+    mbar_wait(&sm.bars[bar_full(dir, buf)], (full_phase >> buf) & 1u);
+    full_phase ^= 1u << buf;
+    return ptile_u32 + (uint32_t)buf * kSeg * row_bytes;
   };
   auto release_ptile = [&](int k) {
     __syncwarp();
@@ -491,13 +388,32 @@ __global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
     const int rows = min(kSeg, T - seg * kSeg);
     event<K>(v, e, f, lane);
     ckpt_store<K>(ck_own + (size_t)seg * (K + 1) * 32, v, e, lane);
-    const float* pt = wait_ptile(k);
+    PROF_MARK(0);
+    const uint32_t pt = wait_ptile(k);
+    PROF_MARK(1);
     if (dir == 0) {
-      for (int r = 0; r < rows; ++r) step<K, true, false>(v, abar, tp_live, pt + r * Cp, blank, f);
+      uint32_t pr = pt;
+      PRow<K> nx = load_prow<K>(tp_live, pr, blank_ofs);
+#pragma unroll 2
+      for (int r = 0; r < rows; ++r) {
+        const PRow<K> cur = nx;
+        pr += (r + 1 < rows) ? row_bytes : 0u;
+        nx = load_prow<K>(tp_live, pr, blank_ofs);
+        step<K, true, false>(v, abar, tp_live, cur, f);
+      }
     } else {
-      for (int r = rows - 1; r >= 0; --r) step<K, false, false>(v, abar, tp_live, pt + r * Cp, blank, f);
+      uint32_t pr = pt + (uint32_t)(rows - 1) * row_bytes;
+      PRow<K> nx = load_prow<K>(tp_live, pr, blank_ofs);
+#pragma unroll 2
+      for (int r = rows - 1; r >= 0; --r) {
+        const PRow<K> cur = nx;
+        pr -= (r > 0) ? row_bytes : 0u;
+        nx = load_prow<K>(tp_live, pr, blank_ofs);
+        step<K, false, false>(v, abar, tp_live, cur, f);
+      }
     }
     release_ptile(k);
+    PROF_MARK(2);
   }
 
   // ------------------------------------------------------------------ meeting: Z
@@ -575,27 +491,56 @@ __global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
   const float gs = a.grad_scale ? a.grad_scale[b] : 1.f;
   const float kappa = -gs / Zm;
   float* gEb = a.gradE + (size_t)b * T * C;
-  float* stored = sm.stored[dir];
-  float* pbk = sm.pbk[dir];
+  const uint32_t stored_u32 = smem_u32(sm.stored(dir));
+  const uint32_t pbk_u32 = smem_u32(sm.pbk(dir));
+  const uint32_t srow_bytes = 4u * (uint32_t)RS;
+  const uint32_t my_block = 4u * (uint32_t)(lane * K);          // where my recomputed values go
+  const uint32_t pair_block = 4u * (uint32_t)((31 - lane) * K); // the block of the lane paired with me
   const size_t outsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
   int bad = 0;   // reason bits: 4 = scale overflow in the recompute, 8 = row-sum certificate
   int obuf = 0;
-  const int* runs = sm.runs + (lane >> 4) * (C + 1) * 2;   // label runs of my half (transposed pass)
-  const int half_col0 = (lane >> 4) ? sm.hist[C] : 0;
+  // transposed pass, labels: lane = chunk slot of the gamma row (32 slots per pass); the
+  // slots of one label are adjacent lanes and are combined by a segmented suffix sum
+  const int nslots = sm.hist[C];
+  const int npass = (nslots + 31) >> 5;
+  const int maxch = sm.hist[C + 1];
+  int slab[kMaxPass];
+  float lk1[kMaxPass], lk2[kMaxPass], lk4[kMaxPass];
+  bool head[kMaxPass];
+#pragma unroll
+  for (int p = 0; p < kMaxPass; ++p) {
+    const int g = 32 * p + lane;
+    const int me = sm.slotlab[g];
+    slab[p] = me;
+    // links never leave the pass: a label's slots do not straddle a multiple of 32
+    lk1[p] = (me >= 0 && lane + 1 < 32 && sm.slotlab[g + 1] == me) ? 1.f : 0.f;
+    lk2[p] = (me >= 0 && lane + 2 < 32 && sm.slotlab[g + 2] == me) ? 1.f : 0.f;
+    lk4[p] = (me >= 0 && lane + 4 < 32 && sm.slotlab[g + 4] == me) ? 1.f : 0.f;
+    head[p] = me >= 0 && (lane == 0 || sm.slotlab[g - 1] != me);
+  }
+  // transposed pass, blank: lane = (frame, half) sums 16 of the 32 lane partials
+  const int frm = lane & 15, hf = lane >> 4;
+  const uint32_t pbrow_u32 = pbk_u32 + 4u * (uint32_t)(frm * 33 + hf * 16);
+  const uint32_t slot_ofs = 16u * (uint32_t)lane;
+
+  // checkpoint of the first phase-2 segment (the next one is prefetched inside the loop)
+  float w[K];
+  int ew;
+  if (n2 > 0) ckpt_load<K>(ck_other + (size_t)seg_of(n1) * (K + 1) * 32, w, ew, lane);
 
   for (int k2 = 0; k2 < n2; ++k2) {
     const int k = n1 + k2;
     const int seg = seg_of(k);
     const int rows = min(kSeg, T - seg * kSeg);
+    PROF_MARK(3);
     event<K>(v, e, f, lane);
-    const float* pt = wait_ptile(k);
+    PROF_MARK(0);
+    const uint32_t pt = wait_ptile(k);
+    PROF_MARK(1);
 
     // ---- recompute the opposite direction over this segment in the complementary scale:
     // stored * live = posterior * Zm, i.e. exponent(stored lane) = eZ - exponent(live lane)
     {
-      float w[K];
-      int ew;
-      ckpt_load<K>(ck_other + (size_t)seg * (K + 1) * 32, w, ew, lane);
       const int ex_live = __shfl_sync(kFull, e, 31 - lane);   // the live lane paired with me
       int erc = kUndef;
       float sc = 0.f;
@@ -617,85 +562,148 @@ __global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
       }
       // the recompute walks the frames in the opposite order to the live sweep
       if (dir == 0) {
-        for (int r = rows - 1; r >= 0; --r) {
-          step<K, false, false>(w, abar, tp_rc, pt + r * Cp, blank, fr);
-          float4* dst = reinterpret_cast<float4*>(stored + (size_t)r * RS + lane * K);
+        uint32_t pr = pt + (uint32_t)(rows - 1) * row_bytes;
+        uint32_t dst = stored_u32 + (uint32_t)(rows - 1) * srow_bytes + my_block;
+        PRow<K> nx = load_prow<K>(tp_rc, pr, blank_ofs);
+#pragma unroll 2
+        for (int r = rows - 1; r >= 0; --r, dst -= srow_bytes) {
+          const PRow<K> cur = nx;
+          pr -= (r > 0) ? row_bytes : 0u;
+          nx = load_prow<K>(tp_rc, pr, blank_ofs);
+          step<K, false, false>(w, abar, tp_rc, cur, fr);
 #pragma unroll
-          for (int i = 0; i < K; i += 4) dst[i >> 2] = make_float4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+          for (int i = 0; i < K; i += 4) sts128(dst + 4u * i, w[i], w[i + 1], w[i + 2], w[i + 3]);
         }
       } else {
-        for (int r = 0; r < rows; ++r) {
-          step<K, true, false>(w, abar, tp_rc, pt + r * Cp, blank, fr);
-          float4* dst = reinterpret_cast<float4*>(stored + (size_t)r * RS + lane * K);
+        uint32_t pr = pt;
+        uint32_t dst = stored_u32 + my_block;
+        PRow<K> nx = load_prow<K>(tp_rc, pr, blank_ofs);
+#pragma unroll 2
+        for (int r = 0; r < rows; ++r, dst += srow_bytes) {
+          const PRow<K> cur = nx;
+          pr += (r + 1 < rows) ? row_bytes : 0u;
+          nx = load_prow<K>(tp_rc, pr, blank_ofs);
+          step<K, true, false>(w, abar, tp_rc, cur, fr);
 #pragma unroll
-          for (int i = 0; i < K; i += 4) dst[i >> 2] = make_float4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+          for (int i = 0; i < K; i += 4) sts128(dst + 4u * i, w[i], w[i + 1], w[i + 2], w[i + 3]);
         }
       }
+      // prefetch the checkpoint of the next segment (consumed at the top of the next iteration)
+      if (k2 + 1 < n2) ckpt_load<K>(ck_other + (size_t)seg_of(k + 1) * (K + 1) * 32, w, ew, lane);
       __syncwarp();
     }
+    PROF_MARK(4);
 
-    // ---- live sweep over the segment: posterior(state) * Zm = abar * stored
-    auto combine_row = [&](int r) {
-      float st[K];
-      float* row = stored + (size_t)r * RS;
-      float4* src = reinterpret_cast<float4*>(row + (31 - lane) * K);
+    // ---- live sweep over the segment: posterior(state) * Zm = abar * stored.
+    // Row r+1's stored block and p values are fetched while row r is computed.  A block is
+    // read by exactly one lane, which clears it right away so that the row can be re-used
+    // for the sorted posteriors with every padding column reading as zero.
+    {
+      const int rstep = (dir == 0) ? 1 : -1;
+      int r = (dir == 0) ? 0 : rows - 1;
+      uint32_t pr = pt + (uint32_t)r * row_bytes;
+      uint32_t row = stored_u32 + (uint32_t)r * srow_bytes;
+      float stn[K];
+      auto fetch_block = [&](uint32_t rw) {
 #pragma unroll
-      for (int i = 0; i < K; i += 4) {
-        const float4 q = src[i >> 2];
-        st[i] = q.x; st[i + 1] = q.y; st[i + 2] = q.z; st[i + 3] = q.w;
-        // the block is read by this lane only: clear it, so that the row can be re-used
-        // for the sorted posteriors with every padding column reading as zero
-        src[i >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      __syncwarp();
-      if (dir == 0) step<K, true, true>(v, abar, tp_live, pt + r * Cp, blank, f);
-      else step<K, false, true>(v, abar, tp_live, pt + r * Cp, blank, f);
-      float pbsum = 0.f;
+        for (int i = 0; i < K; i += 4) {
+          const float4 q = lds128(rw + pair_block + 4u * i);
+          stn[i] = q.x; stn[i + 1] = q.y; stn[i + 2] = q.z; stn[i + 3] = q.w;
+          sts128(rw + pair_block + 4u * i, 0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      fetch_block(row);
+      PRow<K> nx = load_prow<K>(tp_live, pr, blank_ofs);
+#pragma unroll 2
+      for (int it = 0; it < rows; ++it, r += rstep) {
+        float st[K];
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const bool lab = ((i & 1) == 1) == (dir == 0);
-        const float g = abar[i] * st[K - 1 - i];
-        if (lab) row[tp_live.gcol[i >> 1]] = g;
-        else pbsum += g;
+        for (int i = 0; i < K; ++i) st[i] = stn[i];
+        const PRow<K> cur = nx;
+        const uint32_t row_cur = row;
+        const bool more = it + 1 < rows;
+        if (more) {
+          pr = (dir == 0) ? pr + row_bytes : pr - row_bytes;
+          row = (dir == 0) ? row + srow_bytes : row - srow_bytes;
+          fetch_block(row);
+        }
+        nx = load_prow<K>(tp_live, pr, blank_ofs);
+        __syncwarp();   // every lane has fetched (and cleared) its block of row_cur
+        if (dir == 0) step<K, true, true>(v, abar, tp_live, cur, f);
+        else step<K, false, true>(v, abar, tp_live, cur, f);
+        float pbsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const bool lab = ((i & 1) == 1) == (dir == 0);
+          const float g = abar[i] * st[K - 1 - i];
+          if (lab) sts(row_cur + tp_live.gofs[i >> 1], g);
+          else pbsum += g;
+        }
+        sts(pbk_u32 + 4u * (uint32_t)(r * 33 + lane), pbsum);
       }
-      pbk[r * 33 + lane] = pbsum;
-    };
-    if (dir == 0) { for (int r = 0; r < rows; ++r) combine_row(r); }
-    else { for (int r = rows - 1; r >= 0; --r) combine_row(r); }
+    }
     release_ptile(k);
     __syncwarp();
+    PROF_MARK(5);
 
-    // ---- transposed pass: lane = (frame, half); sum the posteriors per label
+    // ---- transposed pass: sum the posteriors per label and write the [rows, C] tile
     {
-      const int frm = lane & 15, hf = lane >> 4;
-      float* ot = sm.out[dir] + (size_t)obuf * outsz;
+      float* ot = sm.out(dir) + (size_t)obuf * outsz;
+      const uint32_t ot_u32 = smem_u32(ot);
       if (lane == 0) bulk_wait_read<1>();   // the store that last read this buffer is done
       __syncwarp();
-      float rowsum = 0.f, bsum = 0.f;
-      if (frm < rows) {
-        const float* grow = stored + (size_t)frm * RS;
-        int col = half_col0;
-        for (int r = 0; runs[2 * r] >= 0; ++r) {
-          const int labc = runs[2 * r], endc = runs[2 * r + 1];
-          float acc = 0.f;
-          for (; col < endc; col += 4) {
-            const float4 q = *reinterpret_cast<const float4*>(grow + col);
-            acc += (q.x + q.y) + (q.z + q.w);
-          }
-          rowsum += acc;
-          ot[frm * C + labc] = acc * kappa;
-        }
-        const float* pr = pbk + frm * 33 + hf * 16;
+      PROF_MARK(6);
+      float tot = 0.f;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) bsum += pr[q];
+      for (int p = 0; p < kMaxPass; ++p) {
+        if (p < npass) {
+          const uint32_t src = stored_u32 + 512u * (uint32_t)p + slot_ofs;
+          const uint32_t dsto = ot_u32 + 4u * (uint32_t)max(slab[p], 0);
+#pragma unroll
+          for (int r0 = 0; r0 < kSeg; r0 += 8) {
+            if (r0 < rows) {
+              float c[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {   // rows >= `rows` hold finite stale data; never stored
+                const float4 q = lds128(src + (uint32_t)(r0 + j) * srow_bytes);
+                c[j] = (q.x + q.y) + (q.z + q.w);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 1), lk1[p], c[j]);
+              if (maxch > 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 2), lk2[p], c[j]);
+              }
+              if (maxch > 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 4), lk4[p], c[j]);
+              }
+              if (head[p]) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (r0 + j < rows) {
+                    sts(dsto + 4u * (uint32_t)((r0 + j) * C), c[j] * kappa);
+                    tot += c[j];
+                  }
+                }
+              }
+            }
+          }
+        }
       }
-      bsum += __shfl_xor_sync(kFull, bsum, 16);
-      rowsum += __shfl_xor_sync(kFull, rowsum, 16);
-      rowsum += bsum;
+      float bs = 0.f;
       if (frm < rows) {
-        if (hf == 0) ot[frm * C + blank] = bsum * kappa;
-        if (!(fabsf(rowsum - Zm) <= 1e-3f * Zm)) bad |= 8;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) bs += lds(pbrow_u32 + 4u * q);
       }
+      tot += bs;
+      const float bsum = bs + __shfl_xor_sync(kFull, bs, 16);
+      if (frm < rows && hf == 0) sts(ot_u32 + 4u * (uint32_t)(frm * C) + blank_ofs, bsum * kappa);
+      // certificate: the posteriors of every frame sum to one, i.e. the segment sums to
+      // rows * Zm.  Range loss can only remove mass, so deficits cannot cancel.
+      tot = warp_sum(tot);
+      if (!(fabsf(tot - (float)rows * Zm) <= 2e-5f * (float)rows * Zm)) bad |= 8;
+      PROF_MARK(7);
       float* dst = gEb + (size_t)seg * kSeg * C;
       const int n = rows * C;
       const bool tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
@@ -713,10 +721,207 @@ __global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
       obuf ^= 1;
       __syncwarp();
     }
+    PROF_MARK(3);
   }
+#ifdef WFST_PROFILE
+  if (b == 0 && lane == 0)
+    printf("dir %d cycles: event+ckpt %lld  wait_ptile %lld  phase1-steps %lld  fence+store %lld  recompute %lld  combine %lld  bulkwait %lld transposed %lld\n",
+           dir, pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3], pf_acc[4], pf_acc[5], pf_acc[6], pf_acc[7]);
+#endif
   if (lane == 0) bulk_wait_all<0>();
   bad = __reduce_or_sync(kFull, (unsigned)bad);
   if (bad && lane == 0) atomicOr(&a.hazard[b], bad);
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
+  constexpr int Sp = 32 * K;
+  extern __shared__ __align__(16) float smem_raw[];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T, C = a.C, Cp = a.Cp, RS = a.RS;
+  FastSmem<K> sm = carve_fast<K>(smem_raw, C, Cp, RS);
+  const int* y = a.targets + a.offsets[b];
+  const int L = a.offsets[b + 1] - a.offsets[b];
+  const int nseg = a.nseg, nA = a.nA;
+  const bool want_grad = a.gradE != nullptr;
+  const float* Eb = a.E + (size_t)b * T * C;
+  const int dump_col = RS - 1;
+
+  // ------------------------------------------------------------------ setup
+  if (threadIdx.x == 0) {
+    for (int d = 0; d < 2; ++d)
+      for (int i = 0; i < kNB; ++i) {
+        mbar_init(&sm.bars[bar_full(d, i)], 1);
+        mbar_init(&sm.bars[bar_empty(d, i)], 1);
+      }
+    for (int i = 0; i < kNR; ++i) mbar_init(&sm.bars[kBarTma + i], 1);
+    mbar_init(&sm.bars[kBarZ], 1);
+    fence_barrier_init();
+  }
+  // zero the regions that rely on it: p-tile padding columns, output tiles (labels that
+  // do not occur in the target keep a zero gradient), blank partials
+  for (int d = 0; d < 2; ++d) {
+    for (int k = threadIdx.x; k < kNB * kSeg * Cp; k += 96) sm.ptile(d)[k] = 0.f;
+    for (int k = threadIdx.x; k < 2 * (int)(((size_t)kSeg * C + 3) & ~(size_t)3); k += 96) sm.out(d)[k] = 0.f;
+    for (int k = threadIdx.x; k < kSeg * 33; k += 96) sm.pbk(d)[k] = 0.f;
+    for (int k = threadIdx.x; k < kSeg * RS; k += 96) sm.stored(d)[k] = 0.f;
+  }
+  // Counting sort of the target positions by label -> columns of the "gamma" row.  The row
+  // is organised in chunk slots of 4 columns; a label with n occurrences owns ceil(n/4)
+  // consecutive slots that never straddle a multiple of 32 slots (one pass of the
+  // transposed reduction = 32 slots, one per lane).
+  for (int k = threadIdx.x; k < C + 4; k += 96) sm.hist[k] = 0;
+  for (int k = threadIdx.x; k < 32 * kMaxPass + 8; k += 96) sm.slotlab[k] = -1;
+  __syncthreads();
+  int has_blank = 0;
+  for (int n = threadIdx.x; n < L; n += 96) {
+    atomicAdd(&sm.hist[y[n]], 1);
+    has_blank |= (y[n] == a.blank);
+  }
+  if (__syncthreads_or(has_blank)) {
+    // a target that contains the blank label shares a gradient column between a label
+    // state and the blank states: leave it to the log-semiring kernel
+    if (threadIdx.x == 0) a.hazard[b] = 1;   // reason 1: blank label inside the target
+    return;
+  }
+  if (threadIdx.x == 0) {
+    int slot = 0, maxch = 0;
+    for (int c = 0; c < C; ++c) {
+      const int cnt = sm.hist[c];
+      sm.hist[c] = 0;
+      if (cnt == 0) continue;
+      const int nch = (cnt + 3) >> 2;
+      if ((slot & 31) + nch > 32) slot = (slot + 31) & ~31;
+      sm.hist[c] = slot * 4;                // becomes the column cursor of label c
+      for (int j = 0; j < nch && slot + j < 32 * kMaxPass; ++j) sm.slotlab[slot + j] = c;
+      slot += nch;
+      maxch = max(maxch, nch);
+    }
+    sm.hist[C] = slot;
+    sm.hist[C + 1] = maxch;
+  }
+  __syncthreads();
+  {
+    const int nslots = sm.hist[C], maxch = sm.hist[C + 1];
+    // layouts the transposed pass cannot hold (very many distinct labels for this K, or one
+    // label more than 32 times) go to the log-semiring kernel
+    if (nslots > 32 * kMaxPass || nslots * 4 > RS - 4 || maxch > 8) {
+      if (threadIdx.x == 0) a.hazard[b] = 16;  // reason 16: gamma row layout does not fit
+      return;
+    }
+  }
+  for (int n = threadIdx.x; n < L; n += 96) sm.gcolpos[n] = atomicAdd(&sm.hist[y[n]], 1);
+  __syncthreads();
+
+  // ===================================================================== producer
+  if (warp == 2) {
+    // Direction 0 consumes tiles 0,1,...; direction 1 consumes nseg-1, nseg-2, ...
+    // Without a gradient only the phase-1 tiles are needed.  The schedule is the sequence
+    // (k, d), k = 0.., d = 0, 1, restricted to k < ntile[d].  Raw [16, C] tiles are
+    // fetched kNR - 1 entries ahead (TMA latency >> conversion time).
+    const int ntile0 = want_grad ? nseg : nA, ntile1 = want_grad ? nseg : (nseg - nA);
+    const int total = max(ntile0, ntile1);
+    const int fr = lane & 15, hh = lane >> 4;
+    const int c0 = hh ? (C + 1) / 2 : 0, c1 = hh ? C : (C + 1) / 2;
+    const int rawsz = (kSeg * C + 3) & ~3;
+    const uint32_t raw_u32 = smem_u32(sm.raw);
+    double msum = 0.0;
+    uint32_t tma_phase = 0u;     // bit per raw slot
+    uint32_t tma_used = 0u;      // bit per raw slot: the entry in it came through TMA
+    uint32_t empty_phase = 0u;   // bit (d * kNB + buf)
+    auto tile_of = [&](int d, int k) { return d == 0 ? k : nseg - 1 - k; };
+    auto next_entry = [&](int& k, int& d) {
+      do {
+        if (d == 0) d = 1; else { d = 0; ++k; }
+      } while (k < total && k >= (d == 0 ? ntile0 : ntile1));
+    };
+    auto issue_raw = [&](int tile, int slot) {
+      const int rows = min(kSeg, T - tile * kSeg);
+      const float* src = Eb + (size_t)tile * kSeg * C;
+      const uint32_t bytes = (uint32_t)rows * C * 4u;
+      float* dst = sm.raw + (size_t)slot * rawsz;
+      const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15u) == 0);
+      if (tma) {
+        if (lane == 0) {
+          mbar_expect_tx(&sm.bars[kBarTma + slot], bytes);
+          bulk_g2s(dst, src, bytes, &sm.bars[kBarTma + slot]);
+        }
+        tma_used |= 1u << slot;
+      } else {
+        for (int q = lane; q < rows * C; q += 32) dst[q] = __ldg(src + q);
+        tma_used &= ~(1u << slot);
+        __syncwarp();
+      }
+    };
+    // cursor of the entry being converted (k, d) and of the next entry to fetch (fk, fd)
+    int k = -1, d = 1;
+    next_entry(k, d);
+    int fk = k, fd = d, fetched = 0, converted = 0;
+    while (k < total) {
+      // keep the raw ring full; slot = entry index mod kNR; a slot is free once its previous
+      // entry has been converted (entries are converted in order)
+      while (fk < total && fetched < converted + kNR) {
+        issue_raw(tile_of(fd, fk), fetched % kNR);
+        ++fetched;
+        next_entry(fk, fd);
+      }
+      const int slot = converted % kNR;
+      const int tile = tile_of(d, k);
+      const int rows = min(kSeg, T - tile * kSeg);
+      const int buf = k % kNB;
+      if (k >= kNB) {  // wait until the consumer has released this p-tile buffer
+        const int bit = d * kNB + buf;
+        mbar_wait(&sm.bars[bar_empty(d, buf)], (empty_phase >> bit) & 1u);
+        empty_phase ^= 1u << bit;
+      }
+      if ((tma_used >> slot) & 1u) {
+        mbar_wait(&sm.bars[kBarTma + slot], (tma_phase >> slot) & 1u);
+        tma_phase ^= 1u << slot;
+      }
+      const uint32_t er = raw_u32 + 4u * (uint32_t)(slot * rawsz + fr * C);
+      const uint32_t pt = smem_u32(sm.ptile(d)) + 4u * (uint32_t)(buf * kSeg * Cp + fr * Cp);
+      float mx = kNegInf;
+      if (fr < rows) {
+#pragma unroll 8
+        for (int c = c0; c < c1; ++c) mx = fmaxf(mx, lds(er + 4u * c));
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 16));
+      if (fr < rows) {
+        // a row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface
+        // through the certificate
+        const float base = (mx == kNegInf) ? 0.f : mx;
+        const float nb = -base * 1.4426950408889634f;
+#pragma unroll 8
+        for (int c = c0; c < c1; ++c)
+          sts(pt + 4u * c, exp2f(fmaf(lds(er + 4u * c), 1.4426950408889634f, nb)));
+        const bool phase1 = (d == 0) ? (tile < nA) : (tile >= nA);
+        if (hh == 0 && phase1) msum += (double)base;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.bars[bar_full(d, buf)]);
+      ++converted;
+      next_entry(k, d);
+    }
+    // loss: log Z = log(Zm) + eZ ln2 + sum_t max_t
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(kFull, msum, o);
+    mbar_wait(&sm.bars[kBarZ], 0u);
+    if (lane == 0) {
+      const float Zm = sm.zx[0];
+      const int eZ = __float_as_int(sm.zx[1]);
+      const bool ok = sm.zx[2] != 0.f;
+      a.z_out[b] = ok ? (float)(log((double)Zm) + (double)eZ * 0.6931471805599453 + msum) : kNegInf;
+    }
+    return;
+  }
+
+  // ===================================================================== A / B
+  if (warp == 0) run_direction<K, 0>(a, sm, b, lane);
+  else run_direction<K, 1>(a, sm, b, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -732,11 +937,9 @@ static int fast_pick_k(int max_target_len) {
 
 static void fast_dims(int K, int C, int& Cp, int& RS) {
   Cp = (C + 1) | 1;
-  // gamma columns: <= Sp/2 posteriors + 3 padding per label + alignment of the second
-  // half (< 48) + the dump column; the row also holds the Sp recomputed values
-  int cols = 16 * K + 3 * C + 48 + 4;
-  if (cols < 32 * K) cols = 32 * K;
-  RS = ((cols + 31) / 32) * 32 + 4;
+  // the row holds the Sp recomputed values, later re-used for the chunk slots of the
+  // sorted posteriors (<= Sp / 4 slots) and the dump column RS - 1
+  RS = 32 * K + 4;
 }
 
 bool ctc_fast_eligible(int T, int C, int max_target_len) {

@@ -30,7 +30,7 @@ class AcceptorBatch(ctypes.Structure):
 
 # name -> (restype, argtypes); the single source of truth for the symbols the
 # library must export (tests/test_capi_symbols.py checks it against the header)
-_I, _Z, _P = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p
+_I, _Z, _P, _I32 = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int32
 SIGNATURES = {
     "wfst_last_error": (ctypes.c_char_p, []),
     "wfst_abi_version": (_I, []),
@@ -46,6 +46,39 @@ SIGNATURES = {
     "wfst_asg_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "wfst_asg_forward_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "wfst_scale_inplace": (_I, [_P, _Z, _P, _P]),
+    # host-side graphs (csrc/graph.cpp)
+    "wfst_graph_create": (_I32, [_I]),
+    "wfst_graph_destroy": (_I, [_I32]),
+    "wfst_graph_add_node": (_I, [_I32, _I, _I]),
+    "wfst_graph_add_arc": (_I, [_I32, _I, _I, _I, _I, ctypes.c_float]),
+    "wfst_graph_add_arcs": (_I, [_I32, _I, _P, _P, _P, _P, _P]),
+    "wfst_graph_num_nodes": (_I, [_I32]),
+    "wfst_graph_num_arcs": (_I, [_I32]),
+    "wfst_graph_arc_sort": (_I, [_I32, _I]),
+    "wfst_graph_mark_arc_sorted": (_I, [_I32, _I]),
+    "wfst_graph_sorted_flags": (_I, [_I32]),
+    "wfst_graph_get_calc_grad": (_I, [_I32]),
+    "wfst_graph_set_calc_grad": (_I, [_I32, _I]),
+    "wfst_graph_set_weights": (_I, [_I32, _P]),
+    "wfst_graph_get_weights": (_I, [_I32, _P]),
+    "wfst_graph_get_arcs": (_I, [_I32, _P, _P, _P, _P]),
+    "wfst_graph_get_node_flags": (_I, [_I32, _P]),
+    "wfst_graph_get_arc_order": (_I, [_I32, _I, _P]),
+    "wfst_graph_get_provenance": (_I, [_I32, _P, _P]),
+    "wfst_graph_compose": (_I32, [_I32, _I32]),
+    "wfst_graph_remove": (_I32, [_I32, _I, _I]),
+    "wfst_graph_project": (_I32, [_I32, _I]),
+    "wfst_graph_linear": (_I32, [_I, _I, _I]),
+    "wfst_graph_loadtxt": (_I32, [ctypes.c_char_p]),
+    "wfst_graph_savetxt": (_I, [_I32, ctypes.c_char_p]),
+    "wfst_graph_load": (_I32, [ctypes.c_char_p]),
+    "wfst_graph_save": (_I, [_I32, ctypes.c_char_p]),
+    "wfst_transducer_alignment_graphs": (_I, [_I32, _I32, _P, _P, _I, _P]),
+    "wfst_graph_viterbi_path": (_I32, [_I32]),
+    "wfst_lattice_viterbi_workspace_bytes": (_Z, [_I, _I, _I]),
+    "wfst_lattice_viterbi": (_I, [_P, _I, _I, _I, ctypes.POINTER(AcceptorBatch), _I, _P, _P, _P, _P, _Z, _P]),
+    "wfst_graph_pack_sizes": (_I, [_P, _I, _P, _P, _P, _P, _P]),
+    "wfst_graph_pack": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lock = threading.Lock()

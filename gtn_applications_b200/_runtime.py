@@ -62,3 +62,12 @@ def reduction_scales(reduction, sizes):
     if reduction != "none":
         raise ValueError("invalid value for reduction '" + str(reduction) + "'")
     return [1.0] * len(sizes)
+
+
+def scale_by(grad, grad_output):
+    """grad *= grad_output in place on the device (no pass over grad when grad_output == 1)"""
+    go = grad_output.detach().to(device=grad.device, dtype=torch.float32).reshape(1)
+    with torch.cuda.device(grad.device):
+        _lib.check(_lib.lib().wfst_scale_inplace(grad.data_ptr(), grad.numel(), go.data_ptr(),
+                                                 stream_ptr(grad.device)))
+    return grad

@@ -1,0 +1,253 @@
+"""Generic WFST transducer criterion on B200 — same interface as the reference's
+criterions/transducer.py (criterion part).
+
+``TransducerLossFunction.forward(ctx, inputs, targets, tokens, lexicon,
+transition_params=None, transitions=None, reduction="none")`` / ``.backward`` ->
+7-tuple with gradients at positions 0 and 4 mirror transducer.py:239-248,340-348;
+``Transducer(tokens, graphemes_to_idx, ngram=0, transitions=None, blank="none",
+allow_repeats=True, reduction="none")`` keeps the ``transition_params`` parameter
+(transducer.py:149-183; part of the checkpoint format, train.py:117).
+
+Per utterance the reference builds, in Python under the GIL, target o lexicon, the token
+decomposition DAG and the alignment acceptor (transducer.py:265-276), intersects it with
+the emissions graph and runs forward_score / backward on the CPU.  Here the host graphs
+of the whole batch are built in C++ on a thread pool (wfst_transducer_alignment_graphs),
+packed once, and every utterance's lattice is scored by one launch of the generic
+lattice kernel; with a transition graph the normaliser Z(emissions o transitions) is a
+second launch over a single shared graph."""
+import itertools
+
+import numpy as np
+import torch
+
+from .. import _lib, _runtime as rt
+from .. import graph as G
+from ..lattice import lattice_forward_backward
+
+
+def make_scalar_graph(weight):
+    """transducer.py:15-20"""
+    g = G.Graph()
+    g.add_node(True)
+    g.add_node(False, True)
+    g.add_arc(0, 1, 0, 0, weight)
+    return g
+
+
+def make_chain_graph(sequence):
+    """transducer.py:23-29"""
+    g = G.Graph(False)
+    g.add_node(True)
+    for i, s in enumerate(sequence):
+        g.add_node(False, i == len(sequence) - 1)
+        g.add_arc(i, i + 1, int(s))
+    return g
+
+
+def make_transitions_graph(ngram, num_tokens, calc_grad=False):
+    """Dense n-gram acceptor (transducer.py:32-58); for ngram > 1 a final </s> node is
+    reached by epsilon arcs from every other node."""
+    g = G.Graph(calc_grad)
+    g.add_node(True, ngram == 1)
+    state = {(): 0}
+    for n in range(1, ngram):
+        for hist in itertools.product(range(num_tokens), repeat=n):
+            src = state[hist[:-1]]
+            dst = g.add_node(False, ngram == 1)
+            state[hist] = dst
+            g.add_arc(src, dst, hist[-1])
+    for hist in itertools.product(range(num_tokens), repeat=ngram):
+        g.add_arc(state[hist[:-1]], state[hist[1:]], hist[-1])
+    if ngram > 1:
+        end = g.add_node(False, True)
+        for src in range(end):
+            g.add_arc(src, end, G.epsilon)
+    return g
+
+
+def make_lexicon_graph(word_pieces, graphemes_to_idx):
+    """Letters -> word-piece transducer (transducer.py:61-75): one loop through node 0
+    per word piece, the output label on its last letter."""
+    g = G.Graph(False)
+    g.add_node(True, True)
+    for i, wp in enumerate(word_pieces):
+        prev = 0
+        for ch in wp[:-1]:
+            n = g.add_node()
+            g.add_arc(prev, n, graphemes_to_idx[ch], G.epsilon)
+            prev = n
+        g.add_arc(prev, 0, graphemes_to_idx[wp[-1]], i)
+    g.arc_sort()
+    return g
+
+
+def make_token_graph(token_list, blank="none", allow_repeats=True):
+    """Per-token emission models (transducer.py:78-123).  The O(V^2) no-repeat arcs are
+    added in bulk."""
+    if not allow_repeats and blank != "optional":
+        raise ValueError("Must use blank='optional' if disallowing repeats.")
+    n = len(token_list)
+    g = G.Graph(False)
+    g.add_node(True, True)
+    for _ in range(n):
+        g.add_node(False, blank != "forced")
+    if blank != "none":
+        g.add_node()
+        g.add_arc(0, n + 1, n, G.epsilon)
+        g.add_arc(n + 1, 0, G.epsilon)
+    if allow_repeats:
+        for i in range(n):
+            g.add_arc((n + 1) if blank == "forced" else 0, i + 1, i)
+            g.add_arc(i + 1, i + 1, i, G.epsilon)
+            if blank == "forced":
+                g.add_arc(i + 1, n + 1, n, G.epsilon)
+            else:
+                g.add_arc(i + 1, 0, G.epsilon)
+        return g
+    # no repeats: per token i, in the reference's arc order: (0 -> i+1, i), (i+1 -> i+1, i:eps),
+    # (i+1 -> blank, n:eps), then (i+1 -> j+1, j) for every j != i
+    per = 3 + (n - 1)
+    src = np.empty(n * per, dtype=np.int32)
+    dst = np.empty_like(src)
+    il = np.empty_like(src)
+    ol = np.empty_like(src)
+    others = np.arange(n, dtype=np.int32)
+    for i in range(n):
+        o = i * per
+        src[o:o + 3] = (0, i + 1, i + 1)
+        dst[o:o + 3] = (i + 1, i + 1, n + 1)
+        il[o:o + 3] = (i, i, n)
+        ol[o:o + 3] = (i, G.epsilon, G.epsilon)
+        js = others[others != i]
+        src[o + 3:o + per] = i + 1
+        dst[o + 3:o + per] = js + 1
+        il[o + 3:o + per] = js
+        ol[o + 3:o + per] = js
+    g.add_arcs(src, dst, il, ol)
+    return g
+
+
+class TransducerLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, targets, tokens, lexicon, transition_params=None, transitions=None,
+                reduction="none"):
+        B, T, C = inputs.shape
+        rt.require_cuda(inputs, "inputs")
+        if transitions is not None and transition_params is None:
+            raise ValueError("Specified transitions, but not transition params.")
+        if reduction == "mean":
+            scales = [(1.0 / len(t) if len(t) > 0 else 1.0) for t in targets]
+        else:
+            scales = [1.0] * B      # like the reference, anything but "mean" is "none" (transducer.py:302-305)
+        e = rt.to_device(inputs.detach())
+        dev = e.device
+        L = _lib.lib()
+        flat = np.ascontiguousarray([int(x) for t in targets for x in t], dtype=np.int32)
+        offs = np.zeros(B + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(t) for t in targets])
+        import ctypes
+        handles = (ctypes.c_int32 * B)()
+        _lib.check(L.wfst_transducer_alignment_graphs(
+            tokens._h, lexicon._h, flat.ctypes.data, offs.ctypes.data, B, handles))
+        aligns = [G.Graph(_handle=h) for h in handles]
+        need_e = ctx.needs_input_grad[0]
+        need_t = transitions is not None and ctx.needs_input_grad[4]
+        with torch.cuda.device(dev):
+            sc = torch.tensor(scales, dtype=torch.float32, device=dev)
+            tp = prov = None
+            if transitions is not None:
+                # alignments := intersect(transitions, alignments) (transducer.py:279-281); the
+                # composed arc weights are the transition weights of their first parent
+                tp = transition_params.detach().to(dev, torch.float32).contiguous()
+                composed, prov = [], []
+                for g in aligns:
+                    c = G.intersect(transitions, g)
+                    c.arc_sort()
+                    composed.append(c)
+                    prov.append(c.provenance()[0])
+                aligns = composed
+            packed = G.pack_graphs(aligns, dev)
+            weights = None
+            if transitions is not None:
+                prov_idx = torch.from_numpy(np.concatenate(prov).astype(np.int64)).to(dev)
+                weights = tp[prov_idx] if prov_idx.numel() else torch.zeros(0, device=dev)
+            # loss_b = -(Z_align - Z_norm) * scale_b; mean over b (transducer.py:283-309)
+            gs = -sc / B
+            z_align, g_e, g_w = lattice_forward_backward(
+                e, packed, grad_scale=gs, want_grad_emissions=need_e, want_grad_weights=need_t,
+                weights=weights)
+            score = z_align
+            g_tp = None
+            if transitions is not None:
+                shared = G.pack_graphs([transitions], dev)
+                z_norm, _, g_wn = lattice_forward_backward(
+                    e, shared, grad_scale=-gs, want_grad_emissions=False, want_grad_weights=need_t,
+                    weights=tp, shared=True, accumulate_into=g_e if need_e else None)
+                score = z_align - z_norm
+                if need_t:
+                    g_tp = g_wn.clone()
+                    g_tp.index_add_(0, prov_idx, g_w)
+            loss = (-score * sc).mean()
+        ctx.grads = (g_e if need_e else None, g_tp)
+        ctx.devices = (inputs.device, transition_params.device if transition_params is not None else None)
+        return loss if inputs.is_cuda else loss.cpu()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        g_e, g_tp = ctx.grads
+        ctx.grads = None
+        if g_e is not None:
+            g_e = rt.scale_by(g_e, grad_output)
+            if g_e.device != ctx.devices[0]:
+                g_e = g_e.to(ctx.devices[0])
+        if g_tp is not None:
+            g_tp = rt.scale_by(g_tp, grad_output)
+            if g_tp.device != ctx.devices[1]:
+                g_tp = g_tp.to(ctx.devices[1])
+        return g_e, None, None, None, g_tp, None, None
+
+
+TransducerLoss = TransducerLossFunction.apply
+
+
+class Transducer(torch.nn.Module):
+    """A generic transducer loss function (transducer.py:126-197).
+
+    tokens: list of iterables (letters, word pieces, words ...) naming the model outputs;
+    graphemes_to_idx: grapheme -> index; ngram: order of a dense token-level transition
+    model (0 = none); transitions: a transition Graph (instead of ngram); blank: 'none' |
+    'optional' | 'forced'; allow_repeats: if False consecutive equal tokens are not
+    allowed in an alignment (needs blank='optional')."""
+
+    def __init__(self, tokens, graphemes_to_idx, ngram=0, transitions=None, blank="none",
+                 allow_repeats=True, reduction="none"):
+        super().__init__()
+        if blank not in ["optional", "forced", "none"]:
+            raise ValueError("Invalid value specificed for blank. Must be in ['optional', 'forced', 'none']")
+        self.tokens = make_token_graph(tokens, blank=blank, allow_repeats=allow_repeats)
+        self.lexicon = make_lexicon_graph(tokens, graphemes_to_idx)
+        self.ngram = ngram
+        if ngram > 0 and transitions is not None:
+            raise ValueError("Only one of ngram and transitions may be specified")
+        if ngram > 0:
+            transitions = make_transitions_graph(ngram, len(tokens) + int(blank != "none"), True)
+        if transitions is not None:
+            self.transitions = transitions
+            self.transitions.arc_sort()
+            self.transition_params = torch.nn.Parameter(torch.zeros(self.transitions.num_arcs()))
+        else:
+            self.transitions = None
+            self.transition_params = None
+        self.reduction = reduction
+
+    def forward(self, inputs, targets):
+        if self.transitions is None:
+            inputs = torch.nn.functional.log_softmax(inputs, dim=2)
+        self.tokens.arc_sort(True)
+        targets = [t.tolist() if torch.is_tensor(t) else list(t) for t in targets]
+        return TransducerLoss(inputs, targets, self.tokens, self.lexicon, self.transition_params,
+                              self.transitions, self.reduction)
+
+    def viterbi(self, outputs):
+        from ..decode import transducer_viterbi
+        return transducer_viterbi(self, outputs)

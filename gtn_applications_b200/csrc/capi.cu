@@ -223,6 +223,26 @@ int wfst_asg_forward_backward(const float* emissions, const float* transitions,
   return launch_finalize(zfcc, zfal, 1.f, B, grad_scale, loss, mean_loss, st);
 }
 
+// ----------------------------------------------------------------- viterbi
+size_t wfst_lattice_viterbi_workspace_bytes(int B, int T, int max_nodes) {
+  return viterbi_workspace_bytes(B, T, max_nodes);
+}
+
+int wfst_lattice_viterbi(const float* emissions, int B, int T, int C,
+                         const wfst_acceptor_batch_t* graphs, int shared_graph, float* scores,
+                         int32_t* labels, int32_t* arcs, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  WFST_REQUIRE(emissions && graphs && scores && labels && arcs && workspace, "null pointer argument");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0, "bad shape B=%d T=%d C=%d", B, T, C);
+  WFST_REQUIRE(shared_graph ? graphs->B == 1 : graphs->B == B, "graph batch does not match B");
+  if (workspace_bytes < viterbi_workspace_bytes(B, T, graphs->max_nodes)) {
+    set_error("workspace too small");
+    return WFST_ERR_WORKSPACE;
+  }
+  return launch_viterbi(emissions, B, T, C, *graphs, shared_graph, scores, labels, arcs, workspace,
+                        (cudaStream_t)stream);
+}
+
 int wfst_scale_inplace(float* x, size_t n, const float* scale, void* stream) {
   WFST_REQUIRE(x && scale, "null pointer argument");
   return launch_scale(x, n, scale, (cudaStream_t)stream);

@@ -1,0 +1,686 @@
+// Host-side WFST container and the small-graph algebra the transducer / STC criteria need
+// before the GPU lattice kernels run: the per-utterance graphs of
+// criterions/transducer.py:260-281 (chain o lexicon, project, epsilon removal, tokens o
+// decompositions) are built here in C++, on a pool of host threads, and packed into the
+// CSR batch layout of wfst_acceptor_batch_t.  This replaces the corresponding calls into
+// the external GTN library (gtn.Graph / compose / intersect / remove / project_* /
+// arc_sort / load / loadtxt); node and arc numbering follows GTN's construction order so
+// that graph indices are bit-identical to the reference run on the oracle.
+//
+// Storage is structure-of-arrays (src / dst / ilabel / olabel / weight per arc) with
+// per-node in/out lists kept as index vectors that arc_sort permutes; composition walks
+// state pairs breadth-first from the start pairs after a backward co-reachability pass.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/wfst_b200.h"
+
+namespace wfst {
+void set_error(const char* fmt, ...);
+
+namespace {
+
+constexpr int kEpsilon = -1;
+
+struct HostGraph {
+  std::vector<uint8_t> flags;           // bit0 start, bit1 accept
+  std::vector<int32_t> starts, accepts; // in insertion order
+  std::vector<int32_t> src, dst, il, ol;
+  std::vector<float> w;
+  std::vector<std::vector<int32_t>> in, out;
+  bool il_sorted = false, ol_sorted = false;
+  bool calc_grad = false;
+  // provenance of a composed graph: arc k came from (a1[k], a2[k]) (-1 = epsilon move)
+  std::vector<int32_t> prov1, prov2;
+
+  int num_nodes() const { return (int)flags.size(); }
+  int num_arcs() const { return (int)src.size(); }
+  int add_node(bool start, bool accept) {
+    int id = num_nodes();
+    flags.push_back((uint8_t)((start ? 1 : 0) | (accept ? 2 : 0)));
+    in.emplace_back();
+    out.emplace_back();
+    if (start) starts.push_back(id);
+    if (accept) accepts.push_back(id);
+    return id;
+  }
+  int add_arc(int s, int d, int i, int o, float weight) {
+    int id = num_arcs();
+    src.push_back(s); dst.push_back(d); il.push_back(i); ol.push_back(o); w.push_back(weight);
+    out[s].push_back(id);
+    in[d].push_back(id);
+    il_sorted = ol_sorted = false;
+    return id;
+  }
+  void make_accept(int n) {
+    if (!(flags[n] & 2)) { flags[n] |= 2; accepts.push_back(n); }
+  }
+  void arc_sort(bool by_olabel) {
+    if ((by_olabel && ol_sorted) || (!by_olabel && il_sorted)) return;
+    const std::vector<int32_t>& key = by_olabel ? ol : il;
+    auto less = [&key](int32_t a, int32_t b) { return key[a] < key[b]; };
+    for (auto& v : in) std::stable_sort(v.begin(), v.end(), less);
+    for (auto& v : out) std::stable_sort(v.begin(), v.end(), less);
+    il_sorted = !by_olabel;
+    ol_sorted = by_olabel;
+  }
+};
+
+// ---- handle table ---------------------------------------------------------------
+std::mutex g_mu;
+std::vector<std::unique_ptr<HostGraph>> g_graphs;
+std::vector<int32_t> g_free;
+
+int32_t put(std::unique_ptr<HostGraph> g) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_free.empty()) {
+    int32_t h = g_free.back();
+    g_free.pop_back();
+    g_graphs[h] = std::move(g);
+    return h;
+  }
+  g_graphs.push_back(std::move(g));
+  return (int32_t)g_graphs.size() - 1;
+}
+HostGraph* get(int32_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (h < 0 || h >= (int32_t)g_graphs.size() || !g_graphs[h]) return nullptr;
+  return g_graphs[h].get();
+}
+
+// ---- composition ----------------------------------------------------------------
+// Enumerates (arc of A at node na, arc of B at node nb) with A.olabel == B.ilabel in the
+// order GTN's matchers produce them: nested loops when neither
+// side is sorted; the unsorted side in list order with a binary search into the sorted
+// side when one is; the shorter list as the query when both are.
+struct PairMatcher {
+  const HostGraph& A;
+  const HostGraph& B;
+  int mode;  // 0 none sorted, 1 A sorted (query B), 2 B sorted (query A), 3 both
+  PairMatcher(const HostGraph& a, const HostGraph& b) : A(a), B(b) {
+    mode = (a.ol_sorted && b.il_sorted) ? 3 : (a.ol_sorted ? 1 : (b.il_sorted ? 2 : 0));
+  }
+  template <class F>
+  void for_each(int na, int nb, bool incoming, F&& emit) const {
+    const std::vector<int32_t>& la = incoming ? A.in[na] : A.out[na];
+    const std::vector<int32_t>& lb = incoming ? B.in[nb] : B.out[nb];
+    bool search_a;
+    switch (mode) {
+      case 0: search_a = false; break;
+      case 1: search_a = true; break;
+      case 2: search_a = false; break;
+      default: search_a = la.size() > lb.size();
+    }
+    const std::vector<int32_t>& query = search_a ? lb : la;
+    const std::vector<int32_t>& search = search_a ? la : lb;
+    auto qlab = [&](int32_t arc) { return search_a ? B.il[arc] : A.ol[arc]; };
+    auto slab = [&](int32_t arc) { return search_a ? A.ol[arc] : B.il[arc]; };
+    size_t lo = 0;
+    for (size_t q = 0; q < query.size(); ++q) {
+      const int32_t qa = query[q];
+      const int ql = qlab(qa);
+      size_t s = 0;
+      if (mode != 0) {
+        auto first = search.begin() + (mode == 3 ? lo : 0);
+        s = std::lower_bound(first, search.end(), ql,
+                             [&](int32_t arc, int v) { return slab(arc) < v; }) - search.begin();
+        if (mode == 3) lo = s;
+      }
+      for (; s < search.size(); ++s) {
+        const int32_t sa = search[s];
+        const int sl = slab(sa);
+        if (sl == ql) emit(search_a ? sa : qa, search_a ? qa : sa);
+        else if (mode != 0 && ql < sl) break;
+      }
+    }
+  }
+};
+
+std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B) {
+  PairMatcher m(A, B);
+  const size_t NA = (size_t)A.num_nodes();
+  auto key = [NA](int a, int b) { return (size_t)a + NA * (size_t)b; };
+  // backward pass: which state pairs can reach an accepting pair
+  std::vector<uint8_t> live(NA * (size_t)B.num_nodes(), 0);
+  {
+    std::deque<std::pair<int, int>> todo;
+    for (int fa : A.accepts)
+      for (int fb : B.accepts) {
+        live[key(fa, fb)] = 1;
+        todo.emplace_back(fa, fb);
+      }
+    while (!todo.empty()) {
+      auto [ca, cb] = todo.front();
+      todo.pop_front();
+      bool eps_pair = false;
+      m.for_each(ca, cb, true, [&](int32_t i, int32_t j) {
+        eps_pair = eps_pair || A.ol[i] == kEpsilon;
+        size_t k = key(A.src[i], B.src[j]);
+        if (!live[k]) { live[k] = 1; todo.emplace_back(A.src[i], B.src[j]); }
+      });
+      if (eps_pair) continue;
+      for (int32_t i : A.in[ca]) {
+        if (A.ol[i] != kEpsilon) { if (A.ol_sorted) break; else continue; }
+        size_t k = key(A.src[i], cb);
+        if (!live[k]) { live[k] = 1; todo.emplace_back(A.src[i], cb); }
+      }
+      for (int32_t j : B.in[cb]) {
+        if (B.il[j] != kEpsilon) { if (B.il_sorted) break; else continue; }
+        size_t k = key(ca, B.src[j]);
+        if (!live[k]) { live[k] = 1; todo.emplace_back(ca, B.src[j]); }
+      }
+    }
+  }
+  // forward pass: nodes numbered in breadth-first discovery order
+  auto out = std::make_unique<HostGraph>();
+  out->calc_grad = A.calc_grad || B.calc_grad;
+  std::vector<int32_t> id(live.size(), -1);
+  std::deque<std::pair<int, int>> todo;
+  for (int sa : A.starts)
+    for (int sb : B.starts) {
+      size_t k = key(sa, sb);
+      if (!live[k]) continue;
+      id[k] = out->add_node(true, (A.flags[sa] & 2) && (B.flags[sb] & 2));
+      todo.emplace_back(sa, sb);
+    }
+  auto node_for = [&](int a, int b) -> int {
+    size_t k = key(a, b);
+    if (!live[k]) return -1;
+    if (id[k] < 0) {
+      id[k] = out->add_node((A.flags[a] & 1) && (B.flags[b] & 1), (A.flags[a] & 2) && (B.flags[b] & 2));
+      todo.emplace_back(a, b);
+    }
+    return id[k];
+  };
+  while (!todo.empty()) {
+    auto [ca, cb] = todo.front();
+    todo.pop_front();
+    const int cur = id[key(ca, cb)];
+    bool eps_pair = false;
+    m.for_each(ca, cb, false, [&](int32_t i, int32_t j) {
+      eps_pair = eps_pair || A.ol[i] == kEpsilon;
+      int d = node_for(A.dst[i], B.dst[j]);
+      if (d < 0) return;
+      out->add_arc(cur, d, A.il[i], B.ol[j], A.w[i] + B.w[j]);
+      out->prov1.push_back(i);
+      out->prov2.push_back(j);
+    });
+    if (eps_pair) continue;
+    for (int32_t i : A.out[ca]) {
+      if (A.ol[i] != kEpsilon) { if (A.ol_sorted) break; else continue; }
+      int d = node_for(A.dst[i], cb);
+      if (d < 0) continue;
+      out->add_arc(cur, d, A.il[i], kEpsilon, A.w[i]);
+      out->prov1.push_back(i);
+      out->prov2.push_back(-1);
+    }
+    for (int32_t j : B.out[cb]) {
+      if (B.il[j] != kEpsilon) { if (B.il_sorted) break; else continue; }
+      int d = node_for(ca, B.dst[j]);
+      if (d < 0) continue;
+      out->add_arc(cur, d, kEpsilon, B.ol[j], B.w[j]);
+      out->prov1.push_back(-1);
+      out->prov2.push_back(j);
+    }
+  }
+  return out;
+}
+
+// gtn.remove(g, ilabel, olabel): nodes kept = start nodes and nodes with an in-arc that is
+// not (ilabel:olabel); each kept node absorbs the closure over matching arcs; weights dropped.
+std::unique_ptr<HostGraph> remove_label(const HostGraph& g, int il, int ol) {
+  auto hit = [&](int32_t a) { return g.il[a] == il && g.ol[a] == ol; };
+  auto out = std::make_unique<HostGraph>();
+  std::vector<int32_t> map(g.num_nodes(), -1);
+  for (int n = 0; n < g.num_nodes(); ++n) {
+    bool keep = g.flags[n] & 1;
+    if (!keep)
+      for (int32_t a : g.in[n])
+        if (!hit(a)) { keep = true; break; }
+    if (keep) map[n] = out->add_node(g.flags[n] & 1, false);
+  }
+  std::vector<int32_t> stamp(g.num_nodes(), -1);
+  std::deque<int32_t> todo;
+  for (int n = 0; n < g.num_nodes(); ++n) {
+    const int cur = map[n];
+    if (cur < 0) continue;
+    todo.push_back(n);
+    stamp[n] = n;
+    while (!todo.empty()) {
+      const int32_t u = todo.front();
+      todo.pop_front();
+      if (g.flags[u] & 2) out->make_accept(cur);
+      for (int32_t a : g.out[u]) {
+        const int32_t d = g.dst[a];
+        if (hit(a)) {
+          if (stamp[d] != n) { stamp[d] = n; todo.push_back(d); }
+        } else {
+          out->add_arc(cur, map[d], g.il[a], g.ol[a], 0.f);
+        }
+      }
+    }
+  }
+  return out;
+}
+
+std::unique_ptr<HostGraph> project(const HostGraph& g, bool input) {
+  auto out = std::make_unique<HostGraph>();
+  out->calc_grad = g.calc_grad;
+  for (int n = 0; n < g.num_nodes(); ++n) out->add_node(g.flags[n] & 1, g.flags[n] & 2);
+  for (int a = 0; a < g.num_arcs(); ++a) {
+    const int l = input ? g.il[a] : g.ol[a];
+    out->add_arc(g.src[a], g.dst[a], l, l, g.w[a]);
+  }
+  return out;
+}
+
+std::unique_ptr<HostGraph> chain(const int32_t* seq, int n) {
+  auto g = std::make_unique<HostGraph>();
+  g->add_node(true, false);
+  for (int i = 0; i < n; ++i) {
+    g->add_node(false, i == n - 1);
+    g->add_arc(i, i + 1, seq[i], seq[i], 0.f);
+  }
+  return g;
+}
+
+// alignment acceptor of one utterance (criterions/transducer.py:265-276)
+std::unique_ptr<HostGraph> alignment_graph(const HostGraph& tokens, const HostGraph& lexicon,
+                                           const int32_t* target, int n) {
+  auto tgt = chain(target, n);
+  tgt->arc_sort(true);
+  auto decomps = remove_label(*project(*compose_graphs(*tgt, lexicon), false), kEpsilon, kEpsilon);
+  decomps->arc_sort(false);
+  auto align = project(*remove_label(*compose_graphs(tokens, *decomps), kEpsilon, kEpsilon), true);
+  align->arc_sort(false);
+  return align;
+}
+
+template <class F>
+void parallel_for(int n, F&& fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)std::max(n, 1));
+  if (nt <= 1) {
+    for (int i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t)
+    pool.emplace_back([&] {
+      for (int i; (i = next.fetch_add(1)) < n;) fn(i);
+    });
+  for (auto& t : pool) t.join();
+}
+
+}  // namespace
+}  // namespace wfst
+
+using namespace wfst;
+
+#define GRAPH_OR_FAIL(var, h)                                   \
+  HostGraph* var = get(h);                                      \
+  if (!var) {                                                   \
+    set_error("invalid graph handle %d", (int)(h));             \
+    return WFST_ERR_INVALID;                                    \
+  }
+
+extern "C" {
+
+int32_t wfst_graph_create(int calc_grad) {
+  auto g = std::make_unique<HostGraph>();
+  g->calc_grad = calc_grad != 0;
+  return put(std::move(g));
+}
+
+int wfst_graph_destroy(int32_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (h < 0 || h >= (int32_t)g_graphs.size() || !g_graphs[h]) return WFST_ERR_INVALID;
+  g_graphs[h].reset();
+  g_free.push_back(h);
+  return WFST_OK;
+}
+
+int wfst_graph_add_node(int32_t h, int start, int accept) {
+  GRAPH_OR_FAIL(g, h);
+  return g->add_node(start != 0, accept != 0);
+}
+
+int wfst_graph_add_arc(int32_t h, int src, int dst, int ilabel, int olabel, float weight) {
+  GRAPH_OR_FAIL(g, h);
+  if (src < 0 || dst < 0 || src >= g->num_nodes() || dst >= g->num_nodes()) {
+    set_error("add_arc: node index out of range");
+    return WFST_ERR_INVALID;
+  }
+  return g->add_arc(src, dst, ilabel, olabel, weight);
+}
+
+int wfst_graph_add_arcs(int32_t h, int n, const int32_t* src, const int32_t* dst,
+                        const int32_t* ilabel, const int32_t* olabel, const float* weight) {
+  GRAPH_OR_FAIL(g, h);
+  for (int k = 0; k < n; ++k) {
+    if (src[k] < 0 || dst[k] < 0 || src[k] >= g->num_nodes() || dst[k] >= g->num_nodes()) {
+      set_error("add_arcs: node index out of range");
+      return WFST_ERR_INVALID;
+    }
+    g->add_arc(src[k], dst[k], ilabel[k], olabel ? olabel[k] : ilabel[k], weight ? weight[k] : 0.f);
+  }
+  return WFST_OK;
+}
+
+int wfst_graph_num_nodes(int32_t h) { GRAPH_OR_FAIL(g, h); return g->num_nodes(); }
+int wfst_graph_num_arcs(int32_t h) { GRAPH_OR_FAIL(g, h); return g->num_arcs(); }
+
+int wfst_graph_arc_sort(int32_t h, int by_olabel) { GRAPH_OR_FAIL(g, h); g->arc_sort(by_olabel != 0); return WFST_OK; }
+int wfst_graph_mark_arc_sorted(int32_t h, int by_olabel) {
+  GRAPH_OR_FAIL(g, h);
+  if (by_olabel) g->ol_sorted = true; else g->il_sorted = true;
+  return WFST_OK;
+}
+int wfst_graph_sorted_flags(int32_t h) { GRAPH_OR_FAIL(g, h); return (g->il_sorted ? 1 : 0) | (g->ol_sorted ? 2 : 0); }
+int wfst_graph_get_calc_grad(int32_t h) { GRAPH_OR_FAIL(g, h); return g->calc_grad ? 1 : 0; }
+int wfst_graph_set_calc_grad(int32_t h, int v) { GRAPH_OR_FAIL(g, h); g->calc_grad = v != 0; return WFST_OK; }
+
+int wfst_graph_set_weights(int32_t h, const float* w) {
+  GRAPH_OR_FAIL(g, h);
+  if (g->num_arcs()) std::memcpy(g->w.data(), w, sizeof(float) * g->num_arcs());
+  return WFST_OK;
+}
+int wfst_graph_get_weights(int32_t h, float* w) {
+  GRAPH_OR_FAIL(g, h);
+  if (g->num_arcs()) std::memcpy(w, g->w.data(), sizeof(float) * g->num_arcs());
+  return WFST_OK;
+}
+// src / dst / ilabel / olabel [num_arcs] (any may be NULL)
+int wfst_graph_get_arcs(int32_t h, int32_t* src, int32_t* dst, int32_t* ilabel, int32_t* olabel) {
+  GRAPH_OR_FAIL(g, h);
+  const size_t n = sizeof(int32_t) * g->num_arcs();
+  if (n) {
+    if (src) std::memcpy(src, g->src.data(), n);
+    if (dst) std::memcpy(dst, g->dst.data(), n);
+    if (ilabel) std::memcpy(ilabel, g->il.data(), n);
+    if (olabel) std::memcpy(olabel, g->ol.data(), n);
+  }
+  return WFST_OK;
+}
+int wfst_graph_get_node_flags(int32_t h, uint8_t* flags) {
+  GRAPH_OR_FAIL(g, h);
+  if (g->num_nodes()) std::memcpy(flags, g->flags.data(), g->num_nodes());
+  return WFST_OK;
+}
+// per-node arc lists flattened in node order (after arc_sort this is the sorted order)
+int wfst_graph_get_arc_order(int32_t h, int incoming, int32_t* order) {
+  GRAPH_OR_FAIL(g, h);
+  size_t k = 0;
+  for (auto& v : (incoming ? g->in : g->out))
+    for (int32_t a : v) order[k++] = a;
+  return WFST_OK;
+}
+// provenance of a composed graph; fills -1 when the graph is not a composition
+int wfst_graph_get_provenance(int32_t h, int32_t* arc_first, int32_t* arc_second) {
+  GRAPH_OR_FAIL(g, h);
+  for (int k = 0; k < g->num_arcs(); ++k) {
+    arc_first[k] = k < (int)g->prov1.size() ? g->prov1[k] : -1;
+    arc_second[k] = k < (int)g->prov2.size() ? g->prov2[k] : -1;
+  }
+  return WFST_OK;
+}
+
+int32_t wfst_graph_compose(int32_t a, int32_t b) {
+  HostGraph* ga = get(a);
+  HostGraph* gb = get(b);
+  if (!ga || !gb) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
+  return put(compose_graphs(*ga, *gb));
+}
+int32_t wfst_graph_remove(int32_t h, int ilabel, int olabel) {
+  HostGraph* g = get(h);
+  if (!g) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
+  return put(remove_label(*g, ilabel, olabel));
+}
+int32_t wfst_graph_project(int32_t h, int input) {
+  HostGraph* g = get(h);
+  if (!g) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
+  return put(project(*g, input != 0));
+}
+int32_t wfst_graph_linear(int M, int N, int calc_grad) {
+  auto g = std::make_unique<HostGraph>();
+  g->calc_grad = calc_grad != 0;
+  g->add_node(true, M == 0);
+  for (int m = 1; m <= M; ++m) {
+    g->add_node(false, m == M);
+    for (int n = 0; n < N; ++n) g->add_arc(m - 1, m, n, n, 0.f);
+  }
+  g->il_sorted = g->ol_sorted = true;
+  return put(std::move(g));
+}
+
+// text format of tests/trans_backoff_test.txt: start nodes / accept nodes / arcs
+int32_t wfst_graph_loadtxt(const char* path) {
+  FILE* f = std::fopen(path, "r");
+  if (!f) { set_error("loadtxt: cannot open %s", path); return WFST_ERR_INVALID; }
+  std::vector<std::string> lines;
+  char buf[4096];
+  while (std::fgets(buf, sizeof(buf), f)) lines.emplace_back(buf);
+  std::fclose(f);
+  if (lines.size() < 2) { set_error("loadtxt: %s is truncated", path); return WFST_ERR_INVALID; }
+  auto ints = [](const std::string& s) {
+    std::vector<int> v;
+    const char* p = s.c_str();
+    char* e;
+    for (long x = std::strtol(p, &e, 10); p != e; x = std::strtol(p, &e, 10)) { v.push_back((int)x); p = e; }
+    return v;
+  };
+  auto starts = ints(lines[0]), accepts = ints(lines[1]);
+  struct Arc { int s, d, i, o; float w; };
+  std::vector<Arc> arcs;
+  int maxn = -1;
+  for (int s : starts) maxn = std::max(maxn, s);
+  for (int s : accepts) maxn = std::max(maxn, s);
+  for (size_t k = 2; k < lines.size(); ++k) {
+    Arc a{0, 0, 0, 0, 0.f};
+    double w = 0.0;
+    int n = std::sscanf(lines[k].c_str(), "%d %d %d %d %lf", &a.s, &a.d, &a.i, &a.o, &w);
+    if (n <= 0) continue;
+    if (n < 3) { set_error("loadtxt: bad arc line %zu", k + 1); return WFST_ERR_INVALID; }
+    if (n == 3) a.o = a.i;
+    a.w = (float)w;
+    maxn = std::max(maxn, std::max(a.s, a.d));
+    arcs.push_back(a);
+  }
+  std::vector<uint8_t> fl(maxn + 1, 0);
+  for (int s : starts) fl[s] |= 1;
+  for (int s : accepts) fl[s] |= 2;
+  auto g = std::make_unique<HostGraph>();
+  g->calc_grad = true;
+  for (int n = 0; n <= maxn; ++n) g->add_node(fl[n] & 1, fl[n] & 2);
+  for (auto& a : arcs) g->add_arc(a.s, a.d, a.i, a.o, a.w);
+  return put(std::move(g));
+}
+
+int wfst_graph_savetxt(int32_t h, const char* path) {
+  GRAPH_OR_FAIL(g, h);
+  FILE* f = std::fopen(path, "w");
+  if (!f) { set_error("savetxt: cannot open %s", path); return WFST_ERR_INVALID; }
+  for (size_t k = 0; k < g->starts.size(); ++k) std::fprintf(f, k ? " %d" : "%d", g->starts[k]);
+  std::fprintf(f, "\n");
+  for (size_t k = 0; k < g->accepts.size(); ++k) std::fprintf(f, k ? " %d" : "%d", g->accepts[k]);
+  std::fprintf(f, "\n");
+  for (int a = 0; a < g->num_arcs(); ++a)
+    std::fprintf(f, "%d %d %d %d %.9g\n", g->src[a], g->dst[a], g->il[a], g->ol[a], g->w[a]);
+  std::fclose(f);
+  return WFST_OK;
+}
+
+// binary: int32 {num_nodes, num_start, num_accept, num_arcs}, start ids, accept ids, then
+// per arc {src, dst, ilabel, olabel} int32 + weight float32
+int wfst_graph_save(int32_t h, const char* path) {
+  GRAPH_OR_FAIL(g, h);
+  FILE* f = std::fopen(path, "wb");
+  if (!f) { set_error("save: cannot open %s", path); return WFST_ERR_INVALID; }
+  int32_t hdr[4] = {g->num_nodes(), (int32_t)g->starts.size(), (int32_t)g->accepts.size(), g->num_arcs()};
+  std::fwrite(hdr, 4, 4, f);
+  std::fwrite(g->starts.data(), 4, g->starts.size(), f);
+  std::fwrite(g->accepts.data(), 4, g->accepts.size(), f);
+  for (int a = 0; a < g->num_arcs(); ++a) {
+    int32_t rec[4] = {g->src[a], g->dst[a], g->il[a], g->ol[a]};
+    std::fwrite(rec, 4, 4, f);
+    std::fwrite(&g->w[a], 4, 1, f);
+  }
+  std::fclose(f);
+  return WFST_OK;
+}
+
+int32_t wfst_graph_load(const char* path) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { set_error("load: cannot open %s", path); return WFST_ERR_INVALID; }
+  int32_t hdr[4];
+  if (std::fread(hdr, 4, 4, f) != 4) { std::fclose(f); set_error("load: truncated"); return WFST_ERR_INVALID; }
+  std::vector<int32_t> st(hdr[1]), ac(hdr[2]);
+  bool ok = std::fread(st.data(), 4, st.size(), f) == st.size() &&
+            std::fread(ac.data(), 4, ac.size(), f) == ac.size();
+  std::vector<uint8_t> fl(hdr[0], 0);
+  for (int s : st) if (s >= 0 && s < hdr[0]) fl[s] |= 1;
+  for (int s : ac) if (s >= 0 && s < hdr[0]) fl[s] |= 2;
+  auto g = std::make_unique<HostGraph>();
+  g->calc_grad = true;
+  for (int n = 0; n < hdr[0]; ++n) g->add_node(fl[n] & 1, fl[n] & 2);
+  for (int a = 0; ok && a < hdr[3]; ++a) {
+    int32_t rec[4];
+    float w;
+    ok = std::fread(rec, 4, 4, f) == 4 && std::fread(&w, 4, 1, f) == 1;
+    if (ok) {
+      if (rec[0] < 0 || rec[1] < 0 || rec[0] >= hdr[0] || rec[1] >= hdr[0]) { ok = false; break; }
+      g->add_arc(rec[0], rec[1], rec[2], rec[3], w);
+    }
+  }
+  std::fclose(f);
+  if (!ok) { set_error("load: %s is truncated or corrupt", path); return WFST_ERR_INVALID; }
+  return put(std::move(g));
+}
+
+// Kahn-order tropical shortest path with back-pointers; ties keep the first maximum in
+// the node's in-list order (strict >).  Returns a chain graph of the best path's arcs.
+int32_t wfst_graph_viterbi_path(int32_t h) {
+  HostGraph* g = get(h);
+  if (!g) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
+  const int N = g->num_nodes();
+  const float NEG = -INFINITY;
+  std::vector<float> score(N, NEG);
+  std::vector<int32_t> best(N, -1), deg(N);
+  std::deque<int32_t> ready;
+  for (int n = 0; n < N; ++n) { deg[n] = (int)g->in[n].size(); if (!deg[n]) ready.push_back(n); }
+  int seen = 0;
+  while (!ready.empty()) {
+    const int n = ready.front();
+    ready.pop_front();
+    ++seen;
+    float m = (g->flags[n] & 1) ? 0.f : NEG;
+    int arg = -1;
+    for (int32_t a : g->in[n]) {
+      const float v = score[g->src[a]] + g->w[a];
+      if (v > m) { m = v; arg = a; }
+    }
+    score[n] = m;
+    best[n] = arg;
+    for (int32_t a : g->out[n]) if (--deg[g->dst[a]] == 0) ready.push_back(g->dst[a]);
+  }
+  if (seen != N) { set_error("viterbi_path: graph has a cycle"); return WFST_ERR_INVALID; }
+  int end = -1;
+  float m = NEG;
+  for (int n : g->accepts) if (score[n] > m) { m = score[n]; end = n; }
+  std::vector<int32_t> path;
+  for (int n = end; n >= 0 && best[n] >= 0; n = g->src[best[n]]) path.push_back(best[n]);
+  std::reverse(path.begin(), path.end());
+  auto out = std::make_unique<HostGraph>();
+  if (end >= 0) {
+    out->add_node(true, path.empty());
+    for (size_t k = 0; k < path.size(); ++k) {
+      const int32_t a = path[k];
+      out->add_node(false, k + 1 == path.size());
+      out->add_arc((int)k, (int)k + 1, g->il[a], g->ol[a], g->w[a]);
+    }
+  }
+  return put(std::move(out));
+}
+
+// Builds the alignment acceptor of every utterance of a batch on host threads
+// (criterions/transducer.py:260-276; the reference runs this under gtn.parallel_for
+// with the GIL taken for every Python-side step).  out_handles [B].
+int wfst_transducer_alignment_graphs(int32_t tokens, int32_t lexicon, const int32_t* targets,
+                                     const int32_t* target_offsets, int B, int32_t* out_handles) {
+  HostGraph* tk = get(tokens);
+  HostGraph* lx = get(lexicon);
+  if (!tk || !lx) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
+  tk->arc_sort(true);  // Transducer.forward: self.tokens.arc_sort(True) (transducer.py:188)
+  std::vector<std::unique_ptr<HostGraph>> built(B);
+  parallel_for(B, [&](int b) {
+    built[b] = alignment_graph(*tk, *lx, targets + target_offsets[b],
+                               target_offsets[b + 1] - target_offsets[b]);
+  });
+  for (int b = 0; b < B; ++b) out_handles[b] = put(std::move(built[b]));
+  return WFST_OK;
+}
+
+// Sizes and packing of a batch of acceptors into the lattice kernel's layout
+// (wfst_acceptor_batch_t); host arrays are filled, the caller uploads them.
+int wfst_graph_pack_sizes(const int32_t* handles, int B, int32_t* total_nodes, int32_t* total_arcs,
+                          int32_t* max_nodes, int32_t* max_arcs, int32_t* has_epsilon) {
+  int tn = 0, ta = 0, mn = 0, ma = 0, eps = 0;
+  for (int b = 0; b < B; ++b) {
+    GRAPH_OR_FAIL(g, handles[b]);
+    tn += g->num_nodes(); ta += g->num_arcs();
+    mn = std::max(mn, g->num_nodes()); ma = std::max(ma, g->num_arcs());
+    for (int a = 0; a < g->num_arcs(); ++a) eps |= (g->il[a] == kEpsilon);
+  }
+  *total_nodes = tn; *total_arcs = ta; *max_nodes = mn; *max_arcs = ma; *has_epsilon = eps;
+  return WFST_OK;
+}
+
+int wfst_graph_pack(const int32_t* handles, int B, int32_t* node_offsets, int32_t* arc_offsets,
+                    uint8_t* node_flags, int32_t* in_ptr, int32_t* in_src, int32_t* in_label,
+                    int32_t* in_arc, int32_t* out_ptr, int32_t* out_dst, int32_t* out_label,
+                    int32_t* out_arc, float* weights) {
+  std::vector<HostGraph*> gs(B);
+  node_offsets[0] = arc_offsets[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    gs[b] = get(handles[b]);
+    if (!gs[b]) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
+    node_offsets[b + 1] = node_offsets[b] + gs[b]->num_nodes();
+    arc_offsets[b + 1] = arc_offsets[b] + gs[b]->num_arcs();
+  }
+  parallel_for(B, [&](int b) {
+    const HostGraph& g = *gs[b];
+    const int n0 = node_offsets[b], a0 = arc_offsets[b];
+    std::memcpy(node_flags + n0, g.flags.data(), g.num_nodes());
+    if (g.num_arcs()) std::memcpy(weights + a0, g.w.data(), sizeof(float) * g.num_arcs());
+    int32_t* ip = in_ptr + n0 + b;
+    int32_t* op = out_ptr + n0 + b;
+    int ki = 0, ko = 0;
+    for (int v = 0; v < g.num_nodes(); ++v) {
+      ip[v] = ki;
+      for (int32_t a : g.in[v]) {
+        in_src[a0 + ki] = g.src[a]; in_label[a0 + ki] = g.il[a]; in_arc[a0 + ki] = a; ++ki;
+      }
+      op[v] = ko;
+      for (int32_t a : g.out[v]) {
+        out_dst[a0 + ko] = g.dst[a]; out_label[a0 + ko] = g.il[a]; out_arc[a0 + ko] = a; ++ko;
+      }
+    }
+    ip[g.num_nodes()] = ki;
+    op[g.num_nodes()] = ko;
+  });
+  return WFST_OK;
+}
+
+}  // extern "C"

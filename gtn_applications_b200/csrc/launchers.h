@@ -28,4 +28,8 @@ size_t ctc_fast_workspace_bytes(int B, int T, int max_target_len);
 int launch_ctc_fast(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                     int blank, int max_target_len, const float* grad_scale, float* z_out,
                     float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
+// best path (viterbi.cu)
+size_t viterbi_workspace_bytes(int B, int T, int max_nodes);
+int launch_viterbi(const float* E, int B, int T, int C, const wfst_acceptor_batch_t& g, int shared,
+                   float* scores, int32_t* labels, int32_t* arcs, void* workspace, cudaStream_t st);
 }  // namespace wfst

@@ -156,6 +156,81 @@ WFST_API int wfst_asg_forward_backward(const float* emissions, const float* tran
                               float* grad_transitions, void* workspace, size_t workspace_bytes,
                               void* stream);
 
+/* ------------------------------------------------------------------------
+ * Host-side graphs — replaces the gtn.Graph objects and small-graph operations the
+ * reference performs per utterance before scoring (criterions/transducer.py:23-123,
+ * 260-281; criterions/stc.py:22-64; utils.py:261 gtn.load; tests use gtn.loadtxt):
+ * gtn.Graph / add_node / add_arc / arc_sort / mark_arc_sorted / set_weights /
+ * compose|intersect / remove / project_input|output / linear_graph / load / save.
+ * Graphs live in the library and are named by int32 handles (>= 0); functions that
+ * return a handle return a negative error code on failure.  Node and arc numbering
+ * follows GTN's construction order (composition: breadth-first from the start pairs
+ * after a backward co-reachability pass, arcs in matcher order), epsilon = -1.
+ * ---------------------------------------------------------------------- */
+WFST_API int32_t wfst_graph_create(int calc_grad);
+WFST_API int wfst_graph_destroy(int32_t graph);
+WFST_API int wfst_graph_add_node(int32_t graph, int start, int accept);      /* returns the node id */
+WFST_API int wfst_graph_add_arc(int32_t graph, int src, int dst, int ilabel, int olabel,
+                                float weight);                                /* returns the arc id */
+WFST_API int wfst_graph_add_arcs(int32_t graph, int n, const int32_t* src, const int32_t* dst,
+                                 const int32_t* ilabel, const int32_t* olabel, const float* weight);
+WFST_API int wfst_graph_num_nodes(int32_t graph);
+WFST_API int wfst_graph_num_arcs(int32_t graph);
+WFST_API int wfst_graph_arc_sort(int32_t graph, int by_olabel);
+WFST_API int wfst_graph_mark_arc_sorted(int32_t graph, int by_olabel);
+WFST_API int wfst_graph_sorted_flags(int32_t graph);              /* bit0 ilabel-sorted, bit1 olabel-sorted */
+WFST_API int wfst_graph_get_calc_grad(int32_t graph);
+WFST_API int wfst_graph_set_calc_grad(int32_t graph, int calc_grad);
+WFST_API int wfst_graph_set_weights(int32_t graph, const float* weights);     /* HOST pointer, num_arcs floats */
+WFST_API int wfst_graph_get_weights(int32_t graph, float* weights);
+WFST_API int wfst_graph_get_arcs(int32_t graph, int32_t* src, int32_t* dst, int32_t* ilabel,
+                                 int32_t* olabel);
+WFST_API int wfst_graph_get_node_flags(int32_t graph, uint8_t* flags);         /* bit0 start, bit1 accept */
+WFST_API int wfst_graph_get_arc_order(int32_t graph, int incoming, int32_t* order);
+WFST_API int wfst_graph_get_provenance(int32_t graph, int32_t* arc_first, int32_t* arc_second);
+WFST_API int32_t wfst_graph_compose(int32_t first, int32_t second);           /* also gtn.intersect */
+WFST_API int32_t wfst_graph_remove(int32_t graph, int ilabel, int olabel);
+WFST_API int32_t wfst_graph_project(int32_t graph, int input);
+WFST_API int32_t wfst_graph_linear(int M, int N, int calc_grad);
+WFST_API int32_t wfst_graph_loadtxt(const char* path);
+WFST_API int wfst_graph_savetxt(int32_t graph, const char* path);
+WFST_API int32_t wfst_graph_load(const char* path);
+WFST_API int wfst_graph_save(int32_t graph, const char* path);
+
+/* Alignment acceptors of a whole batch (transducer.py:260-276), built on host threads:
+ * project_input(remove(compose(tokens, remove(project_output(compose(chain(y_b), lexicon)))))).
+ * targets are grapheme indices, concatenated; out_handles [B]. */
+WFST_API int wfst_transducer_alignment_graphs(int32_t tokens, int32_t lexicon,
+                                              const int32_t* targets,
+                                              const int32_t* target_offsets, int B,
+                                              int32_t* out_handles);
+
+/* Packs B host graphs into the arrays of wfst_acceptor_batch_t (HOST buffers sized from
+ * wfst_graph_pack_sizes; the caller uploads them).  Arc lists keep their arc_sort order. */
+WFST_API int wfst_graph_pack_sizes(const int32_t* handles, int B, int32_t* total_nodes,
+                                   int32_t* total_arcs, int32_t* max_nodes, int32_t* max_arcs,
+                                   int32_t* has_epsilon);
+WFST_API int wfst_graph_pack(const int32_t* handles, int B, int32_t* node_offsets,
+                             int32_t* arc_offsets, uint8_t* node_flags, int32_t* in_ptr,
+                             int32_t* in_src, int32_t* in_label, int32_t* in_arc, int32_t* out_ptr,
+                             int32_t* out_dst, int32_t* out_label, int32_t* out_arc, float* weights);
+
+/* ------------------------------------------------------------------------
+ * Best path (tropical semiring) — replaces gtn.viterbi_path(gtn.intersect(emissions, A))
+ * (criterions/asg.py:225, criterions/transducer.py:215-221).
+ *   scores [B] best path score (-inf: none); labels / arcs [B, T]: ilabel and original arc
+ *   index of the acceptor arc taken at each frame (-1 when there is no path).
+ * ---------------------------------------------------------------------- */
+WFST_API size_t wfst_lattice_viterbi_workspace_bytes(int B, int T, int max_nodes);
+WFST_API int wfst_lattice_viterbi(const float* emissions, int B, int T, int C,
+                                  const wfst_acceptor_batch_t* graphs, int shared_graph,
+                                  float* scores, int32_t* labels, int32_t* arcs, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+/* Host-side best path of a small acyclic graph (the alignment -> token mapping of
+ * Transducer.viterbi, transducer.py:222-229): returns a chain graph with the arcs of the
+ * best path, first maximum in in-list order on ties (GTN's traversal order). */
+WFST_API int32_t wfst_graph_viterbi_path(int32_t graph);
+
 /* Multiplies x[0..n) in place by *scale (a device scalar); returns immediately on
  * the device when *scale == 1 (the common loss.backward() case), so autograd's
  * grad_output costs no pass over the [B,T,C] gradient (ctc.py:87, asg.py:174). */

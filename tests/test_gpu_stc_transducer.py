@@ -1,0 +1,217 @@
+"""GPU parity for the criteria that run on the generic lattice kernel: STC
+(STCLossFunction / STC module) and the word-piece transducer (TransducerLossFunction /
+Transducer module, with and without an epsilon-free transition graph), plus the Viterbi
+decoders, against the float64 oracle, the reference's known answers and the committed
+fixtures.  Tolerance: see test_gpu_ctc.py."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import _golden as G
+import ref_criterions as rc
+from test_gpu_ctc import assert_close, assert_close_f32_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------- STC
+def test_stc_known_answers():
+    from gtn_applications_b200.criterions.stc import STC
+    with np.errstate(divide="ignore"):
+        lp = torch.log(torch.tensor([0.0, 1.0, 1.0, 0.0, 0.0, 1.0]).view(3, 1, 2)).cuda()
+    assert abs(STC(0, 1, 1, 1)(lp, [[1, 1]]).item()) < 1e-6               # gtn_stc_test.py:25-37
+    lp = torch.log_softmax(torch.zeros(3, 1, 4), 2).cuda()
+    loss = STC(0, 1, 1, 1, "none")(lp, [[1, 2]])
+    assert abs(loss.item() + math.log(0.25 * 0.25 * 2.5)) < 1e-5          # gtn_stc_test.py:39-51
+
+
+@pytest.mark.parametrize("case", ["fn_none", "fn_mean"])
+def test_stc_function_fixtures_and_oracle(gtn64, case):
+    from gtn_applications_b200.criterions.stc import STCLoss
+    z = G.load("stc")
+    tg = G.unpack(z[case + "_targets"], z[case + "_offsets"])
+    x = torch.tensor(z[case + "_emissions"], device="cuda", requires_grad=True)
+    loss = STCLoss(x, tg, float(z[case + "_prob"]), str(z[case + "_reduction"]))
+    loss.backward()
+    want = float(z[case + "_loss"])
+    assert abs(loss.item() - want) <= 1e-4 * max(1.0, abs(want))
+    assert_close_f32_fixture(x.grad.cpu().numpy(), z[case + "_grad"])
+    ref = rc.stc(gtn64, z[case + "_emissions"], tg, float(z[case + "_prob"]), str(z[case + "_reduction"]))
+    assert abs(loss.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert_close(x.grad.cpu().numpy(), ref["grad"])
+
+
+def test_stc_module_fixture():
+    from gtn_applications_b200.criterions.stc import STC
+    z = G.load("stc")
+    crit = STC(0, p0=0.5, plast=0.9, thalf=3, reduction="mean")
+    crit.train()
+    logits = torch.tensor(z["module_logits"], device="cuda", requires_grad=True)
+    tg = G.unpack(z["module_targets"], z["module_offsets"])
+    loss = crit(torch.log_softmax(logits, 2), tg)
+    loss.backward()
+    assert crit.nstep == 1
+    assert abs(loss.item() - float(z["module_loss"])) <= 1e-4 * abs(float(z["module_loss"]))
+    assert_close_f32_fixture(logits.grad.cpu().numpy(), z["module_grad_logits"])
+
+
+def test_stc_errors():
+    from gtn_applications_b200.criterions.stc import STC, STCLoss
+    with pytest.raises(ValueError, match="invalid value for reduction"):
+        STCLoss(torch.zeros(1, 3, 4, device="cuda"), [[1]], 0.5, "sum")
+    with pytest.raises(AssertionError):
+        STC(1)
+
+
+# ------------------------------------------------------------------ transducer
+TOKENS, G2I = ["a", "b", "ab", "ba", "aba"], {"a": 0, "b": 1}
+
+
+@pytest.mark.parametrize("name,blank,rep", [("wp_none", "none", True), ("wp_opt", "optional", True),
+                                            ("wp_norep", "optional", False), ("wp_forced", "forced", True)])
+def test_transducer_wordpiece_fixtures(name, blank, rep):
+    from gtn_applications_b200.criterions.transducer import Transducer
+    z = G.load("transducer")
+    tg = G.unpack(z["wp_targets"], z["wp_offsets"])
+    crit = Transducer(TOKENS, G2I, blank=blank, allow_repeats=rep, reduction="mean")
+    x = torch.tensor(z[name + "_logits"], device="cuda", requires_grad=True)
+    loss = crit(x, tg)
+    loss.backward()
+    want = float(z[name + "_loss"])
+    assert abs(loss.item() - want) <= 1e-4 * max(1.0, abs(want))
+    assert_close_f32_fixture(x.grad.cpu().numpy(), z[name + "_grad_logits"])
+    pred = crit.viterbi(x.detach())
+    assert [p.tolist() for p in pred] == G.unpack(z[name + "_viterbi"], z[name + "_viterbi_offsets"])
+
+
+def test_transducer_known_answers():
+    from gtn_applications_b200.criterions.transducer import Transducer
+    import test_oracle_golden as lit
+    lp = torch.log(torch.tensor([1.0, 0.0, 0.0, 1.0, 1.0, 0.0]).view(1, 3, 2)).cuda()
+    # transducer_test.py:100-126 (no blank / optional blank / no repeats)
+    assert abs(Transducer(["a", "b"], {"a": 0, "b": 1})(lp, [[0, 1, 0]]).item()) < 1e-6
+    assert abs(Transducer(["a"], {"a": 0}, blank="optional")(lp, [[0, 0]]).item()) < 1e-6
+    assert abs(Transducer(["a"], {"a": 0}, blank="optional", allow_repeats=False)(lp, [[0, 0]]).item()) < 1e-6
+    # transducer_test.py:143-216: the two warp-ctc vectors through the transducer
+    toks, g2i = ["a", "b", "c", "d", "e"], {"a": 0, "b": 1, "c": 2, "d": 3, "e": 4}
+    for probs, labels, want, want_grad, rep in ((lit.WARP_CTC_1, [[0, 1, 2, 1, 0]], 3.34211, lit.WARP_CTC_1_GRAD, True),
+                                                (lit.WARP_CTC_2, [[0, 1, 1, 0]], 5.42262, lit.WARP_CTC_2_GRAD, False)):
+        x = torch.log(torch.tensor(probs, dtype=torch.float32)).cuda().requires_grad_(True)
+        loss = Transducer(toks, g2i, blank="optional", allow_repeats=rep)(x, labels)
+        loss.backward()
+        assert abs(loss.item() - want) < 5e-5
+        np.testing.assert_allclose(x.grad.cpu().numpy(), want_grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("reduction", ["none", "mean"])
+def test_transducer_equals_ctc(reduction):
+    # transducer_test.py:275-316: single-grapheme tokens + optional blank + no repeats = CTC
+    from gtn_applications_b200.criterions.transducer import Transducer
+    from gtn_applications_b200.criterions.ctc import CTCLoss
+    T, N, B = 20, 15, 5
+    tgt = [[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10], [1, 1], [0, 2, 3], [0, 0, 0, 0, 0], [0, 4, 8, 12]]
+    x = torch.randn(B, T, N, generator=torch.Generator().manual_seed(0)).cuda().requires_grad_(True)
+    crit = Transducer([(t,) for t in range(N - 1)], {t: t for t in range(N - 1)}, blank="optional",
+                      allow_repeats=False, reduction=reduction)
+    a = CTCLoss(torch.log_softmax(x, 2), tgt, N - 1, reduction)
+    a.backward()
+    ga = x.grad.clone()
+    x.grad = None
+    b = crit(x, tgt)
+    b.backward()
+    assert abs(a.item() - b.item()) <= 1e-4 * abs(a.item())
+    torch.testing.assert_close(ga, x.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_transducer_with_asg_transitions(gtn64):
+    # transducer_test.py:420-508: ASG as a transducer with a learned bigram transition graph
+    from gtn_applications_b200.criterions.transducer import Transducer
+    from gtn_applications_b200.criterions.asg import ASGLossFunction
+    import test_oracle_golden as lit
+    N = 6
+    crit = Transducer([(n,) for n in range(N)], {n: n for n in range(N)},
+                      transitions=ASGLossFunction.create_transitions_graph(torch.zeros(N + 1, N))).cuda()
+    x = torch.tensor(lit.ASG_EMISSIONS, dtype=torch.float32, device="cuda", requires_grad=True)
+    loss = crit(x, lit.ASG_LABELS)
+    loss.backward()
+    assert abs(loss.item() - 7.47995) < 5e-5
+    np.testing.assert_allclose(x.grad.cpu().numpy(), lit.ASG_GRAD, rtol=1e-3, atol=1e-5)
+    tg = crit.transition_params.grad[N:].view(N, N).cpu().numpy()
+    np.testing.assert_allclose(tg, lit.ASG_TRANS_GRAD, rtol=1e-2, atol=1e-5)
+    # random parameters against the float64 oracle
+    rng = np.random.default_rng(1)
+    params = rng.standard_normal(N + N * N).astype(np.float32) * 0.5
+    crit.transition_params.data = torch.tensor(params, device="cuda")
+    crit.transition_params.grad = None
+    x.grad = None
+    loss = crit(x, lit.ASG_LABELS)
+    loss.backward()
+    o = rc.Transducer(gtn64, [(n,) for n in range(N)], {n: n for n in range(N)},
+                      transitions=rc.asg_transitions_graph(gtn64, np.zeros((N + 1, N), dtype=np.float32)))
+    ref = o.loss(lit.ASG_EMISSIONS, lit.ASG_LABELS, params)
+    assert abs(loss.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert_close(x.grad.cpu().numpy(), ref["grad"])
+    assert_close(crit.transition_params.grad.cpu().numpy(), ref["grad_transitions"])
+    assert list(crit.state_dict().keys()) == ["transition_params"]
+
+
+def test_transducer_random_wordpieces_against_oracle(gtn64):
+    from gtn_applications_b200.criterions.transducer import Transducer
+    rng = np.random.default_rng(7)
+    tokens = ["a", "b", "c", "ab", "bc", "ca", "abc", "cab", "aa"]
+    g2i = {"a": 0, "b": 1, "c": 2}
+    B, T = 4, 70
+    tg = [rng.integers(0, 3, size=n).tolist() for n in (12, 1, 30, 7)]
+    x = rng.standard_normal((B, T, len(tokens) + 1)).astype(np.float32)
+    crit = Transducer(tokens, g2i, blank="optional", allow_repeats=False, reduction="mean")
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    loss = crit(xt, tg)
+    loss.backward()
+    o = rc.Transducer(gtn64, tokens, g2i, blank="optional", allow_repeats=False, reduction="mean")
+    ref = o.loss(G.log_softmax(x), tg)
+    assert abs(loss.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert_close(xt.grad.cpu().numpy(), G.through_log_softmax(x, ref["grad"]))
+
+
+def test_epsilon_transitions_are_refused_loudly():
+    from gtn_applications_b200.criterions.transducer import Transducer
+    crit = Transducer([(0,), (1,)], {0: 0, 1: 1}, ngram=2, blank="optional", allow_repeats=False).cuda()
+    with pytest.raises(NotImplementedError, match="epsilon"):
+        crit(torch.zeros(1, 4, 3, device="cuda"), [[0, 1]])
+
+
+# --------------------------------------------------------------------- viterbi
+def test_asg_viterbi_known_answer_and_fixture():
+    from gtn_applications_b200.criterions.asg import ASG
+    # gtn_asg_test.py:107-124
+    crit = ASG(3, 1, False).cuda()
+    crit.transitions.data = torch.tensor([0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2, 0, 2, 0, 0],
+                                         dtype=torch.float32, device="cuda").view(5, 4)
+    x = torch.tensor([0, 0, 0, 7, 0, 5, 4, 3, 0, 5, 8, 5, 0, 5, 4, 3], dtype=torch.float32, device="cuda").view(1, 4, 4)
+    assert crit.viterbi(x)[0].tolist() == [2, 1, 0]
+    z = G.load("asg")
+    crit = ASG(4, num_replabels=2, use_garbage=True).cuda()
+    crit.transitions.data = torch.tensor(z["module_transitions"], device="cuda")
+    got = crit.viterbi(torch.tensor(z["module_emissions"], device="cuda"))
+    assert [g.tolist() for g in got] == G.unpack(z["module_viterbi"], z["module_viterbi_offsets"])
+
+
+def test_transducer_viterbi_known_answers():
+    # transducer_test.py:318-365 and 510-532
+    from gtn_applications_b200.criterions.transducer import Transducer
+    from gtn_applications_b200.criterions.asg import ASGLossFunction
+    e1 = torch.tensor([0, 4, 0, 1, 0, 2, 1, 1, 0, 0, 0, 2, 0, 0, 0, 2, 8, 0, 0, 2], dtype=torch.float).view(5, 4)
+    e2 = torch.tensor([0, 2, 1, 7, 0, 2, 9, 1, 0, 0, 0, 2, 0, 0, 5, 2, 1, 0, 0, 2], dtype=torch.float).view(5, 4)
+    em = torch.stack([e1, e2]).cuda()
+    crit = Transducer(["a", "b", "c", "d"], {"a": 0, "b": 1, "c": 2, "d": 3}, blank="none")
+    assert [p.tolist() for p in crit.viterbi(em)] == [[1, 3, 0], [3, 2, 3, 2, 3]]
+    crit = Transducer(["a", "b", "c"], {"a": 0, "b": 1, "c": 2}, blank="optional", allow_repeats=False)
+    assert [p.tolist() for p in crit.viterbi(em)] == [[1, 0], [2, 2]]
+    N = 3
+    crit = Transducer([(n,) for n in range(N)], {n: n for n in range(N)},
+                      transitions=ASGLossFunction.create_transitions_graph(torch.zeros(N + 1, N))).cuda()
+    crit.transition_params.data = torch.tensor([0, 0, 0, 0, 2, 0, 0, 0, 2, 2, 0, 0], dtype=torch.float32, device="cuda")
+    x = torch.tensor([0, 0, 7, 5, 4, 3, 5, 8, 5, 5, 4, 3], dtype=torch.float32, device="cuda").view(1, 4, 3)
+    assert crit.viterbi(x)[0].tolist() == [2, 1, 0]

@@ -1,0 +1,166 @@
+"""CPU tests of the product's host-side graph library (csrc/graph.cpp through the C ABI;
+no GPU needed): node / arc numbering and arc-list order must be BIT-EXACT with the oracle
+restatement of GTN and with the fixtures produced from the reference's own constructors
+("arc/state indices bit-exact", north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import _golden as GOLD
+import ref_criterions as rc
+from gtn_applications_b200 import graph as G
+from gtn_applications_b200.criterions import asg as pasg, ctc as pctc, stc as pstc, transducer as ptr
+
+KEYS = ("start", "accept", "src", "dst", "ilabel", "olabel")
+
+
+def same(prod, oracle_graph, weights=True):
+    x, y = prod.arrays(), rc.graph_arrays(oracle_graph)
+    for k in KEYS:
+        np.testing.assert_array_equal(x[k], y[k], err_msg=k)
+    if weights:
+        np.testing.assert_allclose(x["weight"], y["weight"], rtol=1e-6)
+    np.testing.assert_array_equal(prod.arc_order(False), np.array(oracle_graph.out_order(), dtype=np.int32))
+    np.testing.assert_array_equal(prod.arc_order(True), np.array(oracle_graph.in_order(), dtype=np.int32))
+
+
+def test_ctc_asg_stc_constructors_match_oracle_and_fixtures(gtn32):
+    z = GOLD.load("ctc")
+    g = pctc.CTCLossFunction.create_ctc_graph([3, 3, 1, 0, 0, 2], 5)
+    same(g, rc.ctc_graph(gtn32, [3, 3, 1, 0, 0, 2], 5))
+    ref = GOLD.graph_of(z, "graph")
+    for k in KEYS:
+        np.testing.assert_array_equal(g.arrays()[k], ref[k])
+    np.testing.assert_array_equal(g.arc_order(True), z["graph_in_order"])
+    np.testing.assert_array_equal(g.arc_order(False), z["graph_out_order"])
+    import torch
+    tr = torch.randn(4, 3)
+    same(pasg.ASGLossFunction.create_transitions_graph(tr), rc.asg_transitions_graph(gtn32, tr.numpy()))
+    same(pasg.ASGLossFunction.create_force_align_graph([2, 0, 0, 1]), rc.asg_force_align_graph(gtn32, [2, 0, 0, 1]))
+    same(pstc.STCLossFunction.create_stc_graph([2, 1, 1], 4, 0.5), rc.stc_graph(gtn32, [2, 1, 1], 4, 0.5))
+    z = GOLD.load("stc")
+    ref = GOLD.graph_of(z, "graph")
+    for k in KEYS:
+        np.testing.assert_array_equal(pstc.STCLossFunction.create_stc_graph([2, 1, 1], 4, 0.5).arrays()[k], ref[k])
+
+
+@pytest.mark.parametrize("blank,rep", [("none", True), ("optional", True), ("optional", False), ("forced", True)])
+def test_transducer_graphs_match_oracle(gtn32, blank, rep):
+    import ctypes
+    from gtn_applications_b200 import _lib
+    tokens, g2i = ["a", "b", "ab", "ba", "aba"], {"a": 0, "b": 1}
+    o = rc.Transducer(gtn32, tokens, g2i, blank=blank, allow_repeats=rep)
+    tk = ptr.make_token_graph(tokens, blank, rep)
+    lx = ptr.make_lexicon_graph(tokens, g2i)
+    same(tk, o.tokens)
+    same(lx, o.lexicon)
+    tg = [[0, 1, 0], [1, 1, 0, 1, 0, 0], [0], [1, 0, 0, 0, 1, 1, 0, 1]]
+    flat = np.array([t for x in tg for t in x], dtype=np.int32)
+    off = np.zeros(len(tg) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(t) for t in tg])
+    hs = (ctypes.c_int32 * len(tg))()
+    _lib.check(_lib.lib().wfst_transducer_alignment_graphs(tk._h, lx._h, flat.ctypes.data,
+                                                           off.ctypes.data, len(tg), hs))
+    o.tokens.arc_sort(True)
+    for b, y in enumerate(tg):
+        same(G.Graph(_handle=hs[b]), o.alignment_graph(y))
+
+
+def test_wordpiece_graphs_match_fixtures():
+    z = GOLD.load("transducer")
+    tokens, g2i = ["a", "b", "ab", "ba", "aba"], {"a": 0, "b": 1}
+    for name, blank, rep in (("wp_none", "none", True), ("wp_opt", "optional", True),
+                             ("wp_norep", "optional", False), ("wp_forced", "forced", True)):
+        for prefix, g in (("_tokens", ptr.make_token_graph(tokens, blank, rep)),
+                          ("_lexicon", ptr.make_lexicon_graph(tokens, g2i))):
+            ref = GOLD.graph_of(z, name + prefix)
+            for k in KEYS:
+                np.testing.assert_array_equal(g.arrays()[k], ref[k], err_msg=name + prefix + k)
+
+
+@pytest.mark.parametrize("ngram", [1, 2, 3])
+def test_ngram_transition_graphs(gtn32, ngram):
+    same(ptr.make_transitions_graph(ngram, 4), rc.ngram_transitions_graph(gtn32, ngram, 4))
+
+
+def test_compose_with_epsilon_transitions_and_provenance(gtn32, tmp_path):
+    # loaded back-off graph (tests/trans_backoff_test.txt content comes from the fixture)
+    z = GOLD.load("transducer")
+    a = GOLD.graph_of(z, "backoff_file")
+    g = G.Graph(True)
+    for s, acc in zip(a["start"], a["accept"]):
+        g.add_node(bool(s), bool(acc))
+    g.add_arcs(a["src"], a["dst"], a["ilabel"], a["olabel"], a["weight"])
+    og = gtn32.Graph(True)
+    for s, acc in zip(a["start"], a["accept"]):
+        og.add_node(bool(s), bool(acc))
+    for s, d, i, o, w in zip(a["src"], a["dst"], a["ilabel"], a["olabel"], a["weight"]):
+        og.add_arc(int(s), int(d), int(i), int(o), float(w))
+    g.arc_sort()
+    og.arc_sort()
+    N = 5
+    tokens = [(n,) for n in range(N)]
+    g2i = {n: n for n in range(N)}
+    o = rc.Transducer(gtn32, tokens, g2i, blank="optional", allow_repeats=False)
+    o.tokens.arc_sort(True)
+    oal = o.alignment_graph([0, 1, 0])
+    tk = ptr.make_token_graph(tokens, "optional", False)
+    lx = ptr.make_lexicon_graph(tokens, g2i)
+    tk.arc_sort(True)
+    tgt = ptr.make_chain_graph([0, 1, 0])
+    tgt.arc_sort(True)
+    dec = G.remove(G.project_output(G.compose(tgt, lx)))
+    dec.arc_sort()
+    pal = G.project_input(G.remove(G.compose(tk, dec)))
+    pal.arc_sort()
+    same(pal, oal)
+    same(G.intersect(g, pal), gtn32.intersect(og, oal))
+    # emissions o transitions with epsilon back-off arcs (transducer.py:287)
+    same(G.intersect(G.linear_graph(3, N + 1), g), gtn32.intersect(gtn32.linear_graph(3, N + 1), og))
+    # text / binary round trips
+    p = os.path.join(tmp_path, "g.txt")
+    G.savetxt(p, g)
+    assert G.equal(G.loadtxt(p), g)
+    same(G.loadtxt(p), gtn32.loadtxt(p))
+    p = os.path.join(tmp_path, "g.bin")
+    G.save(p, g)
+    assert G.equal(G.load(p), g)
+    gtn32.save(os.path.join(tmp_path, "o.bin"), og)
+    assert G.equal(G.load(os.path.join(tmp_path, "o.bin")), g)   # same binary format as the oracle's
+
+
+def test_isomorphic_equal_and_viterbi_path(gtn32):
+    a = ptr.make_transitions_graph(2, 3)
+    b = ptr.make_transitions_graph(2, 3)
+    assert G.equal(a, b) and G.isomorphic(a, b)
+    c = ptr.make_transitions_graph(2, 4)
+    assert not G.isomorphic(a, c)
+    # best path with ties: first maximum in in-list order, as the oracle does
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        g, og = G.Graph(False), gtn32.Graph(False)
+        n = 8
+        for k in range(n):
+            g.add_node(k == 0, k == n - 1)
+            og.add_node(k == 0, k == n - 1)
+        for k in range(30):
+            s = int(rng.integers(0, n - 1))
+            d = int(rng.integers(s + 1, n))
+            lab, w = int(rng.integers(0, 5)), float(rng.integers(0, 3))
+            g.add_arc(s, d, lab, lab + 1, w)
+            og.add_arc(s, d, lab, lab + 1, w)
+        same(G.viterbi_path(g), gtn32.viterbi_path(og))
+
+
+def test_errors():
+    g = G.Graph()
+    g.add_node()
+    with pytest.raises(ValueError):
+        g.add_arc(0, 3, 1)
+    with pytest.raises(ValueError):
+        ptr.make_token_graph(["a"], blank="none", allow_repeats=False)
+    with pytest.raises(ValueError):
+        ptr.Transducer(["a"], {"a": 0}, blank="sometimes")
+    with pytest.raises(ValueError):
+        ptr.Transducer(["a"], {"a": 0}, ngram=1, transitions=G.Graph())

@@ -241,7 +241,7 @@ def run_gpu(args):
     loss_value = float(out[B].item())
 
     # ---- e2e: the user-facing call with HOST inputs (pinned), copies inside the timed region
-    host = [(b[0].cpu().pin_memory(), b[3].tolist()) for b in batches[:4]]
+    host = [(b[0].cpu().pin_memory(), b[3]) for b in batches[:4]]   # targets: [B, L] int tensor
     e2e_steps = max(3, min(args.steps, 20))
 
     def e2e_step(i):

@@ -42,17 +42,32 @@ def stream_ptr(device):
 def pack_targets(targets, num_classes, device):
     """list[list[int]] -> (flat int32, offsets int32 [B+1], lengths list, max_len) on `device`.
     Labels are validated on the host (the kernels index emissions with them)."""
+    import itertools
+    import numpy as np
+    if torch.is_tensor(targets) and targets.dim() == 2:
+        # extension over the reference (which takes Python lists): a rectangular integer
+        # tensor [B, L] skips the per-label Python work
+        B, L = targets.shape
+        t = targets.detach().to("cpu", torch.int32).contiguous()
+        if t.numel() and (int(t.min()) < 0 or int(t.max()) >= num_classes):
+            raise ValueError("target label outside [0, %d)" % num_classes)
+        host = torch.empty(B * L + B + 1, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        host[:B * L] = t.reshape(-1)
+        host[B * L:] = torch.arange(B + 1, dtype=torch.int32) * L
+        dev = host.to(device, non_blocking=True)
+        return dev[:B * L], dev[B * L:], [L] * B, L
     lengths = [len(t) for t in targets]
-    flat = [int(x) for t in targets for x in t]
-    if flat and (min(flat) < 0 or max(flat) >= num_classes):
+    total = sum(lengths)
+    flat = np.fromiter(itertools.chain.from_iterable(targets), dtype=np.int64, count=total)
+    if total and (flat.min() < 0 or flat.max() >= num_classes):
         raise ValueError("target label outside [0, %d)" % num_classes)
-    offsets = [0]
-    for n in lengths:
-        offsets.append(offsets[-1] + n)
-    host = torch.tensor(flat + offsets, dtype=torch.int32)
-    dev = host.to(device, non_blocking=False)
-    n = len(flat)
-    return dev[:n], dev[n:], lengths, (max(lengths) if lengths else 0)
+    host = torch.empty(total + len(lengths) + 1, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+    buf = host.numpy()
+    buf[:total] = flat
+    buf[total] = 0
+    np.cumsum(lengths, out=buf[total + 1:])
+    dev = host.to(device, non_blocking=True)
+    return dev[:total], dev[total:], lengths, (max(lengths) if lengths else 0)
 
 
 def reduction_scales(reduction, sizes):

@@ -62,6 +62,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop_evt = threading.Event()
+        self._rec = threading.Event()
+        self.ready = threading.Event()
 
     def run(self):
         try:
@@ -75,7 +77,11 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
             }
+            self.ready.set()
             while not self._stop_evt.is_set():
+                if not self._rec.is_set():
+                    time.sleep(0.001)
+                    continue
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -84,9 +90,13 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.004)
         except Exception as e:  # pragma: no cover
             self.reasons.add("nvml_unavailable:" + type(e).__name__)
+            self.ready.set()
+
+    def begin(self):
+        self._rec.set()
 
     def stop(self):
         self._stop_evt.set()
@@ -218,11 +228,13 @@ def run_gpu(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.ready.wait(timeout=5)
     launches0 = _lib.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     start.record(stream)
     for i in range(args.steps):
         evs[i][0].record(stream)
@@ -304,7 +316,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ctc_cfg2", choices=sorted(WORKLOADS))

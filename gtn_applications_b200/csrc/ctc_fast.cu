@@ -1,36 +1,42 @@
-// Fast CTC forward+backward for sm_100a: scaled-probability recursion with the
-// whole CTC chain of an utterance resident in the registers of ONE warp per
-// direction.  Replaces, for CTC, the reference's per-utterance
+// Fast CTC forward+backward for sm_100a: scaled-probability recursion with the whole CTC
+// chain of an utterance resident in the registers of one warp per direction, and the
+// remaining stages of the computation pipelined over helper warps.  Replaces, for CTC,
+// the reference's per-utterance
 //   create_ctc_graph -> intersect -> forward_score -> backward
 // (criterions/ctc.py:15-29,40-51,78-81).
 //
-// Layout of one thread block (= one utterance), 96 threads:
-//   warp 0 "A": alpha direction (time ascending),  states j = s
-//   warp 1 "B": beta  direction (time descending), states j = Sp-1-s  (mirrored)
-//   warp 2 "P": producer — TMA-loads [16, C] emission tiles into shared memory and
-//               turns them into p[t,c] = exp(E[t,c] - max_c E[t,c]) tiles for A and B
+// One thread block (= one utterance) has 7 warps:
+//   L0 "live alpha"  time ascending,  states j = s
+//   L1 "live beta"   time descending, states j = Sp-1-s (mirrored)
+//   P  producer      TMA-loads [8, C] emission tiles and turns them into
+//                    p[t,c] = exp(E[t,c] - max_c E[t,c]) tiles for both directions
+//   R0, R1 recompute the OPPOSITE recursion of L0 / L1 over a segment from a checkpoint
+//   X0, X1 reduce    the per-state posteriors of a segment over states with equal label
+//                    and send the [8, C] gradient tile to HBM (bulk async store)
 // Both directions run the SAME recursion (the beta recursion written for
-// beta~_t(s) = p_t(lab s) * beta_t(s) is the alpha recursion on the reversed target
-// and reversed time):  v'[j] = (v[j] + v[j-1] + skip[j] * v[j-2]) * p_t[lab j].
-// Lane l owns K consecutive states j in [l*K, (l+1)*K); neighbours come from one or
-// two warp shuffles per frame.  Values are float32 mantissas with one power-of-two
-// exponent per lane, re-normalised every 16 frames ("event").
+// beta~_t(s) = p_t(lab s) * beta_t(s) is the alpha recursion on the reversed target and
+// reversed time):  v'[j] = (v[j] + v[j-1] + skip[j] * v[j-2]) * p_t[lab j].
+// Lane l owns K consecutive states; neighbours come from one or two warp shuffles per
+// frame.  Values are float32 mantissas with one power-of-two exponent per lane,
+// re-normalised every 16 frames ("event").
 //
 // Schedule (meet in the middle + recompute; nothing of size T x S ever leaves the SM):
-//   phase 1: A sweeps segments [0, nA), B sweeps segments [nA, nseg) downwards; each
-//            writes a checkpoint (K values + exponent per lane) per 16-frame segment.
+//   phase 1: L0 sweeps segments [0, nA), L1 sweeps [nA, nseg) downwards; each writes a
+//            checkpoint (K values + exponent per lane) per 8-frame segment.
 //   meeting: Z = sum_s alpha(s) * beta(s) at the boundary.
-//   phase 2: A continues upwards through [nA, nseg): per segment it re-runs the beta
-//            recursion from B's checkpoint (stored in shared memory, scaled so that
-//            stored * live = posterior * Zm), then advances alpha and multiplies;
-//            B does the mirror image downwards through [0, nA).
-//   The per-state posteriors of a segment are reduced over states with equal label by a
-//   "transposed" pass (lane = frame) and leave as a [16, C] tile via a bulk async store.
+//   phase 2: L0 continues upwards through [nA, nseg).  For each segment R0 has re-run the
+//            beta recursion from L1's checkpoint into a shared-memory ring (it runs up to
+//            two segments ahead); L0 advances alpha frame by frame and multiplies,
+//            posterior(s) * Zm = abar(s) * stored(s) * 2^(eL + eR - eZ); X0 then sums the
+//            posteriors per label (lane = 4-column chunk of a label-sorted row, segmented
+//            suffix sum by shuffles) and stores the gradient tile.  L1 / R1 / X1 mirror
+//            this downwards through [0, nA).
 //
-// Robustness: a frame's posteriors must sum to one.  Every row sum is checked against Z
-// (|sum - Z| <= 1e-3 Z, finite); any violation (possible only if float32 range was
-// exceeded inside a 16-frame window) flags the utterance in `hazard`, and the
-// log-semiring kernel (lattice.cuh, CtcTopo) recomputes it.  No CPU fallback.
+// Robustness: a frame's posteriors sum to one.  Every segment's total is checked against
+// rows * Z (2e-5, finite); a violation (possible only if float32 range was exceeded inside
+// a window, which can only lose mass), Z out of range, a blank label inside the target or a
+// label layout that does not fit flag the utterance in `hazard`, and the log-semiring
+// kernel (lattice.cuh, CtcTopo) recomputes it on the GPU.  No CPU fallback.
 #include "common.cuh"
 #include "launchers.h"
 
@@ -44,10 +50,11 @@ namespace wfst {
 #define PROF_MARK(i)
 #endif
 
-constexpr int kSeg = 16;              // frames per segment / tile
+constexpr int kSeg = 8;               // frames per segment / tile
+constexpr int kEventEvery = 2;        // lanes are renormalised every kEventEvery segments (16 frames)
 constexpr int kUndef = -(1 << 19);    // "no exponent": lane holds only zeros
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kNB = 2;                // p-tile ring depth per direction
+constexpr int kNB = 4;                // p-tile ring depth per direction (the recompute warp runs ahead)
 constexpr int kNR = 4;                // raw (TMA) staging slots of the producer
 constexpr int kMaxPass = 4;           // transposed pass: up to 4 x 32 chunk slots per gamma row
 
@@ -59,11 +66,12 @@ struct CtcFastArgs {
   const float* grad_scale;
   float* z_out;     // [B] log Z
   float* gradE;     // [B, T, C] or null
-  float* ckpt;      // [B][2][nseg + 1][K + 1][32]
+  float* ckpt;      // [B][2][nseg + 1][32][ck_stride(K)]
   int* hazard;      // [B]
   int nseg, nA;
   int Cp;           // p-tile row stride (odd, > C); column C is always 0
-  int RS;           // row stride of the stored/gamma buffer (= 4 mod 32, >= Sp and >= gamma columns)
+  int RS;           // row stride of the recomputed ("stored") rows: Sp + 4
+  int GW;           // row stride of the sorted posterior ("gamma") rows: 4 * slots + 4
 };
 
 // Explicit shared-state-space accesses on 32-bit addresses: generic pointers made the
@@ -232,197 +240,545 @@ __device__ __forceinline__ void event(float (&v)[K], int& e, float& f, int lane)
   }
 }
 
-// checkpoint I/O: ckpt[slot][lane], slot K holds the exponent
+// checkpoint I/O: per lane a 16-byte aligned record of kCk(K) floats (K values, then the
+// exponent), moved with 128-bit accesses
+template <int K>
+__host__ __device__ constexpr int ck_stride() { return (K + 1 + 3) & ~3; }
 template <int K>
 __device__ __forceinline__ void ckpt_store(float* base, const float (&v)[K], int e, int lane) {
+  float4* p = reinterpret_cast<float4*>(base + (size_t)lane * ck_stride<K>());
 #pragma unroll
-  for (int i = 0; i < K; ++i) base[i * 32 + lane] = v[i];
-  base[K * 32 + lane] = __int_as_float(e);
+  for (int i = 0; i < K; i += 4) p[i >> 2] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  p[K >> 2] = make_float4(__int_as_float(e), 0.f, 0.f, 0.f);
 }
 template <int K>
 __device__ __forceinline__ void ckpt_load(const float* base, float (&v)[K], int& e, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(base + (size_t)lane * ck_stride<K>());
 #pragma unroll
-  for (int i = 0; i < K; ++i) v[i] = base[i * 32 + lane];
-  e = __float_as_int(base[K * 32 + lane]);
+  for (int i = 0; i < K; i += 4) {
+    const float4 q = p[i >> 2];
+    v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+  }
+  e = __float_as_int(p[K >> 2].x);
+}
+
+// factor that converts the left neighbour's scale to this lane's (0 when either is undefined)
+__device__ __forceinline__ float neighbor_factor(int e, int lane) {
+  const int el = __shfl_up_sync(kFull, e, 1);
+  if (lane == 0 || !defined_exp(el) || !defined_exp(e)) return 0.f;
+  const int dd = el - e;
+  return (dd < -126) ? 0.f : pow2i(min(dd, 126));
 }
 
 // ---------------------------------------------------------------------------
-// shared memory carve-up
+// shared memory
 // ---------------------------------------------------------------------------
-template <int K>
+// mbarrier indices
+constexpr int kBarPFull = 0;                   // [2][kNB]  p tile ready (producer -> L, R)
+constexpr int kBarPEmpty = kBarPFull + 2 * kNB;  // [2][kNB]  p tile released (count 2: L and R)
+constexpr int kBarTma = kBarPEmpty + 2 * kNB;  // [kNR]     raw tile landed
+constexpr int kBarSFull = kBarTma + kNR;       // [2][2]    stored segment ready (R -> L)
+constexpr int kBarSEmpty = kBarSFull + 4;      // [2][2]    stored segment consumed (L -> R)
+constexpr int kBarGFull = kBarSEmpty + 4;      // [2][2]    gamma segment ready (L -> X)
+constexpr int kBarGEmpty = kBarGFull + 4;      // [2][2]    gamma segment consumed (X -> L)
+constexpr int kBarZ = kBarGEmpty + 4;          // Z published (L1 -> P, R, X); count 1
+constexpr int kNumBars = kBarZ + 1;
+
 struct FastSmem {
-  static constexpr int Sp = 32 * K;
-  // per direction
-  // (two explicit members instead of arrays: indexing an array of pointers with the
-  // runtime direction would push the whole struct into local memory)
-  float *stored0, *stored1;   // [kSeg][RS] recomputed opposite-direction values; row r is re-used
-                              // for the sorted per-state posteriors ("gamma") once it has been read
-  float *pbk0, *pbk1;         // [kSeg][33] blank partials
-  float *out0, *out1;         // [2][kSeg*C] output tiles (double buffered)
-  float *ptile0, *ptile1;     // [kNB][kSeg][Cp]
-  __device__ __forceinline__ float* stored(int d) const { return d ? stored1 : stored0; }
-  __device__ __forceinline__ float* pbk(int d) const { return d ? pbk1 : pbk0; }
-  __device__ __forceinline__ float* out(int d) const { return d ? out1 : out0; }
-  __device__ __forceinline__ float* ptile(int d) const { return d ? ptile1 : ptile0; }
-  // shared
-  float* raw;         // [kNR][kSeg*C] TMA staging (16B aligned)
-  int* gcolpos;       // [Sp/2] gamma column of target position n
-  int* slotlab;       // [32*kMaxPass + 8] label of each 4-column chunk slot of the gamma row (-1: unused)
-  int* hist;          // [C + 4] scratch for the counting sort; [C]: #slots, [C+1]: max chunks per label
-  uint64_t* bars;     // full[2][kNB], empty[2][kNB], tma[2], zready
-  float* zx;          // Zm, eZ (as int bits), valid flag
-  double* msum;       // sum of per-frame maxima (phase-1 frames)
+  // per direction d (two explicit members: indexing an array of pointers with a runtime
+  // direction would push the struct into local memory)
+  uint32_t stored[2];   // [2 buf][kSeg][RS]  recomputed opposite-direction values
+  uint32_t sexp[2];     // [2 buf][32]        their lane exponents (int)
+  uint32_t gam[2];      // [2 buf][kSeg][GW]  label-sorted per-state posteriors (pads stay 0)
+  uint32_t pbk[2];      // [2 buf][kSeg][33]  blank partial sums per lane
+  uint32_t out[2];      // [2 buf][kSeg*C]    gradient tiles
+  uint32_t ptile[2];    // [kNB][kSeg][Cp]    p tiles
+  uint32_t raw;         // [kNR][kSeg*C]      TMA staging
+  uint32_t bars;        // [kNumBars] mbarriers
+  int* gcolpos;         // [Sp/2] gamma column of target position n
+  int* slotlab;         // [32*kMaxPass + 8] label of each 4-column chunk slot (-1: unused)
+  int* hist;            // [C + 4] counting-sort scratch; [C]: #slots, [C+1]: max chunks per label
+  float* zx;            // Zm, eZ (int bits), valid flag
+  float* out_ptr[2];    // generic pointers of the out tiles (bulk store source)
 };
 
-__host__ __device__ inline size_t fast_smem_floats(int K, int C, int Cp, int RS) {
-  const int Sp = 32 * K;
-  size_t per_dir = (size_t)kSeg * RS + kSeg * 33 + 2 * (((size_t)kSeg * C + 3) & ~3) +
+__host__ __device__ inline size_t fast_smem_floats(int K, int C, int Cp, int RS, int GW) {
+  const size_t outsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
+  size_t per_dir = 2 * (size_t)kSeg * RS + 64 + 2 * (size_t)kSeg * GW + 2 * kSeg * 33 + 2 * outsz +
                    (size_t)kNB * kSeg * Cp;
   per_dir = (per_dir + 3) & ~(size_t)3;
-  size_t shared = kNR * (((size_t)kSeg * C + 3) & ~3) + Sp / 2 + (32 * kMaxPass + 8) + (C + 4) + 2 * 16 + 8 + 4;
+  size_t shared = kNR * outsz + 2 * kNumBars + 16 * K + (32 * kMaxPass + 8) + (C + 4) + 8;
   return 2 * per_dir + shared + 16;
 }
 
-template <int K>
-__device__ __forceinline__ FastSmem<K> carve_fast(float* base, int C, int Cp, int RS) {
-  constexpr int Sp = 32 * K;
-  FastSmem<K> s;
+__device__ __forceinline__ FastSmem carve_fast(float* base, int K, int C, int Cp, int RS, int GW) {
+  FastSmem s;
   float* p = base;
   const size_t outsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
-  s.raw = p; p += kNR * outsz;                     // 16B aligned (base is)
-  s.out0 = p; p += 2 * outsz;
-  s.out1 = p; p += 2 * outsz;
-  s.stored0 = p; p += (size_t)kSeg * RS;
-  s.stored1 = p; p += (size_t)kSeg * RS;
-  s.bars = reinterpret_cast<uint64_t*>(p); p += 2 * 16;      // up to 16 barriers
-  s.msum = reinterpret_cast<double*>(p); p += 4;
+  s.raw = smem_u32(p); p += kNR * outsz;                    // 16B aligned (base is)
+  for (int d = 0; d < 2; ++d) { s.out[d] = smem_u32(p); s.out_ptr[d] = p; p += 2 * outsz; }
+  for (int d = 0; d < 2; ++d) { s.stored[d] = smem_u32(p); p += 2 * (size_t)kSeg * RS; }
+  for (int d = 0; d < 2; ++d) { s.gam[d] = smem_u32(p); p += 2 * (size_t)kSeg * GW; }
+  s.bars = smem_u32(p); p += 2 * kNumBars;
   s.zx = p; p += 4;
-  s.pbk0 = p; p += kSeg * 33;
-  s.pbk1 = p; p += kSeg * 33;
-  s.ptile0 = p; p += (size_t)kNB * kSeg * Cp;
-  s.ptile1 = p; p += (size_t)kNB * kSeg * Cp;
-  s.gcolpos = reinterpret_cast<int*>(p); p += Sp / 2;
+  for (int d = 0; d < 2; ++d) { s.sexp[d] = smem_u32(p); p += 64; }
+  for (int d = 0; d < 2; ++d) { s.pbk[d] = smem_u32(p); p += 2 * kSeg * 33; }
+  for (int d = 0; d < 2; ++d) { s.ptile[d] = smem_u32(p); p += (size_t)kNB * kSeg * Cp; }
+  s.gcolpos = reinterpret_cast<int*>(p); p += 16 * K;
   s.slotlab = reinterpret_cast<int*>(p); p += 32 * kMaxPass + 8;
   s.hist = reinterpret_cast<int*>(p); p += C + 4;
   return s;
 }
 
-// barrier indices
-__device__ __forceinline__ int bar_full(int d, int i) { return d * kNB + i; }
-__device__ __forceinline__ int bar_empty(int d, int i) { return 2 * kNB + d * kNB + i; }
-constexpr int kBarTma = 4 * kNB;      // + raw slot
-constexpr int kBarZ = 4 * kNB + kNR;
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// mbarrier helpers on 32-bit shared addresses
+__device__ __forceinline__ void bar_init(uint32_t bars, int idx, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * idx), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bars, int idx, uint32_t count = 1) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * idx), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bars, int idx, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * idx), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bars, int idx, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WFST_BW_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra WFST_BD_%=;\n"
+      "bra WFST_BW_%=;\n"
+      "WFST_BD_%=:\n"
+      "}\n" ::"r"(bars + 8u * idx), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: the
+  // warp sleeps in hardware until the phase completes instead of spinning on issue slots
 }
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// common per-block constants
+struct Ctx {
+  int b, lane, T, C, Cp, RS, GW, L, nseg, nA;
+  const int* y;
+  bool want_grad;
+};
+
+__device__ __forceinline__ int seg_of(int dir, int k, int nseg) { return dir == 0 ? k : nseg - 1 - k; }
+
 // ---------------------------------------------------------------------------
-// One direction of one utterance (a whole warp).  DIR 0: alpha, time ascending, states
+// P: producer.  Direction 0 consumes tiles 0,1,...; direction 1 consumes nseg-1, nseg-2, ...
+// Without a gradient only the phase-1 tiles are needed.  The schedule is the sequence
+// (k, d), k = 0.., d = 0, 1, restricted to k < ntile[d].  Raw [8, C] tiles are fetched
+// kNR - 1 entries ahead (TMA latency >> conversion time).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void role_producer(const CtcFastArgs& a, const FastSmem& sm, const Ctx& cx) {
+  const int lane = cx.lane, T = cx.T, C = cx.C, Cp = cx.Cp, nseg = cx.nseg, nA = cx.nA;
+  const float* Eb = a.E + (size_t)cx.b * T * C;
+  const int ntile0 = cx.want_grad ? nseg : nA, ntile1 = cx.want_grad ? nseg : (nseg - nA);
+  const int total = max(ntile0, ntile1);
+  const int fr = lane & 7, part = lane >> 3;                       // 8 frames x 4 label quarters
+  const int c0 = (C * part) / 4, c1 = (C * (part + 1)) / 4;
+  const int rawsz = (kSeg * C + 3) & ~3;
+  double msum = 0.0;
+  uint32_t tma_phase = 0u, tma_used = 0u, empty_phase = 0u;
+  auto next_entry = [&](int& k, int& d) {
+    do {
+      if (d == 0) d = 1; else { d = 0; ++k; }
+    } while (k < total && k >= (d == 0 ? ntile0 : ntile1));
+  };
+  auto issue_raw = [&](int tile, int slot) {
+    const int rows = min(kSeg, T - tile * kSeg);
+    const float* src = Eb + (size_t)tile * kSeg * C;
+    const uint32_t bytes = (uint32_t)rows * C * 4u;
+    const uint32_t dst = sm.raw + 4u * (uint32_t)(slot * rawsz);
+    const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15u) == 0);
+    if (tma) {
+      if (lane == 0) {
+        bar_expect_tx(sm.bars, kBarTma + slot, bytes);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+            "l"(src), "r"(bytes), "r"(sm.bars + 8u * (kBarTma + slot))
+            : "memory");
+      }
+      tma_used |= 1u << slot;
+    } else {
+      for (int q = lane; q < rows * C; q += 32) sts(dst + 4u * q, __ldg(src + q));
+      tma_used &= ~(1u << slot);
+      __syncwarp();
+    }
+  };
+  int k = -1, d = 1;
+  next_entry(k, d);
+  int fk = k, fd = d, fetched = 0, converted = 0;
+  PROF_DECL;
+  while (k < total) {
+    PROF_MARK(3);
+    while (fk < total && fetched < converted + kNR) {
+      issue_raw(seg_of(fd, fk, nseg), fetched % kNR);
+      ++fetched;
+      next_entry(fk, fd);
+    }
+    const int slot = converted % kNR;
+    const int tile = seg_of(d, k, nseg);
+    const int rows = min(kSeg, T - tile * kSeg);
+    const int buf = k % kNB;
+    PROF_MARK(0);
+    if (k >= kNB) {  // wait until the consumers have released this p-tile buffer
+      const int bit = d * kNB + buf;
+      bar_wait(sm.bars, kBarPEmpty + bit, (empty_phase >> bit) & 1u);
+      empty_phase ^= 1u << bit;
+    }
+    PROF_MARK(1);
+    if ((tma_used >> slot) & 1u) {
+      bar_wait(sm.bars, kBarTma + slot, (tma_phase >> slot) & 1u);
+      tma_phase ^= 1u << slot;
+    }
+    PROF_MARK(2);
+    const uint32_t er = sm.raw + 4u * (uint32_t)(slot * rawsz + fr * C);
+    const uint32_t pt = sm.ptile[d] + 4u * (uint32_t)(buf * kSeg * Cp + fr * Cp);
+    // register-blocked in chunks of 8 labels per lane: all loads of a chunk are issued
+    // before any dependent instruction (the shared-memory accessors are volatile asm)
+    const bool live = fr < rows;
+    float mx = kNegInf;
+    for (int cb = c0; cb < c1; cb += 8) {
+      float ev[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ev[i] = lds(er + 4u * (uint32_t)min(cb + i, c1 - 1));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, ev[i]);
+    }
+    if (!live) mx = kNegInf;
+    mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 16));
+    // a row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface through the
+    // certificate
+    const float base = (mx == kNegInf) ? 0.f : mx;
+    const float nb = -base * 1.4426950408889634f;
+    for (int cb = c0; cb < c1; cb += 8) {
+      float ev[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ev[i] = lds(er + 4u * (uint32_t)min(cb + i, c1 - 1));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ev[i] = exp2f(fmaf(ev[i], 1.4426950408889634f, nb));
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (live && cb + i < c1) sts(pt + 4u * (uint32_t)(cb + i), ev[i]);
+    }
+    {
+      const bool phase1 = (d == 0) ? (tile < nA) : (tile >= nA);
+      if (live && part == 0 && phase1) msum += (double)base;
+    }
+    __syncwarp();
+    if (lane == 0) bar_arrive(sm.bars, kBarPFull + d * kNB + buf);
+    ++converted;
+    next_entry(k, d);
+  }
+  PROF_MARK(3);
+#ifdef WFST_PROFILE
+  if (cx.b == 0 && lane == 0) printf("P cycles: issue %lld  wait_pempty %lld  wait_tma %lld  convert %lld\n", pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3]);
+#endif
+  // loss: log Z = log(Zm) + eZ ln2 + sum_t max_t
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(kFull, msum, o);
+  bar_wait(sm.bars, kBarZ, 0u);
+  if (lane == 0) {
+    const float Zm = sm.zx[0];
+    const int eZ = __float_as_int(sm.zx[1]);
+    const bool ok = sm.zx[2] != 0.f;
+    a.z_out[cx.b] = ok ? (float)(log((double)Zm) + (double)eZ * 0.6931471805599453 + msum) : kNegInf;
+  }
+}
+
+// p-tile ring of one direction, as seen by a consumer warp
+struct PTileRing {
+  uint32_t bars, base, row_bytes;
+  int dir;
+  uint32_t phase;   // bit per buffer
+  __device__ __forceinline__ uint32_t wait(int k) {
+    const int buf = k % kNB;
+    bar_wait(bars, kBarPFull + dir * kNB + buf, (phase >> buf) & 1u);
+    phase ^= 1u << buf;
+    return base + (uint32_t)buf * kSeg * row_bytes;
+  }
+  // consumers that skipped tiles [from, to) must still flip their phase bits for them
+  __device__ __forceinline__ void skip(int from, int to) {
+    for (int k = from; k < to; ++k) phase ^= 1u << (k % kNB);
+  }
+  __device__ __forceinline__ void release(int k, int lane, uint32_t count) {
+    __syncwarp();
+    if (lane == 0) bar_arrive(bars, kBarPEmpty + dir * kNB + (k % kNB), count);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// R: recompute.  R<DIR> serves L<DIR>: it runs the OPPOSITE orientation over the segments
+// of L<DIR>'s phase 2, from the checkpoints the other live warp wrote in phase 1, in its
+// natural scale, into a two-segment ring; the lane exponents go along.
+// ---------------------------------------------------------------------------
+template <int K, int DIR>
+__device__ __forceinline__ void role_recompute(const CtcFastArgs& a, const FastSmem& sm, const Ctx& cx) {
+  constexpr bool ODD = (DIR == 1);   // orientation of the recompute = 1 - DIR; ODD <=> orientation 0
+  const int lane = cx.lane, nseg = cx.nseg, nA = cx.nA, T = cx.T;
+  bar_wait(sm.bars, kBarZ, 0u);      // phase 1 (and every checkpoint) is complete
+  if (!cx.want_grad || sm.zx[2] == 0.f) return;
+  const int n1 = (DIR == 0) ? nA : nseg - nA;
+  const int n2 = nseg - n1;
+  LaneTopo<K> tp;
+  build_topo<K, ODD>(tp, lane, cx.y, cx.L, cx.C, sm.gcolpos, 0);
+  const float* ck = a.ckpt + ((size_t)cx.b * 2 + (1 - DIR)) * (size_t)(nseg + 1) * ck_stride<K>() * 32;
+  PTileRing ring{sm.bars, sm.ptile[DIR], 4u * (uint32_t)cx.Cp, DIR, 0u};
+  ring.skip(0, n1);
+  const uint32_t blank_ofs = 4u * (uint32_t)a.blank;
+  const uint32_t srow = 4u * (uint32_t)cx.RS;
+  const uint32_t my_block = 4u * (uint32_t)(lane * K);
+  uint32_t sempty_phase = 0u;
+  float w[K], dummy[K];
+  int ew;
+  if (n2 > 0) ckpt_load<K>(ck + (size_t)seg_of(DIR, n1, nseg) * ck_stride<K>() * 32, w, ew, lane);
+  PROF_DECL;
+  for (int k2 = 0; k2 < n2; ++k2) {
+    const int k = n1 + k2;
+    const int seg = seg_of(DIR, k, nseg);
+    const int rows = min(kSeg, T - seg * kSeg);
+    const int buf = k2 & 1;
+    PROF_MARK(2);
+    if (k2 >= 2) {
+      bar_wait(sm.bars, kBarSEmpty + DIR * 2 + buf, (sempty_phase >> buf) & 1u);
+      sempty_phase ^= 1u << buf;
+    }
+    PROF_MARK(0);
+    const uint32_t pt = ring.wait(k);
+    PROF_MARK(1);
+    const float fr = neighbor_factor(ew, lane);
+    const uint32_t sbase = sm.stored[DIR] + (uint32_t)buf * kSeg * srow + my_block;
+    sts(sm.sexp[DIR] + 4u * (uint32_t)(buf * 32 + lane), __int_as_float(ew));
+    // the recompute walks the frames in the opposite order to the live sweep
+    if (DIR == 0) {
+      uint32_t pr = pt + (uint32_t)(rows - 1) * ring.row_bytes;
+      uint32_t dst = sbase + (uint32_t)(rows - 1) * srow;
+      PRow<K> nx = load_prow<K>(tp, pr, blank_ofs);
+#pragma unroll 1
+      for (int r = rows - 1; r >= 0; --r, dst -= srow) {
+        const PRow<K> cur = nx;
+        pr -= (r > 0) ? ring.row_bytes : 0u;
+        nx = load_prow<K>(tp, pr, blank_ofs);
+        step<K, ODD, false>(w, dummy, tp, cur, fr);
+#pragma unroll
+        for (int i = 0; i < K; i += 4) sts128(dst + 4u * i, w[i], w[i + 1], w[i + 2], w[i + 3]);
+      }
+    } else {
+      uint32_t pr = pt;
+      uint32_t dst = sbase;
+      PRow<K> nx = load_prow<K>(tp, pr, blank_ofs);
+#pragma unroll 1
+      for (int r = 0; r < rows; ++r, dst += srow) {
+        const PRow<K> cur = nx;
+        pr += (r + 1 < rows) ? ring.row_bytes : 0u;
+        nx = load_prow<K>(tp, pr, blank_ofs);
+        step<K, ODD, false>(w, dummy, tp, cur, fr);
+#pragma unroll
+        for (int i = 0; i < K; i += 4) sts128(dst + 4u * i, w[i], w[i + 1], w[i + 2], w[i + 3]);
+      }
+    }
+    // next checkpoint (consumed at the top of the next iteration)
+    if (k2 + 1 < n2) ckpt_load<K>(ck + (size_t)seg_of(DIR, k + 1, nseg) * ck_stride<K>() * 32, w, ew, lane);
+    __syncwarp();
+    if (lane == 0) bar_arrive(sm.bars, kBarSFull + DIR * 2 + buf);
+    ring.release(k, lane, 1);
+  }
+  PROF_MARK(2);
+#ifdef WFST_PROFILE
+  if (cx.b == 0 && lane == 0)
+    printf("R%d cycles: wait_sempty %lld  wait_ptile %lld  compute %lld\n", DIR, pf_acc[0], pf_acc[1], pf_acc[2]);
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// X: per-label reduction of a segment's posteriors + gradient tile store.  The direction
+// is a runtime argument and the pass loop is not unrolled: X0 and X1 share one small
+// body (the warps of a block run seven different loops at once; keeping each of them
+// small matters for the instruction cache).
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void role_reduce(const CtcFastArgs& a, const FastSmem& sm, const Ctx& cx, int dir) {
+  const int lane = cx.lane, nseg = cx.nseg, nA = cx.nA, T = cx.T, C = cx.C;
+  bar_wait(sm.bars, kBarZ, 0u);
+  if (!cx.want_grad || sm.zx[2] == 0.f) return;
+  const float Zm = sm.zx[0];
+  const float gs = a.grad_scale ? a.grad_scale[cx.b] : 1.f;
+  const float kappa = -gs / Zm;
+  const int n1 = (dir == 0) ? nA : nseg - nA;
+  const int n2 = nseg - n1;
+  float* gEb = a.gradE + (size_t)cx.b * T * C;
+  const int outsz = (kSeg * C + 3) & ~3;
+  const uint32_t grow = 4u * (uint32_t)cx.GW;
+  const uint32_t blank_ofs = 4u * (uint32_t)a.blank;
+  const uint32_t gam0 = dir ? sm.gam[1] : sm.gam[0];
+  const uint32_t pbk0 = dir ? sm.pbk[1] : sm.pbk[0];
+  const uint32_t out0 = dir ? sm.out[1] : sm.out[0];
+  const float* outp = dir ? sm.out_ptr[1] : sm.out_ptr[0];
+  // labels: lane = chunk slot (32 slots per pass); slots of one label are adjacent lanes
+  const int nslots = sm.hist[C];
+  const int npass = (nslots + 31) >> 5;
+  const int maxch = sm.hist[C + 1];
+  // blank: lane = (frame, quarter) sums 8 of the 32 lane partials
+  const int frm = lane & 7, qtr = lane >> 3;
+  int bad = 0;
+  uint32_t gfull_phase = 0u;
+  PROF_DECL;
+  for (int k2 = 0; k2 < n2; ++k2) {
+    const int seg = seg_of(dir, n1 + k2, nseg);
+    const int rows = min(kSeg, T - seg * kSeg);
+    const int buf = k2 & 1;
+    PROF_MARK(1);
+    bar_wait(sm.bars, kBarGFull + dir * 2 + buf, (gfull_phase >> buf) & 1u);
+    gfull_phase ^= 1u << buf;
+    PROF_MARK(0);
+    const uint32_t ot = out0 + 4u * (uint32_t)(buf * outsz);
+    if (lane == 0) bulk_wait_read<1>();   // the store that last read this out buffer is done
+    __syncwarp();
+    const uint32_t gbase = gam0 + (uint32_t)buf * kSeg * grow + 16u * (uint32_t)lane;
+    float tot = 0.f;
+#pragma unroll 1
+    for (int p = 0; p < npass; ++p) {
+      const int g = 32 * p + lane;
+      const int me = sm.slotlab[g];
+      // links never leave the pass: a label's slots do not straddle a multiple of 32
+      const float lk1 = (me >= 0 && lane + 1 < 32 && sm.slotlab[g + 1] == me) ? 1.f : 0.f;
+      const float lk2 = (me >= 0 && lane + 2 < 32 && sm.slotlab[g + 2] == me) ? 1.f : 0.f;
+      const float lk4 = (me >= 0 && lane + 4 < 32 && sm.slotlab[g + 4] == me) ? 1.f : 0.f;
+      const bool head = me >= 0 && (lane == 0 || sm.slotlab[g - 1] != me);
+      const uint32_t src = gbase + 512u * (uint32_t)p;
+      const uint32_t dsto = ot + 4u * (uint32_t)max(me, 0);
+      float c[kSeg];
+#pragma unroll
+      for (int j = 0; j < kSeg; ++j) {   // rows >= `rows` hold finite stale data; never stored
+        const float4 q = lds128(src + (uint32_t)j * grow);
+        c[j] = (q.x + q.y) + (q.z + q.w);
+      }
+#pragma unroll
+      for (int j = 0; j < kSeg; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 1), lk1, c[j]);
+      if (maxch > 2) {
+#pragma unroll
+        for (int j = 0; j < kSeg; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 2), lk2, c[j]);
+      }
+      if (maxch > 4) {
+#pragma unroll
+        for (int j = 0; j < kSeg; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 4), lk4, c[j]);
+      }
+      if (head) {
+#pragma unroll
+        for (int j = 0; j < kSeg; ++j) {
+          if (j < rows) {
+            sts(dsto + 4u * (uint32_t)(j * C), c[j] * kappa);
+            tot += c[j];
+          }
+        }
+      }
+    }
+    float bs = 0.f;
+    if (frm < rows) {
+      const uint32_t pb = pbk0 + 4u * (uint32_t)(buf * kSeg * 33 + frm * 33 + qtr * 8);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bs += lds(pb + 4u * q);
+    }
+    tot += bs;
+    float bsum = bs + __shfl_xor_sync(kFull, bs, 8);
+    bsum += __shfl_xor_sync(kFull, bsum, 16);
+    if (frm < rows && qtr == 0) sts(ot + 4u * (uint32_t)(frm * C) + blank_ofs, bsum * kappa);
+    // certificate: the posteriors of every frame sum to one, i.e. the segment sums to rows * Zm.
+    // Range loss can only remove mass, so deficits cannot cancel.
+    tot = warp_sum(tot);
+    if (!(fabsf(tot - (float)rows * Zm) <= 2e-5f * (float)rows * Zm)) bad |= 8;
+    __syncwarp();
+    if (lane == 0) bar_arrive(sm.bars, kBarGEmpty + dir * 2 + buf);   // gamma / pbk are consumed
+    float* dst = gEb + (size_t)seg * kSeg * C;
+    const int n = rows * C;
+    const bool tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
+    if (tma) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ot),
+                     "r"((uint32_t)n * 4u)
+                     : "memory");
+        bulk_commit();
+      }
+    } else {
+      const float* src = outp + (size_t)buf * outsz;
+      for (int q = lane; q < n; q += 32) dst[q] = src[q];
+    }
+    __syncwarp();
+  }
+  PROF_MARK(1);
+#ifdef WFST_PROFILE
+  if (cx.b == 0 && lane == 0) printf("X%d cycles: wait_gfull %lld  compute %lld\n", dir, pf_acc[0], pf_acc[1]);
+#endif
+  if (lane == 0) bulk_wait_all<0>();
+  bad = __reduce_or_sync(kFull, (unsigned)bad);
+  if (bad && lane == 0) atomicOr(&a.hazard[cx.b], bad);
+}
+
+// ---------------------------------------------------------------------------
+// L: the live sweep of one direction (whole warp).  DIR 0: alpha, time ascending, states
 // j = s.  DIR 1: beta, time descending, mirrored states j = Sp-1-s.
 // ---------------------------------------------------------------------------
 template <int K, int DIR>
-__device__ __forceinline__ void run_direction(const CtcFastArgs& a, const FastSmem<K>& sm, int b, int lane) {
+__device__ __forceinline__ void role_live(const CtcFastArgs& a, const FastSmem& sm, const Ctx& cx) {
   constexpr int Sp = 32 * K;
-  constexpr int dir = DIR;
-  const int T = a.T, C = a.C, Cp = a.Cp, RS = a.RS;
-  const int* y = a.targets + a.offsets[b];
-  const int L = a.offsets[b + 1] - a.offsets[b];
-  const int nseg = a.nseg, nA = a.nA;
-  const bool want_grad = a.gradE != nullptr;
-  const int dump_col = RS - 1;
-  float* ck_own = a.ckpt + ((size_t)b * 2 + dir) * (size_t)(nseg + 1) * (K + 1) * 32;
-  const float* ck_other = a.ckpt + ((size_t)b * 2 + (1 - dir)) * (size_t)(nseg + 1) * (K + 1) * 32;
-  const int blank = a.blank;
-
-  LaneTopo<K> tp_live, tp_rc;   // live orientation = dir, recompute orientation = 1 - dir
-  if (dir == 0) {
-    build_topo<K, true>(tp_live, lane, y, L, C, sm.gcolpos, dump_col);
-    build_topo<K, false>(tp_rc, lane, y, L, C, sm.gcolpos, dump_col);
-  } else {
-    build_topo<K, false>(tp_live, lane, y, L, C, sm.gcolpos, dump_col);
-    build_topo<K, true>(tp_rc, lane, y, L, C, sm.gcolpos, dump_col);
-  }
+  constexpr bool ODD = (DIR == 0);
+  const int lane = cx.lane, nseg = cx.nseg, nA = cx.nA, T = cx.T, b = cx.b;
+  float* ck_own = a.ckpt + ((size_t)b * 2 + DIR) * (size_t)(nseg + 1) * ck_stride<K>() * 32;
+  const float* ck_other = a.ckpt + ((size_t)b * 2 + (1 - DIR)) * (size_t)(nseg + 1) * ck_stride<K>() * 32;
+  LaneTopo<K> tp;
+  build_topo<K, ODD>(tp, lane, cx.y, cx.L, cx.C, sm.gcolpos, cx.GW - 1);
 
   float v[K], abar[K];
   int e = kUndef;
   float f = 0.f;
-#pragma unroll
-  for (int i = 0; i < K; ++i) v[i] = 0.f;
   {
     // virtual pre-frame state: all mass on the start state of this orientation
-    const int S = 2 * L + 1;
-    const int jstart = (dir == 0) ? 0 : Sp - S;
+    const int S = 2 * cx.L + 1;
+    const int jstart = (DIR == 0) ? 0 : Sp - S;
     const bool mine = (jstart / K == lane);
     const int jm = jstart % K;
 #pragma unroll
     for (int i = 0; i < K; ++i) v[i] = (mine && jm == i) ? 1.f : 0.f;   // selects, no dynamic index
     if (mine) e = 0;
   }
-
-  PROF_DECL;
-  uint32_t full_phase = 0u;   // bit per p-tile buffer
-  auto seg_of = [&](int k) { return dir == 0 ? k : nseg - 1 - k; };
-  const uint32_t ptile_u32 = smem_u32(sm.ptile(dir));
-  const uint32_t row_bytes = 4u * (uint32_t)Cp;
+  PTileRing ring{sm.bars, sm.ptile[DIR], 4u * (uint32_t)cx.Cp, DIR, 0u};
   const uint32_t blank_ofs = 4u * (uint32_t)a.blank;
-  // returns the shared address of the tile's first row
-  auto wait_ptile = [&](int k) -> uint32_t {
-    const int buf = k % kNB;
-    mbar_wait(&sm.bars[bar_full(dir, buf)], (full_phase >> buf) & 1u);
-    full_phase ^= 1u << buf;
-    return ptile_u32 + (uint32_t)buf * kSeg * row_bytes;
-  };
-  auto release_ptile = [&](int k) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.bars[bar_empty(dir, k % kNB)]);
-  };
 
   // ------------------------------------------------------------------ phase 1
-  const int n1 = (dir == 0) ? nA : nseg - nA;
+  PROF_DECL;
+  const int n1 = (DIR == 0) ? nA : nseg - nA;
   for (int k = 0; k < n1; ++k) {
-    const int seg = seg_of(k);
+    const int seg = seg_of(DIR, k, nseg);
     const int rows = min(kSeg, T - seg * kSeg);
-    event<K>(v, e, f, lane);
-    ckpt_store<K>(ck_own + (size_t)seg * (K + 1) * 32, v, e, lane);
+    if (k % kEventEvery == 0) event<K>(v, e, f, lane);
+    ckpt_store<K>(ck_own + (size_t)seg * ck_stride<K>() * 32, v, e, lane);
     PROF_MARK(0);
-    const uint32_t pt = wait_ptile(k);
+    const uint32_t pt = ring.wait(k);
     PROF_MARK(1);
-    if (dir == 0) {
-      uint32_t pr = pt;
-      PRow<K> nx = load_prow<K>(tp_live, pr, blank_ofs);
+    uint32_t pr = (DIR == 0) ? pt : pt + (uint32_t)(rows - 1) * ring.row_bytes;
+    PRow<K> nx = load_prow<K>(tp, pr, blank_ofs);
 #pragma unroll 2
-      for (int r = 0; r < rows; ++r) {
-        const PRow<K> cur = nx;
-        pr += (r + 1 < rows) ? row_bytes : 0u;
-        nx = load_prow<K>(tp_live, pr, blank_ofs);
-        step<K, true, false>(v, abar, tp_live, cur, f);
-      }
-    } else {
-      uint32_t pr = pt + (uint32_t)(rows - 1) * row_bytes;
-      PRow<K> nx = load_prow<K>(tp_live, pr, blank_ofs);
-#pragma unroll 2
-      for (int r = rows - 1; r >= 0; --r) {
-        const PRow<K> cur = nx;
-        pr -= (r > 0) ? row_bytes : 0u;
-        nx = load_prow<K>(tp_live, pr, blank_ofs);
-        step<K, false, false>(v, abar, tp_live, cur, f);
-      }
+    for (int it = 0; it < rows; ++it) {
+      const PRow<K> cur = nx;
+      if (it + 1 < rows) pr = (DIR == 0) ? pr + ring.row_bytes : pr - ring.row_bytes;
+      nx = load_prow<K>(tp, pr, blank_ofs);
+      step<K, ODD, false>(v, abar, tp, cur, f);
     }
-    release_ptile(k);
+    ring.release(k, lane, 2);   // no recompute warp reads phase-1 tiles
     PROF_MARK(2);
   }
 
   // ------------------------------------------------------------------ meeting: Z
-  // A publishes its state (extra checkpoint slot nseg of its own area); B combines.
-  if (dir == 0) ckpt_store<K>(ck_own + (size_t)nseg * (K + 1) * 32, v, e, lane);
+  // L0 publishes its state (extra checkpoint slot nseg of its own area); L1 combines.
+  if (DIR == 0) ckpt_store<K>(ck_own + (size_t)nseg * ck_stride<K>() * 32, v, e, lane);
   named_sync(1, 64);
-  if (dir == 1) {
+  if (DIR == 1) {
     event<K>(v, e, f, lane);     // consistent exponents / f for the shuffle below
-    // pre-emission sums of B's next frame: bb = v[j] + v[j-1] + skip * v[j-2]
+    // pre-emission sums of L1's next frame: bb = v[j] + v[j-1] + skip * v[j-2]
     float bb[K];
     {
       const float in1 = __shfl_up_sync(kFull, v[K - 1], 1) * f;
@@ -434,22 +790,19 @@ __device__ __forceinline__ void run_direction(const CtcFastArgs& a, const FastSm
         float s = v[i] + a1;
         if (lab) {
           const float a2 = (i >= 2) ? v[i - 2] : in2;
-          s = fmaf(tp_live.skipm[i >> 1], a2, s);
+          s = fmaf(tp.skipm[i >> 1], a2, s);
         }
         bb[i] = s;
       }
     }
     float av[K];
     int ea;
-    ckpt_load<K>(ck_other + (size_t)nseg * (K + 1) * 32, av, ea, 31 - lane);
+    ckpt_load<K>(ck_other + (size_t)nseg * ck_stride<K>() * 32, av, ea, 31 - lane);
     float P = 0.f;
 #pragma unroll
     for (int i = 0; i < K; ++i) P = fmaf(bb[i], av[K - 1 - i], P);
     int Eabs = kUndef;
     if (P > 0.f && defined_exp(e) && defined_exp(ea)) Eabs = e + ea;
-#ifdef WFST_DEBUG_Z
-    if (b == 0) printf("Z lane %d: P=%g e=%d ea=%d f=%g v0=%g vK=%g bb0=%g av0=%g avK=%g\n", lane, P, e, ea, f, v[0], v[K-1], bb[0], av[0], av[K-1]);
-#endif
     int Emax = Eabs;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) Emax = max(Emax, __shfl_xor_sync(kFull, Emax, o));
@@ -475,260 +828,107 @@ __device__ __forceinline__ void run_direction(const CtcFastArgs& a, const FastSm
     }
   }
   named_sync(1, 64);
-  if (dir == 1 && lane == 0) mbar_arrive(&sm.bars[kBarZ]);
-  const float Zm = sm.zx[0];
+  if (DIR == 1 && lane == 0) bar_arrive(sm.bars, kBarZ);
   const int eZ = __float_as_int(sm.zx[1]);
   const bool zok = sm.zx[2] != 0.f;
-  if (!want_grad) return;
+  if (!cx.want_grad) return;
 
   // ------------------------------------------------------------------ phase 2
-  const int n2 = (dir == 0) ? nseg - nA : nA;
+  const int n2 = nseg - n1;
   if (!zok) {
-    // keep the producer's ring moving so that it can terminate
-    for (int k2 = 0; k2 < n2; ++k2) { wait_ptile(n1 + k2); release_ptile(n1 + k2); }
+    // keep the producer's ring moving so that it can terminate (the R warp has left too)
+    for (int k2 = 0; k2 < n2; ++k2) { ring.wait(n1 + k2); ring.release(n1 + k2, lane, 2); }
     return;
   }
-  const float gs = a.grad_scale ? a.grad_scale[b] : 1.f;
-  const float kappa = -gs / Zm;
-  float* gEb = a.gradE + (size_t)b * T * C;
-  const uint32_t stored_u32 = smem_u32(sm.stored(dir));
-  const uint32_t pbk_u32 = smem_u32(sm.pbk(dir));
-  const uint32_t srow_bytes = 4u * (uint32_t)RS;
-  const uint32_t my_block = 4u * (uint32_t)(lane * K);          // where my recomputed values go
-  const uint32_t pair_block = 4u * (uint32_t)((31 - lane) * K); // the block of the lane paired with me
-  const size_t outsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
-  int bad = 0;   // reason bits: 4 = scale overflow in the recompute, 8 = row-sum certificate
-  int obuf = 0;
-  // transposed pass, labels: lane = chunk slot of the gamma row (32 slots per pass); the
-  // slots of one label are adjacent lanes and are combined by a segmented suffix sum
-  const int nslots = sm.hist[C];
-  const int npass = (nslots + 31) >> 5;
-  const int maxch = sm.hist[C + 1];
-  int slab[kMaxPass];
-  float lk1[kMaxPass], lk2[kMaxPass], lk4[kMaxPass];
-  bool head[kMaxPass];
-#pragma unroll
-  for (int p = 0; p < kMaxPass; ++p) {
-    const int g = 32 * p + lane;
-    const int me = sm.slotlab[g];
-    slab[p] = me;
-    // links never leave the pass: a label's slots do not straddle a multiple of 32
-    lk1[p] = (me >= 0 && lane + 1 < 32 && sm.slotlab[g + 1] == me) ? 1.f : 0.f;
-    lk2[p] = (me >= 0 && lane + 2 < 32 && sm.slotlab[g + 2] == me) ? 1.f : 0.f;
-    lk4[p] = (me >= 0 && lane + 4 < 32 && sm.slotlab[g + 4] == me) ? 1.f : 0.f;
-    head[p] = me >= 0 && (lane == 0 || sm.slotlab[g - 1] != me);
-  }
-  // transposed pass, blank: lane = (frame, half) sums 16 of the 32 lane partials
-  const int frm = lane & 15, hf = lane >> 4;
-  const uint32_t pbrow_u32 = pbk_u32 + 4u * (uint32_t)(frm * 33 + hf * 16);
-  const uint32_t slot_ofs = 16u * (uint32_t)lane;
-
-  // checkpoint of the first phase-2 segment (the next one is prefetched inside the loop)
-  float w[K];
-  int ew;
-  if (n2 > 0) ckpt_load<K>(ck_other + (size_t)seg_of(n1) * (K + 1) * 32, w, ew, lane);
+  const uint32_t srow = 4u * (uint32_t)cx.RS;
+  const uint32_t grow = 4u * (uint32_t)cx.GW;
+  const uint32_t pair_block = 4u * (uint32_t)((31 - lane) * K);   // the block of the lane paired with me
+  int bad = 0;   // reason bit 4: scale overflow when pairing live and recomputed values
+  uint32_t sfull_phase = 0u, gempty_phase = 0u;
 
   for (int k2 = 0; k2 < n2; ++k2) {
     const int k = n1 + k2;
-    const int seg = seg_of(k);
+    const int seg = seg_of(DIR, k, nseg);
     const int rows = min(kSeg, T - seg * kSeg);
+    const int buf = k2 & 1;
     PROF_MARK(3);
-    event<K>(v, e, f, lane);
+    if (k % kEventEvery == 0) event<K>(v, e, f, lane);
     PROF_MARK(0);
-    const uint32_t pt = wait_ptile(k);
+    const uint32_t pt = ring.wait(k);
     PROF_MARK(1);
-
-    // ---- recompute the opposite direction over this segment in the complementary scale:
-    // stored * live = posterior * Zm, i.e. exponent(stored lane) = eZ - exponent(live lane)
-    {
-      const int ex_live = __shfl_sync(kFull, e, 31 - lane);   // the live lane paired with me
-      int erc = kUndef;
-      float sc = 0.f;
-      if (defined_exp(ex_live)) {
-        erc = eZ - ex_live;
-        if (defined_exp(ew)) {
-          const int dd = ew - erc;
-          if (dd > 126) bad |= 4;
-          else sc = (dd < -126) ? 0.f : pow2i(dd);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < K; ++i) w[i] *= sc;
-      const int el = __shfl_up_sync(kFull, erc, 1);
-      float fr = 0.f;
-      if (lane > 0 && defined_exp(el) && defined_exp(erc)) {
-        const int dd = el - erc;
-        fr = (dd < -126) ? 0.f : pow2i(min(dd, 126));
-      }
-      // the recompute walks the frames in the opposite order to the live sweep
-      if (dir == 0) {
-        uint32_t pr = pt + (uint32_t)(rows - 1) * row_bytes;
-        uint32_t dst = stored_u32 + (uint32_t)(rows - 1) * srow_bytes + my_block;
-        PRow<K> nx = load_prow<K>(tp_rc, pr, blank_ofs);
-#pragma unroll 2
-        for (int r = rows - 1; r >= 0; --r, dst -= srow_bytes) {
-          const PRow<K> cur = nx;
-          pr -= (r > 0) ? row_bytes : 0u;
-          nx = load_prow<K>(tp_rc, pr, blank_ofs);
-          step<K, false, false>(w, abar, tp_rc, cur, fr);
-#pragma unroll
-          for (int i = 0; i < K; i += 4) sts128(dst + 4u * i, w[i], w[i + 1], w[i + 2], w[i + 3]);
-        }
-      } else {
-        uint32_t pr = pt;
-        uint32_t dst = stored_u32 + my_block;
-        PRow<K> nx = load_prow<K>(tp_rc, pr, blank_ofs);
-#pragma unroll 2
-        for (int r = 0; r < rows; ++r, dst += srow_bytes) {
-          const PRow<K> cur = nx;
-          pr += (r + 1 < rows) ? row_bytes : 0u;
-          nx = load_prow<K>(tp_rc, pr, blank_ofs);
-          step<K, true, false>(w, abar, tp_rc, cur, fr);
-#pragma unroll
-          for (int i = 0; i < K; i += 4) sts128(dst + 4u * i, w[i], w[i + 1], w[i + 2], w[i + 3]);
-        }
-      }
-      // prefetch the checkpoint of the next segment (consumed at the top of the next iteration)
-      if (k2 + 1 < n2) ckpt_load<K>(ck_other + (size_t)seg_of(k + 1) * (K + 1) * 32, w, ew, lane);
-      __syncwarp();
-    }
+    bar_wait(sm.bars, kBarSFull + DIR * 2 + buf, (sfull_phase >> buf) & 1u);
+    sfull_phase ^= 1u << buf;
     PROF_MARK(4);
-
-    // ---- live sweep over the segment: posterior(state) * Zm = abar * stored.
-    // Row r+1's stored block and p values are fetched while row r is computed.  A block is
-    // read by exactly one lane, which clears it right away so that the row can be re-used
-    // for the sorted posteriors with every padding column reading as zero.
+    // posterior * Zm = abar * stored * 2^(eL + eR - eZ): one factor per lane pair and segment
+    float g = 0.f;
     {
-      const int rstep = (dir == 0) ? 1 : -1;
-      int r = (dir == 0) ? 0 : rows - 1;
-      uint32_t pr = pt + (uint32_t)r * row_bytes;
-      uint32_t row = stored_u32 + (uint32_t)r * srow_bytes;
+      const int er = __float_as_int(lds(sm.sexp[DIR] + 4u * (uint32_t)(buf * 32 + 31 - lane)));
+      if (defined_exp(e) && defined_exp(er)) {
+        const int dd = e + er - eZ;
+        if (dd > 126) bad |= 4;
+        else g = (dd < -126) ? 0.f : pow2i(dd);
+      }
+    }
+    if (k2 >= 2) {   // X has consumed the gamma / pbk buffer used two segments ago
+      bar_wait(sm.bars, kBarGEmpty + DIR * 2 + buf, (gempty_phase >> buf) & 1u);
+      gempty_phase ^= 1u << buf;
+    }
+    PROF_MARK(5);
+    const uint32_t sbase = sm.stored[DIR] + (uint32_t)buf * kSeg * srow + pair_block;
+    const uint32_t gbase = sm.gam[DIR] + (uint32_t)buf * kSeg * grow;
+    const uint32_t pbase = sm.pbk[DIR] + 4u * (uint32_t)(buf * kSeg * 33 + lane);
+    {
+      int r = (DIR == 0) ? 0 : rows - 1;
+      uint32_t pr = pt + (uint32_t)r * ring.row_bytes;
       float stn[K];
-      auto fetch_block = [&](uint32_t rw) {
+      auto fetch_block = [&](int rr) {
 #pragma unroll
         for (int i = 0; i < K; i += 4) {
-          const float4 q = lds128(rw + pair_block + 4u * i);
+          const float4 q = lds128(sbase + (uint32_t)rr * srow + 4u * i);
           stn[i] = q.x; stn[i + 1] = q.y; stn[i + 2] = q.z; stn[i + 3] = q.w;
-          sts128(rw + pair_block + 4u * i, 0.f, 0.f, 0.f, 0.f);
         }
       };
-      fetch_block(row);
-      PRow<K> nx = load_prow<K>(tp_live, pr, blank_ofs);
+      fetch_block(r);
+      PRow<K> nx = load_prow<K>(tp, pr, blank_ofs);
 #pragma unroll 2
-      for (int it = 0; it < rows; ++it, r += rstep) {
+      for (int it = 0; it < rows; ++it) {
         float st[K];
 #pragma unroll
-        for (int i = 0; i < K; ++i) st[i] = stn[i];
+        for (int i = 0; i < K; ++i) st[i] = stn[i] * g;
         const PRow<K> cur = nx;
-        const uint32_t row_cur = row;
-        const bool more = it + 1 < rows;
-        if (more) {
-          pr = (dir == 0) ? pr + row_bytes : pr - row_bytes;
-          row = (dir == 0) ? row + srow_bytes : row - srow_bytes;
-          fetch_block(row);
+        const int rc = r;
+        if (it + 1 < rows) {
+          r = (DIR == 0) ? r + 1 : r - 1;
+          pr = (DIR == 0) ? pr + ring.row_bytes : pr - ring.row_bytes;
+          fetch_block(r);
         }
-        nx = load_prow<K>(tp_live, pr, blank_ofs);
-        __syncwarp();   // every lane has fetched (and cleared) its block of row_cur
-        if (dir == 0) step<K, true, true>(v, abar, tp_live, cur, f);
-        else step<K, false, true>(v, abar, tp_live, cur, f);
+        nx = load_prow<K>(tp, pr, blank_ofs);
+        step<K, ODD, true>(v, abar, tp, cur, f);
         float pbsum = 0.f;
+        const uint32_t gr = gbase + (uint32_t)rc * grow;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          const bool lab = ((i & 1) == 1) == (dir == 0);
-          const float g = abar[i] * st[K - 1 - i];
-          if (lab) sts(row_cur + tp_live.gofs[i >> 1], g);
-          else pbsum += g;
+          const bool lab = ((i & 1) == 1) == ODD;
+          const float gm = abar[i] * st[K - 1 - i];
+          if (lab) sts(gr + tp.gofs[i >> 1], gm);
+          else pbsum += gm;
         }
-        sts(pbk_u32 + 4u * (uint32_t)(r * 33 + lane), pbsum);
+        sts(pbase + 4u * (uint32_t)(rc * 33), pbsum);
       }
     }
-    release_ptile(k);
     __syncwarp();
-    PROF_MARK(5);
-
-    // ---- transposed pass: sum the posteriors per label and write the [rows, C] tile
-    {
-      float* ot = sm.out(dir) + (size_t)obuf * outsz;
-      const uint32_t ot_u32 = smem_u32(ot);
-      if (lane == 0) bulk_wait_read<1>();   // the store that last read this buffer is done
-      __syncwarp();
-      PROF_MARK(6);
-      float tot = 0.f;
-#pragma unroll
-      for (int p = 0; p < kMaxPass; ++p) {
-        if (p < npass) {
-          const uint32_t src = stored_u32 + 512u * (uint32_t)p + slot_ofs;
-          const uint32_t dsto = ot_u32 + 4u * (uint32_t)max(slab[p], 0);
-#pragma unroll
-          for (int r0 = 0; r0 < kSeg; r0 += 8) {
-            if (r0 < rows) {
-              float c[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {   // rows >= `rows` hold finite stale data; never stored
-                const float4 q = lds128(src + (uint32_t)(r0 + j) * srow_bytes);
-                c[j] = (q.x + q.y) + (q.z + q.w);
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 1), lk1[p], c[j]);
-              if (maxch > 2) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 2), lk2[p], c[j]);
-              }
-              if (maxch > 4) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 4), lk4[p], c[j]);
-              }
-              if (head[p]) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (r0 + j < rows) {
-                    sts(dsto + 4u * (uint32_t)((r0 + j) * C), c[j] * kappa);
-                    tot += c[j];
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
-      float bs = 0.f;
-      if (frm < rows) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) bs += lds(pbrow_u32 + 4u * q);
-      }
-      tot += bs;
-      const float bsum = bs + __shfl_xor_sync(kFull, bs, 16);
-      if (frm < rows && hf == 0) sts(ot_u32 + 4u * (uint32_t)(frm * C) + blank_ofs, bsum * kappa);
-      // certificate: the posteriors of every frame sum to one, i.e. the segment sums to
-      // rows * Zm.  Range loss can only remove mass, so deficits cannot cancel.
-      tot = warp_sum(tot);
-      if (!(fabsf(tot - (float)rows * Zm) <= 2e-5f * (float)rows * Zm)) bad |= 8;
-      PROF_MARK(7);
-      float* dst = gEb + (size_t)seg * kSeg * C;
-      const int n = rows * C;
-      const bool tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
-      if (tma) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          bulk_s2g(dst, ot, (uint32_t)n * 4u);
-          bulk_commit();
-        }
-      } else {
-        __syncwarp();
-        for (int q = lane; q < n; q += 32) dst[q] = ot[q];
-      }
-      obuf ^= 1;
-      __syncwarp();
+    if (lane == 0) {
+      bar_arrive(sm.bars, kBarSEmpty + DIR * 2 + buf);   // R may refill this stored buffer
+      bar_arrive(sm.bars, kBarGFull + DIR * 2 + buf);    // X may reduce this gamma buffer
     }
-    PROF_MARK(3);
+    ring.release(k, lane, 1);
+    PROF_MARK(6);
   }
 #ifdef WFST_PROFILE
   if (b == 0 && lane == 0)
-    printf("dir %d cycles: event+ckpt %lld  wait_ptile %lld  phase1-steps %lld  fence+store %lld  recompute %lld  combine %lld  bulkwait %lld transposed %lld\n",
-           dir, pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3], pf_acc[4], pf_acc[5], pf_acc[6], pf_acc[7]);
+    printf("L%d cycles: event+ckpt %lld  wait_ptile %lld  phase1-steps %lld  misc %lld  wait_sfull %lld  wait_gempty %lld  combine %lld\n",
+           DIR, pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3], pf_acc[4], pf_acc[5], pf_acc[6]);
 #endif
-  if (lane == 0) bulk_wait_all<0>();
   bad = __reduce_or_sync(kFull, (unsigned)bad);
   if (bad && lane == 0) atomicOr(&a.hazard[b], bad);
 }
@@ -737,55 +937,57 @@ __device__ __forceinline__ void run_direction(const CtcFastArgs& a, const FastSm
 // the kernel
 // ---------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
-  constexpr int Sp = 32 * K;
+__global__ void __launch_bounds__(224, (K <= 12) ? 2 : 1) ctc_fast_kernel(CtcFastArgs a) {
   extern __shared__ __align__(16) float smem_raw[];
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = a.T, C = a.C, Cp = a.Cp, RS = a.RS;
-  FastSmem<K> sm = carve_fast<K>(smem_raw, C, Cp, RS);
-  const int* y = a.targets + a.offsets[b];
-  const int L = a.offsets[b + 1] - a.offsets[b];
-  const int nseg = a.nseg, nA = a.nA;
-  const bool want_grad = a.gradE != nullptr;
-  const float* Eb = a.E + (size_t)b * T * C;
-  const int dump_col = RS - 1;
+  const int warp = threadIdx.x >> 5;
+  Ctx cx;
+  cx.b = blockIdx.x;
+  cx.lane = threadIdx.x & 31;
+  cx.T = a.T; cx.C = a.C; cx.Cp = a.Cp; cx.RS = a.RS; cx.GW = a.GW;
+  cx.nseg = a.nseg; cx.nA = a.nA;
+  cx.y = a.targets + a.offsets[cx.b];
+  cx.L = a.offsets[cx.b + 1] - a.offsets[cx.b];
+  cx.want_grad = a.gradE != nullptr;
+  const int C = a.C, L = cx.L;
+  const int* y = cx.y;
+  FastSmem sm = carve_fast(smem_raw, K, C, a.Cp, a.RS, a.GW);
+  const int NT = blockDim.x;
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
-    for (int d = 0; d < 2; ++d)
-      for (int i = 0; i < kNB; ++i) {
-        mbar_init(&sm.bars[bar_full(d, i)], 1);
-        mbar_init(&sm.bars[bar_empty(d, i)], 1);
-      }
-    for (int i = 0; i < kNR; ++i) mbar_init(&sm.bars[kBarTma + i], 1);
-    mbar_init(&sm.bars[kBarZ], 1);
+    for (int i = 0; i < kNumBars; ++i) {
+      const bool two = i >= kBarPEmpty && i < kBarPEmpty + 2 * kNB;
+      bar_init(sm.bars, i, two ? 2u : 1u);
+    }
     fence_barrier_init();
   }
-  // zero the regions that rely on it: p-tile padding columns, output tiles (labels that
-  // do not occur in the target keep a zero gradient), blank partials
-  for (int d = 0; d < 2; ++d) {
-    for (int k = threadIdx.x; k < kNB * kSeg * Cp; k += 96) sm.ptile(d)[k] = 0.f;
-    for (int k = threadIdx.x; k < 2 * (int)(((size_t)kSeg * C + 3) & ~(size_t)3); k += 96) sm.out(d)[k] = 0.f;
-    for (int k = threadIdx.x; k < kSeg * 33; k += 96) sm.pbk(d)[k] = 0.f;
-    for (int k = threadIdx.x; k < kSeg * RS; k += 96) sm.stored(d)[k] = 0.f;
+  // zero what relies on it: p-tile padding columns, gradient tiles (labels that do not occur in
+  // the target keep a zero gradient), gamma rows (padding columns of the chunk slots), blank partials
+  {
+    const int outsz = (kSeg * C + 3) & ~3;
+    for (int d = 0; d < 2; ++d) {
+      for (int k = threadIdx.x; k < kNB * kSeg * a.Cp; k += NT) sts(sm.ptile[d] + 4u * k, 0.f);
+      for (int k = threadIdx.x; k < 2 * outsz; k += NT) sts(sm.out[d] + 4u * k, 0.f);
+      for (int k = threadIdx.x; k < 2 * kSeg * a.GW; k += NT) sts(sm.gam[d] + 4u * k, 0.f);
+      for (int k = threadIdx.x; k < 2 * kSeg * 33; k += NT) sts(sm.pbk[d] + 4u * k, 0.f);
+    }
   }
   // Counting sort of the target positions by label -> columns of the "gamma" row.  The row
   // is organised in chunk slots of 4 columns; a label with n occurrences owns ceil(n/4)
   // consecutive slots that never straddle a multiple of 32 slots (one pass of the
   // transposed reduction = 32 slots, one per lane).
-  for (int k = threadIdx.x; k < C + 4; k += 96) sm.hist[k] = 0;
-  for (int k = threadIdx.x; k < 32 * kMaxPass + 8; k += 96) sm.slotlab[k] = -1;
+  for (int k = threadIdx.x; k < C + 4; k += NT) sm.hist[k] = 0;
+  for (int k = threadIdx.x; k < 32 * kMaxPass + 8; k += NT) sm.slotlab[k] = -1;
   __syncthreads();
   int has_blank = 0;
-  for (int n = threadIdx.x; n < L; n += 96) {
+  for (int n = threadIdx.x; n < L; n += NT) {
     atomicAdd(&sm.hist[y[n]], 1);
     has_blank |= (y[n] == a.blank);
   }
   if (__syncthreads_or(has_blank)) {
-    // a target that contains the blank label shares a gradient column between a label
-    // state and the blank states: leave it to the log-semiring kernel
-    if (threadIdx.x == 0) a.hazard[b] = 1;   // reason 1: blank label inside the target
+    // a target that contains the blank label shares a gradient column between a label state
+    // and the blank states: leave it to the log-semiring kernel
+    if (threadIdx.x == 0) a.hazard[cx.b] = 1;   // reason 1
     return;
   }
   if (threadIdx.x == 0) {
@@ -807,121 +1009,24 @@ __global__ void __launch_bounds__(96, 2) ctc_fast_kernel(CtcFastArgs a) {
   __syncthreads();
   {
     const int nslots = sm.hist[C], maxch = sm.hist[C + 1];
-    // layouts the transposed pass cannot hold (very many distinct labels for this K, or one
-    // label more than 32 times) go to the log-semiring kernel
-    if (nslots > 32 * kMaxPass || nslots * 4 > RS - 4 || maxch > 8) {
-      if (threadIdx.x == 0) a.hazard[b] = 16;  // reason 16: gamma row layout does not fit
+    // layouts the transposed pass cannot hold go to the log-semiring kernel
+    if (nslots > 32 * kMaxPass || nslots * 4 > a.GW - 4 || maxch > 8) {
+      if (threadIdx.x == 0) a.hazard[cx.b] = 16;  // reason 16
       return;
     }
   }
-  for (int n = threadIdx.x; n < L; n += 96) sm.gcolpos[n] = atomicAdd(&sm.hist[y[n]], 1);
+  for (int n = threadIdx.x; n < L; n += NT) sm.gcolpos[n] = atomicAdd(&sm.hist[y[n]], 1);
   __syncthreads();
 
-  // ===================================================================== producer
-  if (warp == 2) {
-    // Direction 0 consumes tiles 0,1,...; direction 1 consumes nseg-1, nseg-2, ...
-    // Without a gradient only the phase-1 tiles are needed.  The schedule is the sequence
-    // (k, d), k = 0.., d = 0, 1, restricted to k < ntile[d].  Raw [16, C] tiles are
-    // fetched kNR - 1 entries ahead (TMA latency >> conversion time).
-    const int ntile0 = want_grad ? nseg : nA, ntile1 = want_grad ? nseg : (nseg - nA);
-    const int total = max(ntile0, ntile1);
-    const int fr = lane & 15, hh = lane >> 4;
-    const int c0 = hh ? (C + 1) / 2 : 0, c1 = hh ? C : (C + 1) / 2;
-    const int rawsz = (kSeg * C + 3) & ~3;
-    const uint32_t raw_u32 = smem_u32(sm.raw);
-    double msum = 0.0;
-    uint32_t tma_phase = 0u;     // bit per raw slot
-    uint32_t tma_used = 0u;      // bit per raw slot: the entry in it came through TMA
-    uint32_t empty_phase = 0u;   // bit (d * kNB + buf)
-    auto tile_of = [&](int d, int k) { return d == 0 ? k : nseg - 1 - k; };
-    auto next_entry = [&](int& k, int& d) {
-      do {
-        if (d == 0) d = 1; else { d = 0; ++k; }
-      } while (k < total && k >= (d == 0 ? ntile0 : ntile1));
-    };
-    auto issue_raw = [&](int tile, int slot) {
-      const int rows = min(kSeg, T - tile * kSeg);
-      const float* src = Eb + (size_t)tile * kSeg * C;
-      const uint32_t bytes = (uint32_t)rows * C * 4u;
-      float* dst = sm.raw + (size_t)slot * rawsz;
-      const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15u) == 0);
-      if (tma) {
-        if (lane == 0) {
-          mbar_expect_tx(&sm.bars[kBarTma + slot], bytes);
-          bulk_g2s(dst, src, bytes, &sm.bars[kBarTma + slot]);
-        }
-        tma_used |= 1u << slot;
-      } else {
-        for (int q = lane; q < rows * C; q += 32) dst[q] = __ldg(src + q);
-        tma_used &= ~(1u << slot);
-        __syncwarp();
-      }
-    };
-    // cursor of the entry being converted (k, d) and of the next entry to fetch (fk, fd)
-    int k = -1, d = 1;
-    next_entry(k, d);
-    int fk = k, fd = d, fetched = 0, converted = 0;
-    while (k < total) {
-      // keep the raw ring full; slot = entry index mod kNR; a slot is free once its previous
-      // entry has been converted (entries are converted in order)
-      while (fk < total && fetched < converted + kNR) {
-        issue_raw(tile_of(fd, fk), fetched % kNR);
-        ++fetched;
-        next_entry(fk, fd);
-      }
-      const int slot = converted % kNR;
-      const int tile = tile_of(d, k);
-      const int rows = min(kSeg, T - tile * kSeg);
-      const int buf = k % kNB;
-      if (k >= kNB) {  // wait until the consumer has released this p-tile buffer
-        const int bit = d * kNB + buf;
-        mbar_wait(&sm.bars[bar_empty(d, buf)], (empty_phase >> bit) & 1u);
-        empty_phase ^= 1u << bit;
-      }
-      if ((tma_used >> slot) & 1u) {
-        mbar_wait(&sm.bars[kBarTma + slot], (tma_phase >> slot) & 1u);
-        tma_phase ^= 1u << slot;
-      }
-      const uint32_t er = raw_u32 + 4u * (uint32_t)(slot * rawsz + fr * C);
-      const uint32_t pt = smem_u32(sm.ptile(d)) + 4u * (uint32_t)(buf * kSeg * Cp + fr * Cp);
-      float mx = kNegInf;
-      if (fr < rows) {
-#pragma unroll 8
-        for (int c = c0; c < c1; ++c) mx = fmaxf(mx, lds(er + 4u * c));
-      }
-      mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 16));
-      if (fr < rows) {
-        // a row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface
-        // through the certificate
-        const float base = (mx == kNegInf) ? 0.f : mx;
-        const float nb = -base * 1.4426950408889634f;
-#pragma unroll 8
-        for (int c = c0; c < c1; ++c)
-          sts(pt + 4u * c, exp2f(fmaf(lds(er + 4u * c), 1.4426950408889634f, nb)));
-        const bool phase1 = (d == 0) ? (tile < nA) : (tile >= nA);
-        if (hh == 0 && phase1) msum += (double)base;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.bars[bar_full(d, buf)]);
-      ++converted;
-      next_entry(k, d);
-    }
-    // loss: log Z = log(Zm) + eZ ln2 + sum_t max_t
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(kFull, msum, o);
-    mbar_wait(&sm.bars[kBarZ], 0u);
-    if (lane == 0) {
-      const float Zm = sm.zx[0];
-      const int eZ = __float_as_int(sm.zx[1]);
-      const bool ok = sm.zx[2] != 0.f;
-      a.z_out[b] = ok ? (float)(log((double)Zm) + (double)eZ * 0.6931471805599453 + msum) : kNegInf;
-    }
-    return;
+  switch (warp) {
+    case 0: role_live<K, 0>(a, sm, cx); break;
+    case 1: role_live<K, 1>(a, sm, cx); break;
+    case 2: role_producer(a, sm, cx); break;
+    case 3: role_recompute<K, 0>(a, sm, cx); break;
+    case 4: role_recompute<K, 1>(a, sm, cx); break;
+    case 5: role_reduce(a, sm, cx, 0); break;
+    default: role_reduce(a, sm, cx, 1); break;
   }
-
-  // ===================================================================== A / B
-  if (warp == 0) run_direction<K, 0>(a, sm, b, lane);
-  else run_direction<K, 1>(a, sm, b, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -935,35 +1040,39 @@ static int fast_pick_k(int max_target_len) {
   return 0;
 }
 
-static void fast_dims(int K, int C, int& Cp, int& RS) {
+static void fast_dims(int K, int C, int max_target_len, int& Cp, int& RS, int& GW) {
   Cp = (C + 1) | 1;
-  // the row holds the Sp recomputed values, later re-used for the chunk slots of the
-  // sorted posteriors (<= Sp / 4 slots) and the dump column RS - 1
   RS = 32 * K + 4;
+  // chunk slots: ceil(n_c / 4) per label, plus the slots skipped so that no label straddles
+  // a multiple of 32 (fewer than 8 per pass), plus the dump column
+  const int labels = (C - 1 < max_target_len) ? C - 1 : max_target_len;
+  int slots = (max_target_len + 3 * labels + 3) / 4 + 8;
+  if (slots > 32 * kMaxPass) slots = 32 * kMaxPass;
+  GW = 4 * slots + 4;
 }
 
 bool ctc_fast_eligible(int T, int C, int max_target_len) {
   if (T < 1) return false;
   const int K = fast_pick_k(max_target_len);
   if (K == 0) return false;
-  int Cp, RS;
-  fast_dims(K, C, Cp, RS);
-  return fast_smem_floats(K, C, Cp, RS) * sizeof(float) <= 227 * 1024;
+  int Cp, RS, GW;
+  fast_dims(K, C, max_target_len, Cp, RS, GW);
+  return fast_smem_floats(K, C, Cp, RS, GW) * sizeof(float) <= 227 * 1024;
 }
 
 size_t ctc_fast_workspace_bytes(int B, int T, int max_target_len) {
   const int K = fast_pick_k(max_target_len);
   const int nseg = (T + kSeg - 1) / kSeg;
-  return align_up((size_t)B * 2 * (nseg + 1) * (K + 1) * 32 * sizeof(float), 256) +
+  return align_up((size_t)B * 2 * (nseg + 1) * ((K + 4) & ~3) * 32 * sizeof(float), 256) +
          align_up((size_t)B * sizeof(int), 256);
 }
 
 template <int K>
 static int launch_fast_k(const CtcFastArgs& a, cudaStream_t st) {
-  size_t smem = fast_smem_floats(K, a.C, a.Cp, a.RS) * sizeof(float);
+  size_t smem = fast_smem_floats(K, a.C, a.Cp, a.RS, a.GW) * sizeof(float);
   auto kern = ctc_fast_kernel<K>;
   WFST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<a.B, 96, smem, st>>>(a);
+  kern<<<a.B, 224, smem, st>>>(a);
   g_launches++;
   WFST_CUDA_CHECK(cudaGetLastError());
   return WFST_OK;
@@ -978,10 +1087,10 @@ int launch_ctc_fast(const float* E, const int* targets, const int* offsets, int 
   a.grad_scale = grad_scale; a.z_out = z_out; a.gradE = gradE;
   a.nseg = (T + kSeg - 1) / kSeg;
   a.nA = a.nseg / 2;
-  fast_dims(K, C, a.Cp, a.RS);
+  fast_dims(K, C, max_target_len, a.Cp, a.RS, a.GW);
   a.ckpt = (float*)workspace;
   a.hazard = (int*)((char*)workspace +
-                    align_up((size_t)B * 2 * (a.nseg + 1) * (K + 1) * 32 * sizeof(float), 256));
+                    align_up((size_t)B * 2 * (a.nseg + 1) * ((K + 4) & ~3) * 32 * sizeof(float), 256));
   *hazard_out = a.hazard;
   WFST_CUDA_CHECK(cudaMemsetAsync(a.hazard, 0, (size_t)B * sizeof(int), st));
   switch (K) {

@@ -41,6 +41,8 @@ struct HostPathBuffers {
 static HostPathBuffers g_host;
 // test hook: route CTC through the log-semiring kernel only
 static int g_force_generic = 0;
+// test hook: 2 = skip the paired kernel (exercise the single-utterance scaled kernel)
+static int g_force_generic_kind = 0;
 
 }  // namespace wfst
 
@@ -50,14 +52,37 @@ extern "C" {
 
 const char* wfst_last_error(void) { return g_err; }
 int wfst_abi_version(void) { return WFST_ABI_VERSION; }
-int wfst_debug_force_generic_ctc(int on) { int old = g_force_generic; g_force_generic = on; return old; }
+int wfst_debug_force_generic_ctc(int on) {
+  // 0: default dispatch; 1: log-semiring kernel only; 2: no paired kernel
+  int old = g_force_generic ? 1 : g_force_generic_kind;
+  g_force_generic = (on == 1);
+  g_force_generic_kind = (on == 2) ? 2 : 0;
+  return old;
+}
 unsigned long long wfst_launch_count(void) { return g_launches.load(); }
 
 // --------------------------------------------------------------------- CTC
+// scaled-probability kernels, in order of preference: paired (two utterances per block,
+// packed FP32), single (larger targets), none (log-semiring kernel only)
+static int ctc_scaled_kind(int T, int C, int max_target_len) {
+  if (g_force_generic) return 0;
+  if (g_force_generic_kind != 2 && ctc_pair_eligible(T, C, max_target_len)) return 2;
+  if (ctc_fast_eligible(T, C, max_target_len)) return 1;
+  return 0;
+}
+static size_t ctc_scaled_workspace_bytes(int B, int T, int C, int max_target_len) {
+  size_t n = 0;
+  if (ctc_pair_eligible(T, C, max_target_len)) n = ctc_pair_workspace_bytes(B, T, max_target_len);
+  if (ctc_fast_eligible(T, C, max_target_len)) {
+    size_t m = ctc_fast_workspace_bytes(B, T, max_target_len);
+    if (m > n) n = m;
+  }
+  return n;
+}
 // workspace: [alpha history of the log-semiring kernel][scores B][fast-path checkpoints + hazard]
 size_t wfst_ctc_workspace_bytes(int B, int T, int C, int max_target_len) {
   size_t n = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
-  if (ctc_fast_eligible(T, C, max_target_len)) n += ctc_fast_workspace_bytes(B, T, max_target_len);
+  n += ctc_scaled_workspace_bytes(B, T, C, max_target_len);
   return n;
 }
 
@@ -81,12 +106,15 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
   size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1);
   float* z = (float*)((char*)workspace + hb);
   int rc;
-  if (ctc_fast_eligible(T, C, max_target_len) && !g_force_generic) {
+  const int kind = ctc_scaled_kind(T, C, max_target_len);
+  if (kind != 0) {
     // scaled-probability kernel; utterances it flags are redone by the log-semiring kernel
     int* hazard = nullptr;
     void* fws = (char*)workspace + hb + align_up((size_t)B * sizeof(float), 256);
-    rc = launch_ctc_fast(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
-                         grad_scale, z, grad, fws, &hazard, st);
+    rc = kind == 2 ? launch_ctc_pair(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+                                     grad_scale, z, grad, fws, &hazard, st)
+                   : launch_ctc_fast(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+                                     grad_scale, z, grad, fws, &hazard, st);
     if (rc != WFST_OK) return rc;
     rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
                     z, grad, hist, hazard, st);
@@ -102,9 +130,10 @@ int wfst_debug_ctc_hazards(const void* workspace, int B, int T, int C, int max_t
                             int32_t* host_flags) {
   WFST_REQUIRE(workspace && host_flags, "null pointer argument");
   for (int b = 0; b < B; ++b) host_flags[b] = -1;
-  if (!ctc_fast_eligible(T, C, max_target_len)) return WFST_OK;
+  const int kind = ctc_scaled_kind(T, C, max_target_len);
+  if (kind == 0) return WFST_OK;
   size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
-  size_t fb = ctc_fast_workspace_bytes(B, T, max_target_len);
+  size_t fb = kind == 2 ? ctc_pair_workspace_bytes(B, T, max_target_len) : ctc_fast_workspace_bytes(B, T, max_target_len);
   const char* hz = (const char*)workspace + hb + fb - align_up((size_t)B * sizeof(int), 256);
   WFST_CUDA_CHECK(cudaDeviceSynchronize());
   WFST_CUDA_CHECK(cudaMemcpy(host_flags, hz, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost));

@@ -28,6 +28,12 @@ size_t ctc_fast_workspace_bytes(int B, int T, int max_target_len);
 int launch_ctc_fast(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                     int blank, int max_target_len, const float* grad_scale, float* z_out,
                     float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
+// paired fast CTC (ctc_pair.cu): two utterances per block, packed FP32 arithmetic
+bool ctc_pair_eligible(int T, int C, int max_target_len);
+size_t ctc_pair_workspace_bytes(int B, int T, int max_target_len);
+int launch_ctc_pair(const float* E, const int* targets, const int* offsets, int B, int T, int C,
+                    int blank, int max_target_len, const float* grad_scale, float* z_out,
+                    float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
 // best path (viterbi.cu)
 size_t viterbi_workspace_bytes(int B, int T, int max_nodes);
 int launch_viterbi(const float* E, int B, int T, int C, const wfst_acceptor_batch_t& g, int shared,

@@ -65,6 +65,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNB = 4;                // p-tile ring depth per direction
 constexpr int kNR = 3;                // raw (TMA) staging slots per producer warp
 constexpr int kMaxPass = 4;           // label reduction: up to 4 x 32 chunk slots
+constexpr int kU = 4;                 // frames unrolled in the hot loops (code size vs address updates)
 constexpr int kPbkRow = 66;           // floats per row of blank partials (32 lanes x 2 + pad)
 
 struct Args {
@@ -147,6 +148,13 @@ __device__ __forceinline__ void sts128(uint32_t a, p2 x, p2 y) {
   asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(x), "l"(y) : "memory");
 }
 
+// 2^x for x <= 0 (one MUFU; results below the normal range flush to zero, which is what a
+// probability that small is worth here)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ bool defined_exp(int e) { return e > kUndef / 2; }
 __device__ __forceinline__ float pow2i(int d) {  // 2^d for d in [-126, 127]
   return __uint_as_float((uint32_t)(d + 127) << 23);
@@ -203,7 +211,7 @@ __host__ __device__ inline Layout make_layout(int K, int C, int CS, int NAB) {
   L.abuf = p;   p += 2 * (size_t)NAB * kSeg * 2 * RS;    // [d][buf][row][4 pad + 32 x (K + 1)][u]
   L.pbk = p;    p += 2 * (size_t)NAB * kSeg * kPbkRow;   // [d][buf][row][lane][u] (+pad)
   L.lexp = p;   p += 2 * (size_t)NAB * 2 * 32;           // [d][buf][u][lane] (int)
-  L.ptile = p;  p += 2 * (size_t)kNB * kSeg * 2 * Cp;    // [d][buf][row][Cp][u]
+  L.ptile = p;  p += 2 * (size_t)kNB * kSeg * 2 * Cp;    // [d][buf][row][u][Cp]
   p = (p + 3) & ~(size_t)3;
   L.bars = p;   p += 2 * kNumBars;
   p = (p + 3) & ~(size_t)3;
@@ -246,7 +254,7 @@ struct Topo {
 
 // orientation o: slot j holds state s = j (o = 0) or s = Sp-2-j (o = 1)
 template <int K>
-__device__ __forceinline__ void build_topo(Topo<K>& tp, const Ctx& cx, int o) {
+__device__ __forceinline__ void build_topo(Topo<K>& tp, const Ctx& cx, int o, int plane) {
   constexpr int Sp = 32 * K;
 #pragma unroll
   for (int q = 0; q < K / 2; ++q) {
@@ -264,14 +272,15 @@ __device__ __forceinline__ void build_topo(Topo<K>& tp, const Ctx& cx, int o) {
         const int n2 = o == 0 ? n - 1 : n + 1;   // two positions earlier IN THIS ORIENTATION
         if (n2 >= 0 && n2 < L && cx.y[u][n2] != cx.y[u][n]) sk[u] = 1.f;
       }
-      tp.labofs[u][q] = 4u * (uint32_t)(2 * col + u);
+      tp.labofs[u][q] = 4u * (uint32_t)(u * plane + col);
     }
     tp.skipm[q] = pk(sk[0], sk[1]);
   }
 }
 
-// The p values one frame needs.  A p tile is [8 rows][CS columns][2 utterances]; its rows
-// are in the order the live warp of the direction consumes them.
+// The p values one frame needs.  A p tile is [8 rows][2 utterances][CS + 1 columns] (one plane
+// per utterance: the labels of a gather then fall into distinct banks); its rows are in the
+// order the live warp of the direction consumes them.
 template <int K>
 struct PRow {
   p2 pl[K / 2];
@@ -294,12 +303,22 @@ __device__ __forceinline__ TileAddr<K> tile_addr(const Topo<K>& tp, uint32_t pt,
   return t;
 }
 template <int K, int CS>
+__device__ __forceinline__ void advance_rows(TileAddr<K>& t, int rows) {
+  const uint32_t o = (uint32_t)(rows * (8 * (CS + 1)));
+#pragma unroll
+  for (int q = 0; q < K / 2; ++q) {
+    t.la[0][q] += o;
+    t.la[1][q] += o;
+  }
+  t.pba += o;
+}
+template <int K, int CS>
 __device__ __forceinline__ PRow<K> load_prow(const TileAddr<K>& t, int it) {
   PRow<K> p;
   const uint32_t o = (uint32_t)it * (8u * (CS + 1));
 #pragma unroll
   for (int q = 0; q < K / 2; ++q) p.pl[q] = pk(lds(t.la[0][q] + o), lds(t.la[1][q] + o));
-  p.pb = lds64(t.pba + o);
+  p.pb = pk(lds(t.pba + o), lds(t.pba + o + 4u * (CS + 1)));
   return p;
 }
 
@@ -325,67 +344,77 @@ __device__ __forceinline__ void step(p2 (&v)[K], p2 (&abar)[K], const Topo<K>& t
   }
 }
 
-// Event for one utterance's components (scalar bookkeeping): returns the two power-of-two
-// factors to apply in sequence, updates e and the neighbour factor f.
+// Event: renormalise the lane (max mantissa in [1,2)) and make the lane exponents
+// consistent from left to right (the direction mass flows):
 //   * a lane that holds only zeros takes the exponent of its left neighbour, so mass
 //     arriving during the next 16 frames arrives unscaled;
 //   * a lane with own mass never sits more than D below its left neighbour, where D is
 //     small enough that a wave crossing several lanes inside one 16-frame window cannot
 //     overflow: D * (lanes crossed) + log2(3^16) < 127.
+// This is the prefix composition of the maps x -> max(c, x - d) with (c, d) = (own
+// exponent, D) or (undefined, 0), which is associative: a 5-step warp scan.  "Undefined" is
+// any value below kUndef / 2, so max / minus need no special cases; (c, d) travel in one
+// shuffle as c * 2048 + d (d < 2048).  Both utterances are scanned side by side.
 template <int K>
-__device__ __forceinline__ void event_scalar(float m, int& e, float& f, float& sc1, float& sc2, int lane) {
+__device__ __forceinline__ void event2(p2 (&v)[K], int (&e)[2], p2& f, int lane) {
   constexpr int kChain = (32 + K - 1) / K + 1;   // lanes a wave can cross in 16 frames
   constexpr int D = 96 / kChain;
-  int eown = kUndef;
-  sc1 = 1.f;
-  sc2 = 1.f;
-  if (m > 0.f) {
-    int ex = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;
-    ex = min(max(ex, -126), 126);
-    sc1 = pow2i(-ex);
-    eown = (defined_exp(e) ? e : 0) + ex;
-  }
-  // prefix composition of x -> max(c, x - d), (c, d) packed in one int: c * 2048 + d
-  int c = eown, d = defined_exp(eown) ? D : 0;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int packed = __shfl_up_sync(kFull, c * 2048 + d, o);
-    const int pd = packed & 2047;
-    const int pc = (packed - pd) / 2048;
-    if (lane >= o) {
-      if (defined_exp(pc)) c = defined_exp(c) ? max(c, pc - d) : pc - d;
-      d += pd;
-    }
-  }
-  const int E = c;
-  if (defined_exp(E) && defined_exp(eown) && E != eown) {
-    const int sh = eown - E;  // < 0
-    sc2 = (sh < -126) ? 0.f : pow2i(sh);
-  }
-  e = defined_exp(E) ? E : kUndef;
-  const int el = __shfl_up_sync(kFull, e, 1);
-  if (lane == 0 || !defined_exp(el) || !defined_exp(e)) {
-    f = 0.f;
-  } else {
-    f = pow2c(el - e);   // el - e <= D by construction
-  }
-}
-
-template <int K>
-__device__ __noinline__ void event2(p2 (&v)[K], int (&e)[2], p2& f, int lane) {
-  float m0 = lo(v[0]), m1 = hi(v[0]);
+  float m[2] = {lo(v[0]), hi(v[0])};
 #pragma unroll
   for (int i = 1; i < K; ++i) {
-    m0 = fmaxf(m0, lo(v[i]));
-    m1 = fmaxf(m1, hi(v[i]));
+    m[0] = fmaxf(m[0], lo(v[i]));
+    m[1] = fmaxf(m[1], hi(v[i]));
   }
-  float f0, f1, a0, a1, b0, b1;
-  event_scalar<K>(m0, e[0], f0, a0, b0, lane);
-  event_scalar<K>(m1, e[1], f1, a1, b1, lane);
-  const p2 s1 = pk(a0, a1), s2 = pk(b0, b1);
+  int ex[2], eown[2], c[2], d[2];
 #pragma unroll
-  for (int i = 0; i < K; ++i) v[i] = mul2(mul2(v[i], s1), s2);
-  f = pk(f0, f1);
+  for (int u = 0; u < 2; ++u) {
+    ex[u] = min(max((int)((__float_as_uint(m[u]) >> 23) & 0xffu) - 127, -126), 126);
+    const bool has = m[u] > 0.f;
+    if (!has) ex[u] = 0;
+    eown[u] = has ? (defined_exp(e[u]) ? e[u] : 0) + ex[u] : kUndef;
+    c[u] = eown[u];
+    d[u] = has ? D : 0;
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int pc[2], pd[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int packed = __shfl_up_sync(kFull, c[u] * 2048 + d[u], o);
+      pd[u] = packed & 2047;
+      pc[u] = packed >> 11;            // arithmetic shift: floor((c * 2048 + d) / 2048) = c
+    }
+    if (lane >= o) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        c[u] = max(c[u], max(pc[u], kUndef) - d[u]);
+        d[u] += pd[u];
+      }
+    }
+  }
+  int t[2];           // total power-of-two shift applied to the lane
+  float fv[2];
+  bool deep = false;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int E = defined_exp(c[u]) ? c[u] : kUndef;
+    t[u] = -ex[u] + ((defined_exp(E) && defined_exp(eown[u])) ? eown[u] - E : 0);   // second term <= 0
+    e[u] = E;
+    const int el = __shfl_up_sync(kFull, E, 1);
+    fv[u] = (lane == 0 || !defined_exp(el) || !defined_exp(E)) ? 0.f : pow2c(el - E);   // el - E <= D
+    deep = deep || t[u] < -126;
+  }
+  f = pk(fv[0], fv[1]);
+  {
+    const p2 s1 = pk(pow2i(max(t[0], -126)), pow2i(max(t[1], -126)));
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = mul2(v[i], s1);
+  }
+  if (__any_sync(kFull, deep)) {   // a lane pushed far below its own maximum: second factor
+    const p2 s2 = pk(pow2c(t[0] - max(t[0], -126)), pow2c(t[1] - max(t[1], -126)));
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = mul2(v[i], s2);
+  }
 }
 
 // checkpoint: per lane 2K+4 floats (K pairs, then the two exponents), 128-bit accesses
@@ -423,8 +452,11 @@ struct PTileRing {
     phase ^= 1u << buf;
     return base + (uint32_t)buf * tile_bytes;
   }
-  __device__ __forceinline__ void skip(int from, int to) {
-    for (int k = from; k < to; ++k) phase ^= 1u << (k % kNB);
+  // for a consumer that does not see every tile: the parity of use k of its buffer
+  __device__ __forceinline__ uint32_t wait_use(int k) {
+    const int buf = k % kNB;
+    bar_wait(bars, kBarPFull + dir * kNB + buf, (uint32_t)(k / kNB) & 1u);
+    return base + (uint32_t)buf * tile_bytes;
   }
   __device__ __forceinline__ void release(int k, int lane, uint32_t count) {
     __syncwarp();
@@ -511,7 +543,7 @@ __device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, con
     const uint32_t er1 = er0 + 4u * rawsz;
     // tile row = the step at which the live warp of direction d consumes frame fr
     const int trow = d == 0 ? fr : rows - 1 - fr;
-    const uint32_t pt = sm.ptile + (uint32_t)((d * kNB + buf) * kSeg + (live ? trow : 0)) * (8u * (CS + 1)) + 8u * (uint32_t)c0;
+    const uint32_t pt = sm.ptile + (uint32_t)((d * kNB + buf) * kSeg + (live ? trow : 0)) * (8u * (CS + 1)) + 4u * (uint32_t)c0;
     // loads run past the lane's quarter (into the next row / the slack behind the staging
     // area); those elements are masked
     float ev0[NPL], ev1[NPL];
@@ -538,9 +570,12 @@ __device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, con
     const float nb0 = -base0 * 1.4426950408889634f, nb1 = -base1 * 1.4426950408889634f;
 #pragma unroll
     for (int i2 = 0; i2 < NPL; ++i2) {
-      const float q0 = exp2f(fmaf(ev0[i2], 1.4426950408889634f, nb0));
-      const float q1 = exp2f(fmaf(ev1[i2], 1.4426950408889634f, nb1));
-      if (live && i2 < cnt) sts64(pt + 8u * i2, pk(q0, q1));
+      const float q0 = ex2_fast(fmaf(ev0[i2], 1.4426950408889634f, nb0));
+      const float q1 = ex2_fast(fmaf(ev1[i2], 1.4426950408889634f, nb1));
+      if (live && i2 < cnt) {
+        sts(pt + 4u * i2, q0);
+        sts(pt + 4u * (CS + 1) + 4u * i2, q1);
+      }
     }
     if (live && part == 0 && phase1) {
       ps.msum[0] += (double)base0;
@@ -602,7 +637,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   const int lane = cx.lane, nseg = cx.nseg, nA = cx.nA, T = cx.T, NAB = cx.NAB;
   float* ck = a.ckpt + (size_t)blockIdx.x * nseg * 32 * ck_floats<K>();
   Topo<K> tp;
-  build_topo<K>(tp, cx, d);
+  build_topo<K>(tp, cx, d, CS + 1);
 
   p2 v[K], abar[K];
   int e[2] = {kUndef, kUndef};
@@ -624,7 +659,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     for (int i = 0; i < K; ++i) v[i] = pk(x[0][i], x[1][i]);
   }
   PTileRing ring{sm.bars, sm.ptile + (uint32_t)d * kNB * TILEB, TILEB, d, 0u};
-  const uint32_t blank_ofs = 8u * (uint32_t)a.blank;
+  const uint32_t blank_ofs = 4u * (uint32_t)a.blank;
 
   // ------------------------------------------------------------------ phase 1
   const int n1 = d == 0 ? nA : nseg - nA;
@@ -639,9 +674,11 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     const TileAddr<K> ta = tile_addr<K>(tp, ring.wait(k), blank_ofs);
     PROF_MARK(1);
     if (rows == kSeg) {
+      // kU frames per trip; the row after the last one is prefetched too (it is the first row of
+      // the next trip, or a harmless read past the tile)
       PRow<K> nx = load_prow<K, CS>(ta, 0);
 #pragma unroll
-      for (int it = 0; it < kSeg; ++it) {
+      for (int it = 0; it < kSeg; ++it) {   // fully unrolled: in phase 1 only L and P compete for the instruction cache
         const PRow<K> cur = nx;
         if (it + 1 < kSeg) nx = load_prow<K, CS>(ta, it + 1);
         step<K, false>(v, abar, tp, cur, f);
@@ -752,20 +789,26 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
       stsi(le, e[0]);
       stsi(le + 128u, e[1]);
     }
-    const TileAddr<K> ta = tile_addr<K>(tp, ring.wait(k), blank_ofs);
+    TileAddr<K> ta = tile_addr<K>(tp, ring.wait(k), blank_ofs);
     PROF_MARK(5);
     // rows of the segment buffer are in step order, like the p tile
-    const uint32_t ar = sm.abuf + (uint32_t)((d * NAB + buf) * kSeg) * ROWB + myblock;
+    uint32_t ar = sm.abuf + (uint32_t)((d * NAB + buf) * kSeg) * ROWB + myblock;
     if (rows == kSeg) {
       PRow<K> nx = load_prow<K, CS>(ta, 0);
+#pragma unroll 1
+      for (int h = 0; h < kSeg / kU; ++h) {
 #pragma unroll
-      for (int it = 0; it < kSeg; ++it) {
-        const PRow<K> cur = nx;
-        if (it + 1 < kSeg) nx = load_prow<K, CS>(ta, it + 1);
-        step<K, true>(v, abar, tp, cur, f);
+        for (int it = 0; it < kU; ++it) {
+          const PRow<K> cur = nx;
+          nx = load_prow<K, CS>(ta, it + 1);
+          step<K, true>(v, abar, tp, cur, f);
 #pragma unroll
-        for (int i = 0; i < K; ++i) sts64(ar + (uint32_t)it * ROWB + 8u * i, abar[i]);
+          for (int i = 0; i < K; ++i) sts64(ar + (uint32_t)it * ROWB + 8u * i, abar[i]);
+        }
+        advance_rows<K, CS>(ta, kU);
+        ar += kU * ROWB;
       }
+      ar -= kSeg * ROWB;
     } else {
 #pragma unroll 1
       for (int it = 0; it < rows; ++it) {
@@ -812,7 +855,7 @@ __device__ __forceinline__ void rc_frame(p2 (&w)[K], const Topo<K>& tp, const PR
 }
 
 template <int K, int CS>
-__device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx& cx, const int d) {
+__device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx& cx, const int d, const int x) {
   constexpr int Sp = 32 * K;
   constexpr uint32_t ROWB = 8u * (32 * (K + 1) + 4);   // 4 pad pairs + 32 lane blocks of K + 1 pairs
   constexpr uint32_t TILEB = 8u * (CS + 1) * kSeg;
@@ -824,25 +867,24 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   const int n1 = d == 0 ? nA : nseg - nA;
   const int n2 = nseg - n1;
   Topo<K> tp;
-  build_topo<K>(tp, cx, 1 - d);
+  build_topo<K>(tp, cx, 1 - d, CS + 1);
   const float* ck = a.ckpt + (size_t)blockIdx.x * nseg * 32 * ck_floats<K>();
   PTileRing ring{sm.bars, sm.ptile + (uint32_t)d * kNB * TILEB, TILEB, d, 0u};
-  ring.skip(0, n1);
-  const uint32_t blank_ofs = 8u * (uint32_t)a.blank;
+  const uint32_t blank_ofs = 4u * (uint32_t)a.blank;
   const uint32_t pblock = 8u * (uint32_t)(4 + (31 - lane) * (K + 1));   // partner block in an abar row
-  uint32_t afull_phase = 0u;
   int bad = 0;   // reason 4: scale overflow when pairing live and recomputed values
   p2 w[K];
   int ew[2];
-  if (n2 > 0) ckpt_load<K>(ck + (size_t)seg_of(d, n1, nseg) * 32 * ck_floats<K>(), w, ew, lane);
+  // the two RC warps of a direction take alternate segments
+  if (x < n2) ckpt_load<K>(ck + (size_t)seg_of(d, n1 + x, nseg) * 32 * ck_floats<K>(), w, ew, lane);
   PROF_DECL;
-  for (int k2 = 0, buf = 0; k2 < n2; ++k2, buf = (buf + 1 == NAB) ? 0 : buf + 1) {
+  for (int k2 = x; k2 < n2; k2 += 2) {
     const int k = n1 + k2;
     const int seg = seg_of(d, k, nseg);
     const int rows = min(kSeg, T - seg * kSeg);
+    const int buf = k2 % NAB;
     PROF_MARK(2);
-    bar_wait(sm.bars, kBarAFull + d * kMaxAB + buf, (afull_phase >> buf) & 1u);
-    afull_phase ^= 1u << buf;
+    bar_wait(sm.bars, kBarAFull + d * kMaxAB + buf, (uint32_t)(k2 / NAB) & 1u);
     PROF_MARK(0);
     // scales
     float g[2], h[2], fr[2];
@@ -870,17 +912,27 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     }
     const p2 f2 = pk(fr[0], fr[1]), h2 = pk(h[0], h[1]);
     PROF_MARK(2);
-    const TileAddr<K> ta = tile_addr<K>(tp, ring.wait(k), blank_ofs);
+    TileAddr<K> ta = tile_addr<K>(tp, ring.wait_use(k), blank_ofs);
     PROF_MARK(1);
     const uint32_t ar = sm.abuf + (uint32_t)((d * NAB + buf) * kSeg) * ROWB + pblock;
     const uint32_t pb = sm.pbk + 4u * (uint32_t)(((d * NAB + buf) * kSeg) * kPbkRow + 2 * lane);
     if (rows == kSeg) {
-      PRow<K> nx = load_prow<K, CS>(ta, kSeg - 1);
+      // against L's step order, kU frames per trip; th / ah / bh point at the trip's lowest row
+      TileAddr<K> th = ta;
+      advance_rows<K, CS>(th, kSeg - kU);
+      uint32_t ah = ar + (kSeg - kU) * ROWB, bh = pb + (kSeg - kU) * (4u * kPbkRow);
+      PRow<K> nx = load_prow<K, CS>(th, kU - 1);
+#pragma unroll 1
+      for (int h = 0; h < kSeg / kU; ++h) {
 #pragma unroll
-      for (int it = kSeg - 1; it >= 0; --it) {
-        const PRow<K> cur = nx;
-        if (it > 0) nx = load_prow<K, CS>(ta, it - 1);
-        rc_frame<K>(w, tp, cur, f2, h2, ar + (uint32_t)it * ROWB, pb + (uint32_t)it * (4u * kPbkRow));
+        for (int it = kU - 1; it >= 0; --it) {
+          const PRow<K> cur = nx;
+          nx = load_prow<K, CS>(th, it - 1);   // it = 0: the last row of the next trip (or a harmless read)
+          rc_frame<K>(w, tp, cur, f2, h2, ah + (uint32_t)it * ROWB, bh + (uint32_t)it * (4u * kPbkRow));
+        }
+        advance_rows<K, CS>(th, -kU);
+        ah -= kU * ROWB;
+        bh -= kU * (4u * kPbkRow);
       }
     } else {
 #pragma unroll 1
@@ -890,7 +942,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
       }
     }
     // next checkpoint (consumed at the top of the next iteration)
-    if (k2 + 1 < n2) ckpt_load<K>(ck + (size_t)seg_of(d, k + 1, nseg) * 32 * ck_floats<K>(), w, ew, lane);
+    if (k2 + 2 < n2) ckpt_load<K>(ck + (size_t)seg_of(d, k + 2, nseg) * 32 * ck_floats<K>(), w, ew, lane);
     __syncwarp();
     if (lane == 0) bar_arrive(sm.bars, kBarCFull + d * kMaxAB + buf);
     ring.release(k, lane, 1);
@@ -898,7 +950,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   PROF_MARK(2);
 #ifdef WFST_PROFILE
   if (blockIdx.x == 0 && lane == 0)
-    printf("RC%d cycles: wait_afull %lld wait_ptile %lld compute %lld\n", d, pf_acc[0], pf_acc[1], pf_acc[2]);
+    printf("RC%d.%d cycles: wait_afull %lld wait_ptile %lld compute %lld\n", d, x, pf_acc[0], pf_acc[1], pf_acc[2]);
 #endif
   bad = __reduce_or_sync(kFull, (unsigned)bad);
   if (bad && lane == 0) {
@@ -908,38 +960,34 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
 }
 
 // ---------------------------------------------------------------------------
-// X: per-label reduction of a segment's posteriors + gradient tile store.
+// X<d, u>: per-label reduction of a segment's posteriors of utterance u in direction d +
+// gradient tile store.  (d, u are runtime values: the four X warps share one copy of the code.)
 // ---------------------------------------------------------------------------
 template <int K>
-__device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const Ctx& cx, const int d) {
+__device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const Ctx& cx, const int d, const int ux) {
   constexpr int Sp = 32 * K;
   constexpr uint32_t ROWB = 8u * (32 * (K + 1) + 4);   // 4 pad pairs + 32 lane blocks of K + 1 pairs
   const int lane = cx.lane, nseg = cx.nseg, nA = cx.nA, T = cx.T, C = cx.C, NAB = cx.NAB;
   bar_wait(sm.bars, kBarZ, 0u);
-  const bool okz[2] = {lds(sm.zx + 8u) != 0.f, lds(sm.zx + 24u) != 0.f};
-  if (!cx.want_grad || !(okz[0] || okz[1])) return;
+  const bool ok0 = lds(sm.zx + 8u) != 0.f, ok1 = lds(sm.zx + 24u) != 0.f;
+  if (!cx.want_grad || !(ok0 || ok1)) return;
   const int n1 = d == 0 ? nA : nseg - nA;
   const int n2 = nseg - n1;
   const uint32_t rawsz = cx.rawsz;
   const uint32_t blank_ofs = 4u * (uint32_t)a.blank;
-  float Zm[2], kappa[2];
-  bool act[2];
-  int nslots[2], maxch[2];
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    Zm[u] = lds(sm.zx + 16u * u);
-    const float gs = a.grad_scale ? a.grad_scale[cx.b[u]] : 1.f;
-    kappa[u] = -gs / Zm[u];
-    act[u] = cx.live[u] && okz[u];
-    nslots[u] = sm.hist[u * (C + 4) + C];
-    maxch[u] = sm.hist[u * (C + 4) + C + 1];
-  }
+  const int bu = ux ? cx.b[1] : cx.b[0];
+  const bool dup = ux == 1 && cx.b[1] == cx.b[0];
+  const float Zm = lds(sm.zx + 16u * ux);
+  const float kappa = -(a.grad_scale ? a.grad_scale[bu] : 1.f) / Zm;
+  const bool act = (ux ? cx.live[1] && ok1 : cx.live[0] && ok0);
+  const int nslots = sm.hist[ux * (C + 4) + C], maxch = sm.hist[ux * (C + 4) + C + 1];
+  const int npass = (nslots + 31) >> 5;
   // per-pass constants of this lane -> shared table (one 128-bit load per pass later):
   // row-relative byte offsets of the 4 sorted positions of my chunk slot, link flags, label
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int* slotlab = sm.slotlab + u * (32 * kMaxPass + 8);
-    const int* colpos = sm.colpos + u * (4 * 32 * kMaxPass);
+  const uint32_t xt = sm.xtab + 16u * (uint32_t)(((d * 2 + ux) * kMaxPass) * 32 + lane);
+  {
+    const int* slotlab = sm.slotlab + ux * (32 * kMaxPass + 8);
+    const int* colpos = sm.colpos + ux * (4 * 32 * kMaxPass);
     for (int p = 0; p < kMaxPass; ++p) {
       const int gsl = 32 * p + lane;
       const int me = slotlab[gsl];
@@ -954,10 +1002,9 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
       for (int q = 0; q < 4; ++q) {
         const int n = colpos[4 * gsl + q];
         const int jl = d == 0 ? 2 * n + 1 : Sp - 3 - 2 * n;
-        off[q] = n >= 0 ? 8u * (uint32_t)(4 + (jl / K) * (K + 1) + jl % K) + 4u * u : 4u * u;   // row pad 0 is always zero
+        off[q] = n >= 0 ? 8u * (uint32_t)(4 + (jl / K) * (K + 1) + jl % K) + 4u * ux : 4u * ux;   // row pad 0 is always zero
       }
-      const uint32_t xa = sm.xtab + 16u * (uint32_t)(((d * 2 + u) * kMaxPass + p) * 32 + lane);
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(xa), "r"(off[0] | (off[1] << 16)),
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(xt + 512u * p), "r"(off[0] | (off[1] << 16)),
                    "r"(off[2] | (off[3] << 16)), "r"(fl | ((uint32_t)max(me, 0) << 8)), "r"(0u)
                    : "memory");
     }
@@ -967,6 +1014,7 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
   const int frm = lane & 7, qtr = lane >> 3;
   int bad = 0;
   uint32_t cfull_phase = 0u;
+  float* gE = a.gradE + (size_t)bu * T * C;
   PROF_DECL;
   for (int k2 = 0, buf = 0; k2 < n2; ++k2, buf = (buf + 1 == NAB) ? 0 : buf + 1) {
     const int seg = seg_of(d, n1 + k2, nseg);
@@ -976,31 +1024,21 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
     bar_wait(sm.bars, kBarCFull + d * kMaxAB + buf, (cfull_phase >> buf) & 1u);
     cfull_phase ^= 1u << buf;
     PROF_MARK(0);
-    if (lane == 0) bulk_wait_read<1>();   // the stores that last read these out buffers are done
-    __syncwarp();
-    const uint32_t ab = sm.abuf + (uint32_t)((d * NAB + buf) * kSeg) * ROWB;
-    // buffer row j holds the frame of step j: frame row r = j (d = 0) or rows-1-j (d = 1)
-    const int rsign = d == 0 ? 1 : -1, rbase = d == 0 ? 0 : rows - 1;
-    // blank sums of both utterances
-    p2 bs = pk(0.f, 0.f);
-    {
-      const uint32_t pb = sm.pbk + 4u * (uint32_t)(((d * NAB + buf) * kSeg + frm) * kPbkRow + 2 * (qtr * 8));
+    if (act) {
+      if (lane == 0) bulk_wait_read<1>();   // the store that last read this out buffer is done
+      __syncwarp();
+      const uint32_t ab = sm.abuf + (uint32_t)((d * NAB + buf) * kSeg) * ROWB;
+      const uint32_t ot = sm.out + 4u * (uint32_t)(((d * 2 + ob) * 2 + ux) * rawsz);
+      // buffer row j holds the frame of step j: frame row r = j (d = 0) or rows-1-j (d = 1)
+      const int rsign = d == 0 ? 1 : -1, rbase = d == 0 ? 0 : rows - 1;
+      // blank partial sums: 8 loads in flight while the label passes run
+      float bq[8];
+      {
+        const uint32_t pb = sm.pbk + 4u * (uint32_t)(((d * NAB + buf) * kSeg + frm) * kPbkRow + 2 * (qtr * 8) + ux);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) bs = add2(bs, lds64(pb + 8u * q));
-    }
-    float bsv[2] = {lo(bs), hi(bs)};
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (frm >= rows) bsv[u] = 0.f;
-      float t = bsv[u] + __shfl_xor_sync(kFull, bsv[u], 8);
-      t += __shfl_xor_sync(kFull, t, 16);
-      const float part = bsv[u];
-      bsv[u] = t;                       // full blank sum of step frm
-      if (!act[u]) continue;            // uniform
-      const uint32_t ot = sm.out + 4u * (uint32_t)(((d * 2 + ob) * 2 + u) * rawsz);
-      float tot = part;
-      const int npass = (nslots[u] + 31) >> 5;
-      const uint32_t xt = sm.xtab + 16u * (uint32_t)(((d * 2 + u) * kMaxPass) * 32 + lane);
+        for (int q = 0; q < 8; ++q) bq[q] = lds(pb + 8u * q);
+      }
+      float tot = 0.f;
 #pragma unroll 1
       for (int p = 0; p < npass; ++p) {
         uint32_t w0, w1, w2, w3;
@@ -1017,11 +1055,11 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
         }
 #pragma unroll
         for (int j = 0; j < kSeg; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 1), lk1, c[j]);
-        if (maxch[u] > 2) {
+        if (maxch > 2) {
 #pragma unroll
           for (int j = 0; j < kSeg; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 2), lk2, c[j]);
         }
-        if (maxch[u] > 4) {
+        if (maxch > 4) {
 #pragma unroll
           for (int j = 0; j < kSeg; ++j) c[j] = fmaf(__shfl_down_sync(kFull, c[j], 4), lk4, c[j]);
         }
@@ -1031,65 +1069,64 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
 #pragma unroll
           for (int j = 0; j < kSeg; ++j) {
             if (j < rows) {
-              sts(dsto, c[j] * kappa[u]);
+              sts(dsto, c[j] * kappa);
               tot += c[j];
             }
             dsto += dstep;
           }
         }
       }
-      if (frm < rows && qtr == 0)
-        sts(ot + 4u * (uint32_t)((rbase + rsign * frm) * C) + blank_ofs, bsv[u] * kappa[u]);
+      float bs = ((bq[0] + bq[1]) + (bq[2] + bq[3])) + ((bq[4] + bq[5]) + (bq[6] + bq[7]));
+      if (frm >= rows) bs = 0.f;
+      tot += bs;
+      bs += __shfl_xor_sync(kFull, bs, 8);
+      bs += __shfl_xor_sync(kFull, bs, 16);   // full blank sum of step frm
+      if (frm < rows && qtr == 0) sts(ot + 4u * (uint32_t)((rbase + rsign * frm) * C) + blank_ofs, bs * kappa);
       // certificate: the posteriors of every frame sum to one, i.e. the segment sums to rows * Zm
       tot = warp_sum(tot);
-      if (!(fabsf(tot - (float)rows * Zm[u]) <= 2e-5f * (float)rows * Zm[u])) bad |= 8 << u;
-    }
-    __syncwarp();
-    if (lane == 0) bar_arrive(sm.bars, kBarAEmpty + d * kMaxAB + buf);   // products / partials consumed
-    const int n = rows * C;
-    bool fenced = false;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (!act[u] || (u == 1 && cx.b[1] == cx.b[0])) continue;
-      float* dst = a.gradE + ((size_t)cx.b[u] * T + (size_t)seg * kSeg) * C;
-      const uint32_t ot = sm.out + 4u * (uint32_t)(((d * 2 + ob) * 2 + u) * rawsz);
-      const bool tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
-      if (tma) {
-        if (!fenced) { fence_proxy_async_smem(); __syncwarp(); }
-        fenced = true;
-        if (lane == 0)
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ot),
-                       "r"((uint32_t)n * 4u)
-                       : "memory");
-      } else {
-        const float* src = sm.out_gen + (size_t)((d * 2 + ob) * 2 + u) * rawsz;
-        for (int q = lane; q < n; q += 32) dst[q] = src[q];
+      if (!(fabsf(tot - (float)rows * Zm) <= 2e-5f * (float)rows * Zm)) bad = 8;
+      __syncwarp();
+      if (lane == 0) bar_arrive(sm.bars, kBarAEmpty + d * kMaxAB + buf);   // products / partials consumed
+      if (!dup) {
+        const int n = rows * C;
+        float* dst = gE + (size_t)seg * kSeg * C;
+        const bool tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
+        if (tma) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ot),
+                         "r"((uint32_t)n * 4u)
+                         : "memory");
+        } else {
+          const float* src = sm.out_gen + (size_t)((d * 2 + ob) * 2 + ux) * rawsz;
+          for (int q = lane; q < n; q += 32) dst[q] = src[q];
+        }
       }
+      if (lane == 0) bulk_commit();   // one group per segment (possibly empty)
+      __syncwarp();
+    } else {
+      if (lane == 0) bar_arrive(sm.bars, kBarAEmpty + d * kMaxAB + buf);
     }
-    if (lane == 0) bulk_commit();   // one group per segment (possibly empty)
-    __syncwarp();
   }
   PROF_MARK(1);
 #ifdef WFST_PROFILE
-  if (blockIdx.x == 0 && lane == 0) printf("X%d cycles: wait_cfull %lld compute %lld\n", d, pf_acc[0], pf_acc[1]);
+  if (blockIdx.x == 0 && lane == 0) printf("X%d.%d cycles: wait_cfull %lld compute %lld\n", d, ux, pf_acc[0], pf_acc[1]);
 #endif
   if (lane == 0) bulk_wait_all<0>();
   bad = __reduce_or_sync(kFull, (unsigned)bad);
-  if (bad && lane == 0) {
-    if (bad & 8) atomicOr(&a.hazard[cx.b[0]], 8);
-    if ((bad & 16) && cx.b[1] != cx.b[0]) atomicOr(&a.hazard[cx.b[1]], 8);
-  }
+  if (bad && lane == 0 && !dup) atomicOr(&a.hazard[bu], 8);
 }
 
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
 template <int K, int CS>
-__global__ void __launch_bounds__(256, 1) ctc_pair_kernel(Args a) {
+__global__ void __launch_bounds__(384, 1) ctc_pair_kernel(Args a) {
   extern __shared__ __align__(16) float smem_raw[];
   constexpr int Sp = 32 * K;
   const int warp = threadIdx.x >> 5;
-  const int NT = 256;
+  const int NT = 384;
   const int C = a.C;
   Ctx cx;
   cx.lane = threadIdx.x & 31;
@@ -1125,7 +1162,7 @@ __global__ void __launch_bounds__(256, 1) ctc_pair_kernel(Args a) {
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumBars; ++i) {
-      const bool two = i >= kBarPEmpty && i < kBarPEmpty + 2 * kNB;
+      const bool two = (i >= kBarPEmpty && i < kBarPEmpty + 2 * kNB) || (i >= kBarAEmpty && i < kBarAEmpty + 2 * kMaxAB);
       bar_init(sm.bars, i, two ? 2u : 1u);
     }
     fence_barrier_init();
@@ -1203,10 +1240,12 @@ __global__ void __launch_bounds__(256, 1) ctc_pair_kernel(Args a) {
   if (!cx.live[0]) { cx.y[0] = cx.y[1]; cx.L[0] = cx.L[1]; }
   if (!cx.live[1]) { cx.y[1] = cx.y[0]; cx.L[1] = cx.L[0]; }
 
+  // warp -> scheduler partition is warp % 4: each partition gets one of {L0, L1, RC0.0, RC1.0},
+  // one of the second recompute warps / producers and one reduction warp
   if (warp < 2) role_live<K, CS>(a, sm, cx, warp);
-  else if (warp < 4) role_rc<K, CS>(a, sm, cx, warp - 2);
-  else if (warp < 6) role_reduce<K>(a, sm, cx, warp - 4);
-  else role_producer<CS>(a, sm, cx, warp - 6);
+  else if (warp < 6) role_rc<K, CS>(a, sm, cx, warp & 1, (warp - 2) >> 1);     // RC0.0 RC1.0 RC0.1 RC1.1
+  else if (warp < 10) role_reduce<K>(a, sm, cx, warp & 1, (warp - 6) >> 1);    // X0.0 X1.0 X0.1 X1.1
+  else role_producer<CS>(a, sm, cx, warp - 10);
 }
 
 static int pick_k(int max_target_len) {
@@ -1236,7 +1275,7 @@ static int launch_kc(const Args& a, cudaStream_t st) {
   const size_t smem = make_layout(K, a.C, CS, a.NAB).total * sizeof(float);
   auto kern = ctc_pair_kernel<K, CS>;
   WFST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(a.B + 1) / 2, 256, smem, st>>>(a);
+  kern<<<(a.B + 1) / 2, 384, smem, st>>>(a);
   g_launches++;
   WFST_CUDA_CHECK(cudaGetLastError());
   return WFST_OK;

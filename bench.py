@@ -14,8 +14,10 @@ the scalar loss per step.  Rank 0 prints ONE JSON line.
 
 Timing: W >= 3 warm-up steps, then K steps bracketed by barrier + synchronize, timed
 with CUDA events on the launching (current) stream, max over ranks.  The inputs
-rotate over ROT distinct batches (ROT x 30.7 MB > the 126 MB L2) and each step also
-streams the > L2 alpha history, so no step finds its inputs in L2.
+rotate over ROT distinct batches (ROT x 30.7 MB > the 126 MB L2), so no step finds its
+inputs in L2.  Besides the contract's keys the line carries `ctc_module_on_logits`: the
+step the reference's CTC module runs (log_softmax + loss + backward to the logits,
+criterions/ctc.py:107) with the log-softmax fused into the kernel and as two steps.
 """
 import argparse
 import json
@@ -276,6 +278,44 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
 
+    # ---- the CTC module on logits (device resident): fused log-softmax vs log_softmax + CTCLoss
+    module_line = None
+    if world == 1:
+        from gtn_applications_b200.criterions.ctc import CTCLogitsLoss, CTCLogitsLossFunction
+        xs = [torch.randn(B, T, C, device=dev, generator=torch.Generator(device=dev).manual_seed(50 + r))
+              for r in range(ROT)]
+        tgl = batches[0][3].tolist()
+
+        def fused(i):
+            x = xs[i % ROT].requires_grad_(True)
+            x.grad = None
+            CTCLogitsLoss(x, tgl, C - 1, "mean").backward()
+
+        def two_step(i):
+            x = xs[i % ROT].requires_grad_(True)
+            x.grad = None
+            CTCLoss(torch.log_softmax(x, 2), tgl, C - 1, "mean").backward()
+
+        def time_it(fn, n):
+            for i in range(3):
+                fn(i)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for i in range(n):
+                fn(i)
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / n
+
+        n_mod = max(3, min(args.steps, 30))
+        if CTCLogitsLossFunction.supported(xs[0], tgl):
+            f_ms, t_ms = time_it(fused, n_mod), time_it(two_step, n_mod)
+            module_line = {"fused_ms_per_step": f_ms, "two_step_ms_per_step": t_ms,
+                           "fused_utterances_per_s": B / (f_ms * 1e-3), "steps": n_mod,
+                           "what": "CTC module step on [B,T,C] logits in HBM incl. Python/launch overhead: "
+                                   "CTCLogitsLoss vs CTCLoss(log_softmax(x))"}
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         alg_bytes = 8.0 * T * C * B            # read E once + write grad once
@@ -305,6 +345,8 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": kern_ms},
         }
+        if module_line is not None:
+            line["ctc_module_on_logits"] = module_line
         if world == 1 and not args.no_cpu_baseline:
             base, _, _ = cpu_baseline_run(args.workload, args.cpu_seconds)
             line["cpu_baseline"] = base

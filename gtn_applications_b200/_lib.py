@@ -39,6 +39,9 @@ SIGNATURES = {
     "wfst_debug_ctc_hazards": (_I, [_P, _I, _I, _I, _I, _P]),
     "wfst_ctc_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "wfst_ctc_forward_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "wfst_ctc_logits_supported": (_I, [_I, _I, _I, _I]),
+    "wfst_ctc_logits_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "wfst_ctc_logits_forward_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "wfst_ctc_forward_backward_host": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "wfst_lattice_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "wfst_lattice_forward_backward": (_I, [_P, _I, _I, _I, ctypes.POINTER(AcceptorBatch), _I, _P, _P,

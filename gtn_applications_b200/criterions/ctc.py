@@ -86,6 +86,63 @@ class CTCLossFunction(torch.autograd.Function):
 CTCLoss = CTCLossFunction.apply
 
 
+class CTCLogitsLossFunction(torch.autograd.Function):
+    """``CTCLoss(log_softmax(inputs, 2), targets, blank_idx, reduction)`` — what
+    ``CTC.forward`` computes (criterions/ctc.py:107 followed by ctc.py:31-94) — as ONE
+    kernel on raw logits (wfst_ctc_logits_forward_backward): the log-softmax is applied
+    to the tiles as they are staged, and the gradient that comes back is already
+    d loss / d inputs = scale * (softmax - posterior), the form the reference's golden
+    tests check (tests/gtn_ctc_test.py:64-80).  Shapes the fused kernel does not
+    handle (``supported`` is False) must use log_softmax + CTCLoss."""
+
+    @staticmethod
+    def supported(inputs, targets):
+        if not (inputs.is_cuda and inputs.dtype == torch.float32 and inputs.dim() == 3):
+            return False
+        B, T, C = inputs.shape
+        max_len = max((len(t) for t in targets), default=0)
+        return bool(_lib.lib().wfst_ctc_logits_supported(B, T, C, max_len))
+
+    @staticmethod
+    def forward(ctx, inputs, targets, blank_idx=0, reduction="none"):
+        if inputs.dim() != 3:
+            raise ValueError("inputs must be [B, T, C]")
+        B, T, C = inputs.shape
+        rt.require_cuda(inputs, "inputs")
+        scales = rt.reduction_scales(reduction, [len(t) for t in targets])
+        if len(targets) != B:
+            raise ValueError("need one target sequence per batch entry")
+        if not 0 <= blank_idx < C:
+            raise ValueError("blank_idx outside [0, C)")
+        e = rt.to_device(inputs.detach())
+        dev = e.device
+        with torch.cuda.device(dev):
+            flat, offsets, _, max_len = rt.pack_targets(targets, C, dev)
+            L = _lib.lib()
+            if not L.wfst_ctc_logits_supported(B, T, C, max_len):
+                raise NotImplementedError("fused logits CTC does not handle this shape; use log_softmax + CTCLoss")
+            gscale = torch.tensor([s / B for s in scales], dtype=torch.float32).to(dev)
+            out = torch.empty(B + 1, dtype=torch.float32, device=dev)
+            need_grad = inputs.requires_grad
+            grad = torch.empty_like(e) if need_grad else None
+            ws = rt.workspace(dev, L.wfst_ctc_logits_workspace_bytes(B, T, C, max_len))
+            _lib.check(L.wfst_ctc_logits_forward_backward(
+                e.data_ptr(), flat.data_ptr(), offsets.data_ptr(), B, T, C, int(blank_idx),
+                max_len, gscale.data_ptr(), out.data_ptr(), out[B:].data_ptr(),
+                grad.data_ptr() if need_grad else None, ws.data_ptr(), ws.numel(),
+                rt.stream_ptr(dev)))
+        ctx.grad = grad
+        ctx.input_device = inputs.device
+        ctx.per_utterance_loss = out[:B]
+        loss = out[B]
+        return loss if inputs.is_cuda else loss.cpu()
+
+    backward = staticmethod(CTCLossFunction.backward)
+
+
+CTCLogitsLoss = CTCLogitsLossFunction.apply
+
+
 class CTC(torch.nn.Module):
     """criterions/ctc.py:100-135.  `use_pt` selects torch's ctc_loss exactly as
     the reference does; otherwise the B200 kernel is used."""
@@ -96,6 +153,11 @@ class CTC(torch.nn.Module):
         self.use_pt = use_pt
 
     def forward(self, inputs, targets):
+        if not self.use_pt:
+            tg = [t.tolist() for t in targets]
+            if CTCLogitsLossFunction.supported(inputs, tg):
+                # log_softmax fused into the kernel (same value and gradient as the two steps below)
+                return CTCLogitsLoss(inputs, tg, self.blank, "mean")
         log_probs = torch.nn.functional.log_softmax(inputs, dim=2)
         if self.use_pt:
             lengths = [t.numel() for t in targets]

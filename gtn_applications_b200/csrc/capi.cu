@@ -112,7 +112,7 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
     int* hazard = nullptr;
     void* fws = (char*)workspace + hb + align_up((size_t)B * sizeof(float), 256);
     rc = kind == 2 ? launch_ctc_pair(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
-                                     grad_scale, z, grad, fws, &hazard, st)
+                                     grad_scale, z, grad, fws, &hazard, 0, st)
                    : launch_ctc_fast(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
                                      grad_scale, z, grad, fws, &hazard, st);
     if (rc != WFST_OK) return rc;
@@ -123,6 +123,65 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
                     z, grad, hist, nullptr, st);
   }
   if (rc != WFST_OK) return rc;
+  return launch_finalize(z, nullptr, -1.f, B, grad_scale, loss, mean_loss, st);
+}
+
+
+// ------------------------------------------------- CTC on logits (fused log_softmax)
+// workspace: [CTC workspace][log-probabilities of flagged utterances B*T*C][their d/d log-prob B*T*C]
+int wfst_ctc_logits_supported(int B, int T, int C, int max_target_len) {
+  (void)B;
+  return (!g_force_generic && g_force_generic_kind != 2 && ctc_pair_fused_eligible(T, C, max_target_len)) ? 1 : 0;
+}
+
+size_t wfst_ctc_logits_workspace_bytes(int B, int T, int C, int max_target_len) {
+  return wfst_ctc_workspace_bytes(B, T, C, max_target_len) + 2 * align_up((size_t)B * T * C * sizeof(float), 256);
+}
+
+int wfst_ctc_logits_forward_backward(const float* logits, const int32_t* targets,
+                                     const int32_t* target_offsets, int B, int T, int C, int blank,
+                                     int max_target_len, const float* grad_scale, float* loss,
+                                     float* mean_loss, float* grad, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  WFST_REQUIRE(logits && target_offsets && workspace, "null pointer argument");
+  WFST_REQUIRE(targets || max_target_len == 0, "null targets");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0 && max_target_len >= 0, "bad shape B=%d T=%d C=%d L=%d",
+               B, T, C, max_target_len);
+  WFST_REQUIRE(blank >= 0 && blank < C, "blank %d outside [0,%d)", blank, C);
+  if (!wfst_ctc_logits_supported(B, T, C, max_target_len)) {
+    set_error("fused logits path unsupported for T=%d C=%d L=%d (use log_softmax + wfst_ctc_forward_backward)",
+              T, C, max_target_len);
+    return WFST_ERR_UNSUPPORTED;
+  }
+  WFST_REQUIRE(((uintptr_t)logits & 15) == 0 && ((uintptr_t)grad & 15) == 0, "logits / grad must be 16-byte aligned");
+  if (workspace_bytes < wfst_ctc_logits_workspace_bytes(B, T, C, max_target_len)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes,
+              wfst_ctc_logits_workspace_bytes(B, T, C, max_target_len));
+    return WFST_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* hist = (float*)workspace;
+  const size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1);
+  float* z = (float*)((char*)workspace + hb);
+  void* fws = (char*)workspace + hb + align_up((size_t)B * sizeof(float), 256);
+  const size_t nE = align_up((size_t)B * T * C * sizeof(float), 256);
+  float* lsm = (float*)((char*)workspace + wfst_ctc_workspace_bytes(B, T, C, max_target_len));
+  float* glp = (float*)((char*)lsm + nE);
+  int* hazard = nullptr;
+  int rc = launch_ctc_pair(logits, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
+                           z, grad, fws, &hazard, 1, st);
+  if (rc != WFST_OK) return rc;
+  // utterances the scaled kernel flagged: materialise their log-probabilities, run the
+  // log-semiring kernel on them, chain back to logits (blocks of unflagged utterances exit at once)
+  rc = launch_lsm_rows(logits, hazard, B, T, C, lsm, st);
+  if (rc != WFST_OK) return rc;
+  rc = launch_ctc(lsm, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale, z,
+                  grad ? glp : nullptr, hist, hazard, st);
+  if (rc != WFST_OK) return rc;
+  if (grad) {
+    rc = launch_lsm_backward(lsm, glp, hazard, B, T, C, grad, st);
+    if (rc != WFST_OK) return rc;
+  }
   return launch_finalize(z, nullptr, -1.f, B, grad_scale, loss, mean_loss, st);
 }
 

@@ -79,6 +79,7 @@ struct Args {
   float* ckpt;      // [blocks][nseg][32][2K+4]
   int* hazard;      // [B]
   int nseg, nA, NAB;
+  int fused;        // 1: E holds raw logits; the kernel applies log_softmax and returns d/d logits
 };
 
 // ---- packed pairs -----------------------------------------------------------------
@@ -171,7 +172,9 @@ constexpr int kBarAFull = kBarTma + 2 * kNR;       // [2][kMaxAB] abar segment r
 constexpr int kBarCFull = kBarAFull + 2 * kMaxAB;  // [2][kMaxAB] products ready (RC -> X)
 constexpr int kBarAEmpty = kBarCFull + 2 * kMaxAB; // [2][kMaxAB] segment buffer free (X -> L)
 constexpr int kBarZ = kBarAEmpty + 2 * kMaxAB;     // Z published (L1 -> everyone)
-constexpr int kNumBars = kBarZ + 1;
+constexpr int kSD = 8;                             // > the furthest P can run ahead of X (kNB + kMaxAB tiles)
+constexpr int kBarSDone = kBarZ + 1;               // [2][kSD]    fused mode: softmax tile of phase-2 tile i is in HBM (P -> X)
+constexpr int kNumBars = kBarSDone + 2 * kSD;
 
 __device__ __forceinline__ void bar_init(uint32_t bars, int idx, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * idx), "r"(count));
@@ -568,22 +571,78 @@ __device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, con
     // the certificate
     const float base0 = (mx0 == kNegInf) ? 0.f : mx0, base1 = (mx1 == kNegInf) ? 0.f : mx1;
     const float nb0 = -base0 * 1.4426950408889634f, nb1 = -base1 * 1.4426950408889634f;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int i2 = 0; i2 < NPL; ++i2) {
-      const float q0 = ex2_fast(fmaf(ev0[i2], 1.4426950408889634f, nb0));
-      const float q1 = ex2_fast(fmaf(ev1[i2], 1.4426950408889634f, nb1));
+      ev0[i2] = ex2_fast(fmaf(ev0[i2], 1.4426950408889634f, nb0));   // masked elements: 2^-inf = 0
+      ev1[i2] = ex2_fast(fmaf(ev1[i2], 1.4426950408889634f, nb1));
+      s0 += ev0[i2];
+      s1 += ev1[i2];
       if (live && i2 < cnt) {
-        sts(pt + 4u * i2, q0);
-        sts(pt + 4u * (CS + 1) + 4u * i2, q1);
+        sts(pt + 4u * i2, ev0[i2]);
+        sts(pt + 4u * (CS + 1) + 4u * i2, ev1[i2]);
       }
     }
-    if (live && part == 0 && phase1) {
+    if (a.fused) {
+      // E holds logits: log_softmax(x)_c = x_c - max - log(sum_c 2^...).  The recursion runs on the
+      // unnormalised p, so log Z = log Z~ - sum_t log s_t; d loss / d logits = gs * (p / s - posterior):
+      // the first term leaves from here (the staged raw tile is overwritten in place and stored),
+      // X adds the second with a bulk reduce once this store is known to have landed.
+      s0 += __shfl_xor_sync(kFull, s0, 8);
+      s1 += __shfl_xor_sync(kFull, s1, 8);
+      s0 += __shfl_xor_sync(kFull, s0, 16);
+      s1 += __shfl_xor_sync(kFull, s1, 16);
+      if (live && part == 0 && phase1) {
+        ps.msum[0] -= (double)logf(s0);
+        ps.msum[1] -= (double)logf(s1);
+      }
+      if (!phase1) {
+        if (i > 0) {   // the previous tile's store has landed: tell X
+          if (lane == 0) {
+            bulk_wait_all<0>();
+            bar_arrive(sm.bars, kBarSDone + d * kSD + ((i - 1) % kSD));
+          }
+          __syncwarp();
+        }
+        const float g0 = (a.grad_scale ? a.grad_scale[cx.b[0]] : 1.f) / s0;
+        const float g1 = (a.grad_scale ? a.grad_scale[cx.b[1]] : 1.f) / s1;
+#pragma unroll
+        for (int i2 = 0; i2 < NPL; ++i2) {
+          if (live && i2 < cnt) {
+            sts(er0 + 4u * i2, ev0[i2] * g0);
+            sts(er1 + 4u * i2, ev1[i2] * g1);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)rows * C * 4u;
+          const uint32_t src0 = raw0 + 4u * (uint32_t)(slot * 2) * rawsz;
+          float* dst0 = a.gradE + ((size_t)cx.b[0] * T + (size_t)tile * kSeg) * C;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst0), "r"(src0), "r"(bytes) : "memory");
+          if (cx.b[1] != cx.b[0]) {
+            float* dst1 = a.gradE + ((size_t)cx.b[1] * T + (size_t)tile * kSeg) * C;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst1), "r"(src0 + 4u * rawsz), "r"(bytes) : "memory");
+          }
+          bulk_commit();
+          bulk_wait_read<0>();   // the staging slot may be refilled
+        }
+        __syncwarp();
+      }
+    } else if (live && part == 0 && phase1) {
       ps.msum[0] += (double)base0;
       ps.msum[1] += (double)base1;
     }
     __syncwarp();
     if (lane == 0) bar_arrive(sm.bars, kBarPFull + d * kNB + buf);
     ++ps.converted;
+  }
+  if (a.fused && !phase1 && kcnt > 0) {
+    if (lane == 0) {
+      bulk_wait_all<0>();
+      bar_arrive(sm.bars, kBarSDone + d * kSD + ((kcnt - 1) % kSD));
+    }
+    __syncwarp();
   }
   PROF_MARK(2);
 #ifdef WFST_PROFILE
@@ -1091,7 +1150,16 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
         const int n = rows * C;
         float* dst = gE + (size_t)seg * kSeg * C;
         const bool tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
-        if (tma) {
+        if (a.fused) {
+          // the softmax term of this tile is already in HBM (P<d> stored it; SDone says it landed)
+          bar_wait(sm.bars, kBarSDone + d * kSD + (k2 % kSD), (uint32_t)(k2 / kSD) & 1u);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(ot),
+                         "r"((uint32_t)n * 4u)
+                         : "memory");
+        } else if (tma) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0)
@@ -1310,6 +1378,13 @@ int launch_ctc_pair_cs32(const pairk::Args& a, int K, cudaStream_t st);
 int launch_ctc_pair_cs64(const pairk::Args& a, int K, cudaStream_t st);
 int launch_ctc_pair_cs128(const pairk::Args& a, int K, cudaStream_t st);
 
+// fused log-softmax mode moves gradient tiles with bulk copies only: every tile must be
+// 16-byte aligned and a multiple of 16 bytes long
+bool ctc_pair_fused_eligible(int T, int C, int max_target_len) {
+  if (!ctc_pair_eligible(T, C, max_target_len)) return false;
+  return ((size_t)T * C) % 4 == 0 && ((size_t)(T % pairk::kSeg) * C) % 4 == 0;
+}
+
 bool ctc_pair_eligible(int T, int C, int max_target_len) {
   if (T < 1) return false;
   const int K = pairk::pick_k(max_target_len), CS = pairk::pick_cs(C);
@@ -1326,7 +1401,7 @@ size_t ctc_pair_workspace_bytes(int B, int T, int max_target_len) {
 
 int launch_ctc_pair(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                     int blank, int max_target_len, const float* grad_scale, float* z_out,
-                    float* gradE, void* workspace, int** hazard_out, cudaStream_t st) {
+                    float* gradE, void* workspace, int** hazard_out, int fused, cudaStream_t st) {
   using namespace pairk;
   const int K = pick_k(max_target_len), CS = pick_cs(C);
   Args a{};
@@ -1335,6 +1410,7 @@ int launch_ctc_pair(const float* E, const int* targets, const int* offsets, int 
   a.nseg = (T + kSeg - 1) / kSeg;
   a.nA = a.nseg / 2;
   a.NAB = pick_nab(K, C, CS);
+  a.fused = fused;
   a.ckpt = (float*)workspace;
   a.hazard = (int*)((char*)workspace +
                     align_up((size_t)((B + 1) / 2) * a.nseg * 32 * (2 * K + 4) * sizeof(float), 256));

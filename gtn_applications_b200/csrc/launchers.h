@@ -30,10 +30,18 @@ int launch_ctc_fast(const float* E, const int* targets, const int* offsets, int 
                     float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
 // paired fast CTC (ctc_pair.cu): two utterances per block, packed FP32 arithmetic
 bool ctc_pair_eligible(int T, int C, int max_target_len);
+bool ctc_pair_fused_eligible(int T, int C, int max_target_len);
 size_t ctc_pair_workspace_bytes(int B, int T, int max_target_len);
+// fused != 0: E holds raw logits, the kernel applies log_softmax over C itself and gradE
+// receives d/d logits (criterions/ctc.py:107 followed by ctc.py:31-94)
 int launch_ctc_pair(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                     int blank, int max_target_len, const float* grad_scale, float* z_out,
-                    float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
+                    float* gradE, void* workspace, int** hazard_out, int fused, cudaStream_t st);
+// log_softmax rows / its backward for the utterances with active[b] != 0 (lsm.cu): the
+// fallback of the fused mode
+int launch_lsm_rows(const float* x, const int* active, int B, int T, int C, float* out, cudaStream_t st);
+int launch_lsm_backward(const float* lsm, const float* g, const int* active, int B, int T, int C,
+                        float* out, cudaStream_t st);
 // best path (viterbi.cu)
 size_t viterbi_workspace_bytes(int B, int T, int max_nodes);
 int launch_viterbi(const float* E, int B, int T, int C, const wfst_acceptor_batch_t& g, int shared,

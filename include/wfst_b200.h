@@ -52,7 +52,8 @@ extern "C" {
 /* thread-local message of the last error returned on this thread ("" if none) */
 WFST_API const char* wfst_last_error(void);
 WFST_API int wfst_abi_version(void);
-/* test hook: 1 = run CTC on the log-semiring lattice kernel only (returns the old value) */
+/* test hook: 1 = run CTC on the log-semiring lattice kernel only, 2 = skip the paired
+ * scaled-probability kernel (use the single-utterance one), 0 = default (returns the old value) */
 WFST_API int wfst_debug_force_generic_ctc(int on);
 /* test hook: copies the per-utterance fallback flags of the last CTC call that used
  * `workspace` to the host (1 = recomputed by the log-semiring kernel, -1 = fast path not used) */
@@ -86,6 +87,21 @@ WFST_API int wfst_ctc_forward_backward(const float* emissions, const int32_t* ta
                               int max_target_len, const float* grad_scale, float* loss,
                               float* mean_loss, float* grad, void* workspace,
                               size_t workspace_bytes, void* stream);
+
+/* CTC on raw logits — replaces CTC.forward's log_softmax (criterions/ctc.py:107) followed by
+ * CTCLossFunction (ctc.py:31-94) and the softmax backward autograd runs after it:
+ *   logits [B, T, C] float32 (16-byte aligned), grad [B, T, C] out or NULL:
+ *   grad_scale[b] * (softmax(logits[b]) - posterior), i.e. d(loss_b)/d logits.
+ * Everything else as wfst_ctc_forward_backward.  Only shapes for which
+ * wfst_ctc_logits_supported() returns 1 are handled (WFST_ERR_UNSUPPORTED otherwise; the
+ * caller then composes log_softmax with wfst_ctc_forward_backward). */
+WFST_API int wfst_ctc_logits_supported(int B, int T, int C, int max_target_len);
+WFST_API size_t wfst_ctc_logits_workspace_bytes(int B, int T, int C, int max_target_len);
+WFST_API int wfst_ctc_logits_forward_backward(const float* logits, const int32_t* targets,
+                                     const int32_t* target_offsets, int B, int T, int C, int blank,
+                                     int max_target_len, const float* grad_scale, float* loss,
+                                     float* mean_loss, float* grad, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 
 /* Same computation with HOST buffers: copies inputs to the device, runs the
  * kernels and copies loss / mean_loss (and grad when not NULL) back, then

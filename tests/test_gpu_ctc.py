@@ -148,3 +148,95 @@ def test_full_size_properties():
     ref = torch.nn.functional.ctc_loss(lp.detach().permute(1, 0, 2), tg.cuda(), [T] * B, [L] * B,
                                        blank=C - 1, reduction="none").mean()
     assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+
+
+# --------------------------------------------------------------------------- kernels / dispatch
+def _hazards(B, T, C, L):
+    from gtn_applications_b200 import _lib, _runtime as rt
+    flags = np.zeros(B, dtype=np.int32)
+    ws = rt.workspace(torch.device("cuda:0"), _lib.lib().wfst_ctc_workspace_bytes(B, T, C, L))
+    _lib.check(_lib.lib().wfst_debug_ctc_hazards(ws.data_ptr(), B, T, C, L, flags.ctypes.data))
+    return flags
+
+
+@pytest.mark.parametrize("kind", [0, 2, 1])   # default (paired kernel), single-utterance scaled kernel, log-semiring only
+@pytest.mark.parametrize("B,T,C,lens,scale", [
+    (5, 203, 30, [40, 3, 77, 95, 0], 1.0),          # odd B: the last pair block runs one utterance twice
+    (4, 160, 12, [9, 30, 1, 22], 1.0),
+    (3, 120, 30, [30, 30, 30], 6.0),                # steep scores: utterances leave the scaled kernels
+    (2, 96, 70, [20, 47], 1.0),                     # C > 31: wider p tiles
+])
+def test_every_ctc_kernel_against_numpy_dp(kind, B, T, C, lens, scale):
+    """The three CTC kernels (and the hand-off between them) against the closed-form float64 DP."""
+    import dp_numpy
+    from gtn_applications_b200 import _lib
+    rng = np.random.default_rng(7 * B + T)
+    lp = G.log_softmax(rng.standard_normal((B, T, C)) * scale).astype(np.float32)
+    tg = [rng.integers(0, C - 1, size=n).tolist() for n in lens]
+    ref = dp_numpy.ctc(lp, tg, C - 1, "mean")
+    old = _lib.lib().wfst_debug_force_generic_ctc(kind)
+    try:
+        loss, grad = run(lp, tg, C - 1, "mean")
+    finally:
+        _lib.lib().wfst_debug_force_generic_ctc(old)
+    assert abs(loss - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert_close(grad, ref["grad"])
+
+
+def test_paired_kernel_is_the_default_and_keeps_the_benchmark_shape():
+    """At the benchmark's distribution no utterance may fall back to the log-semiring kernel."""
+    from gtn_applications_b200.criterions.ctc import CTCLoss
+    torch.manual_seed(1)
+    B, T, C, L = 16, 1000, 30, 176
+    lp = torch.log_softmax(torch.randn(B, T, C, device="cuda"), 2).requires_grad_(True)
+    CTCLoss(lp, torch.randint(C - 2, (B, L)).tolist(), C - 1, "none").backward()
+    torch.cuda.synchronize()
+    assert (_hazards(B, T, C, L) == 0).all()
+
+
+@pytest.mark.parametrize("B,T,C,lens,scale", [
+    (4, 150, 28, [20, 20, 20, 20], 1.0),
+    (5, 203, 32, [40, 3, 77, 95, 0], 1.0),          # odd B, partial last tile
+    (3, 120, 30, [30, 30, 30], 6.0),                # flagged utterances: log-softmax fallback chain
+    (2, 64, 8, [40, 3], 1.0),                       # an infeasible alignment rides with a feasible one
+])
+def test_fused_log_softmax_matches_two_step_path_and_oracle(B, T, C, lens, scale):
+    """CTCLogitsLoss(x) == CTCLoss(log_softmax(x)) in value and in d/dx (criterions/ctc.py:107,
+    tests/gtn_ctc_test.py:64-80), and both match the float64 DP pushed through the softmax."""
+    import dp_numpy
+    from gtn_applications_b200.criterions.ctc import CTCLoss, CTCLogitsLoss, CTCLogitsLossFunction
+    rng = np.random.default_rng(11 * B + T)
+    x = (rng.standard_normal((B, T, C)) * scale).astype(np.float32)
+    tg = [rng.integers(0, C - 1, size=n).tolist() for n in lens]
+    a = torch.tensor(x, device="cuda").requires_grad_(True)
+    assert CTCLogitsLossFunction.supported(a, tg)
+    la = CTCLogitsLoss(a, tg, C - 1, "mean")
+    la.backward()
+    b = torch.tensor(x, device="cuda").requires_grad_(True)
+    lb = CTCLoss(torch.log_softmax(b, 2), tg, C - 1, "mean")
+    lb.backward()
+    ref = dp_numpy.ctc(G.log_softmax(x), tg, C - 1, "mean")
+    if math.isinf(ref["loss"]):
+        assert math.isinf(la.item()) and math.isinf(lb.item())
+    else:
+        assert abs(la.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+        assert abs(la.item() - lb.item()) <= 1e-5 * abs(lb.item())
+    want = G.through_log_softmax(x, ref["grad"])
+    assert_close(a.grad.cpu().numpy(), want)
+    assert_close(b.grad.cpu().numpy(), want)
+
+
+def test_ctc_module_uses_fused_path_and_matches_torch():
+    from gtn_applications_b200.criterions.ctc import CTC
+    torch.manual_seed(3)
+    B, T, C = 6, 200, 30
+    x = torch.randn(B, T, C, device="cuda")
+    targets = [torch.randint(C - 1, (n,)) for n in (30, 12, 44, 1, 25, 60)]
+    a = x.clone().requires_grad_(True)
+    la = CTC(C - 1, False)(a, targets)
+    la.backward()
+    b = x.clone().requires_grad_(True)
+    lb = CTC(C - 1, True)(b, targets)          # torch's ctc_loss: mean over (loss_b / L_b), like reduction="mean"
+    lb.backward()
+    assert abs(la.item() - lb.item()) <= 1e-4 * abs(lb.item())
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-3, atol=1e-6)

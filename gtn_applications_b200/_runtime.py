@@ -58,7 +58,12 @@ def pack_targets(targets, num_classes, device):
         return dev[:B * L], dev[B * L:], [L] * B, L
     lengths = [len(t) for t in targets]
     total = sum(lengths)
-    flat = np.fromiter(itertools.chain.from_iterable(targets), dtype=np.int64, count=total)
+    if lengths and all(torch.is_tensor(t) for t in targets):
+        # a list of 1-D label tensors (what train.py hands to CTC.forward): one concatenation
+        # instead of per-label Python work
+        flat = torch.cat([t.detach().reshape(-1) for t in targets]).to("cpu", torch.int64).numpy()
+    else:
+        flat = np.fromiter(itertools.chain.from_iterable(targets), dtype=np.int64, count=total)
     if total and (flat.min() < 0 or flat.max() >= num_classes):
         raise ValueError("target label outside [0, %d)" % num_classes)
     host = torch.empty(total + len(lengths) + 1, dtype=torch.int32, pin_memory=torch.cuda.is_available())

@@ -153,11 +153,10 @@ class CTC(torch.nn.Module):
         self.use_pt = use_pt
 
     def forward(self, inputs, targets):
-        if not self.use_pt:
-            tg = [t.tolist() for t in targets]
-            if CTCLogitsLossFunction.supported(inputs, tg):
-                # log_softmax fused into the kernel (same value and gradient as the two steps below)
-                return CTCLogitsLoss(inputs, tg, self.blank, "mean")
+        if not self.use_pt and CTCLogitsLossFunction.supported(inputs, targets):
+            # log_softmax fused into the kernel (same value and gradient as the two steps below);
+            # the label tensors are packed without a detour through Python lists
+            return CTCLogitsLoss(inputs, list(targets), self.blank, "mean")
         log_probs = torch.nn.functional.log_softmax(inputs, dim=2)
         if self.use_pt:
             lengths = [t.numel() for t in targets]

@@ -1,0 +1,221 @@
+// Dense ASG full-connect lattice for sm_100a: emissions x the bigram transition graph of
+// ASGLossFunction.create_transitions_graph (criterions/asg.py:53-69), i.e. the denominator
+// term forward_score(intersect(g_em, g_tr)) of asg.py:114 and its gtn.backward (asg.py:158).
+// The composed lattice has T*C*C arcs (0.9 M per utterance at C=30, T=1000) but it is a
+// dense layered graph: one frame is a matrix-vector product with the C x C transition
+// matrix.  One warp per utterance, lane = label, the matrix row (and column) of the lane in
+// registers, the previous frame's vector broadcast through 128 bytes of shared memory:
+//   forward   a_t[i] = p_t[i] * sum_j W[i,j] a^_{t-1}[j],   a^_t = a_t / sum_i a_t[i]
+//   backward  b_{t-1}[j] = sum_i W[i,j] p_t[i] b^_t[i],     b^ normalised the same way
+// in the probability domain (W = exp(tr - max), p_t = exp(E_t - max_c E_t)); the removed
+// scales are accumulated in float64, so Z is exact to float32 rounding of the per-frame sums.
+// Posteriors are normalised per frame (every path crosses a frame / a frame boundary exactly
+// once), which needs no global constant:
+//   dZ/dE[t,i]   = a^_t[i] b^_t[i] / sum_i(.)
+//   dZ/dtr[i,j]  = W[i,j] * sum_t a^_{t-1}[j] p_t[i] b^_t[i] / (c_t sum_i a^_t[i] b^_t[i])
+// The forward vectors go to the caller's workspace ([T, C] per utterance, written and read
+// once, coalesced).  Handles C <= 32 and T >= 1; other shapes use the generic lattice kernel.
+#include "common.cuh"
+#include "launchers.h"
+
+namespace wfst {
+
+namespace {
+constexpr int kCP = 36;      // padded row length: a multiple of 4 whose quarter is odd
+constexpr int kWarps = 4;    // utterances per block
+constexpr int kPF = 4;       // frames of emissions / history prefetched ahead
+constexpr unsigned kAll = 0xffffffffu;
+
+__device__ __forceinline__ float dot_row(const float (&row)[kCP], const float* bc) {
+  const float4* v = reinterpret_cast<const float4*>(bc);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int q = 0; q < kCP / 4; ++q) {
+    const float4 a = v[q];   // same address in every lane: broadcast
+    s0 = fmaf(row[4 * q + 0], a.x, s0);
+    s1 = fmaf(row[4 * q + 1], a.y, s1);
+    s2 = fmaf(row[4 * q + 2], a.z, s2);
+    s3 = fmaf(row[4 * q + 3], a.w, s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+__global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
+    const float* __restrict__ E, const float* __restrict__ tr, int B, int T, int C,
+    const float* __restrict__ grad_scale, float sign, float* __restrict__ scores,
+    float* __restrict__ gradE, int accumulate, float* __restrict__ gradTr, float* __restrict__ hist) {
+  __shared__ __align__(16) float bcast[kWarps][2][kCP];
+  __shared__ float red[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * kWarps + warp;
+  const bool valid = lane < C;
+
+  // scale of the transition weights: max over the bigram part / over the start part
+  if (threadIdx.x < 32) {
+    float m = kNegInf, m0 = kNegInf;
+    for (int k = lane; k < C * C; k += 32) m = fmaxf(m, tr[C + k]);
+    for (int k = lane; k < C; k += 32) m0 = fmaxf(m0, tr[k]);
+    m = warp_max(m);
+    m0 = warp_max(m0);
+    if (lane == 0) {
+      red[0] = (m == kNegInf) ? 0.f : m;
+      red[1] = (m0 == kNegInf) ? 0.f : m0;
+    }
+  }
+  for (int k = threadIdx.x; k < kWarps * 2 * kCP; k += blockDim.x) (&bcast[0][0][0])[k] = 0.f;
+  __syncthreads();
+  const float wmax = red[0], w0max = red[1];
+  if (b >= B) return;
+
+  // row i of W (into label i from j) and column i of W (from label i into j), in registers
+  float Wr[kCP], Wc[kCP];
+#pragma unroll
+  for (int j = 0; j < kCP; ++j) {
+    Wr[j] = (valid && j < C) ? __expf(tr[C + lane * C + j] - wmax) : 0.f;
+    Wc[j] = (valid && j < C) ? __expf(tr[C + j * C + lane] - wmax) : 0.f;
+  }
+  const float w0 = valid ? __expf(tr[lane] - w0max) : 0.f;
+
+  const float* Eb = E + (size_t)b * T * C;
+  float* hA = hist + (size_t)b * T * (C + 1);   // [T][C] normalised forward vectors
+  float* hC = hA + (size_t)T * C;               // [T] their normalisers
+  float* bc0 = bcast[warp][0];
+  float* bc1 = bcast[warp][1];
+
+  // ------------------------------------------------------------------ forward
+  double logz = (double)w0max + (double)(T - 1) * (double)wmax;
+  float ahat = 0.f;
+  float xn[kPF];
+#pragma unroll
+  for (int k = 0; k < kPF; ++k) xn[k] = (valid && k < T) ? __ldg(Eb + (size_t)k * C + lane) : kNegInf;
+  for (int t0 = 0; t0 < T; t0 += kPF) {
+    float xc[kPF];
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      xc[k] = xn[k];
+      const int tn = t0 + kPF + k;
+      xn[k] = (valid && tn < T) ? __ldg(Eb + (size_t)tn * C + lane) : kNegInf;
+    }
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      const int t = t0 + k;
+      if (t >= T) break;
+      const float m = warp_max(xc[k]);
+      const float base = (m == kNegInf) ? 0.f : m;
+      const float p = valid ? __expf(xc[k] - base) : 0.f;
+      float a;
+      if (t == 0) {
+        a = p * w0;
+      } else {
+        bc0[lane] = ahat;
+        __syncwarp();
+        a = p * dot_row(Wr, bc0);
+        __syncwarp();
+      }
+      const float c = warp_sum(a);
+      ahat = c > 0.f ? a / c : 0.f;
+      logz += (double)logf(c) + (double)base;
+      if (valid) hA[(size_t)t * C + lane] = ahat;
+      if (lane == 0) hC[t] = c;
+    }
+  }
+  if (lane == 0) scores[b] = (float)logz;
+
+  if (gradE == nullptr && gradTr == nullptr) return;
+  const float gs = sign * (grad_scale ? grad_scale[b] : 1.f);
+
+  // ------------------------------------------------------------------ backward
+  float acc[kCP];
+#pragma unroll
+  for (int j = 0; j < kCP; ++j) acc[j] = 0.f;
+  float bhat = valid ? 1.f : 0.f;
+  float acur = ahat;   // a^_{T-1}
+  float xq[kPF], aq[kPF], cq[kPF];
+  // queue entry k of a chunk starting at t0 (descending): x_t, a^_{t-1}, c_t for t = t0 - k
+#pragma unroll
+  for (int k = 0; k < kPF; ++k) {
+    const int t = T - 1 - k;
+    xq[k] = (valid && t >= 0) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+    aq[k] = (valid && t >= 1) ? hA[(size_t)(t - 1) * C + lane] : 0.f;
+    cq[k] = (t >= 0) ? hC[t] : 1.f;
+  }
+  float* gEb = gradE ? gradE + (size_t)b * T * C : nullptr;
+  for (int t0 = T - 1; t0 >= 0; t0 -= kPF) {
+    float xc[kPF], ac[kPF], cc[kPF];
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      xc[k] = xq[k]; ac[k] = aq[k]; cc[k] = cq[k];
+      const int t = t0 - kPF - k;
+      xq[k] = (valid && t >= 0) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+      aq[k] = (valid && t >= 1) ? hA[(size_t)(t - 1) * C + lane] : 0.f;
+      cq[k] = (t >= 0) ? hC[t] : 1.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      const int t = t0 - k;
+      if (t < 0) break;
+      const float m = warp_max(xc[k]);
+      const float base = (m == kNegInf) ? 0.f : m;
+      const float p = valid ? __expf(xc[k] - base) : 0.f;
+      const float g = acur * bhat;
+      const float G = warp_sum(g);
+      const float gamma = G > 0.f ? g / G : 0.f;
+      if (gEb && valid) {
+        float* dst = gEb + (size_t)t * C + lane;
+        *dst = accumulate ? *dst + gs * gamma : gs * gamma;
+      }
+      if (t == 0) {
+        // arcs 0 -> i+1 (asg.py:60-62): posterior of starting in label i
+        if (gradTr && valid && gamma != 0.f) atomicAdd(&gradTr[lane], gs * gamma);
+        break;
+      }
+      const float r = p * bhat;
+      const float n = cc[k] * G;
+      const float rn = n > 0.f ? r / n : 0.f;
+      bc0[lane] = ac[k];     // a^_{t-1}
+      bc1[lane] = r;
+      __syncwarp();
+      {
+        const float4* v = reinterpret_cast<const float4*>(bc0);
+#pragma unroll
+        for (int q = 0; q < kCP / 4; ++q) {
+          const float4 a4 = v[q];
+          acc[4 * q + 0] = fmaf(a4.x, rn, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(a4.y, rn, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(a4.z, rn, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(a4.w, rn, acc[4 * q + 3]);
+        }
+      }
+      const float bn = dot_row(Wc, bc1);
+      __syncwarp();
+      const float nb = warp_sum(bn);
+      bhat = nb > 0.f ? bn / nb : 0.f;
+      acur = ac[k];
+    }
+  }
+  if (gradTr && valid) {
+    // arcs j+1 -> i+1 with weight index C + i*C + j (asg.py:63-67)
+#pragma unroll
+    for (int j = 0; j < kCP; ++j) {
+      if (j < C) {
+        const float v = gs * Wr[j] * acc[j];
+        if (v != 0.f) atomicAdd(&gradTr[C + lane * C + j], v);
+      }
+    }
+  }
+}
+}  // namespace
+
+bool asg_fcc_dense_eligible(int T, int C) { return T >= 1 && C >= 1 && C <= 32; }
+
+int launch_asg_fcc_dense(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
+                         float sign, float* scores, float* gradE, int accumulate, float* gradTr,
+                         float* hist, cudaStream_t st) {
+  asg_fcc_dense_kernel<<<(B + kWarps - 1) / kWarps, 32 * kWarps, 0, st>>>(
+      E, tr, B, T, C, grad_scale, sign, scores, gradE, accumulate, gradTr, hist);
+  g_launches++;
+  WFST_CUDA_CHECK(cudaGetLastError());
+  return WFST_OK;
+}
+
+}  // namespace wfst

@@ -302,8 +302,11 @@ int wfst_asg_forward_backward(const float* emissions, const float* transitions,
   if (grad_transitions)
     WFST_CUDA_CHECK(cudaMemsetAsync(grad_transitions, 0, (size_t)(C + 1) * C * 4, st));
   // loss = Z_fcc - Z_fal (asg.py:111-115): full-connect writes, force-align subtracts
-  int rc = launch_asg_fcc(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
-                          grad_transitions, hist, st);
+  int rc = (asg_fcc_dense_eligible(T, C) && !g_force_generic)
+               ? launch_asg_fcc_dense(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
+                                      grad_transitions, hist, st)
+               : launch_asg_fcc(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
+                                grad_transitions, hist, st);
   if (rc != WFST_OK) return rc;
   rc = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
                       grad_scale, -1.f, zfal, grad_emissions, 1, grad_transitions, hist, st);

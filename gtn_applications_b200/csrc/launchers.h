@@ -19,6 +19,11 @@ int launch_asg_fal(const float* E, const float* tr, const int* targets, const in
 int launch_asg_fcc(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
                    float sign, float* scores, float* gradE, int accumulate, float* gradTr,
                    float* hist, cudaStream_t st);
+// dense full-connect ASG lattice, one warp per utterance (asg_dense.cu); C <= 32, T >= 1
+bool asg_fcc_dense_eligible(int T, int C);
+int launch_asg_fcc_dense(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
+                         float sign, float* scores, float* gradE, int accumulate, float* gradTr,
+                         float* hist, cudaStream_t st);
 int launch_finalize(const float* za, const float* zb, float sign, int B, const float* grad_scale,
                     float* loss, float* mean_loss, cudaStream_t st);
 int launch_scale(float* x, size_t n, const float* scale, cudaStream_t st);

@@ -72,3 +72,23 @@ def test_module_replabels_garbage_and_checkpoint_names():
     assert abs(loss.item() - float(z["module_loss"])) <= 1e-4 * abs(float(z["module_loss"]))
     assert_close_f32_fixture(x.grad.cpu().numpy(), z["module_grad"])
     assert_close_f32_fixture(crit.transitions.grad.cpu().numpy(), z["module_grad_transitions"])
+
+
+@pytest.mark.parametrize("B,T,C,lens", [(5, 77, 30, [20, 1, 33, 8, 40]), (2, 9, 3, [2, 4]), (3, 130, 32, [5, 60, 17])])
+def test_dense_and_generic_full_connect_kernels_agree(B, T, C, lens):
+    """The dense warp-per-utterance full-connect kernel (C <= 32) and the generic lattice
+    kernel compute the same loss and gradients (the generic path is forced with the CTC hook)."""
+    from gtn_applications_b200 import _lib
+    rng = np.random.default_rng(B + T + C)
+    e = (rng.standard_normal((B, T, C)) * 2).astype(np.float32)
+    tr = rng.standard_normal((C + 1, C)).astype(np.float32)
+    tg = [rng.integers(0, C, size=n).tolist() for n in lens]
+    dense = run(e, tr, tg, "mean")
+    old = _lib.lib().wfst_debug_force_generic_ctc(1)
+    try:
+        generic = run(e, tr, tg, "mean")
+    finally:
+        _lib.lib().wfst_debug_force_generic_ctc(old)
+    assert abs(dense[0] - generic[0]) <= 1e-5 * abs(generic[0])
+    assert_close(dense[1], generic[1])
+    assert_close(dense[2], generic[2])

@@ -25,3 +25,29 @@ for i in range(iters): call(i)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 print("B=%d T=%d C=%d L=%d: %.4f ms per call (all kernels), %.0f utt/s, %.1f GB/s algorithmic" % (B, T, C, L, ms, B / ms * 1e3, 8.0 * B * T * C / ms / 1e6))
+if Lb.wfst_ctc_logits_supported(B, T, C, max_len):
+    xs = [torch.randn(B, T, C, device=dev) for _ in range(4)]
+    ws2 = rt.workspace(dev, Lb.wfst_ctc_logits_workspace_bytes(B, T, C, max_len))
+    def call2(i):
+        _lib.check(Lb.wfst_ctc_logits_forward_backward(xs[i % 4].data_ptr(), flat.data_ptr(), offsets.data_ptr(), B, T, C, C - 1,
+            max_len, gs.data_ptr(), out.data_ptr(), out[B:].data_ptr(), grad.data_ptr(), ws2.data_ptr(), ws2.numel(), rt.stream_ptr(dev)))
+    for i in range(5): call2(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(iters): call2(i)
+    e1.record(); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / iters
+    def two(i):
+        lp = torch.log_softmax(xs[i % 4], 2)
+        _lib.check(Lb.wfst_ctc_forward_backward(lp.data_ptr(), flat.data_ptr(), offsets.data_ptr(), B, T, C, C - 1,
+            max_len, gs.data_ptr(), out.data_ptr(), out[B:].data_ptr(), grad.data_ptr(), ws2.data_ptr(), ws2.numel(), rt.stream_ptr(dev)))
+        s = grad.sum(2, keepdim=True)
+        g = grad - torch.exp(lp) * s          # what autograd's log_softmax backward does
+        return g
+    for i in range(5): two(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(iters): two(i)
+    e1.record(); torch.cuda.synchronize()
+    ms3 = e0.elapsed_time(e1) / iters
+    print("logits path: fused %.4f ms per call; log_softmax + CTC + softmax backward (torch ops) %.4f ms" % (ms2, ms3))

@@ -284,7 +284,7 @@ def run_gpu(args):
         from gtn_applications_b200.criterions.ctc import CTCLogitsLoss, CTCLogitsLossFunction
         xs = [torch.randn(B, T, C, device=dev, generator=torch.Generator(device=dev).manual_seed(50 + r))
               for r in range(ROT)]
-        tgl = batches[0][3].tolist()
+        tgl = batches[0][3]          # [B, L] label tensor: packed without per-label Python work
 
         def fused(i):
             x = xs[i % ROT].requires_grad_(True)

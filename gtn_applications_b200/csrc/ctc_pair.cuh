@@ -5,17 +5,18 @@
 // One thread block handles TWO utterances at once.  Every value of the recursion is a
 // packed pair of floats (x = first utterance, y = second) and all arithmetic on it is a
 // packed FP32 instruction (add/mul/fma.f32x2 -> SASS FADD2 / FMUL2 / FFMA2), which halves
-// the issue slots the dependent per-frame chain needs.  Seven warps per block:
+// the issue slots the dependent per-frame chain needs.  Twelve warps per block:
 //   L0 "live alpha"  time ascending,  index j = s
 //   L1 "live beta"   time descending, index j = Sp-2-s   (mirror that keeps the parity of s)
-//   RC0, RC1         recompute the OPPOSITE recursion of L0 / L1 over a segment from a
-//                    checkpoint and multiply it, frame by frame, with what L stored
-//   X0, X1           sum a segment's per-state posteriors over states with equal label and
-//                    send the [8, C] gradient tiles to HBM (bulk async store)
-//   P                producer: TMA-loads [8, C] emission tiles of both utterances and turns
-//                    them into p[t,c] = exp(E[t,c] - max_c E[t,c]) tiles, interleaved [c][utt]
-// All four recursion warps run the SAME code: label-type states sit at odd slots in both
-// orientations, the direction is a runtime stride.  The recursion is
+//   RC<d>.0, RC<d>.1 recompute the OPPOSITE recursion of L<d> over alternate segments from a
+//                    checkpoint and multiply it, frame by frame, with what L<d> stored
+//   X<d>.<u>         sum a segment's per-state posteriors of utterance u over states with
+//                    equal label and send the [8, C] gradient tile to HBM (bulk async store)
+//   P<d>             producer of direction d: TMA-loads [8, C] emission tiles of both
+//                    utterances and turns them into p[t,c] = exp(E[t,c] - max_c E[t,c]) tiles
+//                    (one plane per utterance, rows in the order L<d> steps through them)
+// All recursion warps run the SAME code: label-type states sit at odd slots in both
+// orientations, the direction is a runtime value.  The recursion is
 //   v'[j] = (v[j] + v[j-1] + skip[j] * v[j-2]) * p_t[lab j]
 // (the beta recursion written for beta~_t(s) = p_t(lab s) * beta_t(s) is the alpha recursion
 // on the reversed target and reversed time).  Lane l owns K consecutive slots; the left
@@ -28,13 +29,16 @@
 //            checkpoint (K pairs + 2 exponents per lane) per 8-frame segment.
 //   meeting: Z = sum_s alpha(s) * (successor sum of beta~)(s) at the boundary.
 //   phase 2: L0 continues upwards through [nA, nseg) and stores the pre-emission sums
-//            ("abar") of every frame of a segment into a shared-memory ring.  RC0 then
-//            re-runs the beta recursion over that segment from L1's checkpoint, rescaled
+//            ("abar") of every frame of a segment into a shared-memory ring.  An RC0 warp
+//            then re-runs the beta recursion over that segment from L1's checkpoint, rescaled
 //            once per segment so that  w * abar = posterior * Zm  with no further factor,
 //            writes the label-state products back IN PLACE and the blank partial sums
-//            per lane next to them.  X0 gathers the products in label-sorted order
-//            (4 positions per lane, segmented suffix sums by shuffles) and stores the
-//            gradient tile.  L1 / RC1 / X1 mirror this downwards through [0, nA).
+//            per lane next to them.  X0.u gathers the products of utterance u in
+//            label-sorted order (4 positions per lane, segmented suffix sums by shuffles)
+//            and stores the gradient tile.  L1 / RC1 / X1 mirror this downwards through [0, nA).
+//   fused mode (Args::fused): E holds raw logits; the producers also form the softmax
+//            denominators, store the softmax term of the gradient themselves, and X adds
+//            the posterior term with a bulk reduce (see produce_range / role_reduce).
 //
 // Robustness: a frame's posteriors sum to one.  Every segment's total is checked against
 // rows * Z (2e-5, finite); a violation (float32 range exceeded inside a window, which can

@@ -124,8 +124,9 @@ struct AsgFalTopo {
   __device__ void init(const Params& p, int b, float* extra) {
     y = p.targets + p.offsets[b];
     L = p.offsets[b + 1] - p.offsets[b];
-    C = p.C; tr = p.tr; gradTr = p.gradTr; gtr = extra;
-    if (gradTr) for (int k = threadIdx.x; k < (C + 1) * C; k += blockDim.x) gtr[k] = 0.f;
+    C = p.C; tr = p.tr; gradTr = p.gradTr;
+    gtr = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(extra) + 7) & ~(uintptr_t)7);   // 64-bit slots
+    if (gradTr) for (int k = threadIdx.x; k < 2 * (C + 1) * C; k += blockDim.x) gtr[k] = 0.f;
     __syncthreads();
   }
   __device__ int lbl(int k) const { return min(max(y[k], 0), C - 1); }
@@ -155,12 +156,17 @@ struct AsgFalTopo {
       f(u, cur, tr[loop], loop);
     }
   }
-  __device__ void add_weight_grad(int idx, float p) const { if (gradTr) atomicAdd(&gtr[idx], p); }
+  // several nodes share a transition: accumulate in 2^-32 fixed point (64-bit shared-memory
+  // integer atomics are native; float ones are compare-and-swap loops) -- also order-independent
+  __device__ void add_weight_grad(int idx, float p) const {
+    if (gradTr) atomicAdd(reinterpret_cast<unsigned long long*>(gtr) + idx, (unsigned long long)__float2ull_rn(p * 4294967296.f));
+  }
   __device__ void finish_weight_grad(float gs) const {
     if (!gradTr) return;
     __syncthreads();
+    const unsigned long long* g64 = reinterpret_cast<const unsigned long long*>(gtr);
     for (int k = threadIdx.x; k < (C + 1) * C; k += blockDim.x)
-      if (gtr[k] != 0.f) atomicAdd(&gradTr[k], gtr[k] * gs);
+      if (g64[k] != 0ull) atomicAdd(&gradTr[k], (float)((double)g64[k] * (1.0 / 4294967296.0)) * gs);
   }
 };
 
@@ -325,7 +331,7 @@ int launch_asg_fal(const float* E, const float* tr, const int* targets, const in
                    float* scores, float* gradE, int accumulate, float* gradTr, float* hist,
                    cudaStream_t st) {
   LatticeArgs a = base_args(E, B, T, C, grad_scale, sign, scores, gradE, accumulate, hist,
-                            max_target_len + 1, gradTr ? (C + 1) * C : 0);
+                            max_target_len + 1, gradTr ? 2 * (C + 1) * C + 2 : 0);
   AsgFalTopo::Params tp{targets, offsets, tr, gradTr, C};
   return launch_lattice<AsgFalTopo>(a, tp, B, max_target_len + 1, st);
 }

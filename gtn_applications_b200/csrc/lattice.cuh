@@ -22,6 +22,8 @@
 
 namespace wfst {
 
+constexpr float kFixOne = 1073741824.f;   // 2^30: fixed-point unit of the posterior tile
+
 struct LatticeArgs {
   const float* E;        // [B, T, C]
   int T, C;
@@ -292,7 +294,10 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
             s += __expf(x - m);
             if (live && x != kNegInf) {
               float p = __expf(x + off);
-              if (want_gE) atomicAdd(&grow[lab], p);
+              // posteriors are accumulated in 2^-30 fixed point: shared-memory integer atomics
+              // are native (float ones are compare-and-swap loops) and the sum does not depend
+              // on the order of the arcs
+              if (want_gE) atomicAdd(reinterpret_cast<unsigned int*>(grow) + lab, __float2uint_rn(p * kFixOne));
               topo.add_weight_grad(arc, p);
             }
           });
@@ -313,11 +318,12 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
       const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
       for (int r = wid; r < rows; r += nw) {
         float* row = gt + r * C;
+        const unsigned int* rowu = reinterpret_cast<const unsigned int*>(row);
         float rs = 0.f;
-        for (int c = lane; c < C; c += 32) rs += row[c];
+        for (int c = lane; c < C; c += 32) rs += (float)rowu[c];
         rs = warp_sum(rs);
-        const float f = (rs > 0.f) ? gs / rs : 0.f;
-        for (int c = lane; c < C; c += 32) row[c] *= f;
+        const float f = (rs > 0.f) ? gs / rs : 0.f;     // the fixed-point scale cancels
+        for (int c = lane; c < C; c += 32) row[c] = (float)rowu[c] * f;
       }
       __syncthreads();
       float* dst = gEb + (size_t)i * Kt * C;

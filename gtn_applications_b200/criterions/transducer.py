@@ -251,3 +251,171 @@ class Transducer(torch.nn.Module):
     def viterbi(self, outputs):
         from ..decode import transducer_viterbi
         return transducer_viterbi(self, outputs)
+
+
+# --------------------------------------------------------------------------- ConvTransduce1D
+def make_kernel_graph(x, blank_idx, blank_optional, spike=False, calc_grad=False):
+    """Kernel acceptor of one lexicon entry (criterions/transducer.py:351-367): start in
+    blank, each sub-token a label state (with self loop unless `spike`) followed by a blank
+    state; with `blank_optional` the blank between different sub-tokens may be skipped."""
+    g = G.Graph(calc_grad)
+    g.add_node(True, len(x) == 0)
+    g.add_arc(0, 0, blank_idx)
+    for i, c in enumerate(x):
+        g.add_node(False, blank_optional and (i + 1) == len(x))
+        g.add_node(False, (i + 1) == len(x))
+        g.add_arc(2 * i, 2 * i + 1, c)
+        if not spike:
+            g.add_arc(2 * i + 1, 2 * i + 1, c)
+        g.add_arc(2 * i + 1, 2 * i + 2, blank_idx)
+        g.add_arc(2 * i + 2, 2 * i + 2, blank_idx)
+        if i > 0 and blank_optional and x[i - 1] != c:
+            g.add_arc(2 * i - 1, 2 * i + 1, c)
+    g.arc_sort(True)
+    g.arc_sort()
+    return g
+
+
+class ConvTransduce1DFunction(torch.autograd.Function):
+    """criterions/transducer.py:461-556.  The reference scores every window of every
+    utterance against every kernel graph with one GTN intersect + forward_score (or
+    viterbi_score) on CPU threads and keeps all graphs alive in a module-level global for
+    the backward pass.  Here the windows become one batch [B*T', kernel_size, C] on the
+    device and each kernel graph is one launch of the lattice kernel in shared-graph mode;
+    backward re-runs the launch with grad_scale = the incoming output gradient, which
+    yields the window gradients (overlap-added into the input gradient) and, summed over
+    windows, the kernel weight gradients.  Nothing is kept between calls but the windows."""
+
+    @staticmethod
+    def forward(ctx, inputs, kernels, kernel_size, stride, kernel_params=None, viterbi=False):
+        from ..decode import lattice_viterbi
+        B, T, C = inputs.shape
+        if T < kernel_size:
+            # Padding should be done outside of this function:
+            raise ValueError(f"Input ({T}) too short for kernel ({kernel_size})")
+        rt.require_cuda(inputs, "inputs")
+        e = rt.to_device(inputs.detach())
+        dev = e.device
+        with torch.cuda.device(dev):
+            win = e.unfold(1, kernel_size, stride)                    # [B, T', C, ks]
+            Tp = win.shape[1]
+            windows = win.permute(0, 1, 3, 2).reshape(B * Tp, kernel_size, C).contiguous()
+            packed = [G.pack_graphs([k], dev) for k in kernels]
+            weights = [None] * len(kernels)
+            if kernel_params is not None:
+                kp = kernel_params.detach().to(dev, torch.float32).contiguous()
+                pos = 0
+                for i, k in enumerate(kernels):
+                    weights[i] = kp[pos:pos + k.num_arcs()]
+                    pos += k.num_arcs()
+            out = torch.empty(B * Tp, len(kernels), dtype=torch.float32, device=dev)
+            paths = []
+            for i, pk in enumerate(packed):
+                if viterbi:
+                    sc, labels, arcs = lattice_viterbi(windows, pk, shared=True, weights=weights[i])
+                    paths.append((labels, arcs))
+                else:
+                    sc, _, _ = lattice_forward_backward(windows, pk, want_grad_emissions=False, shared=True,
+                                                        weights=weights[i])
+                out[:, i] = sc
+        ctx.saved = (windows, packed, weights, paths, [k.num_arcs() for k in kernels])
+        ctx.meta = (B, T, C, Tp, kernel_size, stride, viterbi, inputs.device,
+                    kernel_params.device if kernel_params is not None else None)
+        out = out.view(B, Tp, len(kernels))
+        return out if inputs.is_cuda else out.cpu()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        windows, packed, weights, paths, narcs = ctx.saved
+        B, T, C, Tp, ks, stride, viterbi, in_dev, kp_dev = ctx.meta
+        ctx.saved = None
+        dev = windows.device
+        need_in, need_k = ctx.needs_input_grad[0], ctx.needs_input_grad[4]
+        with torch.cuda.device(dev):
+            deltas = grad_output.detach().to(dev, torch.float32).reshape(B * Tp, len(packed))
+            gwin = torch.zeros_like(windows)
+            kgrads = []
+            for i, pk in enumerate(packed):
+                gs = deltas[:, i].contiguous()
+                if viterbi:
+                    # d viterbi_score / d weights = indicator of the best path's arcs
+                    labels, arcs = paths[i]
+                    if need_in:
+                        gwin.scatter_add_(2, labels.long().unsqueeze(2), gs.view(-1, 1, 1).expand(-1, ks, 1).contiguous())
+                    if need_k:
+                        kg = torch.zeros(narcs[i], dtype=torch.float32, device=dev)
+                        kg.index_add_(0, arcs.long().reshape(-1), gs.view(-1, 1).expand(-1, ks).reshape(-1))
+                        kgrads.append(kg)
+                else:
+                    _, _, g_w = lattice_forward_backward(
+                        windows, pk, grad_scale=gs, want_grad_emissions=need_in, want_grad_weights=need_k,
+                        weights=weights[i], shared=True, accumulate_into=gwin if need_in else None)
+                    if need_k:
+                        kgrads.append(g_w)
+            g_in = None
+            if need_in:
+                g_in = torch.zeros(B, T, C, dtype=torch.float32, device=dev)
+                gw = gwin.view(B, Tp, ks, C)
+                for j in range(ks):     # window t covers frames t*stride + j
+                    g_in[:, j:j + stride * (Tp - 1) + 1:stride] += gw[:, :, j]
+                if g_in.device != in_dev:
+                    g_in = g_in.to(in_dev)
+            g_k = None
+            if need_k:
+                g_k = torch.cat(kgrads) if kgrads else torch.zeros(0, device=dev)
+                if kp_dev is not None and g_k.device != kp_dev:
+                    g_k = g_k.to(kp_dev)
+        return g_in, None, None, None, g_k, None
+
+
+class ConvTransduce1D(torch.nn.Module):
+    """A 1D convolutional transducer layer (criterions/transducer.py:370-455): same
+    constructor, parameters (`kernel_params`) and forward as the reference."""
+
+    def __init__(self, lexicon, kernel_size, stride, blank_idx, blank_optional=True, learn_params=False,
+                 scale="none", normalize="none", viterbi=False, spike=False):
+        super().__init__()
+        import math
+        self.normalize = normalize
+        self.viterbi = viterbi
+        if scale == "none":
+            self.scale = 1.0
+        elif scale == "sqrt":
+            self.scale = math.sqrt(kernel_size)
+        elif scale == "linear":
+            self.scale = kernel_size
+        else:
+            raise ValueError(f"Unknown scale {scale}")
+        if normalize not in ["none", "pre", "post"]:
+            raise ValueError(f"Unknown normalization {normalize}")
+        self.kernel_size = kernel_size
+        assert self.kernel_size % 2 != 0, "Use an odd kernel size for easy padding."
+        self.stride = stride
+
+        def size_with_rep(token):
+            reps = sum(t1 == t2 for t1, t2 in zip(token[:-1], token[1:]))
+            return len(token) + reps
+
+        min_kernel_size = max(size_with_rep(l) for l in lexicon)
+        if kernel_size < min_kernel_size:
+            raise ValueError(f"Kernel size needed of at least {min_kernel_size}.")
+        self.kernels = [make_kernel_graph(l, blank_idx, blank_optional, spike=spike) for l in lexicon]
+        num_arcs = sum(k.num_arcs() for k in self.kernels)
+        self.kernel_params = None
+        if learn_params:
+            self.kernel_params = torch.nn.Parameter(torch.zeros(num_arcs))
+
+    def forward(self, inputs):
+        # inputs are of shape [B, T, C]
+        pad = self.kernel_size // 2
+        inputs = torch.nn.functional.pad(inputs, (0, 0, pad, pad))
+        if self.normalize == "pre":
+            inputs = torch.nn.functional.log_softmax(inputs, dim=2)
+        outputs = ConvTransduce1DFunction.apply(inputs, self.kernels, self.kernel_size, self.stride,
+                                                self.kernel_params, self.viterbi)
+        outputs = outputs / self.scale
+        if self.normalize == "post":
+            outputs = torch.nn.functional.softmax(outputs, dim=2)
+        if self.normalize == "pre":
+            outputs = outputs.exp()
+        return outputs

@@ -245,11 +245,57 @@ def gen_transducer():
     np.savez_compressed(os.path.join(HERE, "transducer.npz"), **out)
 
 
+def gen_conv():
+    """ConvTransduce1D (criterions/transducer.py:351-556): window x lexicon-kernel scores,
+    their gradients w.r.t. the inputs and the (learned) kernel arc weights, forward-score
+    and viterbi modes; plus the kernel graphs themselves."""
+    out = {}
+    lexicon = [(0, 0), (0, 1), (1, 0), (1, 1), (1,)]
+    blank_idx, C = 2, 3
+    for name, ks, stride, B, T, learn, vit, opt, spike, norm, scale in (
+            ("fwd", 5, 3, 2, 8, False, False, True, False, "none", "none"),
+            ("learn", 5, 2, 2, 9, True, False, True, False, "pre", "sqrt"),
+            ("viterbi", 5, 3, 2, 8, True, True, True, False, "none", "none"),
+            ("forced_spike", 7, 4, 1, 11, True, False, False, True, "post", "linear")):
+        torch.manual_seed(11)
+        layer = tr.ConvTransduce1D(lexicon, ks, stride, blank_idx, blank_optional=opt, learn_params=learn,
+                                   scale=scale, normalize=norm, viterbi=vit, spike=spike)
+        if learn:
+            layer.kernel_params.data = torch.randn_like(layer.kernel_params) * 0.5
+        x = torch.randn(B, T, C, requires_grad=True)
+        y = layer(x)
+        go = torch.randn_like(y)
+        y.backward(go)
+        out[name + "_inputs"] = x.detach().numpy()
+        out[name + "_outputs"] = y.detach().numpy()
+        out[name + "_grad_outputs"] = go.numpy()
+        out[name + "_grad_inputs"] = x.grad.numpy()
+        out[name + "_config"] = np.array([ks, stride, blank_idx, int(opt), int(learn), int(vit), int(spike)], dtype=np.int32)
+        out[name + "_normalize"] = np.array(norm)
+        out[name + "_scale"] = np.array(scale)
+        if learn:
+            out[name + "_params"] = layer.kernel_params.detach().numpy()
+            out[name + "_grad_params"] = layer.kernel_params.grad.numpy()
+    flat, off = pack([list(l) for l in lexicon])
+    out["lexicon"] = flat
+    out["lexicon_offsets"] = off
+    for i, (tok, opt, spike) in enumerate((((0, 0), True, False), ((0, 1), False, False), ((0, 1), True, False),
+                                           ((1, 0, 1), True, True), ((), True, False))):
+        out["kg%d_token" % i] = np.array(tok, dtype=np.int32)
+        out["kg%d_flags" % i] = np.array([int(opt), int(spike)], dtype=np.int32)
+        out.update(graph_fields("kg%d" % i, tr.make_kernel_graph(list(tok), blank_idx, opt, spike=spike)))
+    np.savez_compressed(os.path.join(HERE, "conv.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "conv":
+        gen_conv()
+        raise SystemExit(0)
     gen_ctc()
     gen_asg()
     gen_stc()
     gen_transducer()
+    gen_conv()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

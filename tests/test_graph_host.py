@@ -164,3 +164,17 @@ def test_errors():
         ptr.Transducer(["a"], {"a": 0}, blank="sometimes")
     with pytest.raises(ValueError):
         ptr.Transducer(["a"], {"a": 0}, ngram=1, transitions=G.Graph())
+
+
+def test_conv_kernel_graphs_match_reference_constructor():
+    """make_kernel_graph (criterions/transducer.py:351-367): node flags and arc lists
+    bit-exact with what the reference's constructor produced on the oracle shim."""
+    import _golden as Gd
+    from gtn_applications_b200.criterions.transducer import make_kernel_graph
+    z = Gd.load("conv")
+    for i in range(5):
+        tok = z["kg%d_token" % i].tolist()
+        opt, spike = (bool(v) for v in z["kg%d_flags" % i])
+        g = make_kernel_graph(tok, 2, opt, spike=spike).arrays()
+        for k in ("start", "accept", "src", "dst", "ilabel", "olabel"):
+            assert np.array_equal(np.asarray(g[k]).astype(np.int64), z["kg%d_%s" % (i, k)].astype(np.int64)), (i, k)

@@ -25,6 +25,7 @@ class AcceptorBatch(ctypes.Structure):
         ("out_ptr", ctypes.c_void_p), ("out_dst", ctypes.c_void_p), ("out_label", ctypes.c_void_p),
         ("out_arc", ctypes.c_void_p),
         ("weights", ctypes.c_void_p),
+        ("final_weights", ctypes.c_void_p), ("grad_final_weights", ctypes.c_void_p),
     ]
 
 
@@ -109,7 +110,7 @@ def lib():
                 fn = getattr(handle, name)  # AttributeError if the symbol is missing
                 fn.restype = res
                 fn.argtypes = args
-            if handle.wfst_abi_version() != 1:
+            if handle.wfst_abi_version() != 2:
                 raise WfstError("libwfst_b200.so ABI version mismatch")
             _lib = handle
     return _lib

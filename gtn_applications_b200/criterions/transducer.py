@@ -127,6 +127,73 @@ def make_token_graph(token_list, blank="none", allow_repeats=True):
     return g
 
 
+def _graph_has_epsilon(g):
+    cached = getattr(g, "_has_eps", None)
+    if cached is None:
+        from ..epsilon import has_epsilon
+        cached = has_epsilon(g.arrays())
+        try:
+            g._has_eps = cached
+        except AttributeError:
+            pass
+    return cached
+
+
+def _folded_shared(transitions, dev):
+    """(packed, ties) of the epsilon-folded transition graph, cached on the Graph object
+    (the topology does not change between steps; the weights are gathered per call)."""
+    from ..epsilon import FoldedAcceptor, FoldedBatch
+    from ..packing import PackedAcceptors
+    key = "_folded_%s" % str(dev)
+    hit = getattr(transitions, key, None)
+    if hit is None:
+        f = FoldedAcceptor(transitions.arrays())
+        hit = (PackedAcceptors([f.graph_dict()], dev), FoldedBatch([f], dev))
+        try:
+            setattr(transitions, key, hit)
+        except AttributeError:
+            pass
+    return hit
+
+
+def _forward_with_epsilon_transitions(e, aligns, transitions, transition_params, sc, need_e, need_t):
+    """TransducerLossFunction.forward (transducer.py:279-309) when the transition graph has
+    epsilon arcs (ngram > 1: the </s> arcs of make_transitions_graph :52-56; loaded back-off
+    graphs).  intersect(transitions, alignments) is done by the host library with the
+    epsilons in place, exactly as the reference does; then both the composed graphs and the
+    transition graph itself are folded (epsilon.py) and scored by the lattice kernel with
+    final weights.  Gradients return to `transition_params` through the fold's provenance."""
+    from ..epsilon import FoldedAcceptor, FoldedBatch
+    from ..packing import PackedAcceptors
+    B = e.shape[0]
+    dev = e.device
+    tp = transition_params.detach().to(dev, torch.float32).contiguous()
+    folded, prov = [], []
+    for g in aligns:
+        c = G.intersect(transitions, g)
+        c.arc_sort()
+        folded.append(FoldedAcceptor(c.arrays()))
+        prov.append(np.asarray(c.provenance()[0], dtype=np.int64))     # composed arc -> transition arc
+    packed = PackedAcceptors([f.graph_dict() for f in folded], dev)
+    ties = FoldedBatch(folded, dev, orig_index=prov)
+    w, fw, pw = ties.weights(tp)
+    gs = -sc / B
+    z_align, g_e, g_w, g_f = lattice_forward_backward(
+        e, packed, grad_scale=gs, want_grad_emissions=need_e, want_grad_weights=need_t,
+        weights=w, final_weights=fw)
+    spacked, sties = _folded_shared(transitions, dev)
+    sw, sfw, spw = sties.weights(tp)
+    z_norm, _, g_wn, g_fn = lattice_forward_backward(
+        e, spacked, grad_scale=-gs, want_grad_emissions=False, want_grad_weights=need_t,
+        weights=sw, shared=True, accumulate_into=g_e if need_e else None, final_weights=sfw)
+    g_tp = None
+    if need_t:
+        g_tp = ties.scatter_grads(tp.numel(), g_w, g_f, fw, pw) + \
+            sties.scatter_grads(tp.numel(), g_wn, g_fn, sfw, spw)
+    loss = (-(z_align - z_norm) * sc).mean()
+    return loss, g_e, g_tp
+
+
 class TransducerLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inputs, targets, tokens, lexicon, transition_params=None, transitions=None,
@@ -155,6 +222,12 @@ class TransducerLossFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             sc = torch.tensor(scales, dtype=torch.float32, device=dev)
             tp = prov = None
+            if transitions is not None and _graph_has_epsilon(transitions):
+                loss, g_e, g_tp = _forward_with_epsilon_transitions(
+                    e, aligns, transitions, transition_params, sc, need_e, need_t)
+                ctx.grads = (g_e if need_e else None, g_tp)
+                ctx.devices = (inputs.device, transition_params.device)
+                return loss if inputs.is_cuda else loss.cpu()
             if transitions is not None:
                 # alignments := intersect(transitions, alignments) (transducer.py:279-281); the
                 # composed arc weights are the transition weights of their first parent
@@ -247,6 +320,12 @@ class Transducer(torch.nn.Module):
         targets = [t.tolist() if torch.is_tensor(t) else list(t) for t in targets]
         return TransducerLoss(inputs, targets, self.tokens, self.lexicon, self.transition_params,
                               self.transitions, self.reduction)
+
+    def folded_transitions(self, device):
+        """None when the transition graph is epsilon-free, else its folded form (epsilon.py)."""
+        if self.transitions is None or not _graph_has_epsilon(self.transitions):
+            return None
+        return _folded_shared(self.transitions, device)
 
     def viterbi(self, outputs):
         from ..decode import transducer_viterbi

@@ -271,6 +271,8 @@ int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
   g.B = B;
   if (shared_graph && grad_weights)
     WFST_CUDA_CHECK(cudaMemsetAsync(grad_weights, 0, (size_t)graphs->max_arcs * 4, st));
+  if (shared_graph && graphs->grad_final_weights)
+    WFST_CUDA_CHECK(cudaMemsetAsync(graphs->grad_final_weights, 0, (size_t)graphs->max_nodes * 4, st));
   return launch_csr(emissions, T, C, g, shared_graph, grad_scale, 1.f, scores, grad_emissions,
                     accumulate, grad_weights, (float*)workspace, st);
 }

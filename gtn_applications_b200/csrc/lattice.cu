@@ -19,6 +19,7 @@ struct CsrTopo {
   const int* in_ptr; const int* in_src; const int* in_label; const int* in_arc;
   const int* out_ptr; const int* out_dst; const int* out_label; const int* out_arc;
   const uint8_t* flags; const float* w; float* gw; float* gradW;
+  const float* fw; float* gradF;
   int N, A, shared;
 
   __device__ void init(const Params& p, int b, float* extra) {
@@ -32,6 +33,8 @@ struct CsrTopo {
     flags = p.g.node_flags + nb;
     w = p.g.weights ? p.g.weights + ab : nullptr;
     gradW = p.gradW ? p.gradW + ab : nullptr;
+    fw = p.g.final_weights ? p.g.final_weights + nb : nullptr;
+    gradF = p.g.grad_final_weights ? p.g.grad_final_weights + nb : nullptr;
     gw = extra;
     shared = p.shared;
     if (gradW) for (int k = threadIdx.x; k < A; k += blockDim.x) gw[k] = 0.f;
@@ -40,6 +43,11 @@ struct CsrTopo {
   __device__ int num_nodes() const { return N; }
   __device__ bool is_start(int v) const { return flags[v] & 1; }
   __device__ bool is_accept(int v) const { return flags[v] & 2; }
+  __device__ float final_w(int v) const { return fw ? fw[v] : 0.f; }
+  __device__ void add_final_grad(int v, float g) const {
+    if (!gradF) return;
+    if (shared) atomicAdd(&gradF[v], g); else gradF[v] = g;
+  }
   __device__ bool wants_weight_grad() const { return gradW != nullptr; }
   template <class F>
   __device__ void in_arcs(int v, F f) const {
@@ -94,6 +102,8 @@ struct CtcTopo {
   __device__ int num_nodes() const { return S; }
   __device__ bool is_start(int v) const { return v == 0; }
   __device__ bool is_accept(int v) const { return v == S - 1 || v == S - 2; }
+  __device__ float final_w(int) const { return 0.f; }
+  __device__ void add_final_grad(int, float) const {}
   __device__ bool wants_weight_grad() const { return false; }
   template <class F>
   __device__ void in_arcs(int s, F f) const {
@@ -133,6 +143,8 @@ struct AsgFalTopo {
   __device__ int num_nodes() const { return L + 1; }
   __device__ bool is_start(int v) const { return v == 0; }
   __device__ bool is_accept(int v) const { return L > 0 && v == L; }
+  __device__ float final_w(int) const { return 0.f; }
+  __device__ void add_final_grad(int, float) const {}
   __device__ bool wants_weight_grad() const { return gradTr != nullptr; }
   template <class F>
   __device__ void in_arcs(int l, F f) const {
@@ -185,6 +197,8 @@ struct AsgFccTopo {
   __device__ int num_nodes() const { return C + 1; }
   __device__ bool is_start(int v) const { return v == 0; }
   __device__ bool is_accept(int v) const { return v > 0; }
+  __device__ float final_w(int) const { return 0.f; }
+  __device__ void add_final_grad(int, float) const {}
   __device__ bool wants_weight_grad() const { return gradTr != nullptr; }
   template <class F>
   __device__ void in_arcs(int v, F f) const {

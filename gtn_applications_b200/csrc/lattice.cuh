@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
   // ------------------------------------------------------------- Z
   float part = kNegInf;
   for (int v = tid; v < N; v += NT)
-    if (topo.is_accept(v)) part = log_add(part, cur[v]);
+    if (topo.is_accept(v)) part = log_add(part, cur[v] + topo.final_w(v));
   const float Zn = block_lse(part, sm.red);   // relative to cumA
   const double Zd = (double)Zn + cumA;
   const float Z = (float)Zd;
@@ -244,7 +244,12 @@ __global__ void __launch_bounds__(1024, 1) lattice_fwd_bwd_kernel(LatticeArgs a,
   // ------------------------------------------------------------- backward
   // beta_{t+1} lives in `nxt`, beta_t is written to `cur`
   __syncthreads();
-  for (int v = tid; v < N; v += NT) nxt[v] = topo.is_accept(v) ? 0.f : kNegInf;
+  for (int v = tid; v < N; v += NT) {
+    const bool acc = topo.is_accept(v);
+    nxt[v] = acc ? topo.final_w(v) : kNegInf;
+    // posterior of ending in v = d Z / d final weight of v
+    if (acc && cur[v] != kNegInf) topo.add_final_grad(v, __expf(cur[v] + topo.final_w(v) - Zn) * gs);
+  }
   double cumB = 0.0;
   float dB = 0.f;
   if (ntiles > 0) issue_tile(ntiles - 1, (ntiles - 1) & 1);

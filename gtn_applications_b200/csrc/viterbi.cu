@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_viterbi_kernel(ViterbiArgs a)
   const int* in_arc = a.g.in_arc + ab;
   const uint8_t* flags = a.g.node_flags + nb;
   const float* w = a.g.weights ? a.g.weights + ab : nullptr;
+  const float* fw = a.g.final_weights ? a.g.final_weights + nb : nullptr;
   const int T = a.T, C = a.C;
   const float* Eb = a.E + (size_t)b * T * C;
   int32_t* bp = a.bp + (size_t)b * T * a.stride;
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_viterbi_kernel(ViterbiArgs a)
     float best = kNegInf;
     int v = -1;
     for (int q = 0; q < N; ++q)
-      if ((flags[q] & 2) && cur[q] > best) { best = cur[q]; v = q; }
+      if ((flags[q] & 2) && cur[q] + (fw ? fw[q] : 0.f) > best) { best = cur[q] + (fw ? fw[q] : 0.f); v = q; }
     a.scores[b] = best;
     for (int t = T - 1; t >= 0; --t) {
       int k = (v >= 0) ? bp[(size_t)t * a.stride + v] : -1;

@@ -8,7 +8,7 @@ from . import _lib, _runtime as rt
 from . import graph as G
 
 
-def lattice_viterbi(emissions, packed, shared=False, weights=None):
+def lattice_viterbi(emissions, packed, shared=False, weights=None, final_weights=None):
     """Best path through emissions o acceptor for every utterance.  Returns (scores [B],
     labels [B,T] int32, arcs [B,T] int32) on the device."""
     B, T, C = emissions.shape
@@ -17,7 +17,7 @@ def lattice_viterbi(emissions, packed, shared=False, weights=None):
     scores = torch.empty(B, dtype=torch.float32, device=dev)
     labels = torch.empty(B, T, dtype=torch.int32, device=dev)
     arcs = torch.empty(B, T, dtype=torch.int32, device=dev)
-    s = packed.struct(weights)
+    s = packed.struct(weights, final_weights)
     with torch.cuda.device(dev):
         ws = rt.workspace(dev, L.wfst_lattice_viterbi_workspace_bytes(B, T, packed.max_nodes))
         _lib.check(L.wfst_lattice_viterbi(
@@ -47,8 +47,15 @@ def transducer_viterbi(crit, outputs):
     if crit.transitions is not None:
         tp = crit.transition_params.detach().to(e.device, torch.float32).contiguous()
         crit.transitions.calc_grad = False
-        packed = G.pack_graphs([crit.transitions], e.device)
-        _, labels, _ = lattice_viterbi(e, packed, shared=True, weights=tp)
+        folded = crit.folded_transitions(e.device)
+        if folded is None:
+            packed = G.pack_graphs([crit.transitions], e.device)
+            _, labels, _ = lattice_viterbi(e, packed, shared=True, weights=tp)
+        else:
+            # epsilon arcs (</s>, back-off) folded into arcs / final weights (epsilon.py)
+            packed, ties = folded
+            w, fw, _ = ties.weights(tp, tropical=True)
+            _, labels, _ = lattice_viterbi(e, packed, shared=True, weights=w, final_weights=fw)
         paths = labels.cpu().tolist()
     else:
         paths = torch.argmax(e, dim=2).cpu().tolist()

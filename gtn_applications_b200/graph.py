@@ -294,6 +294,7 @@ def pack_graphs(graphs, device):
     dev_flags = flags.to(device, non_blocking=True)
     packed = PackedAcceptors.__new__(PackedAcceptors)
     packed.B, packed.num_arcs = B, ta
+    packed.num_nodes = tn
     packed.max_nodes, packed.max_arcs = mn.value, ma.value
     packed.arc_offsets_host = views["arc_offsets"].numpy().copy()
     packed.t, pos = {"node_flags": dev_flags}, 0

@@ -9,10 +9,11 @@ from . import _lib, _runtime as rt
 
 def lattice_forward_backward(emissions, packed, grad_scale=None, want_grad_emissions=True,
                              want_grad_weights=False, weights=None, shared=False,
-                             accumulate_into=None):
+                             accumulate_into=None, final_weights=None):
     """emissions [B,T,C] float32 CUDA; packed: PackedAcceptors.  Returns
     (scores [B], grad_emissions or None, grad_weights or None); gradients are
-    grad_scale[b] * dZ_b/d(.)."""
+    grad_scale[b] * dZ_b/d(.).  With `final_weights` ([nodes], epsilon.py) a fourth value is
+    returned: the gradient w.r.t. the final weights (when want_grad_weights)."""
     B, T, C = emissions.shape
     dev = emissions.device
     L = _lib.lib()
@@ -22,7 +23,10 @@ def lattice_forward_backward(emissions, packed, grad_scale=None, want_grad_emiss
     else:
         g_e, acc = (torch.empty_like(emissions) if want_grad_emissions else None), 0
     g_w = torch.zeros(packed.num_arcs, dtype=torch.float32, device=dev) if want_grad_weights else None
-    s = packed.struct(weights)
+    g_f = None
+    if final_weights is not None and want_grad_weights:
+        g_f = torch.zeros(final_weights.numel(), dtype=torch.float32, device=dev)
+    s = packed.struct(weights, final_weights, g_f)
     with torch.cuda.device(dev):
         ws = rt.workspace(dev, L.wfst_lattice_workspace_bytes(B, T, C, 0, packed.max_nodes))
         _lib.check(L.wfst_lattice_forward_backward(
@@ -31,4 +35,6 @@ def lattice_forward_backward(emissions, packed, grad_scale=None, want_grad_emiss
             g_e.data_ptr() if g_e is not None else None, acc,
             g_w.data_ptr() if g_w is not None else None, ws.data_ptr(), ws.numel(),
             rt.stream_ptr(dev)))
+    if final_weights is not None:
+        return scores, g_e, g_w, g_f
     return scores, g_e, g_w

@@ -52,6 +52,7 @@ class PackedAcceptors:
             in_ptr[n0 + b + 1:n0 + b + N + 1] = np.cumsum(np.bincount(dst, minlength=N))
             out_ptr[n0 + b + 1:n0 + b + N + 1] = np.cumsum(np.bincount(src, minlength=N))
         self.B = B
+        self.num_nodes = nn
         self.num_arcs = na
         self.arc_offsets_host = arc_off
         self.max_nodes = int(np.max(np.diff(node_off))) if B else 0
@@ -62,7 +63,7 @@ class PackedAcceptors:
         for k, v in cols.items():
             self.t[k] = up(v)
 
-    def struct(self, weights=None):
+    def struct(self, weights=None, final_weights=None, grad_final_weights=None):
         s = _lib.AcceptorBatch()
         s.B, s.max_nodes, s.max_arcs = self.B, self.max_nodes, self.max_arcs
         for k in ("node_offsets", "arc_offsets", "node_flags", "in_ptr", "in_src", "in_label",
@@ -70,4 +71,6 @@ class PackedAcceptors:
             setattr(s, k, self.t[k].data_ptr())
         w = self.t["weights"] if weights is None else weights
         s.weights = w.data_ptr()
+        s.final_weights = final_weights.data_ptr() if final_weights is not None else None
+        s.grad_final_weights = grad_final_weights.data_ptr() if grad_final_weights is not None else None
         return s

@@ -41,7 +41,7 @@ extern "C" {
 #define WFST_ERR_UNSUPPORTED (-3) /* shape outside what the kernels handle */
 #define WFST_ERR_WORKSPACE (-4)   /* workspace too small */
 
-#define WFST_ABI_VERSION 1
+#define WFST_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define WFST_API __attribute__((visibility("default")))
@@ -137,6 +137,14 @@ typedef struct {
   const int32_t* out_label;     /* [arcs] */
   const int32_t* out_arc;       /* [arcs] */
   const float* weights;         /* [arcs] original order, or NULL (= 0) */
+  /* ABI 2: final weights.  A path that ends in accept node v scores final_weights[v] on top
+   * (NULL = 0).  This is how acceptors with epsilon arcs (n-gram </s> arcs, back-off arcs:
+   * transducer.py:52-56, scripts/build_transitions.py) reach the kernels: the host folds every
+   * epsilon path into the arc that follows it and every epsilon path into an accept node
+   * into that node's final weight (gtn_applications_b200/epsilon.py). */
+  const float* final_weights;   /* [nodes] or NULL */
+  float* grad_final_weights;    /* [nodes] out or NULL: grad_scale[b] * dZ_b/d final_weights
+                                   (summed over b when the graph is shared) */
 } wfst_acceptor_batch_t;
 
 WFST_API size_t wfst_lattice_workspace_bytes(int B, int T, int C, int total_nodes, int max_nodes);

@@ -22,7 +22,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(handle, n), "missing export " + n
         assert n in _lib.SIGNATURES, "no ctypes binding for " + n
     assert sorted(_lib.SIGNATURES) == names
-    assert _lib.lib().wfst_abi_version() == 1
+    assert _lib.lib().wfst_abi_version() == 2
     assert _lib.lib().wfst_last_error() == b""
 
 

@@ -175,11 +175,54 @@ def test_transducer_random_wordpieces_against_oracle(gtn64):
     assert_close(xt.grad.cpu().numpy(), G.through_log_softmax(x, ref["grad"]))
 
 
-def test_epsilon_transitions_are_refused_loudly():
+@pytest.mark.parametrize("name,ngram,blank,rep", [("ngram1", 1, "optional", False), ("ngram2", 2, "optional", False),
+                                                  ("ngram2_asg", 2, "none", True)])
+def test_ngram_transitions_with_epsilon_arcs_match_reference_fixtures(name, ngram, blank, rep):
+    """make_transitions_graph for ngram > 1 ends in epsilon </s> arcs (transducer.py:52-56):
+    loss, emission gradient, transition-parameter gradient and the Viterbi decode against
+    the reference's own module (fixtures from make_golden.py)."""
     from gtn_applications_b200.criterions.transducer import Transducer
-    crit = Transducer([(0,), (1,)], {0: 0, 1: 1}, ngram=2, blank="optional", allow_repeats=False).cuda()
-    with pytest.raises(NotImplementedError, match="epsilon"):
-        crit(torch.zeros(1, 4, 3, device="cuda"), [[0, 1]])
+    z = G.load("transducer")
+    N = 4
+    crit = Transducer([(i,) for i in range(N)], {i: i for i in range(N)}, ngram=ngram, blank=blank,
+                      allow_repeats=rep, reduction="mean").cuda()
+    crit.transition_params.data = torch.tensor(z[name + "_params"], device="cuda")
+    x = torch.tensor(z[name + "_emissions"], device="cuda", requires_grad=True)
+    tg = G.unpack(z[name + "_targets"], z[name + "_offsets"])
+    loss = crit(x, tg)
+    loss.backward()
+    want = float(z[name + "_loss"])
+    assert abs(loss.item() - want) <= 1e-4 * max(1.0, abs(want))
+    assert_close_f32_fixture(x.grad.cpu().numpy(), z[name + "_grad"])
+    assert_close_f32_fixture(crit.transition_params.grad.cpu().numpy(), z[name + "_grad_params"])
+    vit = crit.viterbi(x.detach())
+    assert [v.tolist() for v in vit] == G.unpack(z[name + "_viterbi"], z[name + "_viterbi_offsets"])
+
+
+def test_backoff_transition_graph_with_epsilon_arcs_matches_reference_fixture(tmp_path):
+    """A loaded back-off graph (tests/trans_backoff_test.txt, transducer_test.py:534-566): epsilon
+    back-off arcs between n-gram states are folded into the arcs that follow them."""
+    from gtn_applications_b200.criterions.transducer import Transducer
+    from gtn_applications_b200 import graph as Gr
+    z = G.load("transducer")
+    g = Gr.Graph(False)
+    for st, ac in zip(z["backoff_file_start"], z["backoff_file_accept"]):
+        g.add_node(bool(st), bool(ac))
+    for s_, d_, il, ol in zip(z["backoff_file_src"], z["backoff_file_dst"], z["backoff_file_ilabel"],
+                              z["backoff_file_olabel"]):
+        g.add_arc(int(s_), int(d_), int(il), int(ol), 0.0)
+    N = 5
+    crit = Transducer([(i,) for i in range(N)], {i: i for i in range(N)}, blank="optional", allow_repeats=False,
+                      transitions=g).cuda()
+    crit.transition_params.data = torch.tensor(z["backoff_params"], device="cuda")
+    x = torch.tensor(z["backoff_emissions"], device="cuda", requires_grad=True)
+    tg = G.unpack(z["backoff_targets"], z["backoff_offsets"])
+    loss = crit(x, tg)
+    loss.backward()
+    want = float(z["backoff_loss"])
+    assert abs(loss.item() - want) <= 1e-4 * max(1.0, abs(want))
+    assert_close_f32_fixture(x.grad.cpu().numpy(), z["backoff_grad"])
+    assert_close_f32_fixture(crit.transition_params.grad.cpu().numpy(), z["backoff_grad_params"])
 
 
 # --------------------------------------------------------------------- viterbi

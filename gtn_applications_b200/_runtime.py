@@ -39,9 +39,12 @@ def stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def pack_targets(targets, num_classes, device):
+def pack_targets(targets, num_classes, device, scales=None):
     """list[list[int]] -> (flat int32, offsets int32 [B+1], lengths list, max_len) on `device`.
-    Labels are validated on the host (the kernels index emissions with them)."""
+    Labels are validated on the host (the kernels index emissions with them).  With `scales`
+    (a list of B floats) a fifth value is returned: the float32 device vector of those scales,
+    shipped in the same pinned staging buffer — one asynchronous H2D copy per call, so that a
+    criterion call never waits for the stream."""
     import itertools
     import numpy as np
     if torch.is_tensor(targets) and targets.dim() == 2:
@@ -51,28 +54,42 @@ def pack_targets(targets, num_classes, device):
         t = targets.detach().to("cpu", torch.int32).contiguous()
         if t.numel() and (int(t.min()) < 0 or int(t.max()) >= num_classes):
             raise ValueError("target label outside [0, %d)" % num_classes)
-        host = torch.empty(B * L + B + 1, dtype=torch.int32, pin_memory=torch.cuda.is_available())
-        host[:B * L] = t.reshape(-1)
-        host[B * L:] = torch.arange(B + 1, dtype=torch.int32) * L
-        dev = host.to(device, non_blocking=True)
-        return dev[:B * L], dev[B * L:], [L] * B, L
-    lengths = [len(t) for t in targets]
-    total = sum(lengths)
-    if lengths and all(torch.is_tensor(t) for t in targets):
-        # a list of 1-D label tensors (what train.py hands to CTC.forward): one concatenation
-        # instead of per-label Python work
-        flat = torch.cat([t.detach().reshape(-1) for t in targets]).to("cpu", torch.int64).numpy()
+        lengths, total = [L] * B, B * L
+        flat = t.reshape(-1).numpy()
+        offs = np.arange(B + 1, dtype=np.int32) * L
     else:
-        flat = np.fromiter(itertools.chain.from_iterable(targets), dtype=np.int64, count=total)
-    if total and (flat.min() < 0 or flat.max() >= num_classes):
-        raise ValueError("target label outside [0, %d)" % num_classes)
-    host = torch.empty(total + len(lengths) + 1, dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        lengths = [len(t) for t in targets]
+        total = sum(lengths)
+        if lengths and all(torch.is_tensor(t) for t in targets):
+            # a list of 1-D label tensors (what train.py hands to CTC.forward): one concatenation
+            # instead of per-label Python work
+            flat = torch.cat([t.detach().reshape(-1) for t in targets]).to("cpu", torch.int64).numpy()
+        else:
+            flat = np.fromiter(itertools.chain.from_iterable(targets), dtype=np.int64, count=total)
+        if total and (flat.min() < 0 or flat.max() >= num_classes):
+            raise ValueError("target label outside [0, %d)" % num_classes)
+        offs = np.zeros(len(lengths) + 1, dtype=np.int32)
+        np.cumsum(lengths, out=offs[1:])
+    nb = len(lengths)
+    ns = nb if scales is not None else 0
+    host = torch.empty(total + nb + 1 + ns, dtype=torch.int32, pin_memory=torch.cuda.is_available())
     buf = host.numpy()
     buf[:total] = flat
-    buf[total] = 0
-    np.cumsum(lengths, out=buf[total + 1:])
+    buf[total:total + nb + 1] = offs
+    if ns:
+        buf[total + nb + 1:].view(np.float32)[:] = np.asarray(scales, dtype=np.float32)
     dev = host.to(device, non_blocking=True)
-    return dev[:total], dev[total:], lengths, (max(lengths) if lengths else 0)
+    out = (dev[:total], dev[total:total + nb + 1], lengths, (max(lengths) if lengths else 0))
+    if scales is not None:
+        out = out + (dev[total + nb + 1:].view(torch.float32),)
+    return out
+
+
+def target_lengths(targets):
+    """lengths of the target sequences; a [B, L] tensor is not iterated row by row"""
+    if torch.is_tensor(targets) and targets.dim() == 2:
+        return [int(targets.shape[1])] * int(targets.shape[0])
+    return [len(t) for t in targets]
 
 
 def reduction_scales(reduction, sizes):

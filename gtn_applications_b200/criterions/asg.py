@@ -98,8 +98,7 @@ class ASGLossFunction(torch.autograd.Function):
         dev = e.device
         with torch.cuda.device(dev):
             tr = transitions.detach().to(dev).contiguous()
-            flat, offsets, _, max_len = rt.pack_targets(targets, C, dev)
-            gscale = torch.tensor([s / B for s in scales], dtype=torch.float32).to(dev)
+            flat, offsets, _, max_len, gscale = rt.pack_targets(targets, C, dev, [s / B for s in scales])
             out = torch.empty(B + 1, dtype=torch.float32, device=dev)
             need_e, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
             g_e = torch.empty_like(e) if need_e else None

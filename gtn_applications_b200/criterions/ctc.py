@@ -41,7 +41,7 @@ class CTCLossFunction(torch.autograd.Function):
             raise ValueError("log_probs must be [B, T, C]")
         B, T, C = log_probs.shape
         rt.require_cuda(log_probs, "log_probs")
-        scales = rt.reduction_scales(reduction, [len(t) for t in targets])
+        scales = rt.reduction_scales(reduction, rt.target_lengths(targets))
         if len(targets) != B:
             raise ValueError("need one target sequence per batch entry")
         if not 0 <= blank_idx < C:
@@ -49,8 +49,7 @@ class CTCLossFunction(torch.autograd.Function):
         e = rt.to_device(log_probs.detach())
         dev = e.device
         with torch.cuda.device(dev):
-            flat, offsets, _, max_len = rt.pack_targets(targets, C, dev)
-            gscale = torch.tensor([s / B for s in scales], dtype=torch.float32).to(dev)
+            flat, offsets, _, max_len, gscale = rt.pack_targets(targets, C, dev, [s / B for s in scales])
             out = torch.empty(B + 1, dtype=torch.float32, device=dev)
             need_grad = log_probs.requires_grad
             grad = torch.empty_like(e) if need_grad else None
@@ -100,7 +99,7 @@ class CTCLogitsLossFunction(torch.autograd.Function):
         if not (inputs.is_cuda and inputs.dtype == torch.float32 and inputs.dim() == 3):
             return False
         B, T, C = inputs.shape
-        max_len = max((len(t) for t in targets), default=0)
+        max_len = max(rt.target_lengths(targets), default=0)
         return bool(_lib.lib().wfst_ctc_logits_supported(B, T, C, max_len))
 
     @staticmethod
@@ -109,7 +108,7 @@ class CTCLogitsLossFunction(torch.autograd.Function):
             raise ValueError("inputs must be [B, T, C]")
         B, T, C = inputs.shape
         rt.require_cuda(inputs, "inputs")
-        scales = rt.reduction_scales(reduction, [len(t) for t in targets])
+        scales = rt.reduction_scales(reduction, rt.target_lengths(targets))
         if len(targets) != B:
             raise ValueError("need one target sequence per batch entry")
         if not 0 <= blank_idx < C:
@@ -117,11 +116,10 @@ class CTCLogitsLossFunction(torch.autograd.Function):
         e = rt.to_device(inputs.detach())
         dev = e.device
         with torch.cuda.device(dev):
-            flat, offsets, _, max_len = rt.pack_targets(targets, C, dev)
+            flat, offsets, _, max_len, gscale = rt.pack_targets(targets, C, dev, [s / B for s in scales])
             L = _lib.lib()
             if not L.wfst_ctc_logits_supported(B, T, C, max_len):
                 raise NotImplementedError("fused logits CTC does not handle this shape; use log_softmax + CTCLoss")
-            gscale = torch.tensor([s / B for s in scales], dtype=torch.float32).to(dev)
             out = torch.empty(B + 1, dtype=torch.float32, device=dev)
             need_grad = inputs.requires_grad
             grad = torch.empty_like(e) if need_grad else None

@@ -206,21 +206,38 @@ def run_gpu(args):
         off = (torch.arange(B + 1, dtype=torch.int32) * L).to(dev)
         batches.append((lp.contiguous(), flat, off, tg))
     gscale = torch.full((B,), 1.0 / (B * world), dtype=torch.float32, device=dev)
-    out = torch.empty(B + 1, dtype=torch.float32, device=dev)
+    NOUT = 4            # loss buffers in rotation: a step's all-reduce may still be in flight
+    outs = [torch.empty(B + 1, dtype=torch.float32, device=dev) for _ in range(NOUT)]
+    out = outs[0]
+    pending = [None] * NOUT
     grad = torch.empty(B, T, C, dtype=torch.float32, device=dev)
     ws = rt.workspace(dev, L_.wfst_ctc_workspace_bytes(B, T, C, L))
     stream = torch.cuda.current_stream(dev)
 
     def step(i):
         lp, flat, off, _ = batches[i % ROT]
+        o = outs[i % NOUT]
+        if pending[i % NOUT] is not None:      # the all-reduce that last used this buffer
+            pending[i % NOUT].wait()
+            pending[i % NOUT] = None
         _lib.check(L_.wfst_ctc_forward_backward(
             lp.data_ptr(), flat.data_ptr(), off.data_ptr(), B, T, C, C - 1, L, gscale.data_ptr(),
-            out.data_ptr(), out[B:].data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(),
+            o.data_ptr(), o[B:].data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(),
             stream.cuda_stream))
         if world > 1:
-            dist.all_reduce(out[B:], op=dist.ReduceOp.SUM)
+            # the scalar loss reduce runs on NCCL's stream behind this step's kernel; the next
+            # step's kernel does not wait for it (it is waited for when its buffer comes round
+            # again and before the timed region ends)
+            pending[i % NOUT] = dist.all_reduce(o[B:], op=dist.ReduceOp.SUM, async_op=True)
+
+    def drain():
+        for k in range(NOUT):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -242,6 +259,7 @@ def run_gpu(args):
         evs[i][0].record(stream)
         step(i)
         evs[i][1].record(stream)
+    drain()                      # every step's loss reduce is complete inside the timed region
     end.record(stream)
     barrier()
     launches = _lib.launch_count() - launches0
@@ -252,7 +270,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kern_ms = float(t[0]), float(t[1])
-    loss_value = float(out[B].item())
+    loss_value = float(outs[(args.steps - 1) % NOUT][B].item())
 
     # ---- e2e: the user-facing call with HOST inputs (pinned), copies inside the timed region.
     # Like a training loop with a prefetching loader, the copy of step i+1's emissions is issued

@@ -49,15 +49,23 @@
 #include "common.cuh"
 #include "launchers.h"
 
+#ifndef WFST_PAIR_WAIT
+#define WFST_PAIR_WAIT 0
+#endif
+
 namespace wfst {
 namespace pairk {
 
 #ifdef WFST_PROFILE
+__device__ long long g_tl[8][64];
+#define PROF_TL(slot, d, k2) do { if (blockIdx.x == 0 && (d) == 0 && (k2) >= 0 && (k2) < 64 && (threadIdx.x & 31) == 0) \
+  g_tl[slot][k2] = clock64(); } while (0)
 #define PROF_DECL long long pf_t0 = clock64(), pf_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define PROF_MARK(i) do { long long pf_t1 = clock64(); pf_acc[i] += pf_t1 - pf_t0; pf_t0 = pf_t1; } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(i)
+#define PROF_TL(tag, d, k2)
 #endif
 
 typedef unsigned long long p2;   // two packed floats: low = utterance 0, high = utterance 1
@@ -70,7 +78,6 @@ constexpr int kNB = 4;                // p-tile ring depth per direction
 constexpr int kNR = 3;                // raw (TMA) staging slots per producer warp
 constexpr int kMaxPass = 4;           // label reduction: up to 4 x 32 chunk slots
 constexpr int kU = 4;                 // frames unrolled in the hot loops (code size vs address updates)
-constexpr int kPbkRow = 66;           // floats per row of blank partials (32 lanes x 2 + pad)
 
 struct Args {
   const float* E;
@@ -168,7 +175,7 @@ __device__ __forceinline__ float pow2i(int d) {  // 2^d for d in [-126, 127]
 __device__ __forceinline__ float pow2c(int d) { return (d < -126) ? 0.f : pow2i(min(d, 126)); }
 
 // ---- mbarriers ---------------------------------------------------------------------
-constexpr int kMaxAB = 3;
+constexpr int kMaxAB = 4;
 constexpr int kBarPFull = 0;                       // [2][kNB]    p tile ready (P -> L, RC)
 constexpr int kBarPEmpty = kBarPFull + 2 * kNB;    // [2][kNB]    p tile released (count 2)
 constexpr int kBarTma = kBarPEmpty + 2 * kNB;      // [2][kNR]    raw tiles landed
@@ -176,7 +183,7 @@ constexpr int kBarAFull = kBarTma + 2 * kNR;       // [2][kMaxAB] abar segment r
 constexpr int kBarCFull = kBarAFull + 2 * kMaxAB;  // [2][kMaxAB] products ready (RC -> X)
 constexpr int kBarAEmpty = kBarCFull + 2 * kMaxAB; // [2][kMaxAB] segment buffer free (X -> L)
 constexpr int kBarZ = kBarAEmpty + 2 * kMaxAB;     // Z published (L1 -> everyone)
-constexpr int kSD = 8;                             // > the furthest P can run ahead of X (kNB + kMaxAB tiles)
+constexpr int kSD = 12;                            // > the furthest P can run ahead of X (kNB + kMaxAB tiles)
 constexpr int kBarSDone = kBarZ + 1;               // [2][kSD]    fused mode: softmax tile of phase-2 tile i is in HBM (P -> X)
 constexpr int kNumBars = kBarSDone + 2 * kSD;
 
@@ -190,6 +197,29 @@ __device__ __forceinline__ void bar_expect_tx(uint32_t bars, int idx, uint32_t b
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * idx), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bar_wait(uint32_t bars, int idx, uint32_t parity) {
+#if WFST_PAIR_WAIT == 1
+  // plain polling
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WFSTP_BW_%=:\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WFSTP_BD_%=;\n"
+      "bra WFSTP_BW_%=;\n"
+      "WFSTP_BD_%=:\n"
+      "}\n" ::"r"(bars + 8u * idx), "r"(parity) : "memory");
+#elif WFST_PAIR_WAIT == 2
+  // try_wait with the default (implementation-defined) suspend time
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WFSTP_BW_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WFSTP_BD_%=;\n"
+      "bra WFSTP_BW_%=;\n"
+      "WFSTP_BD_%=:\n"
+      "}\n" ::"r"(bars + 8u * idx), "r"(parity) : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -199,6 +229,7 @@ __device__ __forceinline__ void bar_wait(uint32_t bars, int idx, uint32_t parity
       "bra WFSTP_BW_%=;\n"
       "WFSTP_BD_%=:\n"
       "}\n" ::"r"(bars + 8u * idx), "r"(parity), "r"(0x989680u) : "memory");
+#endif
 }
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -206,17 +237,17 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 
 // ---- shared memory layout (in floats) ---------------------------------------------
 struct Layout {
-  size_t raw, out, abuf, pbk, lexp, ptile, bars, zx, xtab, colpos, slotlab, hist, total;
+  size_t raw, out, abuf, bnd, lexp, ptile, bars, zx, xtab, colpos, slotlab, hist, total;
 };
 __host__ __device__ inline Layout make_layout(int K, int C, int CS, int NAB) {
   Layout L;
   const size_t rawsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
-  const size_t RS = 32 * ((size_t)K + 1) + 4, Cp = (size_t)CS + 1;
+  const size_t RS = 32 * ((size_t)K / 2 + 1) + 4, BS = 32 * ((size_t)K + 1) + 4, Cp = (size_t)CS + 1;
   size_t p = 0;
   L.raw = p;    p += 2 * (size_t)kNR * 2 * rawsz + 32;   // [d][slot][u][8*C] (+ slack: the producers over-read)
   L.out = p;    p += 2 * 2 * 2 * rawsz;                  // [d][ob][u][8*C]
-  L.abuf = p;   p += 2 * (size_t)NAB * kSeg * 2 * RS;    // [d][buf][row][4 pad + 32 x (K + 1)][u]
-  L.pbk = p;    p += 2 * (size_t)NAB * kSeg * kPbkRow;   // [d][buf][row][lane][u] (+pad)
+  L.abuf = p;   p += 2 * (size_t)NAB * kSeg * 2 * RS;    // [d][buf][row][4 pad + 32 x (K/2 + 1) label slots][u]
+  L.bnd = p;    p += 2 * (size_t)NAB * 2 * BS;           // [d][buf][4 pad + 32 x (K + 1) slots][u]: L's state at the segment boundary
   L.lexp = p;   p += 2 * (size_t)NAB * 2 * 32;           // [d][buf][u][lane] (int)
   L.ptile = p;  p += 2 * (size_t)kNB * kSeg * 2 * Cp;    // [d][buf][row][u][Cp]
   p = (p + 3) & ~(size_t)3;
@@ -232,7 +263,7 @@ __host__ __device__ inline Layout make_layout(int K, int C, int CS, int NAB) {
 }
 
 struct Smem {
-  uint32_t raw, out, abuf, pbk, lexp, ptile, bars, zx, xtab;
+  uint32_t raw, out, abuf, bnd, lexp, ptile, bars, zx, xtab;
   int* colpos;
   int* slotlab;
   int* hist;
@@ -639,6 +670,7 @@ __device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, con
     }
     __syncwarp();
     if (lane == 0) bar_arrive(sm.bars, kBarPFull + d * kNB + buf);
+    if (!phase1) PROF_TL(7, d, i);
     ++ps.converted;
   }
   if (a.fused && !phase1 && kcnt > 0) {
@@ -695,7 +727,8 @@ __device__ __forceinline__ void role_producer(const Args& a, const Smem& sm, con
 template <int K, int CS>
 __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const Ctx& cx, const int d) {
   constexpr int Sp = 32 * K;
-  constexpr uint32_t ROWB = 8u * (32 * (K + 1) + 4);   // 4 pad pairs + 32 lane blocks of K + 1 pairs
+  constexpr uint32_t ROWB = 8u * (32 * (K / 2 + 1) + 4);   // abar row: 4 pad pairs + 32 lane blocks of K/2 label slots + 1 pad
+  constexpr uint32_t BNDB = 8u * (32 * (K + 1) + 4);       // boundary row: 4 pad pairs + 32 lane blocks of K slots + 1 pad
   constexpr uint32_t TILEB = 8u * (CS + 1) * kSeg;
   const int lane = cx.lane, nseg = cx.nseg, nA = cx.nA, T = cx.T, NAB = cx.NAB;
   float* ck = a.ckpt + (size_t)blockIdx.x * nseg * 32 * ck_floats<K>();
@@ -759,10 +792,11 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   // ------------------------------------------------------------------ meeting: Z
   // L0 publishes its state in the layout of an abar row (buffer 0, row 0 of direction 0);
   // L1 combines it with the successor sums of its own state.
-  const uint32_t myblock = 8u * (uint32_t)(4 + lane * (K + 1));
+  const uint32_t myblock = 8u * (uint32_t)(4 + lane * (K / 2 + 1));   // my label slots in an abar row
+  const uint32_t mybnd = 8u * (uint32_t)(4 + lane * (K + 1));         // my slots in a boundary row
   if (d == 0) {
 #pragma unroll
-    for (int i = 0; i < K; ++i) sts64(sm.abuf + myblock + 8u * i, v[i]);
+    for (int i = 0; i < K; ++i) sts64(sm.bnd + mybnd + 8u * i, v[i]);
     stsi(sm.lexp + 4u * (uint32_t)lane, e[0]);
     stsi(sm.lexp + 4u * (uint32_t)(32 + lane), e[1]);
   }
@@ -785,7 +819,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     }
     // partner of my slot i is slot K-2-i of L0's lane 31-lane; of my slot K-1, the last
     // slot of L0's lane 30-lane (= the element just before that block)
-    const uint32_t pblock = sm.abuf + 8u * (uint32_t)(4 + (31 - lane) * (K + 1));
+    const uint32_t pblock = sm.bnd + 8u * (uint32_t)(4 + (31 - lane) * (K + 1));
     p2 av[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) av[i] = lds64(pblock + 8u * i);
@@ -847,13 +881,19 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
       aempty_phase ^= 1u << buf;
     }
     PROF_MARK(4);
+    PROF_TL(0, d, k2);
     {
       const uint32_t le = sm.lexp + 4u * (uint32_t)((d * NAB + buf) * 64 + lane);
       stsi(le, e[0]);
       stsi(le + 128u, e[1]);
+      // state at the segment boundary: the recompute warp checks Z against it (certificate)
+      const uint32_t bb = sm.bnd + (uint32_t)(d * NAB + buf) * BNDB + mybnd;
+#pragma unroll
+      for (int i = 0; i < K; ++i) sts64(bb + 8u * i, v[i]);
     }
     TileAddr<K> ta = tile_addr<K>(tp, ring.wait(k), blank_ofs);
     PROF_MARK(5);
+    PROF_TL(1, d, k2);
     // rows of the segment buffer are in step order, like the p tile
     uint32_t ar = sm.abuf + (uint32_t)((d * NAB + buf) * kSeg) * ROWB + myblock;
     if (rows == kSeg) {
@@ -866,7 +906,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
           nx = load_prow<K, CS>(ta, it + 1);
           step<K, true>(v, abar, tp, cur, f);
 #pragma unroll
-          for (int i = 0; i < K; ++i) sts64(ar + (uint32_t)it * ROWB + 8u * i, abar[i]);
+          for (int q = 0; q < K / 2; ++q) sts64(ar + (uint32_t)it * ROWB + 8u * q, abar[2 * q + 1]);
         }
         advance_rows<K, CS>(ta, kU);
         ar += kU * ROWB;
@@ -878,12 +918,40 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
         const PRow<K> cur = load_prow<K, CS>(ta, it);
         step<K, true>(v, abar, tp, cur, f);
 #pragma unroll
-        for (int i = 0; i < K; ++i) sts64(ar + (uint32_t)it * ROWB + 8u * i, abar[i]);
+        for (int q = 0; q < K / 2; ++q) sts64(ar + (uint32_t)it * ROWB + 8u * q, abar[2 * q + 1]);
       }
     }
     __syncwarp();
     if (lane == 0) bar_arrive(sm.bars, kBarAFull + d * kMaxAB + buf);
     ring.release(k, lane, 1);
+    PROF_TL(2, d, k2);
+  }
+  // certificate, last leg: the sweep must arrive with total mass Z on the two slots that end the
+  // chain in this orientation (the recompute warps check every earlier segment boundary)
+  if (n2 > 0) {
+    int bad = 0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int S = 2 * cx.L[u] + 1;
+      const int jend = d == 0 ? S - 1 : Sp - 2;          // last state of the chain in this orientation
+      const float Zm = lds(sm.zx + 16u * u);
+      const int eZ = ldsi(sm.zx + 16u * u + 4u);
+      const bool okz = lds(sm.zx + 16u * u + 8u) != 0.f;
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const int j = lane * K + i;
+        const float x = u ? hi(v[i]) : lo(v[i]);
+        if (j == jend || (j == jend - 1 && j >= 0)) part += x;
+      }
+      if (part != 0.f) part *= defined_exp(e[u]) ? pow2c(e[u] - eZ) : 0.f;
+      const float tot = warp_sum(part);
+      if (okz && cx.live[u] && !(fabsf(tot - Zm) <= 2e-5f * Zm)) bad |= 8 << u;
+    }
+    if (bad && lane == 0) {
+      if (bad & 8) atomicOr(&a.hazard[cx.b[0]], 8);
+      if ((bad & 16) && cx.b[1] != cx.b[0]) atomicOr(&a.hazard[cx.b[1]], 8);
+    }
   }
   PROF_MARK(6);
 #ifdef WFST_PROFILE
@@ -900,27 +968,24 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
 // that its effective exponent is eZ - eL(partner lane): products need no further factor.
 // ---------------------------------------------------------------------------
 template <int K>
-__device__ __forceinline__ void rc_frame(p2 (&w)[K], const Topo<K>& tp, const PRow<K>& cur, p2 f2, p2 h2,
-                                         uint32_t arow, uint32_t pbrow) {
-  p2 av[K], dummy[K];
+__device__ __forceinline__ void rc_frame(p2 (&w)[K], const Topo<K>& tp, const PRow<K>& cur, p2 f2, p2 h2, uint32_t arow) {
+  // partner of my odd slot i (<= K-3) is label slot (K-3-i)/2 of the partner block; of my slot
+  // K-1, the last label slot of the block before it (one pad pair in between)
+  p2 av[K / 2], dummy[K];
 #pragma unroll
-  for (int i = 0; i < K - 1; ++i) av[i] = lds64(arow + 8u * i);
-  const p2 ext = lds64(arow - 16u);   // last slot of the previous block (one pad pair in between)
+  for (int q = 0; q < K / 2 - 1; ++q) av[q] = lds64(arow + 8u * q);
+  const p2 ext = lds64(arow - 16u);
   step<K, false>(w, dummy, tp, cur, f2);
-  p2 pbs = pk(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i <= K - 2; ++i) {
-    if (i & 1) sts64(arow + 8u * (K - 2 - i), mul2(w[i], av[K - 2 - i]));
-    else pbs = fma2(w[i], av[K - 2 - i], pbs);
-  }
+  for (int q = 0; q < K / 2 - 1; ++q) sts64(arow + 8u * q, mul2(w[K - 3 - 2 * q], av[q]));
   sts64(arow - 16u, mul2(mul2(w[K - 1], ext), h2));
-  sts64(pbrow, pbs);
 }
 
 template <int K, int CS>
 __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx& cx, const int d, const int x) {
   constexpr int Sp = 32 * K;
-  constexpr uint32_t ROWB = 8u * (32 * (K + 1) + 4);   // 4 pad pairs + 32 lane blocks of K + 1 pairs
+  constexpr uint32_t ROWB = 8u * (32 * (K / 2 + 1) + 4);   // abar row: 4 pad pairs + 32 lane blocks of K/2 label slots + 1 pad
+  constexpr uint32_t BNDB = 8u * (32 * (K + 1) + 4);       // boundary row: 4 pad pairs + 32 lane blocks of K slots + 1 pad
   constexpr uint32_t TILEB = 8u * (CS + 1) * kSeg;
   const int lane = cx.lane, nseg = cx.nseg, nA = cx.nA, T = cx.T, NAB = cx.NAB;
   bar_wait(sm.bars, kBarZ, 0u);      // phase 1 (and every checkpoint) is complete
@@ -934,7 +999,8 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   const float* ck = a.ckpt + (size_t)blockIdx.x * nseg * 32 * ck_floats<K>();
   PTileRing ring{sm.bars, sm.ptile + (uint32_t)d * kNB * TILEB, TILEB, d, 0u};
   const uint32_t blank_ofs = 4u * (uint32_t)a.blank;
-  const uint32_t pblock = 8u * (uint32_t)(4 + (31 - lane) * (K + 1));   // partner block in an abar row
+  const uint32_t pblock = 8u * (uint32_t)(4 + (31 - lane) * (K / 2 + 1));   // partner block in an abar row
+  const uint32_t pbnd = 8u * (uint32_t)(4 + (31 - lane) * (K + 1));        // partner block in a boundary row
   int bad = 0;   // reason 4: scale overflow when pairing live and recomputed values
   p2 w[K];
   int ew[2];
@@ -949,6 +1015,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     PROF_MARK(2);
     bar_wait(sm.bars, kBarAFull + d * kMaxAB + buf, (uint32_t)(k2 / NAB) & 1u);
     PROF_MARK(0);
+    PROF_TL(3, d, k2);
     // scales
     float g[2], h[2], fr[2];
 #pragma unroll
@@ -978,12 +1045,11 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     TileAddr<K> ta = tile_addr<K>(tp, ring.wait_use(k), blank_ofs);
     PROF_MARK(1);
     const uint32_t ar = sm.abuf + (uint32_t)((d * NAB + buf) * kSeg) * ROWB + pblock;
-    const uint32_t pb = sm.pbk + 4u * (uint32_t)(((d * NAB + buf) * kSeg) * kPbkRow + 2 * lane);
     if (rows == kSeg) {
       // against L's step order, kU frames per trip; th / ah / bh point at the trip's lowest row
       TileAddr<K> th = ta;
       advance_rows<K, CS>(th, kSeg - kU);
-      uint32_t ah = ar + (kSeg - kU) * ROWB, bh = pb + (kSeg - kU) * (4u * kPbkRow);
+      uint32_t ah = ar + (kSeg - kU) * ROWB;
       PRow<K> nx = load_prow<K, CS>(th, kU - 1);
 #pragma unroll 1
       for (int h = 0; h < kSeg / kU; ++h) {
@@ -991,17 +1057,41 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
         for (int it = kU - 1; it >= 0; --it) {
           const PRow<K> cur = nx;
           nx = load_prow<K, CS>(th, it - 1);   // it = 0: the last row of the next trip (or a harmless read)
-          rc_frame<K>(w, tp, cur, f2, h2, ah + (uint32_t)it * ROWB, bh + (uint32_t)it * (4u * kPbkRow));
+          rc_frame<K>(w, tp, cur, f2, h2, ah + (uint32_t)it * ROWB);
         }
         advance_rows<K, CS>(th, -kU);
         ah -= kU * ROWB;
-        bh -= kU * (4u * kPbkRow);
       }
     } else {
 #pragma unroll 1
       for (int it = rows - 1; it >= 0; --it) {
         const PRow<K> cur = load_prow<K, CS>(ta, it);
-        rc_frame<K>(w, tp, cur, f2, h2, ar + (uint32_t)it * ROWB, pb + (uint32_t)it * (4u * kPbkRow));
+        rc_frame<K>(w, tp, cur, f2, h2, ar + (uint32_t)it * ROWB);
+      }
+    }
+    {
+      // certificate: sum_s v_L(s) * (successor sum of w)(s) at the segment boundary must be Z
+      // (float32 range can only be exceeded by losing mass or producing inf / NaN)
+      const p2 in1 = mul2(shfl_up2(w[K - 1]), f2);
+      const uint32_t bb = sm.bnd + (uint32_t)(d * NAB + buf) * BNDB + pbnd;
+      p2 acc = pk(0.f, 0.f);
+#pragma unroll
+      for (int i = K - 1; i >= 0; --i) {
+        const p2 a1 = (i >= 1) ? w[i - 1] : in1;
+        p2 sx = add2(w[i], a1);
+        if (i & 1) {
+          const p2 a2 = (i >= 2) ? w[i - 2] : in1;
+          sx = fma2(tp.skipm[i >> 1], a2, sx);
+        }
+        if (i == K - 1) acc = fma2(mul2(sx, h2), lds64(bb - 16u), acc);
+        else acc = fma2(sx, lds64(bb + 8u * (K - 2 - i)), acc);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float tot = warp_sum(u ? hi(acc) : lo(acc));
+        const float Zm = lds(sm.zx + 16u * u);
+        const bool chk = (u ? ok1 : ok0) && cx.live[u];
+        if (chk && !(fabsf(tot - Zm) <= 2e-5f * Zm)) bad |= 16 << u;
       }
     }
     // next checkpoint (consumed at the top of the next iteration)
@@ -1009,6 +1099,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     __syncwarp();
     if (lane == 0) bar_arrive(sm.bars, kBarCFull + d * kMaxAB + buf);
     ring.release(k, lane, 1);
+    PROF_TL(4, d, k2);
   }
   PROF_MARK(2);
 #ifdef WFST_PROFILE
@@ -1019,6 +1110,8 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   if (bad && lane == 0) {
     if (bad & 4) atomicOr(&a.hazard[cx.b[0]], 4);
     if ((bad & 8) && cx.b[1] != cx.b[0]) atomicOr(&a.hazard[cx.b[1]], 4);
+    if (bad & 16) atomicOr(&a.hazard[cx.b[0]], 8);
+    if ((bad & 32) && cx.b[1] != cx.b[0]) atomicOr(&a.hazard[cx.b[1]], 8);
   }
 }
 
@@ -1029,7 +1122,8 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
 template <int K>
 __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const Ctx& cx, const int d, const int ux) {
   constexpr int Sp = 32 * K;
-  constexpr uint32_t ROWB = 8u * (32 * (K + 1) + 4);   // 4 pad pairs + 32 lane blocks of K + 1 pairs
+  constexpr uint32_t ROWB = 8u * (32 * (K / 2 + 1) + 4);   // abar row: 4 pad pairs + 32 lane blocks of K/2 label slots + 1 pad
+  constexpr uint32_t BNDB = 8u * (32 * (K + 1) + 4);       // boundary row: 4 pad pairs + 32 lane blocks of K slots + 1 pad
   const int lane = cx.lane, nseg = cx.nseg, nA = cx.nA, T = cx.T, C = cx.C, NAB = cx.NAB;
   bar_wait(sm.bars, kBarZ, 0u);
   const bool ok0 = lds(sm.zx + 8u) != 0.f, ok1 = lds(sm.zx + 24u) != 0.f;
@@ -1065,7 +1159,7 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
       for (int q = 0; q < 4; ++q) {
         const int n = colpos[4 * gsl + q];
         const int jl = d == 0 ? 2 * n + 1 : Sp - 3 - 2 * n;
-        off[q] = n >= 0 ? 8u * (uint32_t)(4 + (jl / K) * (K + 1) + jl % K) + 4u * ux : 4u * ux;   // row pad 0 is always zero
+        off[q] = n >= 0 ? 8u * (uint32_t)(4 + (jl / K) * (K / 2 + 1) + (jl % K) / 2) + 4u * ux : 4u * ux;   // row pad 0 is always zero
       }
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(xt + 512u * p), "r"(off[0] | (off[1] << 16)),
                    "r"(off[2] | (off[3] << 16)), "r"(fl | ((uint32_t)max(me, 0) << 8)), "r"(0u)
@@ -1073,8 +1167,6 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
     }
   }
   __syncwarp();
-  // blank: lane = (step, quarter) sums 8 of the 32 lane partials
-  const int frm = lane & 7, qtr = lane >> 3;
   int bad = 0;
   uint32_t cfull_phase = 0u;
   float* gE = a.gradE + (size_t)bu * T * C;
@@ -1087,6 +1179,7 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
     bar_wait(sm.bars, kBarCFull + d * kMaxAB + buf, (cfull_phase >> buf) & 1u);
     cfull_phase ^= 1u << buf;
     PROF_MARK(0);
+    if (ux == 0) PROF_TL(5, d, k2);
     if (act) {
       if (lane == 0) bulk_wait_read<1>();   // the store that last read this out buffer is done
       __syncwarp();
@@ -1094,14 +1187,9 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
       const uint32_t ot = sm.out + 4u * (uint32_t)(((d * 2 + ob) * 2 + ux) * rawsz);
       // buffer row j holds the frame of step j: frame row r = j (d = 0) or rows-1-j (d = 1)
       const int rsign = d == 0 ? 1 : -1, rbase = d == 0 ? 0 : rows - 1;
-      // blank partial sums: 8 loads in flight while the label passes run
-      float bq[8];
-      {
-        const uint32_t pb = sm.pbk + 4u * (uint32_t)(((d * NAB + buf) * kSeg + frm) * kPbkRow + 2 * (qtr * 8) + ux);
+      float rs[kSeg];     // per-row sum of the label posteriors this lane is head of
 #pragma unroll
-        for (int q = 0; q < 8; ++q) bq[q] = lds(pb + 8u * q);
-      }
-      float tot = 0.f;
+      for (int j = 0; j < kSeg; ++j) rs[j] = 0.f;
 #pragma unroll 1
       for (int p = 0; p < npass; ++p) {
         uint32_t w0, w1, w2, w3;
@@ -1133,21 +1221,39 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
           for (int j = 0; j < kSeg; ++j) {
             if (j < rows) {
               sts(dsto, c[j] * kappa);
-              tot += c[j];
+              rs[j] += c[j];
             }
             dsto += dstep;
           }
         }
       }
-      float bs = ((bq[0] + bq[1]) + (bq[2] + bq[3])) + ((bq[4] + bq[5]) + (bq[6] + bq[7]));
-      if (frm >= rows) bs = 0.f;
-      tot += bs;
-      bs += __shfl_xor_sync(kFull, bs, 8);
-      bs += __shfl_xor_sync(kFull, bs, 16);   // full blank sum of step frm
-      if (frm < rows && qtr == 0) sts(ot + 4u * (uint32_t)((rbase + rsign * frm) * C) + blank_ofs, bs * kappa);
-      // certificate: the posteriors of every frame sum to one, i.e. the segment sums to rows * Zm
-      tot = warp_sum(tot);
-      if (!(fabsf(tot - (float)rows * Zm) <= 2e-5f * (float)rows * Zm)) bad = 8;
+      // blank posterior of a frame = Zm - (sum of its label posteriors): the posteriors of a frame
+      // sum to Zm, which the recompute warp certifies at every segment boundary.  Transposed
+      // reduction of the 8 row sums: 3 halving steps, then 2 full ones; lanes with lane % 4 == 0
+      // end up with the total of row (lane >> 2).
+      {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
+        float h4[4], h2v[2], h1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = up16 ? rs[i] : rs[i + 4];
+          h4[i] = (up16 ? rs[i + 4] : rs[i]) + __shfl_xor_sync(kFull, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = up8 ? h4[i] : h4[i + 2];
+          h2v[i] = (up8 ? h4[i + 2] : h4[i]) + __shfl_xor_sync(kFull, send, 8);
+        }
+        {
+          const float send = up4 ? h2v[0] : h2v[1];
+          h1 = (up4 ? h2v[1] : h2v[0]) + __shfl_xor_sync(kFull, send, 4);
+        }
+        h1 += __shfl_xor_sync(kFull, h1, 2);
+        h1 += __shfl_xor_sync(kFull, h1, 1);
+        const int row = (up16 ? 4 : 0) + (up8 ? 2 : 0) + (up4 ? 1 : 0);
+        if ((lane & 3) == 0 && row < rows)
+          sts(ot + 4u * (uint32_t)((rbase + rsign * row) * C) + blank_ofs, fmaxf(Zm - h1, 0.f) * kappa);
+      }
       __syncwarp();
       if (lane == 0) bar_arrive(sm.bars, kBarAEmpty + d * kMaxAB + buf);   // products / partials consumed
       if (!dup) {
@@ -1177,6 +1283,7 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
       }
       if (lane == 0) bulk_commit();   // one group per segment (possibly empty)
       __syncwarp();
+      if (ux == 0) PROF_TL(6, d, k2);
     } else {
       if (lane == 0) bar_arrive(sm.bars, kBarAEmpty + d * kMaxAB + buf);
     }
@@ -1184,6 +1291,13 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
   PROF_MARK(1);
 #ifdef WFST_PROFILE
   if (blockIdx.x == 0 && lane == 0) printf("X%d.%d cycles: wait_cfull %lld compute %lld\n", d, ux, pf_acc[0], pf_acc[1]);
+  if (blockIdx.x == 0 && lane == 0 && d == 0 && ux == 0) {
+    const long long t0 = g_tl[1][16];
+    for (int k2 = 16; k2 < 24; ++k2)
+      printf("TL k2=%d: L abuf %lld ptile %lld done %lld | RC start %lld done %lld | X start %lld done %lld | P produced %lld\n", k2,
+             g_tl[0][k2] - t0, g_tl[1][k2] - t0, g_tl[2][k2] - t0, g_tl[3][k2] - t0, g_tl[4][k2] - t0, g_tl[5][k2] - t0,
+             g_tl[6][k2] - t0, g_tl[7][k2] - t0);
+  }
 #endif
   if (lane == 0) bulk_wait_all<0>();
   bad = __reduce_or_sync(kFull, (unsigned)bad);
@@ -1219,7 +1333,7 @@ __global__ void __launch_bounds__(384, 1) ctc_pair_kernel(Args a) {
     sm.raw = base + 4u * (uint32_t)lay.raw;
     sm.out = base + 4u * (uint32_t)lay.out;
     sm.abuf = base + 4u * (uint32_t)lay.abuf;
-    sm.pbk = base + 4u * (uint32_t)lay.pbk;
+    sm.bnd = base + 4u * (uint32_t)lay.bnd;
     sm.lexp = base + 4u * (uint32_t)lay.lexp;
     sm.ptile = base + 4u * (uint32_t)lay.ptile;
     sm.bars = base + 4u * (uint32_t)lay.bars;
@@ -1312,8 +1426,11 @@ __global__ void __launch_bounds__(384, 1) ctc_pair_kernel(Args a) {
   if (!cx.live[0]) { cx.y[0] = cx.y[1]; cx.L[0] = cx.L[1]; }
   if (!cx.live[1]) { cx.y[1] = cx.y[0]; cx.L[1] = cx.L[0]; }
 
-  // warp -> scheduler partition is warp % 4: each partition gets one of {L0, L1, RC0.0, RC1.0},
-  // one of the second recompute warps / producers and one reduction warp
+  // warp -> scheduler partition is warp % 4 (measured: a live warp runs ~35 % slower while a
+  // recompute warp is active on its partition, but every other placement tried -- both
+  // reduction warps, or producer + reduction warp, next to the live warp -- was slower overall)
+  //   partition 0: L0  RC0.1 X0.1      partition 2: RC0.0 X0.0 P0
+  //   partition 1: L1  RC1.1 X1.1      partition 3: RC1.0 X1.0 P1
   if (warp < 2) role_live<K, CS>(a, sm, cx, warp);
   else if (warp < 6) role_rc<K, CS>(a, sm, cx, warp & 1, (warp - 2) >> 1);     // RC0.0 RC1.0 RC0.1 RC1.1
   else if (warp < 10) role_reduce<K>(a, sm, cx, warp & 1, (warp - 6) >> 1);    // X0.0 X1.0 X0.1 X1.1

@@ -151,52 +151,84 @@ std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B
   PairMatcher m(A, B);
   const size_t NA = (size_t)A.num_nodes();
   auto key = [NA](int a, int b) { return (size_t)a + NA * (size_t)b; };
-  // backward pass: which state pairs can reach an accepting pair
-  std::vector<uint8_t> live(NA * (size_t)B.num_nodes(), 0);
+  // Which state pairs can reach an accepting pair?  GTN answers this with a backward sweep
+  // over ALL pairs before the forward build; with a 1000-token graph on one side that sweep
+  // visits ~10^6 pairs per utterance although only a few thousand are reachable from the start.
+  // Here: explore the pairs reachable from the start pairs first (same moves as the forward
+  // build below), record the moves, and propagate co-accessibility backwards along them.  The
+  // forward build only ever asks about reachable pairs, so its result (node numbering, arc
+  // order, provenance) is unchanged.
+  // The products here have ~10^6 state pairs of which a few thousand are ever touched: pairs are
+  // numbered in discovery order through a hash map, everything else is indexed by that number.
+  std::unordered_map<size_t, int32_t> idx;               // pair key -> index in `pairs`
+  idx.reserve(8192);
+  std::vector<std::pair<int, int>> pairs;
+  std::vector<uint8_t> live;                             // by pair index: can reach an accepting pair
   {
-    std::deque<std::pair<int, int>> todo;
-    for (int fa : A.accepts)
-      for (int fb : B.accepts) {
-        live[key(fa, fb)] = 1;
-        todo.emplace_back(fa, fb);
-      }
-    while (!todo.empty()) {
-      auto [ca, cb] = todo.front();
-      todo.pop_front();
+    std::vector<std::pair<int32_t, int32_t>> edges;      // (from, to) in `pairs` indices
+    auto visit = [&](int a, int b) -> int32_t {
+      auto ins = idx.emplace(key(a, b), (int32_t)pairs.size());
+      if (ins.second) pairs.emplace_back(a, b);
+      return ins.first->second;
+    };
+    for (int sa : A.starts)
+      for (int sb : B.starts) visit(sa, sb);
+    for (size_t head = 0; head < pairs.size(); ++head) {
+      const int ca = pairs[head].first, cb = pairs[head].second;
       bool eps_pair = false;
-      m.for_each(ca, cb, true, [&](int32_t i, int32_t j) {
+      m.for_each(ca, cb, false, [&](int32_t i, int32_t j) {
         eps_pair = eps_pair || A.ol[i] == kEpsilon;
-        size_t k = key(A.src[i], B.src[j]);
-        if (!live[k]) { live[k] = 1; todo.emplace_back(A.src[i], B.src[j]); }
+        edges.emplace_back((int32_t)head, visit(A.dst[i], B.dst[j]));
       });
       if (eps_pair) continue;
-      for (int32_t i : A.in[ca]) {
+      for (int32_t i : A.out[ca]) {
         if (A.ol[i] != kEpsilon) { if (A.ol_sorted) break; else continue; }
-        size_t k = key(A.src[i], cb);
-        if (!live[k]) { live[k] = 1; todo.emplace_back(A.src[i], cb); }
+        edges.emplace_back((int32_t)head, visit(A.dst[i], cb));
       }
-      for (int32_t j : B.in[cb]) {
+      for (int32_t j : B.out[cb]) {
         if (B.il[j] != kEpsilon) { if (B.il_sorted) break; else continue; }
-        size_t k = key(ca, B.src[j]);
-        if (!live[k]) { live[k] = 1; todo.emplace_back(ca, B.src[j]); }
+        edges.emplace_back((int32_t)head, visit(ca, B.dst[j]));
       }
     }
+    // reverse adjacency (CSR) over the recorded moves, then a backward sweep from the accepting pairs
+    std::vector<int32_t> rptr(pairs.size() + 1, 0), radj(edges.size());
+    for (auto& e : edges) ++rptr[e.second + 1];
+    for (size_t k = 0; k < pairs.size(); ++k) rptr[k + 1] += rptr[k];
+    {
+      std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1);
+      for (auto& e : edges) radj[fill[e.second]++] = e.first;
+    }
+    std::vector<int32_t> stack;
+    std::vector<uint8_t> co(pairs.size(), 0);
+    for (size_t k = 0; k < pairs.size(); ++k)
+      if ((A.flags[pairs[k].first] & 2) && (B.flags[pairs[k].second] & 2)) { co[k] = 1; stack.push_back((int32_t)k); }
+    while (!stack.empty()) {
+      const int32_t k = stack.back();
+      stack.pop_back();
+      for (int32_t r = rptr[k]; r < rptr[k + 1]; ++r)
+        if (!co[radj[r]]) { co[radj[r]] = 1; stack.push_back(radj[r]); }
+    }
+    live.swap(co);
   }
+  std::vector<int32_t> id(pairs.size(), -1);             // by pair index: node number in the output
+  auto pair_index = [&](int a, int b) -> int32_t {
+    auto it = idx.find(key(a, b));
+    return it == idx.end() ? -1 : it->second;
+  };
   // forward pass: nodes numbered in breadth-first discovery order
   auto out = std::make_unique<HostGraph>();
   out->calc_grad = A.calc_grad || B.calc_grad;
-  std::vector<int32_t> id(live.size(), -1);
   std::deque<std::pair<int, int>> todo;
   for (int sa : A.starts)
     for (int sb : B.starts) {
-      size_t k = key(sa, sb);
-      if (!live[k]) continue;
+      const int32_t k = pair_index(sa, sb);
+      if (k < 0 || !live[k]) continue;
       id[k] = out->add_node(true, (A.flags[sa] & 2) && (B.flags[sb] & 2));
       todo.emplace_back(sa, sb);
     }
   auto node_for = [&](int a, int b) -> int {
-    size_t k = key(a, b);
-    if (!live[k]) return -1;
+    const int32_t k = pair_index(a, b);
+    if (k < 0 || !live[k]) return -1;
     if (id[k] < 0) {
       id[k] = out->add_node((A.flags[a] & 1) && (B.flags[b] & 1), (A.flags[a] & 2) && (B.flags[b] & 2));
       todo.emplace_back(a, b);
@@ -206,7 +238,7 @@ std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B
   while (!todo.empty()) {
     auto [ca, cb] = todo.front();
     todo.pop_front();
-    const int cur = id[key(ca, cb)];
+    const int cur = id[pair_index(ca, cb)];
     bool eps_pair = false;
     m.for_each(ca, cb, false, [&](int32_t i, int32_t j) {
       eps_pair = eps_pair || A.ol[i] == kEpsilon;

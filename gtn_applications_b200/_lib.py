@@ -37,6 +37,7 @@ SIGNATURES = {
     "wfst_abi_version": (_I, []),
     "wfst_launch_count": (ctypes.c_ulonglong, []),
     "wfst_debug_force_generic_ctc": (_I, [_I]),
+    "wfst_debug_force_generic_lattice": (_I, [_I]),
     "wfst_debug_ctc_hazards": (_I, [_P, _I, _I, _I, _I, _P]),
     "wfst_ctc_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "wfst_ctc_forward_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),

@@ -59,6 +59,7 @@ int wfst_debug_force_generic_ctc(int on) {
   g_force_generic_kind = (on == 2) ? 2 : 0;
   return old;
 }
+int wfst_debug_force_generic_lattice(int on) { return lattice_force_generic(on != 0); }
 unsigned long long wfst_launch_count(void) { return g_launches.load(); }
 
 // --------------------------------------------------------------------- CTC
@@ -278,9 +279,36 @@ int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
 }
 
 // --------------------------------------------------------------------- ASG
+// The full-connect and the force-align lattices of one batch are independent until their
+// gradients meet; each is a latency-bound kernel that fills a fraction of the GPU (one warp /
+// a few warps per utterance), so they run side by side: full-connect on the caller's stream,
+// force-align on a side stream of the library, joined by events before the gradients are added.
+namespace wfst {
+struct SideStream {
+  std::mutex mu;
+  cudaStream_t stream[16] = {};
+  cudaEvent_t fork[16] = {}, join[16] = {};
+  int get(int dev, cudaStream_t* s, cudaEvent_t* f, cudaEvent_t* j) {
+    if (dev < 0 || dev >= 16) return WFST_ERR_UNSUPPORTED;
+    if (!stream[dev]) {
+      WFST_CUDA_CHECK(cudaStreamCreateWithFlags(&stream[dev], cudaStreamNonBlocking));
+      WFST_CUDA_CHECK(cudaEventCreateWithFlags(&fork[dev], cudaEventDisableTiming));
+      WFST_CUDA_CHECK(cudaEventCreateWithFlags(&join[dev], cudaEventDisableTiming));
+    }
+    *s = stream[dev]; *f = fork[dev]; *j = join[dev];
+    return WFST_OK;
+  }
+};
+static SideStream g_side;
+}  // namespace wfst
+
+// workspace: [history full-connect][history force-align][z_fcc B][z_fal B][force-align gradient B*T*C]
+static size_t asg_hist_fcc_bytes(int B, int T, int C) { return lattice_hist_bytes(B, T, C, C + 1); }
+static size_t asg_hist_fal_bytes(int B, int T, int C, int L) { return lattice_hist_bytes(B, T, C, L + 1); }
+
 size_t wfst_asg_workspace_bytes(int B, int T, int C, int max_target_len) {
-  int n = max_target_len + 1 > C + 1 ? max_target_len + 1 : C + 1;
-  return lattice_hist_bytes(B, T, C, n) + 2 * align_up((size_t)B * sizeof(float), 256);
+  return asg_hist_fcc_bytes(B, T, C) + asg_hist_fal_bytes(B, T, C, max_target_len) +
+         2 * align_up((size_t)B * sizeof(float), 256) + align_up((size_t)B * T * C * sizeof(float), 256);
 }
 
 int wfst_asg_forward_backward(const float* emissions, const float* transitions,
@@ -296,23 +324,44 @@ int wfst_asg_forward_backward(const float* emissions, const float* transitions,
     return WFST_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  int n = max_target_len + 1 > C + 1 ? max_target_len + 1 : C + 1;
-  size_t hb = lattice_hist_bytes(B, T, C, n), zb = align_up((size_t)B * sizeof(float), 256);
-  float* hist = (float*)workspace;
-  float* zfcc = (float*)((char*)workspace + hb);
-  float* zfal = (float*)((char*)workspace + hb + zb);
+  const size_t hb1 = asg_hist_fcc_bytes(B, T, C), hb2 = asg_hist_fal_bytes(B, T, C, max_target_len),
+               zb = align_up((size_t)B * sizeof(float), 256);
+  char* w = (char*)workspace;
+  float* hist_fcc = (float*)w;
+  float* hist_fal = (float*)(w + hb1);
+  float* zfcc = (float*)(w + hb1 + hb2);
+  float* zfal = (float*)(w + hb1 + hb2 + zb);
+  float* gfal = (float*)(w + hb1 + hb2 + 2 * zb);
   if (grad_transitions)
     WFST_CUDA_CHECK(cudaMemsetAsync(grad_transitions, 0, (size_t)(C + 1) * C * 4, st));
-  // loss = Z_fcc - Z_fal (asg.py:111-115): full-connect writes, force-align subtracts
-  int rc = (asg_fcc_dense_eligible(T, C) && !g_force_generic)
-               ? launch_asg_fcc_dense(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
-                                      grad_transitions, hist, st)
-               : launch_asg_fcc(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
-                                grad_transitions, hist, st);
+  int dev = 0;
+  WFST_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaStream_t s2; cudaEvent_t ev_fork, ev_join;
+  std::lock_guard<std::mutex> lk(g_side.mu);   // the events are shared: enqueue fork..join atomically
+  int rc = g_side.get(dev, &s2, &ev_fork, &ev_join);
   if (rc != WFST_OK) return rc;
-  rc = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
-                      grad_scale, -1.f, zfal, grad_emissions, 1, grad_transitions, hist, st);
+  WFST_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+  WFST_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_fork, 0));
+  // loss = Z_fcc - Z_fal (asg.py:111-115)
+  rc = (asg_fcc_dense_eligible(T, C) && !g_force_generic)
+           ? launch_asg_fcc_dense(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
+                                  grad_transitions, hist_fcc, st)
+           : launch_asg_fcc(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
+                            grad_transitions, hist_fcc, st);
+  int rc2 = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
+                           grad_scale, -1.f, zfal, grad_emissions ? gfal : nullptr, 0, grad_transitions,
+                           hist_fal, s2);
+  // always join, also after a failed launch: the side stream must not stay forked
+  cudaError_t e1 = cudaEventRecord(ev_join, s2);
+  cudaError_t e2 = cudaStreamWaitEvent(st, ev_join, 0);
   if (rc != WFST_OK) return rc;
+  if (rc2 != WFST_OK) return rc2;
+  WFST_CUDA_CHECK(e1);
+  WFST_CUDA_CHECK(e2);
+  if (grad_emissions) {
+    rc = launch_add(grad_emissions, gfal, (size_t)B * T * C, st);
+    if (rc != WFST_OK) return rc;
+  }
   return launch_finalize(zfcc, zfal, 1.f, B, grad_scale, loss, mean_loss, st);
 }
 

@@ -2,6 +2,7 @@
 // entry points built on it.  See include/wfst_b200.h for the contract of each
 // entry point and the reference call sites it replaces.
 #include "lattice.cuh"
+#include "lattice_lean.cuh"
 
 #include <cstring>
 
@@ -226,6 +227,144 @@ struct AsgFccTopo {
   }
 };
 
+
+// ===========================================================================
+// Builders for the lean kernel (lattice_lean.cuh): the same three acceptors,
+// written once per utterance into shared memory as packed arc records.
+// ===========================================================================
+struct CsrLean {
+  using Params = CsrTopo::Params;
+  static constexpr int kDeg = 4;          // arcs per node held in registers; more are allowed
+  static constexpr bool kTail = true;
+  const int* in_ptr; const int* in_src; const int* in_label; const int* in_arc;
+  const int* out_ptr; const int* out_dst; const int* out_label; const int* out_arc;
+  const uint8_t* flags; const float* w; float* gradW; const float* fw; float* gradF;
+  int N, A, shared;
+  __device__ void init(const Params& p, int b) {
+    int gb = p.shared ? 0 : b;
+    int nb = p.g.node_offsets[gb], ab = p.g.arc_offsets[gb];
+    N = p.g.node_offsets[gb + 1] - nb;
+    A = p.g.arc_offsets[gb + 1] - ab;
+    in_ptr = p.g.in_ptr + nb + gb;  out_ptr = p.g.out_ptr + nb + gb;
+    in_src = p.g.in_src + ab;  in_label = p.g.in_label + ab;  in_arc = p.g.in_arc + ab;
+    out_dst = p.g.out_dst + ab; out_label = p.g.out_label + ab; out_arc = p.g.out_arc + ab;
+    flags = p.g.node_flags + nb;
+    w = p.g.weights ? p.g.weights + ab : nullptr;
+    gradW = p.gradW ? p.gradW + ab : nullptr;
+    fw = p.g.final_weights ? p.g.final_weights + nb : nullptr;
+    gradF = p.g.grad_final_weights ? p.g.grad_final_weights + nb : nullptr;
+    shared = p.shared;
+  }
+  __device__ int num_nodes() const { return N; }
+  __device__ int num_slots() const { return A; }
+  __device__ void build(const lean::Build& bd) {
+    for (int v = threadIdx.x; v < N; v += blockDim.x)
+      bd.node(v, in_ptr[v], in_ptr[v + 1], out_ptr[v], out_ptr[v + 1], flags[v] & 1, flags[v] & 2,
+              fw ? fw[v] : 0.f);
+    for (int k = threadIdx.x; k < A; k += blockDim.x) {
+      const int ia = in_arc[k], oa = out_arc[k];
+      bd.in_arc(k, in_src[k], in_label[k], w ? w[ia] : 0.f);
+      bd.out_arc(k, out_dst[k], out_label[k], w ? w[oa] : 0.f, oa);
+    }
+  }
+  __device__ void add_final_grad(int v, float g) const {
+    if (!gradF) return;
+    if (shared) atomicAdd(&gradF[v], g); else gradF[v] = g;
+  }
+  // every arc has exactly one out-arc slot, owned by one thread: plain sums per utterance
+  __device__ void finish(uint32_t s_gw, uint32_t s_gidx, float gs, int want) const {
+    if (!want || !gradW) return;
+    for (int k = threadIdx.x; k < A; k += blockDim.x) {
+      const float v = lean::lds_f(s_gw + 4u * k) * gs;
+      const int idx = (int)lean::lds_u(s_gidx + 4u * k);
+      if (shared) { if (v != 0.f) atomicAdd(&gradW[idx], v); }
+      else gradW[idx] = v;
+    }
+  }
+};
+
+struct CtcLean {
+  using Params = CtcTopo::Params;
+  static constexpr int kDeg = 3;          // self, previous, skip
+  static constexpr bool kTail = false;
+  const int* y; int L, S, blank, C;
+  __device__ void init(const Params& p, int b) {
+    y = p.targets + p.offsets[b];
+    L = p.offsets[b + 1] - p.offsets[b];
+    S = 2 * L + 1; blank = p.blank; C = p.C;
+  }
+  __device__ int num_nodes() const { return S; }
+  __device__ int num_slots() const { return 3 * S; }
+  __device__ int lab(int s) const { return (s & 1) ? min(max(y[(s - 1) >> 1], 0), C - 1) : blank; }
+  __device__ bool skip(int s) const { return (s & 1) && s > 1 && y[(s - 1) >> 1] != y[((s - 1) >> 1) - 1]; }
+  __device__ void build(const lean::Build& bd) {
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+      const int l = lab(s);
+      uint32_t ni = 0, no = 0;
+      bd.in_arc(3 * s + ni++, s, l, 0.f);
+      if (s > 0) bd.in_arc(3 * s + ni++, s - 1, l, 0.f);
+      if (skip(s)) bd.in_arc(3 * s + ni++, s - 2, l, 0.f);
+      bd.out_arc(3 * s + no++, s, l, 0.f, -1);
+      if (s + 1 < S) bd.out_arc(3 * s + no++, s + 1, lab(s + 1), 0.f, -1);
+      if (s + 2 < S && skip(s + 2)) bd.out_arc(3 * s + no++, s + 2, lab(s + 2), 0.f, -1);
+      bd.node(s, 3 * s, 3 * s + ni, 3 * s, 3 * s + no, s == 0, s == S - 1 || s == S - 2, 0.f);
+    }
+  }
+  __device__ void add_final_grad(int, float) const {}
+  __device__ void finish(uint32_t, uint32_t, float, int) const {}
+};
+
+struct AsgFalLean {
+  using Params = AsgFalTopo::Params;
+  static constexpr int kDeg = 2;          // enter, self loop
+  static constexpr bool kTail = false;
+  const int* y; const float* tr; float* gradTr; int L, C; uint32_t s_node_out;
+  __device__ void init(const Params& p, int b) {
+    y = p.targets + p.offsets[b];
+    L = p.offsets[b + 1] - p.offsets[b];
+    C = p.C; tr = p.tr; gradTr = p.gradTr; s_node_out = 0;
+  }
+  __device__ int lbl(int k) const { return min(max(y[k], 0), C - 1); }
+  __device__ int num_nodes() const { return L + 1; }
+  __device__ int num_slots() const { return 2 * (L + 1); }
+  __device__ void build(const lean::Build& bd) {
+    s_node_out = bd.node_out;
+    for (int l = threadIdx.x; l <= L; l += blockDim.x) {
+      uint32_t ni = 0, no = 0;
+      if (l >= 1) {
+        const int cur = lbl(l - 1);
+        const int enter = (l == 1) ? cur : C + cur * C + lbl(l - 2);
+        const int loop = C + cur * C + cur;
+        bd.in_arc(2 * l + ni++, l - 1, cur, tr[enter]);
+        bd.in_arc(2 * l + ni++, l, cur, tr[loop]);
+      }
+      if (l < L) {
+        const int nx = lbl(l);
+        const int enter = (l == 0) ? nx : C + nx * C + lbl(l - 1);
+        bd.out_arc(2 * l + no++, l + 1, nx, tr[enter], enter);
+      }
+      if (l >= 1) {
+        const int cur = lbl(l - 1);
+        const int loop = C + cur * C + cur;
+        bd.out_arc(2 * l + no++, l, cur, tr[loop], loop);
+      }
+      bd.node(l, 2 * l, 2 * l + ni, 2 * l, 2 * l + no, l == 0, L > 0 && l == L, 0.f);
+    }
+  }
+  __device__ void add_final_grad(int, float) const {}
+  // several arcs (and all utterances) share a transition: one atomic per arc and utterance
+  __device__ void finish(uint32_t s_gw, uint32_t s_gidx, float gs, int want) const {
+    if (!want || !gradTr || gs == 0.f) return;
+    for (int u = threadIdx.x; u <= L; u += blockDim.x) {
+      const uint32_t be = lean::lds_u(s_node_out + 4u * u);
+      for (uint32_t k = be & 0xffffu; k < (be >> 16); ++k) {
+        const float v = lean::lds_f(s_gw + 4u * k);
+        if (v != 0.f) atomicAdd(&gradTr[lean::lds_u(s_gidx + 4u * k)], v * gs);
+      }
+    }
+  }
+};
+
 // ===========================================================================
 // small finishing kernels
 // ===========================================================================
@@ -256,6 +395,25 @@ __global__ void scale_inplace_kernel(float* x, size_t n, const float* scale) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) x[i] *= s;
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    float4* x4 = reinterpret_cast<float4*>(x);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const size_t n4 = n / 4;
+    for (size_t k = i; k < n4; k += stride) {
+      float4 a = x4[k];
+      const float4 b = __ldcs(y4 + k);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      x4[k] = a;
+    }
+    for (size_t k = n4 * 4 + i; k < n; k += stride) x[k] += y[k];
+  } else {
+    for (size_t k = i; k < n; k += stride) x[k] += y[k];
+  }
 }
 
 // ===========================================================================
@@ -291,6 +449,55 @@ static int launch_lattice(LatticeArgs a, typename Topo::Params tp, int B, int ma
   return WFST_OK;
 }
 
+
+// Lean kernel when the acceptor fits its limits (lattice_lean.cuh); returns false otherwise.
+static int g_force_generic_lattice = 0;   // test hook: 1 = never use the lean kernel
+
+template <class Builder, int NPT>
+static int launch_lean_npt(const lean::Args& g, typename Builder::Params bp, int B, int nt, size_t smem,
+                           cudaStream_t st) {
+  auto kern = lean::lattice_lean_kernel<Builder, NPT>;
+  WFST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B, nt, smem, st>>>(g, bp);
+  g_launches++;
+  WFST_CUDA_CHECK(cudaGetLastError());
+  return WFST_OK;
+}
+
+template <class Builder>
+static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, int max_nodes, int aslots,
+                            int want_gw, cudaStream_t st, int* rc) {
+  if (g_force_generic_lattice) return false;
+  if (max_nodes < 1 || max_nodes > 16 * 1024 || aslots > 65535 || a.C > 65535) return false;
+  int npt = (max_nodes + 1023) / 1024;
+  npt = npt <= 4 ? npt : (npt <= 8 ? 8 : 16);
+  int nt = ((max_nodes + npt - 1) / npt + 31) / 32 * 32;
+  if (nt < 64) nt = 64;
+  a.npad = (max_nodes + 3) & ~3;
+  if (aslots < 1) aslots = 1;
+  int kt = a.Kt;
+  lean::Layout lay = lean::make_layout(kt, a.C, a.npad, aslots, want_gw);
+  while (lay.total > 227u * 1024u && kt > 4) {
+    kt -= 4;
+    lay = lean::make_layout(kt, a.C, a.npad, aslots, want_gw);
+  }
+  if (lay.total > 227u * 1024u) return false;
+  a.Kt = kt;
+  a.renorm_every = (16 + kt - 1) / kt;
+  lean::Args g{a, aslots, want_gw};
+  switch (npt) {
+    case 1: *rc = launch_lean_npt<Builder, 1>(g, bp, B, nt, lay.total, st); break;
+    case 2: *rc = launch_lean_npt<Builder, 2>(g, bp, B, nt, lay.total, st); break;
+    case 3: *rc = launch_lean_npt<Builder, 3>(g, bp, B, nt, lay.total, st); break;
+    case 4: *rc = launch_lean_npt<Builder, 4>(g, bp, B, nt, lay.total, st); break;
+    case 8: *rc = launch_lean_npt<Builder, 8>(g, bp, B, nt, lay.total, st); break;
+    default: *rc = launch_lean_npt<Builder, 16>(g, bp, B, nt, lay.total, st); break;
+  }
+  return true;
+}
+
+int lattice_force_generic(int on) { int old = g_force_generic_lattice; g_force_generic_lattice = on; return old; }
+
 static size_t hist_bytes(int B, int T, int stride) {
   return align_up((size_t)B * (T + 1) * stride * sizeof(float), 256);
 }
@@ -299,7 +506,8 @@ static size_t hist_bytes(int B, int T, int stride) {
 // ---------------------------------------------------------------------------
 // internal launchers used by capi.cu
 // ---------------------------------------------------------------------------
-static int num_tiles(int T, int C) { int kt = pick_kt(C); return 2 * ((T + kt - 1) / kt + 1); }
+// sized for the smallest tile (4 frames): the lean kernel may shrink Kt to fit shared memory
+static int num_tiles(int T, int C) { (void)C; return 2 * ((T + 3) / 4 + 1); }
 
 static LatticeArgs base_args(const float* E, int B, int T, int C, const float* grad_scale, float sign,
                              float* scores, float* gradE, int accumulate, float* hist,
@@ -328,6 +536,8 @@ int launch_ctc(const float* E, const int* targets, const int* offsets, int B, in
   LatticeArgs a = base_args(E, B, T, C, grad_scale, -1.f, scores, gradE, 0, hist, S, 2 * S + 2);
   a.active = active;
   CtcTopo::Params tp{targets, offsets, blank, C};
+  int rc;
+  if (try_launch_lean<CtcLean>(a, tp, B, S, 3 * S, 0, st, &rc)) return rc;
   return launch_lattice<CtcTopo>(a, tp, B, S, st);
 }
 
@@ -337,6 +547,8 @@ int launch_csr(const float* E, int T, int C, const wfst_acceptor_batch_t& g, int
   LatticeArgs a = base_args(E, g.B, T, C, grad_scale, sign, scores, gradE, accumulate, hist,
                             g.max_nodes, gradW ? g.max_arcs : 0);
   CsrTopo::Params tp{g, gradW, shared};
+  int rc;
+  if (try_launch_lean<CsrLean>(a, tp, g.B, g.max_nodes, g.max_arcs, gradW ? 1 : 0, st, &rc)) return rc;
   return launch_lattice<CsrTopo>(a, tp, g.B, g.max_nodes, st);
 }
 
@@ -347,6 +559,9 @@ int launch_asg_fal(const float* E, const float* tr, const int* targets, const in
   LatticeArgs a = base_args(E, B, T, C, grad_scale, sign, scores, gradE, accumulate, hist,
                             max_target_len + 1, gradTr ? 2 * (C + 1) * C + 2 : 0);
   AsgFalTopo::Params tp{targets, offsets, tr, gradTr, C};
+  int rc;
+  if (try_launch_lean<AsgFalLean>(a, tp, B, max_target_len + 1, 2 * (max_target_len + 1), gradTr ? 1 : 0, st, &rc))
+    return rc;
   return launch_lattice<AsgFalTopo>(a, tp, B, max_target_len + 1, st);
 }
 
@@ -362,6 +577,17 @@ int launch_asg_fcc(const float* E, const float* tr, int B, int T, int C, const f
 int launch_finalize(const float* za, const float* zb, float sign, int B, const float* grad_scale,
                     float* loss, float* mean_loss, cudaStream_t st) {
   finalize_loss_kernel<<<1, 256, 0, st>>>(za, zb, sign, B, grad_scale, loss, mean_loss);
+  g_launches++;
+  WFST_CUDA_CHECK(cudaGetLastError());
+  return WFST_OK;
+}
+
+int launch_add(float* x, const float* y, size_t n, cudaStream_t st) {
+  if (n == 0) return WFST_OK;
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  add_inplace_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n);
   g_launches++;
   WFST_CUDA_CHECK(cudaGetLastError());
   return WFST_OK;

@@ -6,6 +6,8 @@
 
 namespace wfst {
 size_t lattice_hist_bytes(int B, int T, int C, int max_nodes);
+// test hook: 1 = never use the shared-memory ("lean") lattice kernel; returns the old value
+int lattice_force_generic(int on);
 int launch_ctc(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                int blank, int max_target_len, const float* grad_scale, float* scores,
                float* gradE, float* hist, const int* active, cudaStream_t st);
@@ -27,6 +29,8 @@ int launch_asg_fcc_dense(const float* E, const float* tr, int B, int T, int C, c
 int launch_finalize(const float* za, const float* zb, float sign, int B, const float* grad_scale,
                     float* loss, float* mean_loss, cudaStream_t st);
 int launch_scale(float* x, size_t n, const float* scale, cudaStream_t st);
+// x[i] += y[i]
+int launch_add(float* x, const float* y, size_t n, cudaStream_t st);
 // fast CTC (ctc_fast.cu)
 bool ctc_fast_eligible(int T, int C, int max_target_len);
 size_t ctc_fast_workspace_bytes(int B, int T, int max_target_len);

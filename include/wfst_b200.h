@@ -55,6 +55,10 @@ WFST_API int wfst_abi_version(void);
 /* test hook: 1 = run CTC on the log-semiring lattice kernel only, 2 = skip the paired
  * scaled-probability kernel (use the single-utterance one), 0 = default (returns the old value) */
 WFST_API int wfst_debug_force_generic_ctc(int on);
+/* test hook: 1 = the acceptor lattice entry points (CSR, ASG force-align, CTC fallback) use the
+ * generic global-memory kernel even when the acceptor fits the shared-memory ("lean") kernel,
+ * 0 = default (returns the old value) */
+WFST_API int wfst_debug_force_generic_lattice(int on);
 /* test hook: copies the per-utterance fallback flags of the last CTC call that used
  * `workspace` to the host (1 = recomputed by the log-semiring kernel, -1 = fast path not used) */
 WFST_API int wfst_debug_ctc_hazards(const void* workspace, int B, int T, int C, int max_target_len,

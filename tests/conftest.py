@@ -38,3 +38,13 @@ def gtn32():
 def gtn64():
     import gtn64
     return gtn64
+
+
+@pytest.fixture(params=["lean", "generic"])
+def lattice_kernel(request):
+    """Runs a GPU test once on the shared-memory ("lean") lattice kernel (the default) and once
+    with the generic global-memory kernel forced through the C-ABI test hook."""
+    from gtn_applications_b200 import _lib
+    old = _lib.lib().wfst_debug_force_generic_lattice(1 if request.param == "generic" else 0)
+    yield request.param
+    _lib.lib().wfst_debug_force_generic_lattice(old)

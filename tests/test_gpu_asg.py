@@ -29,7 +29,7 @@ def test_known_answer():
 
 
 @pytest.mark.parametrize("case", ["small_none", "small_mean", "mid_mean"])
-def test_fixtures_from_reference(case):
+def test_fixtures_from_reference(case, lattice_kernel):
     z = G.load("asg")
     tg = G.unpack(z[case + "_targets"], z[case + "_offsets"])
     loss, ge, gt = run(z[case + "_emissions"], z[case + "_transitions"], tg, str(z[case + "_reduction"]))
@@ -45,7 +45,7 @@ def test_fixtures_from_reference(case):
     (2, 120, 30, [40, 60], "mean"),
     (3, 64, 80, [10, 31, 5], "none"),     # reference benchmark's N=80 (asg_benchmark.py:19)
 ])
-def test_against_float64_oracle(gtn64, B, T, C, lens, reduction):
+def test_against_float64_oracle(gtn64, B, T, C, lens, reduction, lattice_kernel):
     import ref_criterions as rc
     rng = np.random.default_rng(B * 100 + T)
     e = rng.standard_normal((B, T, C)).astype(np.float32)

@@ -166,7 +166,7 @@ def _hazards(B, T, C, L):
     (3, 120, 30, [30, 30, 30], 6.0),                # steep scores: utterances leave the scaled kernels
     (2, 96, 70, [20, 47], 1.0),                     # C > 31: wider p tiles
 ])
-def test_every_ctc_kernel_against_numpy_dp(kind, B, T, C, lens, scale):
+def test_every_ctc_kernel_against_numpy_dp(kind, B, T, C, lens, scale, lattice_kernel):
     """The three CTC kernels (and the hand-off between them) against the closed-form float64 DP."""
     import dp_numpy
     from gtn_applications_b200 import _lib

@@ -21,8 +21,8 @@ def random_acceptor(rng, N, A, C, weights=True):
 
 
 @pytest.mark.parametrize("B,T,C,N,A", [(3, 9, 5, 6, 20), (4, 33, 17, 40, 160), (2, 70, 1001, 300, 900),
-                                       (5, 16, 8, 1, 3)])
-def test_random_acceptors(B, T, C, N, A):
+                                       (5, 16, 8, 1, 3), (2, 21, 40, 2300, 7000), (2, 40, 6, 3, 40)])
+def test_random_acceptors(B, T, C, N, A, lattice_kernel):
     from gtn_applications_b200.packing import PackedAcceptors
     from gtn_applications_b200.lattice import lattice_forward_backward
     rng = np.random.default_rng(B + T + C)
@@ -46,7 +46,7 @@ def test_random_acceptors(B, T, C, N, A):
         assert_close(gW[a0:a1], rW * gs[b])
 
 
-def test_ctc_chain_through_csr_matches_closed_form_kernel():
+def test_ctc_chain_through_csr_matches_closed_form_kernel(lattice_kernel):
     from gtn_applications_b200.packing import PackedAcceptors
     from gtn_applications_b200.lattice import lattice_forward_backward
     from gtn_applications_b200.criterions.ctc import CTCLoss
@@ -66,7 +66,7 @@ def test_ctc_chain_through_csr_matches_closed_form_kernel():
     torch.testing.assert_close(-gE / B, lp.grad, rtol=1e-4, atol=1e-7)
 
 
-def test_shared_graph_accumulates_weight_gradient():
+def test_shared_graph_accumulates_weight_gradient(lattice_kernel):
     from gtn_applications_b200.packing import PackedAcceptors
     from gtn_applications_b200.lattice import lattice_forward_backward
     rng = np.random.default_rng(11)

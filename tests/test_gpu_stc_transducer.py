@@ -28,7 +28,7 @@ def test_stc_known_answers():
 
 
 @pytest.mark.parametrize("case", ["fn_none", "fn_mean"])
-def test_stc_function_fixtures_and_oracle(gtn64, case):
+def test_stc_function_fixtures_and_oracle(gtn64, case, lattice_kernel):
     from gtn_applications_b200.criterions.stc import STCLoss
     z = G.load("stc")
     tg = G.unpack(z[case + "_targets"], z[case + "_offsets"])
@@ -71,7 +71,7 @@ TOKENS, G2I = ["a", "b", "ab", "ba", "aba"], {"a": 0, "b": 1}
 
 @pytest.mark.parametrize("name,blank,rep", [("wp_none", "none", True), ("wp_opt", "optional", True),
                                             ("wp_norep", "optional", False), ("wp_forced", "forced", True)])
-def test_transducer_wordpiece_fixtures(name, blank, rep):
+def test_transducer_wordpiece_fixtures(name, blank, rep, lattice_kernel):
     from gtn_applications_b200.criterions.transducer import Transducer
     z = G.load("transducer")
     tg = G.unpack(z["wp_targets"], z["wp_offsets"])
@@ -125,7 +125,7 @@ def test_transducer_equals_ctc(reduction):
     torch.testing.assert_close(ga, x.grad, rtol=1e-4, atol=1e-5)
 
 
-def test_transducer_with_asg_transitions(gtn64):
+def test_transducer_with_asg_transitions(gtn64, lattice_kernel):
     # transducer_test.py:420-508: ASG as a transducer with a learned bigram transition graph
     from gtn_applications_b200.criterions.transducer import Transducer
     from gtn_applications_b200.criterions.asg import ASGLossFunction
@@ -177,7 +177,7 @@ def test_transducer_random_wordpieces_against_oracle(gtn64):
 
 @pytest.mark.parametrize("name,ngram,blank,rep", [("ngram1", 1, "optional", False), ("ngram2", 2, "optional", False),
                                                   ("ngram2_asg", 2, "none", True)])
-def test_ngram_transitions_with_epsilon_arcs_match_reference_fixtures(name, ngram, blank, rep):
+def test_ngram_transitions_with_epsilon_arcs_match_reference_fixtures(name, ngram, blank, rep, lattice_kernel):
     """make_transitions_graph for ngram > 1 ends in epsilon </s> arcs (transducer.py:52-56):
     loss, emission gradient, transition-parameter gradient and the Viterbi decode against
     the reference's own module (fixtures from make_golden.py)."""

@@ -11,10 +11,13 @@
 // per-node in/out lists kept as index vectors that arc_sort permutes; composition walks
 // state pairs breadth-first from the start pairs after a backward co-reachability pass.
 #include <algorithm>
+#include <array>
+#include <climits>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -33,16 +36,110 @@ namespace {
 
 constexpr int kEpsilon = -1;
 
+// adjacency list of one node: up to 6 arc ids inline, heap beyond that.  The graphs built per
+// utterance (compose / remove / project chains) have thousands of nodes of degree 1-5;
+// std::vector per node made malloc/free the dominant cost of building them.
+class AdjList {
+ public:
+  AdjList() : sz_(0), cap_(kInline) {}
+  AdjList(const AdjList& o) : sz_(0), cap_(kInline) { assign(o); }
+  AdjList(AdjList&& o) noexcept : sz_(o.sz_), cap_(o.cap_) {
+    if (o.cap_ == kInline) std::memcpy(u_.inl, o.u_.inl, sizeof(u_.inl));
+    else { u_.heap = o.u_.heap; o.cap_ = kInline; }
+    o.sz_ = 0;
+  }
+  AdjList& operator=(const AdjList& o) { if (this != &o) { sz_ = 0; assign(o); } return *this; }
+  AdjList& operator=(AdjList&& o) noexcept {
+    if (this != &o) {
+      if (cap_ != kInline) std::free(u_.heap);
+      sz_ = o.sz_; cap_ = o.cap_;
+      if (o.cap_ == kInline) std::memcpy(u_.inl, o.u_.inl, sizeof(u_.inl));
+      else { u_.heap = o.u_.heap; o.cap_ = kInline; }
+      o.sz_ = 0;
+    }
+    return *this;
+  }
+  ~AdjList() { if (cap_ != kInline) std::free(u_.heap); }
+  size_t size() const { return sz_; }
+  bool empty() const { return sz_ == 0; }
+  int32_t* begin() { return data(); }
+  int32_t* end() { return data() + sz_; }
+  const int32_t* begin() const { return data(); }
+  const int32_t* end() const { return data() + sz_; }
+  int32_t operator[](size_t i) const { return data()[i]; }
+  int32_t& operator[](size_t i) { return data()[i]; }
+  void push_back(int32_t v) {
+    if (sz_ == cap_) {
+      const uint32_t ncap = cap_ * 2;
+      int32_t* p = static_cast<int32_t*>(std::malloc(sizeof(int32_t) * ncap));
+      std::memcpy(p, data(), sizeof(int32_t) * sz_);
+      if (cap_ != kInline) std::free(u_.heap);
+      u_.heap = p; cap_ = ncap;
+    }
+    data()[sz_++] = v;
+  }
+ private:
+  static constexpr uint32_t kInline = 6;
+  int32_t* data() { return cap_ == kInline ? u_.inl : u_.heap; }
+  const int32_t* data() const { return cap_ == kInline ? u_.inl : u_.heap; }
+  void assign(const AdjList& o) { for (int32_t v : o) push_back(v); }
+  union { int32_t inl[kInline]; int32_t* heap; } u_;
+  uint32_t sz_, cap_;
+};
+
 struct HostGraph {
   std::vector<uint8_t> flags;           // bit0 start, bit1 accept
   std::vector<int32_t> starts, accepts; // in insertion order
   std::vector<int32_t> src, dst, il, ol;
   std::vector<float> w;
-  std::vector<std::vector<int32_t>> in, out;
+  std::vector<AdjList> in, out;
   bool il_sorted = false, ol_sorted = false;
   bool calc_grad = false;
   // provenance of a composed graph: arc k came from (a1[k], a2[k]) (-1 = epsilon move)
   std::vector<int32_t> prov1, prov2;
+  // labels of the out-lists in list order, flattened (out_off[n] .. out_off[n+1]): built on
+  // demand for big static graphs (token graphs: 10^6 arcs) so that the matcher's binary
+  // searches run over contiguous memory instead of chasing arc ids
+  mutable std::mutex cache_mu;
+  mutable std::atomic<bool> cache_ok{false};
+  mutable std::vector<int32_t> out_off, out_il_flat, out_ol_flat;
+  // for nodes whose out-list is olabel-sorted over a small dense label range: first position
+  // of every label (lut_off[n] < 0: no table for node n; entry = position or -1)
+  mutable std::vector<int64_t> lut_off;
+  mutable std::vector<int32_t> lut;
+  mutable int32_t lut_min = 0, lut_range = 0;
+  void ensure_label_cache() const {
+    if (cache_ok.load(std::memory_order_acquire)) return;
+    std::lock_guard<std::mutex> lk(cache_mu);
+    if (cache_ok.load(std::memory_order_relaxed)) return;
+    out_off.assign(out.size() + 1, 0);
+    for (size_t n = 0; n < out.size(); ++n) out_off[n + 1] = out_off[n] + (int32_t)out[n].size();
+    out_il_flat.resize(src.size());
+    out_ol_flat.resize(src.size());
+    for (size_t n = 0; n < out.size(); ++n) {
+      int32_t k = out_off[n];
+      for (int32_t a : out[n]) { out_il_flat[k] = il[a]; out_ol_flat[k] = ol[a]; ++k; }
+    }
+    lut_off.assign(out.size(), -1);
+    lut.clear();
+    if (ol_sorted && !ol.empty()) {
+      const auto mm = std::minmax_element(ol.begin(), ol.end());
+      lut_min = *mm.first;
+      lut_range = *mm.second - *mm.first + 1;
+      if (lut_range <= 4096) {
+        for (size_t n = 0; n < out.size(); ++n) {
+          const int32_t deg = out_off[n + 1] - out_off[n];
+          if (deg < 64 || (int64_t)lut.size() + lut_range > (int64_t)1 << 24) continue;
+          lut_off[n] = (int64_t)lut.size();
+          lut.resize(lut.size() + lut_range, -1);
+          int32_t* t = lut.data() + lut_off[n];
+          const int32_t* labs = out_ol_flat.data() + out_off[n];
+          for (int32_t k = deg - 1; k >= 0; --k) t[labs[k] - lut_min] = k;
+        }
+      }
+    }
+    cache_ok.store(true, std::memory_order_release);
+  }
 
   int num_nodes() const { return (int)flags.size(); }
   int num_arcs() const { return (int)src.size(); }
@@ -61,6 +158,7 @@ struct HostGraph {
     out[s].push_back(id);
     in[d].push_back(id);
     il_sorted = ol_sorted = false;
+    cache_ok.store(false, std::memory_order_relaxed);
     return id;
   }
   void make_accept(int n) {
@@ -72,6 +170,7 @@ struct HostGraph {
     auto less = [&key](int32_t a, int32_t b) { return key[a] < key[b]; };
     for (auto& v : in) std::stable_sort(v.begin(), v.end(), less);
     for (auto& v : out) std::stable_sort(v.begin(), v.end(), less);
+    cache_ok.store(false, std::memory_order_relaxed);
     il_sorted = !by_olabel;
     ol_sorted = by_olabel;
   }
@@ -100,6 +199,39 @@ HostGraph* get(int32_t h) {
 }
 
 // ---- composition ----------------------------------------------------------------
+// open-addressing map (state-pair key -> dense index); std::unordered_map spends most of a
+// composition in malloc/free of its nodes
+struct PairIndexMap {
+  std::vector<size_t> keys;
+  std::vector<int32_t> vals;
+  size_t mask = 0, used = 0;
+  static constexpr size_t kEmpty = ~(size_t)0;
+  explicit PairIndexMap(size_t cap_log2 = 13) { keys.assign((size_t)1 << cap_log2, kEmpty); vals.resize(keys.size()); mask = keys.size() - 1; }
+  static size_t hash(size_t k) { return (k * 0x9E3779B97F4A7C15ull) >> 17; }
+  void grow() {
+    std::vector<size_t> ok; std::vector<int32_t> ov;
+    ok.swap(keys); ov.swap(vals);
+    keys.assign(ok.size() * 2, kEmpty); vals.resize(keys.size()); mask = keys.size() - 1;
+    for (size_t i = 0; i < ok.size(); ++i)
+      if (ok[i] != kEmpty) {
+        size_t h = hash(ok[i]) & mask;
+        while (keys[h] != kEmpty) h = (h + 1) & mask;
+        keys[h] = ok[i]; vals[h] = ov[i];
+      }
+  }
+  // returns (value, inserted)
+  std::pair<int32_t, bool> emplace(size_t k, int32_t v) {
+    if ((used + 1) * 2 > keys.size()) grow();
+    size_t h = hash(k) & mask;
+    while (keys[h] != kEmpty) {
+      if (keys[h] == k) return {vals[h], false};
+      h = (h + 1) & mask;
+    }
+    keys[h] = k; vals[h] = v; ++used;
+    return {v, true};
+  }
+};
+
 // Enumerates (arc of A at node na, arc of B at node nb) with A.olabel == B.ilabel in the
 // order GTN's matchers produce them: nested loops when neither
 // side is sorted; the unsorted side in list order with a binary search into the sorted
@@ -108,13 +240,23 @@ struct PairMatcher {
   const HostGraph& A;
   const HostGraph& B;
   int mode;  // 0 none sorted, 1 A sorted (query B), 2 B sorted (query A), 3 both
+  bool cache_a, cache_b;   // flat label arrays available (big graphs only)
+  // per query-side node with a long unsorted out-list: (label, position) sorted — lets a
+  // short sorted list on the other side find its partners without walking the long list
+  mutable std::unordered_map<int, std::vector<std::pair<int32_t, int32_t>>> qindex;
+  mutable std::vector<std::array<int32_t, 3>> hits;
+  static constexpr size_t kBigGraph = 1 << 15;
   PairMatcher(const HostGraph& a, const HostGraph& b) : A(a), B(b) {
     mode = (a.ol_sorted && b.il_sorted) ? 3 : (a.ol_sorted ? 1 : (b.il_sorted ? 2 : 0));
+    cache_a = a.src.size() >= kBigGraph;
+    cache_b = b.src.size() >= kBigGraph;
+    if (cache_a) a.ensure_label_cache();
+    if (cache_b) b.ensure_label_cache();
   }
   template <class F>
   void for_each(int na, int nb, bool incoming, F&& emit) const {
-    const std::vector<int32_t>& la = incoming ? A.in[na] : A.out[na];
-    const std::vector<int32_t>& lb = incoming ? B.in[nb] : B.out[nb];
+    const AdjList& la = incoming ? A.in[na] : A.out[na];
+    const AdjList& lb = incoming ? B.in[nb] : B.out[nb];
     bool search_a;
     switch (mode) {
       case 0: search_a = false; break;
@@ -122,24 +264,67 @@ struct PairMatcher {
       case 2: search_a = false; break;
       default: search_a = la.size() > lb.size();
     }
-    const std::vector<int32_t>& query = search_a ? lb : la;
-    const std::vector<int32_t>& search = search_a ? la : lb;
-    auto qlab = [&](int32_t arc) { return search_a ? B.il[arc] : A.ol[arc]; };
-    auto slab = [&](int32_t arc) { return search_a ? A.ol[arc] : B.il[arc]; };
+    const AdjList& query = search_a ? lb : la;
+    const AdjList& search = search_a ? la : lb;
+    // labels by position in the list: from the flat cache when there is one
+    const int32_t* fa = (!incoming && cache_a) ? A.out_ol_flat.data() + A.out_off[na] : nullptr;
+    const int32_t* fb = (!incoming && cache_b) ? B.out_il_flat.data() + B.out_off[nb] : nullptr;
+    const int32_t* fq = search_a ? fb : fa;
+    const int32_t* fs = search_a ? fa : fb;
+    auto qlab = [&](size_t q) { return fq ? fq[q] : (search_a ? B.il[query[q]] : A.ol[query[q]]); };
+    auto slab = [&](size_t k) { return fs ? fs[k] : (search_a ? A.ol[search[k]] : B.il[search[k]]); };
+    const int32_t* lut_a = (search_a && fa && mode != 0 && A.lut_off[na] >= 0) ? A.lut.data() + A.lut_off[na] : nullptr;
+    if ((mode == 1 || mode == 2) && !incoming && query.size() >= 32 && search.size() * 8 < query.size()) {
+      // same pairs in the same order as the loop below: partners of every label run of the
+      // sorted list, then ordered by position in the query list
+      const int qnode = search_a ? nb : na;
+      auto ins = qindex.try_emplace(qnode);
+      auto& ix = ins.first->second;
+      if (ins.second) {
+        ix.reserve(query.size());
+        for (size_t q = 0; q < query.size(); ++q) ix.emplace_back(qlab(q), (int32_t)q);
+        std::sort(ix.begin(), ix.end());
+      }
+      hits.clear();
+      for (size_t s0 = 0; s0 < search.size();) {
+        const int32_t lab = slab(s0);
+        size_t s1 = s0 + 1;
+        while (s1 < search.size() && slab(s1) == lab) ++s1;
+        auto it = std::lower_bound(ix.begin(), ix.end(), std::make_pair(lab, (int32_t)INT32_MIN));
+        for (; it != ix.end() && it->first == lab; ++it) hits.push_back({it->second, (int32_t)s0, (int32_t)s1});
+        s0 = s1;
+      }
+      std::sort(hits.begin(), hits.end());
+      for (auto& h : hits) {
+        const int32_t qa = query[h[0]];
+        for (int32_t k = h[1]; k < h[2]; ++k) emit(search_a ? search[k] : qa, search_a ? qa : search[k]);
+      }
+      return;
+    }
     size_t lo = 0;
     for (size_t q = 0; q < query.size(); ++q) {
       const int32_t qa = query[q];
-      const int ql = qlab(qa);
-      size_t s = 0;
-      if (mode != 0) {
-        auto first = search.begin() + (mode == 3 ? lo : 0);
-        s = std::lower_bound(first, search.end(), ql,
-                             [&](int32_t arc, int v) { return slab(arc) < v; }) - search.begin();
-        if (mode == 3) lo = s;
+      const int ql = qlab(q);
+      size_t k = 0;
+      if (lut_a) {
+        // olabel-sorted list with a first-position table: no search at all
+        const int32_t off = ql - A.lut_min;
+        const int32_t pos = (off >= 0 && off < A.lut_range) ? lut_a[off] : -1;
+        if (pos < 0) continue;
+        k = (size_t)pos;
+      } else if (mode != 0) {
+        // lower bound of ql in search[lo..) by label
+        size_t a = (mode == 3 ? lo : 0), b = search.size();
+        while (a < b) {
+          const size_t mid = (a + b) / 2;
+          if (slab(mid) < ql) a = mid + 1; else b = mid;
+        }
+        k = a;
+        if (mode == 3) lo = k;
       }
-      for (; s < search.size(); ++s) {
-        const int32_t sa = search[s];
-        const int sl = slab(sa);
+      for (; k < search.size(); ++k) {
+        const int32_t sa = search[k];
+        const int sl = slab(k);
         if (sl == ql) emit(search_a ? sa : qa, search_a ? qa : sa);
         else if (mode != 0 && ql < sl) break;
       }
@@ -154,116 +339,100 @@ std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B
   // Which state pairs can reach an accepting pair?  GTN answers this with a backward sweep
   // over ALL pairs before the forward build; with a 1000-token graph on one side that sweep
   // visits ~10^6 pairs per utterance although only a few thousand are reachable from the start.
-  // Here: explore the pairs reachable from the start pairs first (same moves as the forward
-  // build below), record the moves, and propagate co-accessibility backwards along them.  The
-  // forward build only ever asks about reachable pairs, so its result (node numbering, arc
-  // order, provenance) is unchanged.
+  // Here: explore the pairs reachable from the start pairs first (same moves, in the same order,
+  // as GTN's forward build), RECORD the moves, propagate co-accessibility backwards along
+  // them, then replay the recorded moves of the live pairs to build the output.  The forward
+  // build only ever asks about reachable pairs, so its result (node numbering, arc order,
+  // provenance) is unchanged, and the arc matching runs once instead of twice.
   // The products here have ~10^6 state pairs of which a few thousand are ever touched: pairs are
   // numbered in discovery order through a hash map, everything else is indexed by that number.
-  std::unordered_map<size_t, int32_t> idx;               // pair key -> index in `pairs`
-  idx.reserve(8192);
+  struct Move { int32_t i, j, to; };                     // arcs of A / B (-1: the other side moves on epsilon)
+  PairIndexMap idx;                                      // pair key -> index in `pairs`
   std::vector<std::pair<int, int>> pairs;
+  std::vector<Move> moves;
+  std::vector<int32_t> mbeg;                             // moves of pair k: mbeg[k] .. mbeg[k+1]
   std::vector<uint8_t> live;                             // by pair index: can reach an accepting pair
-  {
-    std::vector<std::pair<int32_t, int32_t>> edges;      // (from, to) in `pairs` indices
-    auto visit = [&](int a, int b) -> int32_t {
-      auto ins = idx.emplace(key(a, b), (int32_t)pairs.size());
-      if (ins.second) pairs.emplace_back(a, b);
-      return ins.first->second;
-    };
-    for (int sa : A.starts)
-      for (int sb : B.starts) visit(sa, sb);
-    for (size_t head = 0; head < pairs.size(); ++head) {
-      const int ca = pairs[head].first, cb = pairs[head].second;
-      bool eps_pair = false;
-      m.for_each(ca, cb, false, [&](int32_t i, int32_t j) {
-        eps_pair = eps_pair || A.ol[i] == kEpsilon;
-        edges.emplace_back((int32_t)head, visit(A.dst[i], B.dst[j]));
-      });
-      if (eps_pair) continue;
-      for (int32_t i : A.out[ca]) {
-        if (A.ol[i] != kEpsilon) { if (A.ol_sorted) break; else continue; }
-        edges.emplace_back((int32_t)head, visit(A.dst[i], cb));
-      }
-      for (int32_t j : B.out[cb]) {
-        if (B.il[j] != kEpsilon) { if (B.il_sorted) break; else continue; }
-        edges.emplace_back((int32_t)head, visit(ca, B.dst[j]));
-      }
-    }
-    // reverse adjacency (CSR) over the recorded moves, then a backward sweep from the accepting pairs
-    std::vector<int32_t> rptr(pairs.size() + 1, 0), radj(edges.size());
-    for (auto& e : edges) ++rptr[e.second + 1];
-    for (size_t k = 0; k < pairs.size(); ++k) rptr[k + 1] += rptr[k];
-    {
-      std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1);
-      for (auto& e : edges) radj[fill[e.second]++] = e.first;
-    }
-    std::vector<int32_t> stack;
-    std::vector<uint8_t> co(pairs.size(), 0);
-    for (size_t k = 0; k < pairs.size(); ++k)
-      if ((A.flags[pairs[k].first] & 2) && (B.flags[pairs[k].second] & 2)) { co[k] = 1; stack.push_back((int32_t)k); }
-    while (!stack.empty()) {
-      const int32_t k = stack.back();
-      stack.pop_back();
-      for (int32_t r = rptr[k]; r < rptr[k + 1]; ++r)
-        if (!co[radj[r]]) { co[radj[r]] = 1; stack.push_back(radj[r]); }
-    }
-    live.swap(co);
-  }
-  std::vector<int32_t> id(pairs.size(), -1);             // by pair index: node number in the output
-  auto pair_index = [&](int a, int b) -> int32_t {
-    auto it = idx.find(key(a, b));
-    return it == idx.end() ? -1 : it->second;
+  auto visit = [&](int a, int b) -> int32_t {
+    auto ins = idx.emplace(key(a, b), (int32_t)pairs.size());
+    if (ins.second) pairs.emplace_back(a, b);
+    return ins.first;
   };
-  // forward pass: nodes numbered in breadth-first discovery order
-  auto out = std::make_unique<HostGraph>();
-  out->calc_grad = A.calc_grad || B.calc_grad;
-  std::deque<std::pair<int, int>> todo;
   for (int sa : A.starts)
-    for (int sb : B.starts) {
-      const int32_t k = pair_index(sa, sb);
-      if (k < 0 || !live[k]) continue;
-      id[k] = out->add_node(true, (A.flags[sa] & 2) && (B.flags[sb] & 2));
-      todo.emplace_back(sa, sb);
-    }
-  auto node_for = [&](int a, int b) -> int {
-    const int32_t k = pair_index(a, b);
-    if (k < 0 || !live[k]) return -1;
-    if (id[k] < 0) {
-      id[k] = out->add_node((A.flags[a] & 1) && (B.flags[b] & 1), (A.flags[a] & 2) && (B.flags[b] & 2));
-      todo.emplace_back(a, b);
-    }
-    return id[k];
-  };
-  while (!todo.empty()) {
-    auto [ca, cb] = todo.front();
-    todo.pop_front();
-    const int cur = id[pair_index(ca, cb)];
+    for (int sb : B.starts) visit(sa, sb);
+  const size_t nstart = pairs.size();
+  for (size_t head = 0; head < pairs.size(); ++head) {
+    const int ca = pairs[head].first, cb = pairs[head].second;
+    mbeg.push_back((int32_t)moves.size());
     bool eps_pair = false;
     m.for_each(ca, cb, false, [&](int32_t i, int32_t j) {
       eps_pair = eps_pair || A.ol[i] == kEpsilon;
-      int d = node_for(A.dst[i], B.dst[j]);
-      if (d < 0) return;
-      out->add_arc(cur, d, A.il[i], B.ol[j], A.w[i] + B.w[j]);
-      out->prov1.push_back(i);
-      out->prov2.push_back(j);
+      moves.push_back({i, j, visit(A.dst[i], B.dst[j])});
     });
     if (eps_pair) continue;
     for (int32_t i : A.out[ca]) {
       if (A.ol[i] != kEpsilon) { if (A.ol_sorted) break; else continue; }
-      int d = node_for(A.dst[i], cb);
-      if (d < 0) continue;
-      out->add_arc(cur, d, A.il[i], kEpsilon, A.w[i]);
-      out->prov1.push_back(i);
-      out->prov2.push_back(-1);
+      moves.push_back({i, -1, visit(A.dst[i], cb)});
     }
     for (int32_t j : B.out[cb]) {
       if (B.il[j] != kEpsilon) { if (B.il_sorted) break; else continue; }
-      int d = node_for(ca, B.dst[j]);
+      moves.push_back({-1, j, visit(ca, B.dst[j])});
+    }
+  }
+  mbeg.push_back((int32_t)moves.size());
+  {
+    // reverse adjacency (CSR) over the recorded moves, then a backward sweep from the accepting pairs
+    std::vector<int32_t> rptr(pairs.size() + 1, 0), radj(moves.size());
+    for (auto& e : moves) ++rptr[e.to + 1];
+    for (size_t k = 0; k < pairs.size(); ++k) rptr[k + 1] += rptr[k];
+    {
+      std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1);
+      for (size_t k = 0; k < pairs.size(); ++k)
+        for (int32_t e = mbeg[k]; e < mbeg[k + 1]; ++e) radj[fill[moves[e].to]++] = (int32_t)k;
+    }
+    std::vector<int32_t> stack;
+    live.assign(pairs.size(), 0);
+    for (size_t k = 0; k < pairs.size(); ++k)
+      if ((A.flags[pairs[k].first] & 2) && (B.flags[pairs[k].second] & 2)) { live[k] = 1; stack.push_back((int32_t)k); }
+    while (!stack.empty()) {
+      const int32_t k = stack.back();
+      stack.pop_back();
+      for (int32_t r = rptr[k]; r < rptr[k + 1]; ++r)
+        if (!live[radj[r]]) { live[radj[r]] = 1; stack.push_back(radj[r]); }
+    }
+  }
+  // forward pass: nodes numbered in breadth-first discovery order over the live pairs
+  std::vector<int32_t> id(pairs.size(), -1);             // by pair index: node number in the output
+  auto out = std::make_unique<HostGraph>();
+  out->calc_grad = A.calc_grad || B.calc_grad;
+  std::deque<int32_t> todo;
+  for (size_t k = 0; k < nstart; ++k) {
+    if (!live[k]) continue;
+    const int sa = pairs[k].first, sb = pairs[k].second;
+    id[k] = out->add_node(true, (A.flags[sa] & 2) && (B.flags[sb] & 2));
+    todo.push_back((int32_t)k);
+  }
+  auto node_for = [&](int32_t k) -> int {
+    if (!live[k]) return -1;
+    if (id[k] < 0) {
+      const int a = pairs[k].first, b = pairs[k].second;
+      id[k] = out->add_node((A.flags[a] & 1) && (B.flags[b] & 1), (A.flags[a] & 2) && (B.flags[b] & 2));
+      todo.push_back(k);
+    }
+    return id[k];
+  };
+  while (!todo.empty()) {
+    const int32_t k = todo.front();
+    todo.pop_front();
+    const int cur = id[k];
+    for (int32_t e = mbeg[k]; e < mbeg[k + 1]; ++e) {
+      const Move& mv = moves[e];
+      const int d = node_for(mv.to);
       if (d < 0) continue;
-      out->add_arc(cur, d, kEpsilon, B.ol[j], B.w[j]);
-      out->prov1.push_back(-1);
-      out->prov2.push_back(j);
+      if (mv.i >= 0 && mv.j >= 0) out->add_arc(cur, d, A.il[mv.i], B.ol[mv.j], A.w[mv.i] + B.w[mv.j]);
+      else if (mv.j < 0) out->add_arc(cur, d, A.il[mv.i], kEpsilon, A.w[mv.i]);
+      else out->add_arc(cur, d, kEpsilon, B.ol[mv.j], B.w[mv.j]);
+      out->prov1.push_back(mv.i);
+      out->prov2.push_back(mv.j);
     }
   }
   return out;

@@ -112,12 +112,20 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
         a = p * dot_row(Wr, bc0);
         __syncwarp();
       }
-      const float c = warp_sum(a);
-      ahat = c > 0.f ? a / c : 0.f;
+      // the normaliser only has to keep the vector in range: the maximum costs one CREDUX on the
+      // dependency chain where a sum costs five shuffle steps (every formula below holds for
+      // any positive c_t as long as a^_t = a_t / c_t)
+      const float c = warp_max(a);
+      ahat = c > 0.f ? __fdividef(a, c) : 0.f;
       logz += (double)logf(c) + (double)base;
       if (valid) hA[(size_t)t * C + lane] = ahat;
       if (lane == 0) hC[t] = c;
     }
+  }
+  {
+    // Z = sum_t log c_t + log sum_i a^_{T-1}[i]
+    const float tail = warp_sum(ahat);
+    logz += (double)logf(tail);
   }
   if (lane == 0) scores[b] = (float)logz;
 
@@ -188,8 +196,8 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
       }
       const float bn = dot_row(Wc, bc1);
       __syncwarp();
-      const float nb = warp_sum(bn);
-      bhat = nb > 0.f ? bn / nb : 0.f;
+      const float nb = warp_max(bn);
+      bhat = nb > 0.f ? __fdividef(bn, nb) : 0.f;
       acur = ac[k];
     }
   }

@@ -100,10 +100,12 @@ __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// full-warp maximum in one instruction (sm_100a: redux.sync.max.f32 -> SASS CREDUX.MAX.F32);
+// all 32 lanes must call it
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -206,7 +206,7 @@ struct PairIndexMap {
   std::vector<int32_t> vals;
   size_t mask = 0, used = 0;
   static constexpr size_t kEmpty = ~(size_t)0;
-  explicit PairIndexMap(size_t cap_log2 = 13) { keys.assign((size_t)1 << cap_log2, kEmpty); vals.resize(keys.size()); mask = keys.size() - 1; }
+  explicit PairIndexMap(size_t cap_log2 = 16) { keys.assign((size_t)1 << cap_log2, kEmpty); vals.resize(keys.size()); mask = keys.size() - 1; }
   static size_t hash(size_t k) { return (k * 0x9E3779B97F4A7C15ull) >> 17; }
   void grow() {
     std::vector<size_t> ok; std::vector<int32_t> ov;
@@ -351,6 +351,9 @@ std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B
   std::vector<std::pair<int, int>> pairs;
   std::vector<Move> moves;
   std::vector<int32_t> mbeg;                             // moves of pair k: mbeg[k] .. mbeg[k+1]
+  pairs.reserve(1 << 15);
+  moves.reserve(1 << 15);
+  mbeg.reserve(1 << 15);
   std::vector<uint8_t> live;                             // by pair index: can reach an accepting pair
   auto visit = [&](int a, int b) -> int32_t {
     auto ins = idx.emplace(key(a, b), (int32_t)pairs.size());

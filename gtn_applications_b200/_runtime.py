@@ -85,6 +85,28 @@ def pack_targets(targets, num_classes, device, scales=None):
     return out
 
 
+def flatten_targets_host(targets):
+    """ragged targets (lists, 1-D tensors or a [B, L] tensor) -> (flat int32, offsets int32 [B+1])
+    numpy arrays on the host, without per-label Python work for tensors (iterating a tensor
+    element by element costs ~1 us per label: 30 ms for a 64 x 400 grapheme batch)"""
+    import itertools
+    import numpy as np
+    if torch.is_tensor(targets) and targets.dim() == 2:
+        B, L = targets.shape
+        flat = targets.detach().to("cpu", torch.int32).contiguous().reshape(-1).numpy()
+        return flat, (np.arange(B + 1, dtype=np.int32) * L)
+    lengths = [len(t) for t in targets]
+    total = sum(lengths)
+    if lengths and all(torch.is_tensor(t) for t in targets):
+        flat = torch.cat([t.detach().reshape(-1) for t in targets]).to("cpu", torch.int32).contiguous().numpy() \
+            if total else np.zeros(0, dtype=np.int32)
+    else:
+        flat = np.fromiter(itertools.chain.from_iterable(targets), dtype=np.int32, count=total)
+    offs = np.zeros(len(lengths) + 1, dtype=np.int32)
+    np.cumsum(lengths, out=offs[1:])
+    return np.ascontiguousarray(flat, dtype=np.int32), offs
+
+
 def target_lengths(targets):
     """lengths of the target sequences; a [B, L] tensor is not iterated row by row"""
     if torch.is_tensor(targets) and targets.dim() == 2:

@@ -209,9 +209,7 @@ class TransducerLossFunction(torch.autograd.Function):
         e = rt.to_device(inputs.detach())
         dev = e.device
         L = _lib.lib()
-        flat = np.ascontiguousarray([int(x) for t in targets for x in t], dtype=np.int32)
-        offs = np.zeros(B + 1, dtype=np.int32)
-        offs[1:] = np.cumsum([len(t) for t in targets])
+        flat, offs = rt.flatten_targets_host(targets)
         import ctypes
         handles = (ctypes.c_int32 * B)()
         _lib.check(L.wfst_transducer_alignment_graphs(
@@ -317,7 +315,6 @@ class Transducer(torch.nn.Module):
         if self.transitions is None:
             inputs = torch.nn.functional.log_softmax(inputs, dim=2)
         self.tokens.arc_sort(True)
-        targets = [t.tolist() if torch.is_tensor(t) else list(t) for t in targets]
         return TransducerLoss(inputs, targets, self.tokens, self.lexicon, self.transition_params,
                               self.transitions, self.reduction)
 

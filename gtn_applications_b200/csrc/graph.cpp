@@ -257,6 +257,12 @@ struct PairMatcher {
   void for_each(int na, int nb, bool incoming, F&& emit) const {
     const AdjList& la = incoming ? A.in[na] : A.out[na];
     const AdjList& lb = incoming ? B.in[nb] : B.out[nb];
+    if (la.empty() || lb.empty()) return;
+    if (la.size() == 1 && lb.size() == 1) {
+      // chain against chain (most state pairs of target o lexicon): one comparison, any mode
+      if (A.ol[la[0]] == B.il[lb[0]]) emit(la[0], lb[0]);
+      return;
+    }
     bool search_a;
     switch (mode) {
       case 0: search_a = false; break;

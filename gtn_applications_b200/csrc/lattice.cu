@@ -236,6 +236,7 @@ struct CsrLean {
   using Params = CsrTopo::Params;
   static constexpr int kDeg = 4;          // arcs per node held in registers; more are allowed
   static constexpr bool kTail = true;
+  static constexpr bool kSort = true;     // irregular degrees: nodes handed to threads by degree
   const int* in_ptr; const int* in_src; const int* in_label; const int* in_arc;
   const int* out_ptr; const int* out_dst; const int* out_label; const int* out_arc;
   const uint8_t* flags; const float* w; float* gradW; const float* fw; float* gradF;
@@ -287,6 +288,7 @@ struct CtcLean {
   using Params = CtcTopo::Params;
   static constexpr int kDeg = 3;          // self, previous, skip
   static constexpr bool kTail = false;
+  static constexpr bool kSort = false;
   const int* y; int L, S, blank, C;
   __device__ void init(const Params& p, int b) {
     y = p.targets + p.offsets[b];
@@ -318,6 +320,7 @@ struct AsgFalLean {
   using Params = AsgFalTopo::Params;
   static constexpr int kDeg = 2;          // enter, self loop
   static constexpr bool kTail = false;
+  static constexpr bool kSort = false;
   const int* y; const float* tr; float* gradTr; int L, C; uint32_t s_node_out;
   __device__ void init(const Params& p, int b) {
     y = p.targets + p.offsets[b];

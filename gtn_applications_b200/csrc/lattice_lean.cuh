@@ -59,7 +59,7 @@ __device__ __forceinline__ void red_add_u(uint32_t a, uint32_t v) {
 
 // byte offsets of the regions inside dynamic shared memory
 struct Layout {
-  uint32_t bars, red, rowsum, tile0, tile1, gtile, alpha0, alpha1, node_in, node_out, nflags, fw,
+  uint32_t bars, red, rowsum, tile0, tile1, gtile, alpha0, alpha1, node_in, node_out, nflags, fw, perm,
       in_pack, out_pack, out_gidx, gw, total;
 };
 
@@ -79,6 +79,7 @@ __host__ __device__ inline Layout make_layout(int Kt, int C, int npad, int aslot
   l.node_in = o; o += (uint32_t)npad * 4u;
   l.node_out = o; o += (uint32_t)npad * 4u;
   l.fw = o; o += (uint32_t)npad * 4u;
+  l.perm = o; o += (uint32_t)npad * 4u;
   l.nflags = o; o += (uint32_t)npad;       // npad is a multiple of 4
   o = (o + 7u) & ~7u;
   // 4 slots of padding: the DEG register slots of the last node are read unconditionally
@@ -172,6 +173,41 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
   uint32_t phase = 0u;   // bit `buf` = parity the next wait on barrier `buf` expects
   __syncthreads();
 
+  // Which nodes a thread owns.  A warp steps through the arcs of its 32 nodes in lock step, so
+  // its cost is the LARGEST degree among them: builders with irregular graphs (kSort) hand out
+  // the nodes in order of decreasing degree (counting sort on max(in, out) degree), snake-wise
+  // over the rounds so that every warp gets heavy and light rounds.  History rows are indexed
+  // by slot (thread + round), which keeps them coalesced in both sweeps.
+  int vnode[NPT];
+  if (Builder::kSort) {
+    const uint32_t s_perm = sb + L.perm;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(red);     // 33 counters
+    if (tid < 34) cnt[tid] = 0u;
+    __syncthreads();
+    auto key_of = [&](int v) {
+      const uint32_t bi = lds_u(s_node_in + 4u * v), bo = lds_u(s_node_out + 4u * v);
+      const uint32_t d = max((bi >> 16) - (bi & 0xffffu), (bo >> 16) - (bo & 0xffffu));
+      return 31u - min(d, 31u);                             // bucket 0 = heaviest
+    };
+    for (int v = tid; v < N; v += NT) atomicAdd(&cnt[key_of(v) + 1], 1u);
+    __syncthreads();
+    if (tid == 0)
+      for (int k = 1; k < 33; ++k) cnt[k] += cnt[k - 1];    // cnt[k] = first slot of bucket k
+    __syncthreads();
+    for (int v = tid; v < N; v += NT) sts_u(s_perm + 4u * atomicAdd(&cnt[key_of(v)], 1u), (uint32_t)v);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      const int q = j * NT + ((j & 1) ? NT - 1 - tid : tid);
+      vnode[j] = (q < N) ? (int)lds_u(s_perm + 4u * q) : -1;
+    }
+    __syncthreads();                                        // `red` is reused below
+  } else {
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) vnode[j] = (tid + j * NT < N) ? tid + j * NT : -1;
+  }
+  auto slot_of = [&](int j) { return (Builder::kSort && (j & 1)) ? j * NT + NT - 1 - tid : j * NT + tid; };
+
   auto is_start = [&](int v) {
     uint32_t f;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(f) : "r"(s_flags + (uint32_t)v));
@@ -237,15 +273,14 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
   // ------------------------------------------------------------- forward
   uint32_t cur = sb + L.alpha0, nxt = sb + L.alpha1;
   double cumA = 0.0;
-  for (int v = tid; v < N; v += NT) {
-    float x = is_start(v) ? 0.f : kNegInf;
-    sts_f(cur + 4u * v, x);
-    hist[v] = x;
-  }
+  for (int v = tid; v < N; v += NT) sts_f(cur + 4u * v, is_start(v) ? 0.f : kNegInf);
+#pragma unroll
+  for (int j = 0; j < NPT; ++j)
+    if (vnode[j] >= 0) hist[slot_of(j)] = is_start(vnode[j]) ? 0.f : kNegInf;
   if (ntiles > 0) issue_tile(0, 0);
   uint32_t be_in[NPT];
 #pragma unroll
-  for (int j = 0; j < NPT; ++j) be_in[j] = (tid + j * NT < N) ? lds_u(s_node_in + 4u * (tid + j * NT)) : 0u;
+  for (int j = 0; j < NPT; ++j) be_in[j] = (vnode[j] >= 0) ? lds_u(s_node_in + 4u * vnode[j]) : 0u;
   __syncthreads();
   for (int i = 0; i < ntiles; ++i) {
     const int buf = i & 1;
@@ -268,8 +303,8 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
       float* hrow = hist + (size_t)(i * Kt + tt + 1) * a.hist_stride;
 #pragma unroll
       for (int j = 0; j < NPT; ++j) {
-        const int v = tid + j * NT;
-        if (v < N) {
+        const int v = vnode[j];
+        if (v >= 0) {
           const uint32_t k0 = be_in[j] & 0xffffu, ke = be_in[j] >> 16;
           // records first, then the gathers they address: independent loads stay in flight together
           uint2 rec[DEG];
@@ -300,7 +335,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
             r = m + __logf(s);
           }
           sts_f(nxt + 4u * v, r);
-          hrow[v] = r;
+          hrow[slot_of(j)] = r;
         }
       }
       __syncthreads();
@@ -344,9 +379,9 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
   uint32_t be_out[NPT];
 #pragma unroll
   for (int j = 0; j < NPT; ++j) {
-    const int u = tid + j * NT;
-    au_next[j] = (u < N && T > 0) ? hist[(size_t)(T - 1) * a.hist_stride + u] : kNegInf;
-    be_out[j] = (u < N) ? lds_u(s_node_out + 4u * u) : 0u;
+    const int u = vnode[j];
+    au_next[j] = (u >= 0 && T > 0) ? hist[(size_t)(T - 1) * a.hist_stride + slot_of(j)] : kNegInf;
+    be_out[j] = (u >= 0) ? lds_u(s_node_out + 4u * u) : 0u;
   }
   __syncthreads();
   for (int i = ntiles - 1; i >= 0; --i) {
@@ -379,8 +414,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
 #pragma unroll
       for (int j = 0; j < NPT; ++j) {
         au[j] = au_next[j];
-        const int u = tid + j * NT;
-        au_next[j] = (u < N && t > 0) ? hist[(size_t)(t - 1) * a.hist_stride + u] : kNegInf;
+        au_next[j] = (vnode[j] >= 0 && t > 0) ? hist[(size_t)(t - 1) * a.hist_stride + slot_of(j)] : kNegInf;
       }
       uint32_t qstar = 0, qtot = 0;
       auto post = [&](float xv, uint32_t rx, uint32_t k, float off) {
@@ -396,8 +430,8 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
       };
 #pragma unroll
       for (int j = 0; j < NPT; ++j) {
-        const int u = tid + j * NT;
-        if (u < N) {
+        const int u = vnode[j];
+        if (u >= 0) {
           const uint32_t k0 = be_out[j] & 0xffffu, ke = be_out[j] >> 16;
           uint2 rec[DEG];
 #pragma unroll

@@ -278,8 +278,10 @@ def pack_graphs(graphs, device):
              "in_src": ta, "in_label": ta, "in_arc": ta, "out_dst": ta, "out_label": ta, "out_arc": ta,
              "weights": ta}
     total = sum(sizes.values())
-    ints = torch.empty(total, dtype=torch.int32).pin_memory()
-    flags = torch.empty(max(tn, 1), dtype=torch.uint8).pin_memory()
+    # allocated pinned (torch caches pinned blocks); .pin_memory() would allocate pageable memory
+    # first and copy it
+    ints = torch.empty(total, dtype=torch.int32, pin_memory=True)
+    flags = torch.empty(max(tn, 1), dtype=torch.uint8, pin_memory=True)
     views, pos = {}, 0
     for k, n in sizes.items():
         views[k] = ints[pos:pos + n]

@@ -38,6 +38,8 @@ SIGNATURES = {
     "wfst_launch_count": (ctypes.c_ulonglong, []),
     "wfst_debug_force_generic_ctc": (_I, [_I]),
     "wfst_debug_force_generic_lattice": (_I, [_I]),
+    "wfst_asg_viterbi_supported": (_I, [_I, _I]),
+    "wfst_asg_viterbi": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "wfst_debug_ctc_hazards": (_I, [_P, _I, _I, _I, _I, _P]),
     "wfst_ctc_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "wfst_ctc_forward_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
@@ -79,6 +81,7 @@ SIGNATURES = {
     "wfst_graph_load": (_I32, [ctypes.c_char_p]),
     "wfst_graph_save": (_I, [_I32, ctypes.c_char_p]),
     "wfst_transducer_alignment_graphs": (_I, [_I32, _I32, _P, _P, _I, _P]),
+    "wfst_transducer_decode_paths": (_I, [_I32, _P, _I, _I, _P, _P]),
     "wfst_graph_viterbi_path": (_I32, [_I32]),
     "wfst_lattice_viterbi_workspace_bytes": (_Z, [_I, _I, _I]),
     "wfst_lattice_viterbi": (_I, [_P, _I, _I, _I, ctypes.POINTER(AcceptorBatch), _I, _P, _P, _P, _P, _Z, _P]),

@@ -53,6 +53,29 @@ def unpack_replabels(tokens, num_replabels):
     return out
 
 
+def unpack_replabels_batch(flat, counts, num_replabels):
+    """unpack_replabels for a whole batch at once: `flat` holds the token sequences of B
+    utterances back to back (`counts[b]` tokens each).  A token >= num_replabels is a label; a
+    replabel token r directly after a label repeats that label r + 1 times; any other replabel
+    is dropped (asg.py:35-49).  Returns a list of B int32 tensors."""
+    import numpy as np
+    flat = np.asarray(flat, dtype=np.int64)
+    counts = np.asarray(counts, dtype=np.int64)
+    B, R = len(counts), num_replabels
+    uid = np.repeat(np.arange(B), counts)
+    prev_same = np.zeros(len(flat), dtype=bool)
+    prev_same[1:] = uid[1:] == uid[:-1]
+    prev_tok = np.zeros(len(flat), dtype=np.int64)
+    prev_tok[1:] = flat[:-1]
+    is_label = flat >= R
+    eff_rep = (~is_label) & prev_same & (prev_tok >= R)
+    reps = np.where(is_label, 1, np.where(eff_rep, flat + 1, 0))
+    vals = np.where(is_label, flat - R, prev_tok - R)
+    out = torch.from_numpy(np.repeat(vals, reps).astype(np.int32))
+    sizes = np.bincount(np.repeat(uid, reps), minlength=B)
+    return list(torch.split(out, sizes.tolist()))
+
+
 class ASGLossFunction(torch.autograd.Function):
     @staticmethod
     def create_transitions_graph(transitions, calc_grad=False):
@@ -162,14 +185,9 @@ class ASG(torch.nn.Module):
         return ASGLoss(inputs, self.transitions, packed, "mean")
 
     def viterbi(self, outputs):
-        from ..decode import asg_viterbi_paths
+        from ..decode import asg_viterbi_collapsed
         B, T, C = outputs.shape
         assert C == self.N, "Wrong number of classes in output."
-        paths = asg_viterbi_paths(outputs, self.transitions)
-        preds = []
-        for path in paths:
-            collapsed = [p for p, _ in itertools.groupby(path)]
-            if self.garbage_idx is not None:
-                collapsed = [p for p in collapsed if p != self.garbage_idx]
-            preds.append(torch.IntTensor(unpack_replabels(collapsed, self.num_replabels)))
-        return preds
+        # repeats merged, then garbage dropped (asg.py:228-233), on the device for the whole batch
+        flat, counts = asg_viterbi_collapsed(outputs, self.transitions, self.garbage_idx)
+        return unpack_replabels_batch(flat, counts, self.num_replabels)

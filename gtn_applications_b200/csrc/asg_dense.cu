@@ -212,7 +212,101 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------
+// Best path through emissions x the same bigram graph (ASG.viterbi, criterions/asg.py:217-226:
+// gtn.viterbi_path(gtn.intersect(g_em, g_tr))).  One warp per utterance, lane = label; the
+// lane's transition row in registers, the previous frame's scores broadcast through shared
+// memory, one byte of back-pointer per (frame, label) in shared memory, backtrace by lane 0.
+// Ties go to the lowest previous label / lowest final label: the order of the in-lists of
+// create_transitions_graph (asg.py:60-67) under GTN's strict '>' (see viterbi.cu).
+__global__ void __launch_bounds__(32) asg_viterbi_dense_kernel(
+    const float* __restrict__ E, const float* __restrict__ tr, int T, int C,
+    float* __restrict__ scores, int32_t* __restrict__ labels) {
+  extern __shared__ __align__(16) unsigned char vsm[];
+  float* bc = reinterpret_cast<float*>(vsm);            // [kCP] scores of the previous frame
+  unsigned char* bp = vsm + kCP * sizeof(float);         // [T][32]
+  const int lane = threadIdx.x, b = blockIdx.x;
+  const bool valid = lane < C;
+  float Wr[kCP];
+#pragma unroll
+  for (int j = 0; j < kCP; ++j) Wr[j] = (valid && j < C) ? tr[C + lane * C + j] : kNegInf;
+  for (int k = lane; k < kCP; k += 32) bc[k] = kNegInf;
+  const float* Eb = E + (size_t)b * T * C;
+  float xn[kPF];
+#pragma unroll
+  for (int k = 0; k < kPF; ++k) xn[k] = (valid && k < T) ? __ldg(Eb + (size_t)k * C + lane) : kNegInf;
+  float delta = kNegInf;
+  for (int t0 = 0; t0 < T; t0 += kPF) {
+    float xc[kPF];
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      xc[k] = xn[k];
+      const int tn = t0 + kPF + k;
+      xn[k] = (valid && tn < T) ? __ldg(Eb + (size_t)tn * C + lane) : kNegInf;
+    }
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      const int t = t0 + k;
+      if (t >= T) break;
+      float best = kNegInf;
+      int arg = 255;
+      if (t == 0) {
+        best = valid ? tr[lane] : kNegInf;               // arcs 0 -> i+1
+      } else {
+        __syncwarp();
+        bc[lane] = delta;
+        __syncwarp();
+        const float4* v = reinterpret_cast<const float4*>(bc);
+#pragma unroll
+        for (int q = 0; q < kCP / 4; ++q) {
+          const float4 d = v[q];
+          float c;
+          c = d.x + Wr[4 * q + 0]; if (c > best) { best = c; arg = 4 * q + 0; }
+          c = d.y + Wr[4 * q + 1]; if (c > best) { best = c; arg = 4 * q + 1; }
+          c = d.z + Wr[4 * q + 2]; if (c > best) { best = c; arg = 4 * q + 2; }
+          c = d.w + Wr[4 * q + 3]; if (c > best) { best = c; arg = 4 * q + 3; }
+        }
+      }
+      delta = valid ? best + xc[k] : kNegInf;
+      bp[(size_t)t * 32 + lane] = (unsigned char)arg;
+    }
+  }
+  // best final label, lowest index on ties
+  float m = warp_max(delta);
+  const unsigned hit = __ballot_sync(kAll, valid && delta == m && m != kNegInf);
+  int cur = hit ? __ffs(hit) - 1 : -1;
+  if (lane == 0) scores[b] = hit ? m : kNegInf;
+  __syncwarp();
+  if (lane == 0) {
+    for (int t = T - 1; t >= 0; --t) {
+      const int prev = (cur >= 0) ? bp[(size_t)t * 32 + cur] : 255;
+      bp[(size_t)t * 32] = (unsigned char)(cur >= 0 ? cur : 255);   // row t is done: reuse its first byte
+      cur = (t > 0 && prev != 255) ? prev : ((t > 0) ? -1 : cur);
+    }
+  }
+  __syncwarp();
+  int32_t* lb = labels + (size_t)b * T;
+  for (int t = lane; t < T; t += 32) {
+    const int v = bp[(size_t)t * 32];
+    lb[t] = (v == 255) ? -1 : v;
+  }
+}
 }  // namespace
+
+bool asg_viterbi_dense_eligible(int T, int C) {
+  return T >= 1 && C >= 1 && C <= 32 && (size_t)T * 32 + kCP * sizeof(float) <= 200 * 1024;
+}
+
+int launch_asg_viterbi_dense(const float* E, const float* tr, int B, int T, int C, float* scores,
+                             int32_t* labels, cudaStream_t st) {
+  const size_t smem = (size_t)T * 32 + kCP * sizeof(float);
+  WFST_CUDA_CHECK(cudaFuncSetAttribute(asg_viterbi_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  asg_viterbi_dense_kernel<<<B, 32, smem, st>>>(E, tr, T, C, scores, labels);
+  g_launches++;
+  WFST_CUDA_CHECK(cudaGetLastError());
+  return WFST_OK;
+}
 
 bool asg_fcc_dense_eligible(int T, int C) { return T >= 1 && C >= 1 && C <= 32; }
 

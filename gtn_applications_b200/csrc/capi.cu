@@ -385,6 +385,19 @@ int wfst_lattice_viterbi(const float* emissions, int B, int T, int C,
                         (cudaStream_t)stream);
 }
 
+int wfst_asg_viterbi_supported(int T, int C) { return asg_viterbi_dense_eligible(T, C) ? 1 : 0; }
+
+int wfst_asg_viterbi(const float* emissions, const float* transitions, int B, int T, int C,
+                     float* scores, int32_t* labels, void* stream) {
+  WFST_REQUIRE(emissions && transitions && scores && labels, "null pointer argument");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0, "bad shape B=%d T=%d C=%d", B, T, C);
+  if (!asg_viterbi_dense_eligible(T, C)) {
+    set_error("dense ASG best path unsupported for T=%d C=%d (use wfst_lattice_viterbi on the transition graph)", T, C);
+    return WFST_ERR_UNSUPPORTED;
+  }
+  return launch_asg_viterbi_dense(emissions, transitions, B, T, C, scores, labels, (cudaStream_t)stream);
+}
+
 int wfst_scale_inplace(float* x, size_t n, const float* scale, void* stream) {
   WFST_REQUIRE(x && scale, "null pointer argument");
   return launch_scale(x, n, scale, (cudaStream_t)stream);

@@ -517,6 +517,49 @@ std::unique_ptr<HostGraph> alignment_graph(const HostGraph& tokens, const HostGr
   return align;
 }
 
+// gtn.viterbi_path of an acyclic graph: best[n] = first maximising in-arc in in-list order
+// (strict >).  Returns null if the graph has a cycle.
+std::unique_ptr<HostGraph> best_path(const HostGraph& g) {
+  const int N = g.num_nodes();
+  const float NEG = -INFINITY;
+  std::vector<float> score(N, NEG);
+  std::vector<int32_t> best(N, -1), deg(N);
+  std::deque<int32_t> ready;
+  for (int n = 0; n < N; ++n) { deg[n] = (int)g.in[n].size(); if (!deg[n]) ready.push_back(n); }
+  int seen = 0;
+  while (!ready.empty()) {
+    const int n = ready.front();
+    ready.pop_front();
+    ++seen;
+    float m = (g.flags[n] & 1) ? 0.f : NEG;
+    int arg = -1;
+    for (int32_t a : g.in[n]) {
+      const float v = score[g.src[a]] + g.w[a];
+      if (v > m) { m = v; arg = a; }
+    }
+    score[n] = m;
+    best[n] = arg;
+    for (int32_t a : g.out[n]) if (--deg[g.dst[a]] == 0) ready.push_back(g.dst[a]);
+  }
+  if (seen != N) return nullptr;
+  int end = -1;
+  float m = NEG;
+  for (int n : g.accepts) if (score[n] > m) { m = score[n]; end = n; }
+  std::vector<int32_t> path;
+  for (int n = end; n >= 0 && best[n] >= 0; n = g.src[best[n]]) path.push_back(best[n]);
+  std::reverse(path.begin(), path.end());
+  auto out = std::make_unique<HostGraph>();
+  if (end >= 0) {
+    out->add_node(true, path.empty());
+    for (size_t k = 0; k < path.size(); ++k) {
+      const int32_t a = path[k];
+      out->add_node(false, k + 1 == path.size());
+      out->add_arc((int)k, (int)k + 1, g.il[a], g.ol[a], g.w[a]);
+    }
+  }
+  return out;
+}
+
 template <class F>
 void parallel_for(int n, F&& fn) {
   unsigned hw = std::thread::hardware_concurrency();
@@ -784,44 +827,38 @@ int32_t wfst_graph_load(const char* path) {
 int32_t wfst_graph_viterbi_path(int32_t h) {
   HostGraph* g = get(h);
   if (!g) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
-  const int N = g->num_nodes();
-  const float NEG = -INFINITY;
-  std::vector<float> score(N, NEG);
-  std::vector<int32_t> best(N, -1), deg(N);
-  std::deque<int32_t> ready;
-  for (int n = 0; n < N; ++n) { deg[n] = (int)g->in[n].size(); if (!deg[n]) ready.push_back(n); }
-  int seen = 0;
-  while (!ready.empty()) {
-    const int n = ready.front();
-    ready.pop_front();
-    ++seen;
-    float m = (g->flags[n] & 1) ? 0.f : NEG;
-    int arg = -1;
-    for (int32_t a : g->in[n]) {
-      const float v = score[g->src[a]] + g->w[a];
-      if (v > m) { m = v; arg = a; }
-    }
-    score[n] = m;
-    best[n] = arg;
-    for (int32_t a : g->out[n]) if (--deg[g->dst[a]] == 0) ready.push_back(g->dst[a]);
-  }
-  if (seen != N) { set_error("viterbi_path: graph has a cycle"); return WFST_ERR_INVALID; }
-  int end = -1;
-  float m = NEG;
-  for (int n : g->accepts) if (score[n] > m) { m = score[n]; end = n; }
-  std::vector<int32_t> path;
-  for (int n = end; n >= 0 && best[n] >= 0; n = g->src[best[n]]) path.push_back(best[n]);
-  std::reverse(path.begin(), path.end());
-  auto out = std::make_unique<HostGraph>();
-  if (end >= 0) {
-    out->add_node(true, path.empty());
-    for (size_t k = 0; k < path.size(); ++k) {
-      const int32_t a = path[k];
-      out->add_node(false, k + 1 == path.size());
-      out->add_arc((int)k, (int)k + 1, g->il[a], g->ol[a], g->w[a]);
-    }
-  }
+  auto out = best_path(*g);
+  if (!out) { set_error("viterbi_path: graph has a cycle"); return WFST_ERR_INVALID; }
   return put(std::move(out));
+}
+
+// Alignment -> token sequence for a batch of best alignments (Transducer.viterbi,
+// criterions/transducer.py:223-233): per utterance a chain of the T frame labels is composed
+// with the token graph, the best path taken, projected on its output labels and epsilons
+// removed.  labels [B, T]; out [B, T] receives the tokens of utterance b at out[b*T ..],
+// out_counts [B] their number.  Runs on host threads (the reference does this per utterance in
+// Python).  The token graph must be ilabel-sorted by the caller (transducer.py:222).
+int wfst_transducer_decode_paths(int32_t tokens, const int32_t* labels, int B, int T,
+                                 int32_t* out, int32_t* out_counts) {
+  HostGraph* tk = get(tokens);
+  if (!tk) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
+  if (B < 0 || T < 0 || (B > 0 && T > 0 && (!labels || !out)) || (B > 0 && !out_counts)) {
+    set_error("bad arguments");
+    return WFST_ERR_INVALID;
+  }
+  std::atomic<int> bad{0};
+  parallel_for(B, [&](int b) {
+    auto ch = chain(labels + (size_t)b * T, T);
+    if (T == 0) ch->make_accept(0);
+    auto best = best_path(*compose_graphs(*ch, *tk));
+    if (!best) { bad = 1; out_counts[b] = 0; return; }
+    auto res = remove_label(*project(*best, false), kEpsilon, kEpsilon);
+    const int n = std::min(res->num_arcs(), T);
+    for (int k = 0; k < n; ++k) out[(size_t)b * T + k] = res->il[k];
+    out_counts[b] = n;
+  });
+  if (bad) { set_error("decode: composed graph has a cycle"); return WFST_ERR_INVALID; }
+  return WFST_OK;
 }
 
 // Builds the alignment acceptor of every utterance of a batch on host threads

@@ -26,6 +26,10 @@ bool asg_fcc_dense_eligible(int T, int C);
 int launch_asg_fcc_dense(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
                          float sign, float* scores, float* gradE, int accumulate, float* gradTr,
                          float* hist, cudaStream_t st);
+// best path through emissions x the bigram graph, one warp per utterance (asg_dense.cu)
+bool asg_viterbi_dense_eligible(int T, int C);
+int launch_asg_viterbi_dense(const float* E, const float* tr, int B, int T, int C, float* scores,
+                             int32_t* labels, cudaStream_t st);
 int launch_finalize(const float* za, const float* zb, float sign, int B, const float* grad_scale,
                     float* loss, float* mean_loss, cudaStream_t st);
 int launch_scale(float* x, size_t n, const float* scale, cudaStream_t st);

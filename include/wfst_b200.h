@@ -235,6 +235,13 @@ WFST_API int wfst_transducer_alignment_graphs(int32_t tokens, int32_t lexicon,
 
 /* Packs B host graphs into the arrays of wfst_acceptor_batch_t (HOST buffers sized from
  * wfst_graph_pack_sizes; the caller uploads them).  Arc lists keep their arc_sort order. */
+/* Alignment -> tokens for a batch of best alignments — the host part of Transducer.viterbi
+ * (criterions/transducer.py:223-233: per utterance compose(chain of frame labels, tokens),
+ * viterbi_path, project_output, remove epsilons), on host threads.  `tokens` must be
+ * ilabel-sorted (transducer.py:222).  labels [B, T] (host); out [B, T] (host) receives the tokens
+ * of utterance b at out[b*T ..], out_counts [B] their number. */
+WFST_API int wfst_transducer_decode_paths(int32_t tokens, const int32_t* labels, int B, int T,
+                                          int32_t* out, int32_t* out_counts);
 WFST_API int wfst_graph_pack_sizes(const int32_t* handles, int B, int32_t* total_nodes,
                                    int32_t* total_arcs, int32_t* max_nodes, int32_t* max_arcs,
                                    int32_t* has_epsilon);
@@ -254,6 +261,20 @@ WFST_API int wfst_lattice_viterbi(const float* emissions, int B, int T, int C,
                                   const wfst_acceptor_batch_t* graphs, int shared_graph,
                                   float* scores, int32_t* labels, int32_t* arcs, void* workspace,
                                   size_t workspace_bytes, void* stream);
+
+/* Best path through emissions x the ASG bigram transition graph — ASG.viterbi
+ * (criterions/asg.py:217-226: gtn.viterbi_path(gtn.intersect(g_emissions, g_transitions)) with
+ * the graph of create_transitions_graph, asg.py:53-69) without building the graph: one warp per
+ * utterance, transitions [(C+1), C] read directly.  Same result as wfst_lattice_viterbi on the
+ * packed transition graph, ties included (lowest previous label, lowest final label).
+ *   labels [B, T] out: label taken at each frame (-1: no path);  scores [B] out.
+ * wfst_asg_viterbi_supported: 1 when the shape fits the dense kernel (C <= 32, T >= 1 and the
+ * back-pointers, 32 bytes per frame, fit shared memory); otherwise the call returns
+ * WFST_ERR_UNSUPPORTED and the caller uses wfst_lattice_viterbi. */
+WFST_API int wfst_asg_viterbi_supported(int T, int C);
+WFST_API int wfst_asg_viterbi(const float* emissions, const float* transitions, int B, int T, int C,
+                              float* scores, int32_t* labels, void* stream);
+
 /* Host-side best path of a small acyclic graph (the alignment -> token mapping of
  * Transducer.viterbi, transducer.py:222-229): returns a chain graph with the arcs of the
  * best path, first maximum in in-list order on ties (GTN's traversal order). */

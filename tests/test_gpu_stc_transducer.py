@@ -241,6 +241,33 @@ def test_asg_viterbi_known_answer_and_fixture():
     assert [g.tolist() for g in got] == G.unpack(z["module_viterbi"], z["module_viterbi_offsets"])
 
 
+@pytest.mark.parametrize("B,T,C,quant", [(7, 50, 30, False), (3, 1, 5, False), (5, 300, 32, True), (4, 64, 9, True)])
+def test_asg_dense_viterbi_matches_generic_best_path(B, T, C, quant):
+    """The dense warp-per-utterance best-path kernel against the generic kernel on the packed
+    transition graph: same labels, also when scores tie (quantised scores force ties)."""
+    from gtn_applications_b200 import graph as GG
+    from gtn_applications_b200.criterions.asg import ASGLossFunction
+    from gtn_applications_b200.decode import asg_viterbi_labels, lattice_viterbi
+    rng = np.random.default_rng(B * 1000 + T + C)
+    e = rng.standard_normal((B, T, C)).astype(np.float32)
+    tr = rng.standard_normal((C + 1, C)).astype(np.float32)
+    if quant:
+        e, tr = np.round(e), np.round(tr)
+    e, tr = torch.tensor(e, device="cuda"), torch.tensor(tr, device="cuda")
+    from gtn_applications_b200 import _lib
+    assert _lib.lib().wfst_asg_viterbi_supported(T, C) == 1
+    dense = asg_viterbi_labels(e, tr)
+    packed = GG.pack_graphs([ASGLossFunction.create_transitions_graph(tr)], e.device)
+    scores, generic, _ = lattice_viterbi(e, packed, shared=True)
+    assert torch.equal(dense, generic)
+    # the path score recomputed from the labels equals the kernel's score
+    lab = dense.long()
+    path = e.gather(2, lab.unsqueeze(2)).squeeze(2).sum(1) + tr[0][lab[:, 0]]
+    if T > 1:
+        path = path + tr[1 + lab[:, 1:], lab[:, :-1]].sum(1)
+    torch.testing.assert_close(path, scores, rtol=1e-5, atol=1e-4)
+
+
 def test_transducer_viterbi_known_answers():
     # transducer_test.py:318-365 and 510-532
     from gtn_applications_b200.criterions.transducer import Transducer

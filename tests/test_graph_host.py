@@ -178,3 +178,33 @@ def test_conv_kernel_graphs_match_reference_constructor():
         g = make_kernel_graph(tok, 2, opt, spike=spike).arrays()
         for k in ("start", "accept", "src", "dst", "ilabel", "olabel"):
             assert np.array_equal(np.asarray(g[k]).astype(np.int64), z["kg%d_%s" % (i, k)].astype(np.int64)), (i, k)
+
+
+@pytest.mark.parametrize("blank,rep", [("none", True), ("optional", True), ("optional", False), ("forced", True)])
+def test_batched_decode_matches_the_per_utterance_pipeline(blank, rep):
+    """wfst_transducer_decode_paths (alignment -> tokens for a whole batch on host threads) against
+    the reference's per-utterance sequence compose(chain, tokens) -> viterbi_path -> project_output
+    -> remove (criterions/transducer.py:223-233) run through the same host library one call at a time."""
+    import ctypes
+    import random
+    from gtn_applications_b200 import _lib
+    rnd = random.Random(5)
+    pieces = ["a", "b", "ab", "ba", "aba", "c", "ca"]
+    tokens = ptr.make_token_graph(pieces, blank=blank, allow_repeats=rep)
+    tokens.arc_sort()
+    V = len(pieces) + (0 if blank == "none" else 1)
+    B, T = 9, 23
+    labels = np.array([[rnd.randrange(V) for _ in range(T)] for _ in range(B)], dtype=np.int32)
+    labels[0, :] = labels[0, 0]                     # one alignment that is a single repeated token
+    out = np.zeros((B, T), dtype=np.int32)
+    counts = np.zeros(B, dtype=np.int32)
+    _lib.check(_lib.lib().wfst_transducer_decode_paths(
+        tokens._h, labels.ctypes.data, B, T, out.ctypes.data, counts.ctypes.data))
+    for b in range(B):
+        chain = G.Graph(False)
+        chain.add_node(True, False)
+        for i, lab in enumerate(labels[b].tolist()):
+            chain.add_node(False, i == T - 1)
+            chain.add_arc(i, i + 1, int(lab))
+        want = G.remove(G.project_output(G.viterbi_path(G.compose(chain, tokens)))).labels_to_list()
+        assert out[b, :counts[b]].tolist() == want

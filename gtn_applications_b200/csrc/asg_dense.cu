@@ -117,15 +117,20 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
       // any positive c_t as long as a^_t = a_t / c_t)
       const float c = warp_max(a);
       ahat = c > 0.f ? __fdividef(a, c) : 0.f;
-      logz += (double)logf(c) + (double)base;
+      logz += (double)base;            // the log c_t terms are summed after the sweep, T/32 per lane
       if (valid) hA[(size_t)t * C + lane] = ahat;
       if (lane == 0) hC[t] = c;
     }
   }
   {
-    // Z = sum_t log c_t + log sum_i a^_{T-1}[i]
+    // Z = sum_t (base_t + log c_t) + log sum_i a^_{T-1}[i]
+    __syncwarp();
+    double lc = 0.0;
+    for (int t = lane; t < T; t += 32) lc += (double)logf(hC[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lc += __shfl_xor_sync(kAll, lc, o);
     const float tail = warp_sum(ahat);
-    logz += (double)logf(tail);
+    logz += lc + (double)logf(tail);
   }
   if (lane == 0) scores[b] = (float)logz;
 
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
       const float p = valid ? __expf(xc[k] - base) : 0.f;
       const float g = acur * bhat;
       const float G = warp_sum(g);
-      const float gamma = G > 0.f ? g / G : 0.f;
+      const float gamma = G > 0.f ? __fdividef(g, G) : 0.f;
       if (gEb && valid) {
         float* dst = gEb + (size_t)t * C + lane;
         *dst = accumulate ? *dst + gs * gamma : gs * gamma;
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
       }
       const float r = p * bhat;
       const float n = cc[k] * G;
-      const float rn = n > 0.f ? r / n : 0.f;
+      const float rn = n > 0.f ? __fdividef(r, n) : 0.f;
       bc0[lane] = ac[k];     // a^_{t-1}
       bc1[lane] = r;
       __syncwarp();

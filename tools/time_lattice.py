@@ -31,6 +31,16 @@ tgt = [torch.tensor(t) for t in tg]
 def asg():
     e.grad = None; tr.grad = None
     ASGLoss(e, tr, tgt, "mean").backward()
+# the same step at the C ABI (no per-call Python work): targets packed once
+from gtn_applications_b200 import _runtime as rt
+flat_a, offs_a, _, maxlen_a, gsc_a = rt.pack_targets(tgt, C, e.device, [1.0 / (B * L)] * B)
+out_a = torch.empty(B + 1, device="cuda"); ge_a = torch.empty_like(e); gt_a = torch.empty_like(tr)
+ws_a = rt.workspace(e.device, L_.wfst_asg_workspace_bytes(B, T, C, maxlen_a))
+def asg_abi():
+    _lib.check(L_.wfst_asg_forward_backward(
+        e.data_ptr(), tr.data_ptr(), flat_a.data_ptr(), offs_a.data_ptr(), B, T, C, maxlen_a, gsc_a.data_ptr(),
+        out_a.data_ptr(), out_a[B:].data_ptr(), ge_a.data_ptr(), gt_a.data_ptr(), ws_a.data_ptr(), ws_a.numel(),
+        torch.cuda.current_stream().cuda_stream))
 lp = torch.log_softmax(torch.randn(B, T, C, device="cuda"), 2).requires_grad_(True)
 tgc = [torch.randint(C - 1, (L,)) for _ in range(B)]
 def ctc():
@@ -63,7 +73,8 @@ def tdc():
 
 for name in ("lean", "generic"):
     old = L_.wfst_debug_force_generic_lattice(1 if name == "generic" else 0)
-    print("%s: cfg3 ASG step %.3f ms" % (name, ev_time(asg)), flush=True)
+    print("%s: cfg3 ASG step %.3f ms (Function + backward), %.3f ms (wfst_asg_forward_backward at the C ABI)"
+          % (name, ev_time(asg), ev_time(asg_abi, 20)), flush=True)
     print("%s: cfg4 transducer lattice kernel (B=64, T=1000, C=%d) %.3f ms" % (name, Ct, ev_time(tdc, 3)), flush=True)
     o2 = L_.wfst_debug_force_generic_ctc(1)
     print("%s: cfg2 CTC on the log-semiring kernel only %.3f ms" % (name, ev_time(ctc, 3)), flush=True)

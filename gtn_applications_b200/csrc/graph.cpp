@@ -369,12 +369,29 @@ std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B
   for (int sa : A.starts)
     for (int sb : B.starts) visit(sa, sb);
   const size_t nstart = pairs.size();
+  // One-step lookahead before a pair is entered: a non-accepting pair with no move out of it
+  // cannot reach an accepting pair, so the move into it would be dropped by the
+  // co-accessibility sweep anyway.  (target o lexicon: every position tries the ~40 word pieces
+  // that start with its letter and all but one or two die on the next letter — 18 k pairs
+  // entered per utterance where 1 k survive.)  Only checked when both out-lists are short.
+  auto dead_end = [&](int a, int b) -> bool {
+    if ((A.flags[a] & 2) && (B.flags[b] & 2)) return false;
+    const AdjList& oa = A.out[a];
+    const AdjList& ob = B.out[b];
+    if (oa.size() > 4 || ob.size() > 4) return false;
+    for (int32_t i : oa) if (A.ol[i] == kEpsilon) return false;
+    for (int32_t j : ob) if (B.il[j] == kEpsilon) return false;
+    for (int32_t i : oa)
+      for (int32_t j : ob) if (A.ol[i] == B.il[j]) return false;
+    return true;
+  };
   for (size_t head = 0; head < pairs.size(); ++head) {
     const int ca = pairs[head].first, cb = pairs[head].second;
     mbeg.push_back((int32_t)moves.size());
     bool eps_pair = false;
     m.for_each(ca, cb, false, [&](int32_t i, int32_t j) {
       eps_pair = eps_pair || A.ol[i] == kEpsilon;
+      if (dead_end(A.dst[i], B.dst[j])) return;
       moves.push_back({i, j, visit(A.dst[i], B.dst[j])});
     });
     if (eps_pair) continue;

@@ -56,6 +56,7 @@ SIGNATURES = {
     # host-side graphs (csrc/graph.cpp)
     "wfst_graph_create": (_I32, [_I]),
     "wfst_graph_destroy": (_I, [_I32]),
+    "wfst_graph_destroy_many": (_I, [_P, _I]),
     "wfst_graph_add_node": (_I, [_I32, _I, _I]),
     "wfst_graph_add_arc": (_I, [_I32, _I, _I, _I, _I, ctypes.c_float]),
     "wfst_graph_add_arcs": (_I, [_I32, _I, _P, _P, _P, _P, _P]),

@@ -214,7 +214,9 @@ class TransducerLossFunction(torch.autograd.Function):
         handles = (ctypes.c_int32 * B)()
         _lib.check(L.wfst_transducer_alignment_graphs(
             tokens._h, lexicon._h, flat.ctypes.data, offs.ctypes.data, B, handles))
-        aligns = [G.Graph(_handle=h) for h in handles]
+        # without a transition graph the alignment graphs are only packed and freed: no Python
+        # wrapper (and no per-graph destructor call) for them
+        aligns = [G.Graph(_handle=h) for h in handles] if transitions is not None else None
         need_e = ctx.needs_input_grad[0]
         need_t = transitions is not None and ctx.needs_input_grad[4]
         with torch.cuda.device(dev):
@@ -237,7 +239,11 @@ class TransducerLossFunction(torch.autograd.Function):
                     composed.append(c)
                     prov.append(c.provenance()[0])
                 aligns = composed
-            packed = G.pack_graphs(aligns, dev)
+            if aligns is None:
+                packed = G.pack_handles(handles, B, dev)
+                G.destroy_handles(handles, B)
+            else:
+                packed = G.pack_graphs(aligns, dev)
             weights = None
             if transitions is not None:
                 prov_idx = torch.from_numpy(np.concatenate(prov).astype(np.int64)).to(dev)

@@ -20,6 +20,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <unistd.h>
+#include <functional>
+#include <condition_variable>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -577,21 +580,76 @@ std::unique_ptr<HostGraph> best_path(const HostGraph& g) {
   return out;
 }
 
+// Persistent worker pool (the counterpart of gtn.parallel_for's thread pool): three
+// parallel sections per transducer step made thread creation a visible cost.  Workers are
+// detached and the pool is never destroyed (no static-destruction races at interpreter exit);
+// a fork()ed child (its threads are gone) builds a new pool on first use.
+class WorkerPool {
+ public:
+  static WorkerPool& instance() {
+    static std::mutex mu;
+    static WorkerPool* pool = nullptr;
+    static pid_t owner = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pool || owner != getpid()) {
+      pool = new WorkerPool();     // a forked child leaks the parent's (thread-less) pool
+      owner = getpid();
+    }
+    return *pool;
+  }
+  int size() const { return nthreads_; }
+  // runs fn(0..n-1); one section at a time
+  void run(int n, const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> section(run_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &fn; n_ = n; next_.store(0); pending_ = nthreads_; ++generation_;
+    }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+ private:
+  WorkerPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    nthreads_ = (int)(hw ? hw : 1);
+    for (int t = 0; t < nthreads_; ++t) std::thread([this] { loop(); }).detach();
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* job;
+      int n;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        job = job_; n = n_;
+      }
+      for (int i; (i = next_.fetch_add(1)) < n;) (*job)(i);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::mutex run_mu_, mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* job_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, pending_ = 0, nthreads_ = 1;
+  uint64_t generation_ = 0;
+};
+
 template <class F>
 void parallel_for(int n, F&& fn) {
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)std::max(n, 1));
-  if (nt <= 1) {
+  if (n <= 1 || std::thread::hardware_concurrency() <= 1) {
     for (int i = 0; i < n; ++i) fn(i);
     return;
   }
-  std::atomic<int> next{0};
-  std::vector<std::thread> pool;
-  for (int t = 0; t < nt; ++t)
-    pool.emplace_back([&] {
-      for (int i; (i = next.fetch_add(1)) < n;) fn(i);
-    });
-  for (auto& t : pool) t.join();
+  const std::function<void(int)> job = [&](int i) { fn(i); };
+  WorkerPool::instance().run(n, job);
 }
 
 }  // namespace
@@ -619,6 +677,22 @@ int wfst_graph_destroy(int32_t h) {
   if (h < 0 || h >= (int32_t)g_graphs.size() || !g_graphs[h]) return WFST_ERR_INVALID;
   g_graphs[h].reset();
   g_free.push_back(h);
+  return WFST_OK;
+}
+
+int wfst_graph_destroy_many(const int32_t* handles, int n) {
+  if (n < 0 || (n > 0 && !handles)) { set_error("bad arguments"); return WFST_ERR_INVALID; }
+  std::vector<std::unique_ptr<HostGraph>> doomed(n);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int k = 0; k < n; ++k) {
+      const int32_t h = handles[k];
+      if (h < 0 || h >= (int32_t)g_graphs.size() || !g_graphs[h]) continue;
+      doomed[k] = std::move(g_graphs[h]);
+      g_free.push_back(h);
+    }
+  }
+  parallel_for(n, [&](int k) { doomed[k].reset(); });
   return WFST_OK;
 }
 

@@ -262,10 +262,19 @@ def isomorphic(a, b):
 # ---- batch packing for the lattice kernel --------------------------------------------
 def pack_graphs(graphs, device):
     """list[Graph] -> packing.PackedAcceptors (device resident) via wfst_graph_pack"""
+    B = len(graphs)
+    return pack_handles((ctypes.c_int32 * B)(*[g._h for g in graphs]), B, device)
+
+
+def destroy_handles(handles, B):
+    """frees B host graphs that were never wrapped in Graph objects (one call, host threads)"""
+    _lib.check(_L().wfst_graph_destroy_many(handles, B))
+
+
+def pack_handles(handles, B, device):
+    """ctypes int32 array of B graph handles -> packing.PackedAcceptors (device resident)"""
     import torch
     from .packing import PackedAcceptors
-    B = len(graphs)
-    handles = (ctypes.c_int32 * B)(*[g._h for g in graphs])
     tn, ta, mn, ma, eps = (ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(),
                            ctypes.c_int32())
     _lib.check(_L().wfst_graph_pack_sizes(handles, B, ctypes.byref(tn), ctypes.byref(ta),

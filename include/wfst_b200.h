@@ -197,6 +197,7 @@ WFST_API int wfst_asg_forward_backward(const float* emissions, const float* tran
  * ---------------------------------------------------------------------- */
 WFST_API int32_t wfst_graph_create(int calc_grad);
 WFST_API int wfst_graph_destroy(int32_t graph);
+WFST_API int wfst_graph_destroy_many(const int32_t* graphs, int n);          /* invalid handles are skipped */
 WFST_API int wfst_graph_add_node(int32_t graph, int start, int accept);      /* returns the node id */
 WFST_API int wfst_graph_add_arc(int32_t graph, int src, int dst, int ilabel, int olabel,
                                 float weight);                                /* returns the arc id */

@@ -1,6 +1,8 @@
 """GPU parity: the CUDA ASG path (ASGLossFunction -> wfst_asg_forward_backward)
 against the float64 oracle, the reference's known-answer vector and the committed
 fixtures.  Tolerance 1e-4 relative (north_star)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -92,3 +94,46 @@ def test_dense_and_generic_full_connect_kernels_agree(B, T, C, lens):
     assert abs(dense[0] - generic[0]) <= 1e-5 * abs(generic[0])
     assert_close(dense[1], generic[1])
     assert_close(dense[2], generic[2])
+
+
+def test_full_size_properties_cfg3():
+    """BASELINE configs[2] (ASG B=256, T=1000, C=30, L=176): size-independent checks.  Both
+    lattices cross every frame exactly once, so the emission-gradient rows sum to zero
+    (full-connect posteriors minus force-align posteriors) and so does the transition gradient
+    (T arcs taken in each lattice); the force-align term is the same on the shared-memory kernel
+    and on the generic kernel; a slice of utterances agrees with the float64 DP."""
+    import dp_numpy
+    from gtn_applications_b200 import _lib
+    from gtn_applications_b200.criterions.asg import ASGLoss
+    torch.manual_seed(0)
+    B, T, C, L = 256, 1000, 30, 176
+    e0 = torch.randn(B, T, C, device="cuda")
+    tr0 = torch.randn(C + 1, C, device="cuda")
+    tg = torch.randint(C, (B, L)).tolist()
+
+    def go():
+        e, tr = e0.clone().requires_grad_(True), tr0.clone().requires_grad_(True)
+        loss = ASGLoss(e, tr, tg, "none")
+        loss.backward()
+        return loss.item(), e.grad, tr.grad
+
+    loss, ge, gt = go()
+    assert math.isfinite(loss)
+    assert float(ge.sum(2).abs().max()) <= 2e-4 / B
+    assert abs(float(gt.sum())) <= 3e-4 * T      # +T and -T per utterance, accumulated in float32
+    old = _lib.lib().wfst_debug_force_generic_lattice(1)
+    try:
+        loss2, ge2, gt2 = go()
+    finally:
+        _lib.lib().wfst_debug_force_generic_lattice(old)
+    assert abs(loss - loss2) <= 1e-5 * abs(loss2)
+    assert_close(ge.cpu().numpy(), ge2.cpu().numpy())
+    assert_close(gt.cpu().numpy(), gt2.cpu().numpy())
+    ref = dp_numpy.asg(e0[:3].cpu().numpy(), tr0.cpu().numpy(), tg[:3], "none")
+    e = e0[:3].clone().requires_grad_(True)
+    tr = tr0.clone().requires_grad_(True)
+    l3 = ASGLoss(e, tr, tg[:3], "none")
+    l3.backward()
+    assert abs(l3.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert_close(e.grad.cpu().numpy(), ref["grad"])
+    assert_close(tr.grad.cpu().numpy(), ref["grad_transitions"])

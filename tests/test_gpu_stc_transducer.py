@@ -285,3 +285,48 @@ def test_transducer_viterbi_known_answers():
     crit.transition_params.data = torch.tensor([0, 0, 0, 0, 2, 0, 0, 0, 2, 2, 0, 0], dtype=torch.float32, device="cuda")
     x = torch.tensor([0, 0, 7, 5, 4, 3, 5, 8, 5, 5, 4, 3], dtype=torch.float32, device="cuda").view(1, 4, 3)
     assert crit.viterbi(x)[0].tolist() == [2, 1, 0]
+
+
+def test_full_size_properties_cfg4():
+    """BASELINE configs[3] (transducer, 1000 word pieces, B=64, T=1000): size-independent checks.
+    Every alignment crosses each frame once, so the emission-gradient rows sum to -scale_b / B;
+    the gradient is non-positive; the shared-memory lattice kernel and the generic kernel agree;
+    the alignment graphs of the batch equal the ones built one utterance at a time."""
+    import random
+    from gtn_applications_b200 import _lib
+    from gtn_applications_b200.criterions.transducer import Transducer, TransducerLoss
+    rnd = random.Random(0)
+    letters = "abcdefghijklmnopqrstuvwxyz"
+    pieces = sorted({"".join(rnd.choice(letters) for _ in range(rnd.randint(1, 4))) for _ in range(1400)})[:1000]
+    pieces = sorted(set(pieces) | set(letters))
+    g2i = {ch: i for i, ch in enumerate(letters)}
+    B, T, NP = 64, 1000, 150
+    crit = Transducer(pieces, g2i, blank="optional", allow_repeats=False, reduction="mean")
+    C = len(pieces) + 1
+    torch.manual_seed(0)
+    e0 = torch.log_softmax(torch.randn(B, T, C, device="cuda"), 2)
+    targets = [[g2i[c] for c in "".join(rnd.choice(pieces) for _ in range(NP))] for _ in range(B)]
+    crit.tokens.arc_sort(True)
+
+    def go():
+        e = e0.clone().requires_grad_(True)
+        loss = TransducerLoss(e, targets, crit.tokens, crit.lexicon, None, None, "mean")
+        loss.backward()
+        return loss.item(), e.grad
+
+    loss, g = go()
+    assert math.isfinite(loss) and loss > 0
+    assert torch.all(g <= 1e-7)
+    want = torch.tensor([-1.0 / (len(t) * B) for t in targets], device="cuda").unsqueeze(1).expand(B, T)
+    torch.testing.assert_close(g.sum(2), want, rtol=3e-4, atol=0)
+    old = _lib.lib().wfst_debug_force_generic_lattice(1)
+    try:
+        loss2, g2 = go()
+    finally:
+        _lib.lib().wfst_debug_force_generic_lattice(old)
+    assert abs(loss - loss2) <= 1e-5 * abs(loss2)
+    assert_close(g.cpu().numpy(), g2.cpu().numpy())
+    # one utterance scored alone gives the same per-utterance gradient (x B)
+    e = e0[:1].clone().requires_grad_(True)
+    TransducerLoss(e, targets[:1], crit.tokens, crit.lexicon, None, None, "mean").backward()
+    assert_close(e.grad[0].cpu().numpy() / B, g[0].cpu().numpy())

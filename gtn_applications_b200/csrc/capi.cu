@@ -59,7 +59,7 @@ int wfst_debug_force_generic_ctc(int on) {
   g_force_generic_kind = (on == 2) ? 2 : 0;
   return old;
 }
-int wfst_debug_force_generic_lattice(int on) { return lattice_force_generic(on != 0); }
+int wfst_debug_force_generic_lattice(int on) { return lattice_force_generic((on >= 1 && on <= 3) ? on : 0); }
 unsigned long long wfst_launch_count(void) { return g_launches.load(); }
 
 // --------------------------------------------------------------------- CTC

@@ -264,7 +264,7 @@ struct CsrLean {
               fw ? fw[v] : 0.f);
     for (int k = threadIdx.x; k < A; k += blockDim.x) {
       const int ia = in_arc[k], oa = out_arc[k];
-      bd.in_arc(k, in_src[k], in_label[k], w ? w[ia] : 0.f);
+      bd.in_arc(k, in_src[k], in_label[k], w ? w[ia] : 0.f, ia);
       bd.out_arc(k, out_dst[k], out_label[k], w ? w[oa] : 0.f, oa);
     }
   }
@@ -272,13 +272,19 @@ struct CsrLean {
     if (!gradF) return;
     if (shared) atomicAdd(&gradF[v], g); else gradF[v] = g;
   }
-  // every arc has exactly one out-arc slot, owned by one thread: plain sums per utterance
-  __device__ void finish(uint32_t s_gw, uint32_t s_gidx, float gs, int want) const {
+  __device__ void zero_weight_grad() const {
+    if (gradW && !shared)
+      for (int k = threadIdx.x; k < A; k += blockDim.x) gradW[k] = 0.f;
+  }
+  // every arc has exactly one slot per direction, owned by one thread: plain sums per utterance
+  // (atomic: the buffer was zeroed and another block — other utterances of a shared graph, or
+  // the other half of the frames in the pair kernel — adds to it as well)
+  __device__ void finish(uint32_t s_gw, uint32_t s_gidx, uint32_t, float gs, int want, bool atomic) const {
     if (!want || !gradW) return;
     for (int k = threadIdx.x; k < A; k += blockDim.x) {
       const float v = lean::lds_f(s_gw + 4u * k) * gs;
       const int idx = (int)lean::lds_u(s_gidx + 4u * k);
-      if (shared) { if (v != 0.f) atomicAdd(&gradW[idx], v); }
+      if (shared || atomic) { if (v != 0.f) atomicAdd(&gradW[idx], v); }
       else gradW[idx] = v;
     }
   }
@@ -303,9 +309,9 @@ struct CtcLean {
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
       const int l = lab(s);
       uint32_t ni = 0, no = 0;
-      bd.in_arc(3 * s + ni++, s, l, 0.f);
-      if (s > 0) bd.in_arc(3 * s + ni++, s - 1, l, 0.f);
-      if (skip(s)) bd.in_arc(3 * s + ni++, s - 2, l, 0.f);
+      bd.in_arc(3 * s + ni++, s, l, 0.f, -1);
+      if (s > 0) bd.in_arc(3 * s + ni++, s - 1, l, 0.f, -1);
+      if (skip(s)) bd.in_arc(3 * s + ni++, s - 2, l, 0.f, -1);
       bd.out_arc(3 * s + no++, s, l, 0.f, -1);
       if (s + 1 < S) bd.out_arc(3 * s + no++, s + 1, lab(s + 1), 0.f, -1);
       if (s + 2 < S && skip(s + 2)) bd.out_arc(3 * s + no++, s + 2, lab(s + 2), 0.f, -1);
@@ -313,7 +319,8 @@ struct CtcLean {
     }
   }
   __device__ void add_final_grad(int, float) const {}
-  __device__ void finish(uint32_t, uint32_t, float, int) const {}
+  __device__ void zero_weight_grad() const {}
+  __device__ void finish(uint32_t, uint32_t, uint32_t, float, int, bool) const {}
 };
 
 struct AsgFalLean {
@@ -321,25 +328,24 @@ struct AsgFalLean {
   static constexpr int kDeg = 2;          // enter, self loop
   static constexpr bool kTail = false;
   static constexpr bool kSort = false;
-  const int* y; const float* tr; float* gradTr; int L, C; uint32_t s_node_out;
+  const int* y; const float* tr; float* gradTr; int L, C;
   __device__ void init(const Params& p, int b) {
     y = p.targets + p.offsets[b];
     L = p.offsets[b + 1] - p.offsets[b];
-    C = p.C; tr = p.tr; gradTr = p.gradTr; s_node_out = 0;
+    C = p.C; tr = p.tr; gradTr = p.gradTr;
   }
   __device__ int lbl(int k) const { return min(max(y[k], 0), C - 1); }
   __device__ int num_nodes() const { return L + 1; }
   __device__ int num_slots() const { return 2 * (L + 1); }
   __device__ void build(const lean::Build& bd) {
-    s_node_out = bd.node_out;
     for (int l = threadIdx.x; l <= L; l += blockDim.x) {
       uint32_t ni = 0, no = 0;
       if (l >= 1) {
         const int cur = lbl(l - 1);
         const int enter = (l == 1) ? cur : C + cur * C + lbl(l - 2);
         const int loop = C + cur * C + cur;
-        bd.in_arc(2 * l + ni++, l - 1, cur, tr[enter]);
-        bd.in_arc(2 * l + ni++, l, cur, tr[loop]);
+        bd.in_arc(2 * l + ni++, l - 1, cur, tr[enter], enter);
+        bd.in_arc(2 * l + ni++, l, cur, tr[loop], loop);
       }
       if (l < L) {
         const int nx = lbl(l);
@@ -355,11 +361,12 @@ struct AsgFalLean {
     }
   }
   __device__ void add_final_grad(int, float) const {}
+  __device__ void zero_weight_grad() const {}   // shared by all utterances: cleared by the host
   // several arcs (and all utterances) share a transition: one atomic per arc and utterance
-  __device__ void finish(uint32_t s_gw, uint32_t s_gidx, float gs, int want) const {
+  __device__ void finish(uint32_t s_gw, uint32_t s_gidx, uint32_t s_node_rec, float gs, int want, bool) const {
     if (!want || !gradTr || gs == 0.f) return;
     for (int u = threadIdx.x; u <= L; u += blockDim.x) {
-      const uint32_t be = lean::lds_u(s_node_out + 4u * u);
+      const uint32_t be = lean::lds_u(s_node_rec + 4u * u);
       for (uint32_t k = be & 0xffffu; k < (be >> 16); ++k) {
         const float v = lean::lds_f(s_gw + 4u * k);
         if (v != 0.f) atomicAdd(&gradTr[lean::lds_u(s_gidx + 4u * k)], v * gs);
@@ -454,7 +461,7 @@ static int launch_lattice(LatticeArgs a, typename Topo::Params tp, int B, int ma
 
 
 // Lean kernel when the acceptor fits its limits (lattice_lean.cuh); returns false otherwise.
-static int g_force_generic_lattice = 0;   // test hook: 1 = never use the lean kernel
+static int g_force_generic_lattice = 0;   // test hook: 1 = never use the lean kernels, 2 = no pair (cluster) kernel, 3 = pair kernel whenever T allows
 
 template <class Builder, int NPT>
 static int launch_lean_npt(const lean::Args& g, typename Builder::Params bp, int B, int nt, size_t smem,
@@ -467,10 +474,21 @@ static int launch_lean_npt(const lean::Args& g, typename Builder::Params bp, int
   return WFST_OK;
 }
 
+template <class Builder, int NPT>
+static int launch_lean_pair_npt(const lean::Args& g, typename Builder::Params bp, int B, int nt, size_t smem,
+                                cudaStream_t st) {
+  auto kern = lean::lattice_lean_pair_kernel<Builder, NPT>;
+  WFST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<2 * B, nt, smem, st>>>(g, bp);      // clusters of two blocks (compile-time cluster dims)
+  g_launches++;
+  WFST_CUDA_CHECK(cudaGetLastError());
+  return WFST_OK;
+}
+
 template <class Builder>
 static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, int max_nodes, int aslots,
                             int want_gw, cudaStream_t st, int* rc) {
-  if (g_force_generic_lattice) return false;
+  if (g_force_generic_lattice == 1) return false;
   if (max_nodes < 1 || max_nodes > 16 * 1024 || aslots > 65535 || a.C > 65535) return false;
   int npt = (max_nodes + 1023) / 1024;
   npt = npt <= 4 ? npt : (npt <= 8 ? 8 : 16);
@@ -488,6 +506,22 @@ static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, i
   a.Kt = kt;
   a.renorm_every = (16 + kt - 1) / kt;
   lean::Args g{a, aslots, want_gw};
+  // two blocks per utterance that meet in the middle (half the dependent frame steps each) when
+  // there are tiles to split and the single-block launch would leave the SMs short of warps
+  // (measured: B=64 x 22 warps 5.4 -> 2.9 ms; B=256 x 12 warps, already issue-bound, 1.9 -> 2.1 ms)
+  const int ntiles = (a.T + kt - 1) / kt;
+  const bool starved = (long long)B * (nt / 32) <= 148LL * 16;
+  if (g_force_generic_lattice != 2 && ntiles >= 2 && (starved || g_force_generic_lattice == 3)) {
+    switch (npt) {
+      case 1: *rc = launch_lean_pair_npt<Builder, 1>(g, bp, B, nt, lay.total, st); break;
+      case 2: *rc = launch_lean_pair_npt<Builder, 2>(g, bp, B, nt, lay.total, st); break;
+      case 3: *rc = launch_lean_pair_npt<Builder, 3>(g, bp, B, nt, lay.total, st); break;
+      case 4: *rc = launch_lean_pair_npt<Builder, 4>(g, bp, B, nt, lay.total, st); break;
+      case 8: *rc = launch_lean_pair_npt<Builder, 8>(g, bp, B, nt, lay.total, st); break;
+      default: *rc = launch_lean_pair_npt<Builder, 16>(g, bp, B, nt, lay.total, st); break;
+    }
+    return true;
+  }
   switch (npt) {
     case 1: *rc = launch_lean_npt<Builder, 1>(g, bp, B, nt, lay.total, st); break;
     case 2: *rc = launch_lean_npt<Builder, 2>(g, bp, B, nt, lay.total, st); break;

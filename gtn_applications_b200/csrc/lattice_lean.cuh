@@ -60,7 +60,7 @@ __device__ __forceinline__ void red_add_u(uint32_t a, uint32_t v) {
 // byte offsets of the regions inside dynamic shared memory
 struct Layout {
   uint32_t bars, red, rowsum, tile0, tile1, gtile, alpha0, alpha1, node_in, node_out, nflags, fw, perm,
-      in_pack, out_pack, out_gidx, gw, total;
+      in_pack, out_pack, out_gidx, in_gidx, gw, xch, total;
 };
 
 __host__ __device__ inline Layout make_layout(int Kt, int C, int npad, int aslots, int want_gw) {
@@ -86,7 +86,10 @@ __host__ __device__ inline Layout make_layout(int Kt, int C, int npad, int aslot
   l.in_pack = o; o += (uint32_t)(aslots + 4) * 8u;
   l.out_pack = o; o += (uint32_t)(aslots + 4) * 8u;
   l.out_gidx = o; o += want_gw ? (uint32_t)aslots * 4u : 0u;
+  l.in_gidx = o; o += want_gw ? (uint32_t)aslots * 4u : 0u;
   l.gw = o; o += want_gw ? (uint32_t)aslots * 4u : 0u;
+  o = (o + 7u) & ~7u;
+  l.xch = o; o += 8u + (uint32_t)npad * 4u;   // pair kernel: peer's boundary vector (+ its float64 offset)
   l.total = (o + 15u) & ~15u;
   return l;
 }
@@ -99,7 +102,7 @@ struct Args {
 
 // what a builder sees while it materialises the acceptor
 struct Build {
-  uint32_t node_in, node_out, nflags, fw, in_pack, out_pack, out_gidx;
+  uint32_t node_in, node_out, nflags, fw, in_pack, out_pack, out_gidx, in_gidx;
   int want_gw;
   __device__ __forceinline__ void node(int v, uint32_t in_beg, uint32_t in_end, uint32_t out_beg,
                                        uint32_t out_end, int start, int accept, float final_w) const {
@@ -109,8 +112,9 @@ struct Build {
     uint8_t f = (uint8_t)((start ? 1 : 0) | (accept ? 2 : 0));
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(nflags + (uint32_t)v), "r"((uint32_t)f) : "memory");
   }
-  __device__ __forceinline__ void in_arc(uint32_t slot, int src, int label, float w) const {
+  __device__ __forceinline__ void in_arc(uint32_t slot, int src, int label, float w, int gidx) const {
     sts_u2(in_pack + 8u * slot, (uint32_t)src | ((uint32_t)label << 16), __float_as_uint(w));
+    if (want_gw) sts_u(in_gidx + 4u * slot, (uint32_t)gidx);
   }
   __device__ __forceinline__ void out_arc(uint32_t slot, int dst, int label, float w, int gidx) const {
     sts_u2(out_pack + 8u * slot, (uint32_t)dst | ((uint32_t)label << 16), __float_as_uint(w));
@@ -142,13 +146,14 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
   const uint32_t s_node_in = sb + L.node_in, s_node_out = sb + L.node_out, s_flags = sb + L.nflags,
                  s_fw = sb + L.fw, s_in = sb + L.in_pack, s_out = sb + L.out_pack,
                  s_gidx = sb + L.out_gidx, s_gw = sb + L.gw;
+  const uint32_t s_in_gidx = sb + L.in_gidx;
 
   Builder bld;
   bld.init(bp, b);
   const int N = bld.num_nodes();
   const int A = bld.num_slots();
   {
-    Build bd{s_node_in, s_node_out, s_flags, s_fw, s_in, s_out, s_gidx, g.want_gw};
+    Build bd{s_node_in, s_node_out, s_flags, s_fw, s_in, s_out, s_gidx, s_in_gidx, g.want_gw};
     // slots no arc owns (gaps of fixed-stride builders, the padding) are read by the register
     // slots of a node and discarded: they must address valid memory (node 0, label 0)
     for (int k = tid; k < g.aslots + 4; k += NT) {
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
   if (!feasible) {
     if (want_gE && !a.accumulate)
       for (size_t k = tid; k < (size_t)T * C; k += NT) gEb[k] = 0.f;
-    bld.finish(s_gw, s_gidx, 0.f, g.want_gw);
+    bld.finish(s_gw, s_gidx, s_node_out, 0.f, g.want_gw, false);
     return;
   }
 
@@ -521,7 +526,476 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
   }
   if (tid == 0) bulk_wait_all<0>();
   __syncthreads();
-  bld.finish(s_gw, s_gidx, gs, g.want_gw);
+  bld.finish(s_gw, s_gidx, s_node_out, gs, g.want_gw, false);
+}
+
+
+// =======================================================================================
+// Pair kernel: the same lattice on a CLUSTER OF TWO thread blocks that meet in the middle.
+// A block of the kernel above walks 2T dependent frame steps (alpha up, then beta down) and
+// that chain, not memory, is what bounds it.  Here rank 0 owns the frames [0, Th) and rank 1
+// the frames [Th, T) of the same utterance:
+//   primary sweep    rank 0: alpha_0 -> alpha_Th (in-arcs, time up)     | rank 1: beta_T -> beta_Th (out-arcs, time down)
+//   exchange         each block stores its boundary vector (and its float64 offset) into the
+//                    PEER's shared memory (st.shared::cluster) + one cluster barrier;
+//                    Z = LSE_v alpha_Th[v] + beta_Th[v] in both blocks
+//   secondary sweep  rank 0: beta_Th -> beta_0 over its frames, posteriors with its alpha rows
+//                    rank 1: alpha_Th -> alpha_T over its frames, posteriors with its beta rows
+// so each block walks T frame steps and twice as many SMs work (B = 64 utterances: 128 SMs).
+// Both ranks run ONE code path: a sweep gathers over the arc records of its direction,
+//   R_{s+1}[n] = LSE_k  val[other node of k] + E[f(s), label k] + w_k,     f(s) = s | T-1-s
+// the primary sweep stores R_1..R_{S-1} (history rows s, slot indexed) and the secondary sweep
+// Q_s = step(Q_{s+1}) takes the posterior of arc k into node n as exp(x_k + R_s[n] - Z).
+// =======================================================================================
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_peer_f(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_peer_u2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
+template <class Builder, int NPT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(1024, 1)
+lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
+  constexpr int DEG = Builder::kDeg;
+  constexpr bool TAIL = Builder::kTail;
+  extern __shared__ __align__(16) unsigned char smem_lean[];
+  const LatticeArgs& a = g.a;
+  const int b = blockIdx.x >> 1;
+  const uint32_t role = cluster_rank();
+  if (a.active && a.active[b] == 0) return;        // both blocks of the pair
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const Layout L = make_layout(a.Kt, a.C, a.npad, g.aslots, g.want_gw);
+  const uint32_t sb = smem_u32(smem_lean);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lean + L.bars);
+  float* red = reinterpret_cast<float*>(smem_lean + L.red);
+  float* gt = reinterpret_cast<float*>(smem_lean + L.gtile);
+  const uint32_t tile_bytes = L.tile1 - L.tile0;
+  auto tilep = [&](int buf) { return reinterpret_cast<float*>(smem_lean + L.tile0 + (uint32_t)buf * tile_bytes); };
+  auto s_tile = [&](int buf) { return sb + L.tile0 + (uint32_t)buf * tile_bytes; };
+  const uint32_t s_gt = sb + L.gtile, s_rowsum = sb + L.rowsum;
+  const uint32_t s_node_in = sb + L.node_in, s_node_out = sb + L.node_out, s_flags = sb + L.nflags,
+                 s_fw = sb + L.fw, s_in = sb + L.in_pack, s_out = sb + L.out_pack,
+                 s_out_gidx = sb + L.out_gidx, s_in_gidx = sb + L.in_gidx, s_gw = sb + L.gw,
+                 s_xch = sb + L.xch;
+  // arc records / node records / arc -> weight index of the two sweeps of this rank
+  const uint32_t s_ppack = role ? s_out : s_in, s_pnode = role ? s_node_out : s_node_in;
+  const uint32_t s_spack = role ? s_in : s_out, s_snode = role ? s_node_in : s_node_out;
+  const uint32_t s_sgidx = role ? s_in_gidx : s_out_gidx;
+
+  Builder bld;
+  bld.init(bp, b);
+  const int N = bld.num_nodes();
+  const int A = bld.num_slots();
+  {
+    Build bd{s_node_in, s_node_out, s_flags, s_fw, s_in, s_out, s_out_gidx, s_in_gidx, g.want_gw};
+    for (int k = tid; k < g.aslots + 4; k += NT) {
+      sts_u2(s_in + 8u * k, 0u, 0u);
+      sts_u2(s_out + 8u * k, 0u, 0u);
+    }
+    __syncthreads();
+    bld.build(bd);
+    if (g.want_gw) {
+      for (int k = tid; k < A; k += NT) sts_f(s_gw + 4u * k, 0.f);
+      // both ranks add their half of the frames to the utterance's weight gradient: rank 0 clears
+      // it here, before the first cluster barrier (shared gradients are cleared by the host)
+      if (role == 0) bld.zero_weight_grad();
+    }
+  }
+  const int T = a.T, C = a.C, Kt = a.Kt;
+  const float* Eb = a.E + (size_t)b * T * C;
+  const int ntiles = (T + Kt - 1) / Kt;            // >= 2 (launcher)
+  const int nt0 = ntiles / 2;                       // tiles of rank 0 (all full)
+  const int ntr = role ? ntiles - nt0 : nt0;        // tiles of this rank
+  const int S0 = nt0 * Kt;
+  const int S = role ? T - S0 : S0;                 // frame steps of this rank
+  float* hist = a.hist + ((size_t)b * (T + 1) + (role ? S0 : 0)) * a.hist_stride;   // rows 0 .. S-1
+  double* offP = a.offs + (size_t)b * a.offs_stride;                                // indexed by global tile
+  auto gtile_of = [&](int j) { return role ? ntiles - 1 - j : j; };
+  auto rows_of = [&](int gti) { return min(Kt, T - gti * Kt); };
+  auto sbase_of = [&](int j) { return role ? (j == 0 ? 0 : rows_of(ntiles - 1) + (j - 1) * Kt) : j * Kt; };
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  uint32_t phase = 0u;
+  __syncthreads();
+
+  auto flag_of = [&](int v) {
+    uint32_t f;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(f) : "r"(s_flags + (uint32_t)v));
+    return f;
+  };
+  auto tile_tma_ok = [&](int gti) {
+    const float* src = Eb + (size_t)gti * Kt * C;
+    uint32_t bytes = (uint32_t)rows_of(gti) * C * 4u;
+    return ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15u) == 0);
+  };
+  auto issue_tile = [&](int gti, int buf) {
+    const float* src = Eb + (size_t)gti * Kt * C;
+    int n = rows_of(gti) * C;
+    if (tile_tma_ok(gti)) {
+      if (tid == 0) {
+        mbar_expect_tx(&bars[buf], (uint32_t)n * 4u);
+        bulk_g2s(tilep(buf), src, (uint32_t)n * 4u, &bars[buf]);
+      }
+    } else {
+      float* dstp = tilep(buf);
+      for (int k = tid; k < n; k += NT) dstp[k] = __ldg(src + k);
+    }
+  };
+  auto wait_tile = [&](int gti, int buf) {
+    if (tile_tma_ok(gti)) {
+      mbar_wait(&bars[buf], (phase >> buf) & 1u);
+      phase ^= 1u << buf;
+    }
+  };
+
+  // node -> thread assignment (see the single-block kernel)
+  int vnode[NPT];
+  if (Builder::kSort) {
+    const uint32_t s_perm = sb + L.perm;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(red);
+    if (tid < 34) cnt[tid] = 0u;
+    __syncthreads();
+    auto key_of = [&](int v) {
+      const uint32_t bi = lds_u(s_node_in + 4u * v), bo = lds_u(s_node_out + 4u * v);
+      const uint32_t d = max((bi >> 16) - (bi & 0xffffu), (bo >> 16) - (bo & 0xffffu));
+      return 31u - min(d, 31u);
+    };
+    for (int v = tid; v < N; v += NT) atomicAdd(&cnt[key_of(v) + 1], 1u);
+    __syncthreads();
+    if (tid == 0)
+      for (int k = 1; k < 33; ++k) cnt[k] += cnt[k - 1];
+    __syncthreads();
+    for (int v = tid; v < N; v += NT) sts_u(s_perm + 4u * atomicAdd(&cnt[key_of(v)], 1u), (uint32_t)v);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      const int q = j * NT + ((j & 1) ? NT - 1 - tid : tid);
+      vnode[j] = (q < N) ? (int)lds_u(s_perm + 4u * q) : -1;
+    }
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) vnode[j] = (tid + j * NT < N) ? tid + j * NT : -1;
+  }
+  auto slot_of = [&](int j) { return (Builder::kSort && (j & 1)) ? j * NT + NT - 1 - tid : j * NT + tid; };
+
+  // label carried by most arcs of the secondary direction
+  uint32_t cstar = 0;
+  if (a.gradE != nullptr) {
+    for (int c = tid; c < C; c += NT) sts_u(s_gt + 4u * c, 0u);
+    __syncthreads();
+    for (int v = tid; v < N; v += NT) {
+      const uint32_t be = lds_u(s_snode + 4u * v);
+      for (uint32_t k = be & 0xffffu; k < (be >> 16); ++k) red_add_u(s_gt + 4u * (lds_u(s_spack + 8u * k) >> 16), 1u);
+    }
+    __syncthreads();
+    uint32_t best = 0;
+    for (int c = tid; c < C; c += NT) {
+      uint32_t n = min(lds_u(s_gt + 4u * c), 0xffffu);
+      best = max(best, (n << 16) | (uint32_t)(0xffff - c));
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    uint32_t* redu = reinterpret_cast<uint32_t*>(red);
+    if (lane == 0) redu[tid >> 5] = best;
+    __syncthreads();
+    best = (lane < ((NT + 31) >> 5)) ? redu[lane] : 0u;
+    best = __reduce_max_sync(0xffffffffu, best);
+    cstar = 0xffffu - (best & 0xffffu);
+    if (cstar >= (uint32_t)C) cstar = 0;
+    __syncthreads();
+  }
+  cluster_sync_all();     // the peer block runs: its shared memory may be written from here on
+
+  // ------------------------------------------------------------- primary sweep
+  uint32_t cur = sb + L.alpha0, nxt = sb + L.alpha1;
+  double cumP = 0.0;
+  auto init_val = [&](int v) {
+    const uint32_t f = flag_of(v);
+    return role ? ((f & 2u) ? lds_f(s_fw + 4u * v) : kNegInf) : ((f & 1u) ? 0.f : kNegInf);
+  };
+  for (int v = tid; v < N; v += NT) sts_f(cur + 4u * v, init_val(v));
+#pragma unroll
+  for (int j = 0; j < NPT; ++j)
+    if (vnode[j] >= 0) hist[slot_of(j)] = init_val(vnode[j]);
+  issue_tile(gtile_of(0), 0);
+  uint32_t be_p[NPT];
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) be_p[j] = (vnode[j] >= 0) ? lds_u(s_pnode + 4u * vnode[j]) : 0u;
+  __syncthreads();
+  for (int jt = 0; jt < ntr; ++jt) {
+    const int buf = jt & 1, gti = gtile_of(jt);
+    wait_tile(gti, buf);
+    if (jt + 1 < ntr) issue_tile(gtile_of(jt + 1), buf ^ 1);
+    const int rows = rows_of(gti), sbase = sbase_of(jt);
+    if (jt % a.renorm_every == 0) {
+      float pm = kNegInf;
+      for (int v = tid; v < N; v += NT) pm = fmaxf(pm, lds_f(cur + 4u * v));
+      const float mx = block_max(pm, red);
+      if (mx != kNegInf && mx != -kNegInf && mx == mx) {
+        for (int v = tid; v < N; v += NT) sts_f(cur + 4u * v, lds_f(cur + 4u * v) - mx);
+        cumP += (double)mx;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) offP[gti] = cumP;
+    for (int r = 0; r < rows; ++r) {
+      const int tt = role ? rows - 1 - r : r;
+      const int s = sbase + r;
+      const uint32_t Et = s_tile(buf) + 4u * (uint32_t)(tt * C);
+      float* hrow = hist + (size_t)(s + 1) * a.hist_stride;
+      const bool keep = s + 1 < S;                   // R_S goes to the peer, not to the history
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int v = vnode[j];
+        if (v >= 0) {
+          const uint32_t k0 = be_p[j] & 0xffffu, ke = be_p[j] >> 16;
+          uint2 rec[DEG];
+#pragma unroll
+          for (int d = 0; d < DEG; ++d) rec[d] = lds_u2(s_ppack + 8u * (k0 + d));
+          float x[DEG];
+#pragma unroll
+          for (int d = 0; d < DEG; ++d) {
+            const float av = lds_f(cur + 4u * (rec[d].x & 0xffffu)), ev = lds_f(Et + 4u * (rec[d].x >> 16));
+            x[d] = (k0 + d < ke) ? av + ev + __uint_as_float(rec[d].y) : kNegInf;
+          }
+          float m = x[0];
+#pragma unroll
+          for (int d = 1; d < DEG; ++d) m = fmaxf(m, x[d]);
+          auto eval = [&](uint32_t k) {
+            const uint2 rr = lds_u2(s_ppack + 8u * k);
+            return lds_f(cur + 4u * (rr.x & 0xffffu)) + lds_f(Et + 4u * (rr.x >> 16)) + __uint_as_float(rr.y);
+          };
+          if (TAIL)
+            for (uint32_t k = k0 + DEG; k < ke; ++k) m = fmaxf(m, eval(k));
+          float rv = kNegInf;
+          if (m != kNegInf) {
+            float sum = 0.f;
+#pragma unroll
+            for (int d = 0; d < DEG; ++d) sum += __expf(x[d] - m);
+            if (TAIL)
+              for (uint32_t k = k0 + DEG; k < ke; ++k) sum += __expf(eval(k) - m);
+            rv = m + __logf(sum);
+          }
+          sts_f(nxt + 4u * v, rv);
+          if (keep) hrow[slot_of(j)] = rv;
+        }
+      }
+      __syncthreads();
+      const uint32_t tmp = cur; cur = nxt; nxt = tmp;
+    }
+  }
+
+  // ------------------------------------------------------------- exchange, Z
+  {
+    const uint32_t peer = map_to_peer(s_xch, role ^ 1u);
+    for (int v = tid; v < N; v += NT) st_peer_f(peer + 8u + 4u * v, lds_f(cur + 4u * v));
+    if (tid == 0) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(cumP);
+      st_peer_u2(peer, (uint32_t)bits, (uint32_t)(bits >> 32));
+    }
+  }
+  cluster_sync_all();
+  double cumQ;
+  {
+    const uint2 cb = lds_u2(s_xch);
+    cumQ = __longlong_as_double((long long)(((unsigned long long)cb.y << 32) | cb.x));
+  }
+  float part = kNegInf;
+  for (int v = tid; v < N; v += NT) part = log_add(part, lds_f(cur + 4u * v) + lds_f(s_xch + 8u + 4u * v));
+  const float Zn = block_lse(part, red);
+  const double Zd = (double)Zn + (cumP + cumQ);     // symmetric: both ranks get the same bits
+  const float Z = (float)Zd;
+  if (tid == 0 && role == 0) a.scores[b] = Z;
+  const bool want_gE = a.gradE != nullptr;
+  const bool want_gW = g.want_gw != 0;
+  if (!want_gE && !want_gW) return;
+  const float gs = a.sign * (a.grad_scale ? a.grad_scale[b] : 1.f);
+  float* gEb = want_gE ? a.gradE + (size_t)b * T * C : nullptr;
+  const bool feasible = (Z != kNegInf) && (Z == Z) && (Z != -kNegInf);
+  if (!feasible) {
+    if (want_gE && !a.accumulate) {
+      const size_t k0 = role ? (size_t)S0 * C : 0, k1 = role ? (size_t)T * C : (size_t)S0 * C;
+      for (size_t k = k0 + tid; k < k1; k += NT) gEb[k] = 0.f;
+    }
+    return;    // weight gradients: the buffer was zeroed by the launcher
+  }
+
+  // ------------------------------------------------------------- secondary sweep
+  __syncthreads();
+  for (int v = tid; v < N; v += NT) sts_f(nxt + 4u * v, lds_f(s_xch + 8u + 4u * v));   // Q_S
+  issue_tile(gtile_of(ntr - 1), (ntr - 1) & 1);
+  float pr_next[NPT];
+  uint32_t be_s[NPT];
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    pr_next[j] = (vnode[j] >= 0) ? hist[(size_t)(S - 1) * a.hist_stride + slot_of(j)] : kNegInf;
+    be_s[j] = (vnode[j] >= 0) ? lds_u(s_snode + 4u * vnode[j]) : 0u;
+  }
+  __syncthreads();
+  for (int jt = ntr - 1; jt >= 0; --jt) {
+    const int buf = jt & 1, gti = gtile_of(jt);
+    wait_tile(gti, buf);
+    if (jt > 0) issue_tile(gtile_of(jt - 1), buf ^ 1);
+    const int rows = rows_of(gti), sbase = sbase_of(jt);
+    if (want_gE) {
+      for (int k = tid; k < rows * C; k += NT) sts_u(s_gt + 4u * k, 0u);
+      if (tid < rows) sts_u(s_rowsum + 4u * tid, 0u);
+    }
+    if ((ntr - 1 - jt) % a.renorm_every == 0) {
+      float pm = kNegInf;
+      for (int v = tid; v < N; v += NT) pm = fmaxf(pm, lds_f(nxt + 4u * v));
+      const float mx = block_max(pm, red);
+      if (mx != kNegInf && mx != -kNegInf && mx == mx) {
+        for (int v = tid; v < N; v += NT) sts_f(nxt + 4u * v, lds_f(nxt + 4u * v) - mx);
+        cumQ += (double)mx;
+      }
+    }
+    __syncthreads();
+    // offset of the history row R_s: rows written during primary tile jt are relative to its
+    // offset; the row a tile starts from belongs to the tile before (R_0: 0)
+    const double off_first = (jt > 0) ? offP[gtile_of(jt - 1)] : 0.0;
+    const double off_tile = offP[gti];
+    for (int r = rows - 1; r >= 0; --r) {
+      const int tt = role ? rows - 1 - r : r;
+      const int s = sbase + r;
+      const uint32_t Et = s_tile(buf) + 4u * (uint32_t)(tt * C);
+      const uint32_t grow = s_gt + 4u * (uint32_t)(tt * C);
+      const float dlt = (float)(((r == 0) ? off_first : off_tile) + cumQ - Zd);
+      float pr[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        pr[j] = pr_next[j];
+        pr_next[j] = (vnode[j] >= 0 && s > 0) ? hist[(size_t)(s - 1) * a.hist_stride + slot_of(j)] : kNegInf;
+      }
+      uint32_t qstar = 0, qtot = 0;
+      auto post = [&](float xv, uint32_t rx, uint32_t k, float off) {
+        const float p = __expf(xv + off);
+        if (want_gE) {
+          const uint32_t q = __float2uint_rn(p * kFixOne);
+          const uint32_t lab = rx >> 16;
+          qtot += q;
+          if (lab == cstar) qstar += q;
+          else if (q != 0u) red_add_u(grow + 4u * lab, q);
+        }
+        if (want_gW && p != 0.f) sts_f(s_gw + 4u * k, lds_f(s_gw + 4u * k) + p);
+      };
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const int u = vnode[j];
+        if (u >= 0) {
+          const uint32_t k0 = be_s[j] & 0xffffu, ke = be_s[j] >> 16;
+          uint2 rec[DEG];
+#pragma unroll
+          for (int d = 0; d < DEG; ++d) rec[d] = lds_u2(s_spack + 8u * (k0 + d));
+          float x[DEG];
+#pragma unroll
+          for (int d = 0; d < DEG; ++d) {
+            const float bv = lds_f(nxt + 4u * (rec[d].x & 0xffffu)), ev = lds_f(Et + 4u * (rec[d].x >> 16));
+            x[d] = (k0 + d < ke) ? ev + __uint_as_float(rec[d].y) + bv : kNegInf;
+          }
+          float m = x[0];
+#pragma unroll
+          for (int d = 1; d < DEG; ++d) m = fmaxf(m, x[d]);
+          uint32_t rr = 0;
+          auto eval = [&](uint32_t k, uint32_t& rx) {
+            const uint2 q = lds_u2(s_spack + 8u * k);
+            rx = q.x;
+            return lds_f(Et + 4u * (q.x >> 16)) + __uint_as_float(q.y) + lds_f(nxt + 4u * (q.x & 0xffffu));
+          };
+          if (TAIL)
+            for (uint32_t k = k0 + DEG; k < ke; ++k) m = fmaxf(m, eval(k, rr));
+          float rv = kNegInf;
+          if (m != kNegInf) {
+            float sum = 0.f;
+#pragma unroll
+            for (int d = 0; d < DEG; ++d) sum += __expf(x[d] - m);
+            if (TAIL)
+              for (uint32_t k = k0 + DEG; k < ke; ++k) sum += __expf(eval(k, rr) - m);
+            rv = m + __logf(sum);
+            if (pr[j] != kNegInf) {
+              const float off = pr[j] + dlt;
+#pragma unroll
+              for (int d = 0; d < DEG; ++d)
+                if (x[d] != kNegInf) post(x[d], rec[d].x, k0 + d, off);
+              if (TAIL)
+                for (uint32_t k = k0 + DEG; k < ke; ++k) {
+                  const float xv = eval(k, rr);
+                  if (xv != kNegInf) post(xv, rr, k, off);
+                }
+            }
+          }
+          sts_f(cur + 4u * u, rv);
+        }
+      }
+      if (want_gE) {
+        __syncwarp();
+        qstar = __reduce_add_sync(0xffffffffu, qstar);
+        qtot = __reduce_add_sync(0xffffffffu, qtot);
+        if (lane == 0) {
+          if (qstar) red_add_u(grow + 4u * cstar, qstar);
+          if (qtot) red_add_u(s_rowsum + 4u * (uint32_t)tt, qtot);
+        }
+      }
+      __syncthreads();
+      const uint32_t tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (want_gE) {
+      const uint32_t* gtu = reinterpret_cast<const uint32_t*>(gt);
+      for (int r = 0; r < rows; ++r) {
+        const uint32_t rs = lds_u(s_rowsum + 4u * (uint32_t)r);
+        const float f = rs ? gs / (float)rs : 0.f;
+        for (int c = tid; c < C; c += NT) gt[r * C + c] = (float)gtu[r * C + c] * f;
+      }
+      float* dst = gEb + (size_t)gti * Kt * C;
+      const int n = rows * C;
+      const bool tma = !a.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
+      if (tma) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          bulk_s2g(dst, gt, (uint32_t)n * 4u);
+          bulk_commit();
+          bulk_wait_read<0>();
+        }
+      } else {
+        __syncthreads();
+        if (a.accumulate) {
+          for (int k = tid; k < n; k += NT) dst[k] += gt[k];
+        } else {
+          for (int k = tid; k < n; k += NT) dst[k] = gt[k];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) bulk_wait_all<0>();
+  __syncthreads();
+  if (role == 1) {
+    // rank 1 ends with alpha_T (in `nxt`, relative to cumQ): posterior of ending in v
+    for (int v = tid; v < N; v += NT) {
+      const float av = lds_f(nxt + 4u * v);
+      if ((flag_of(v) & 2u) && av != kNegInf)
+        bld.add_final_grad(v, __expf((float)((double)av + (double)lds_f(s_fw + 4u * v) + cumQ - Zd)) * gs);
+    }
+  }
+  bld.finish(s_gw, s_sgidx, s_snode, gs, g.want_gw, true);
 }
 
 }  // namespace lean

@@ -56,8 +56,10 @@ WFST_API int wfst_abi_version(void);
  * scaled-probability kernel (use the single-utterance one), 0 = default (returns the old value) */
 WFST_API int wfst_debug_force_generic_ctc(int on);
 /* test hook: 1 = the acceptor lattice entry points (CSR, ASG force-align, CTC fallback) use the
- * generic global-memory kernel even when the acceptor fits the shared-memory ("lean") kernel,
- * 0 = default (returns the old value) */
+ * generic global-memory kernel even when the acceptor fits the shared-memory ("lean") kernels,
+ * 2 = the single-block lean kernel only (no two-block cluster kernel), 3 = the two-block
+ * cluster kernel whenever T allows (by default only when the single-block launch would leave the
+ * SMs short of warps), 0 = default (returns the old value) */
 WFST_API int wfst_debug_force_generic_lattice(int on);
 /* test hook: copies the per-utterance fallback flags of the last CTC call that used
  * `workspace` to the host (1 = recomputed by the log-semiring kernel, -1 = fast path not used) */

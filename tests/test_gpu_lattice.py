@@ -21,7 +21,8 @@ def random_acceptor(rng, N, A, C, weights=True):
 
 
 @pytest.mark.parametrize("B,T,C,N,A", [(3, 9, 5, 6, 20), (4, 33, 17, 40, 160), (2, 70, 1001, 300, 900),
-                                       (5, 16, 8, 1, 3), (2, 21, 40, 2300, 7000), (2, 40, 6, 3, 40)])
+                                       (5, 16, 8, 1, 3), (2, 21, 40, 2300, 7000), (2, 40, 6, 3, 40),
+                                       (3, 300, 6, 40, 150), (2, 531, 17, 25, 90), (2, 129, 9, 12, 30)])
 def test_random_acceptors(B, T, C, N, A, lattice_kernel):
     from gtn_applications_b200.packing import PackedAcceptors
     from gtn_applications_b200.lattice import lattice_forward_backward

@@ -71,8 +71,8 @@ gs = torch.full((Bt,), -1.0 / Bt, device="cuda")
 def tdc():
     lattice_forward_backward(x, packed, grad_scale=gs, want_grad_emissions=True, want_grad_weights=False)
 
-for name in ("lean", "generic"):
-    old = L_.wfst_debug_force_generic_lattice(1 if name == "generic" else 0)
+for name in ("default (lean, two-block cluster)", "lean single block", "generic"):
+    old = L_.wfst_debug_force_generic_lattice({"d": 0, "l": 2, "g": 1}[name[0]])
     print("%s: cfg3 ASG step %.3f ms (Function + backward), %.3f ms (wfst_asg_forward_backward at the C ABI)"
           % (name, ev_time(asg), ev_time(asg_abi, 20)), flush=True)
     print("%s: cfg4 transducer lattice kernel (B=64, T=1000, C=%d) %.3f ms" % (name, Ct, ev_time(tdc, 3)), flush=True)

@@ -20,6 +20,8 @@
 
 namespace wfst {
 
+extern int g_asg_dense_single;
+
 namespace {
 constexpr int kCP = 36;      // padded row length: a multiple of 4 whose quarter is odd
 constexpr int kWarps = 4;    // utterances per block
@@ -219,6 +221,295 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
 }
 
 // ---------------------------------------------------------------------------------------
+// The same lattice on TWO warps per utterance that meet in the middle: the kernel above is a
+// chain of 2T dependent frame steps of one warp; here warp A owns the frames [0, Th) and warp
+// B the frames [Th, T):
+//   A: alpha up over its frames (stores a^_t, c_t)      | B: beta down over its frames (stores b^_t)
+//   exchange a^_{Th-1} and b^_{Th-1} through shared memory (one named barrier)
+//   A: beta down over its frames, posteriors with its    | B: alpha up over its frames, posteriors
+//      stored a^_t (the sweep of the kernel above)       |    with its stored b^_t (the mirror image)
+// Every posterior formula is self-normalised, so the beta normalisers are never needed:
+//   log Z = sum_t (base_t + log c_t) + log sum_i a^_{T-1}[i], the first half of the sum from A,
+//   the second from B's alpha sweep.
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_split_kernel(
+    const float* __restrict__ E, const float* __restrict__ tr, int B, int T, int C,
+    const float* __restrict__ grad_scale, float sign, float* __restrict__ scores,
+    float* __restrict__ gradE, int accumulate, float* __restrict__ gradTr, float* __restrict__ hist) {
+  __shared__ __align__(16) float bcast[kWarps][2][kCP];
+  __shared__ __align__(16) float xch[kWarps][kCP];
+  __shared__ double zpart[kWarps];
+  __shared__ float red[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int role = warp & 1, pair = warp >> 1;
+  const int b = blockIdx.x * (kWarps / 2) + pair;
+  const bool valid = lane < C;
+  if (threadIdx.x < 32) {
+    float m = kNegInf, m0 = kNegInf;
+    for (int k = lane; k < C * C; k += 32) m = fmaxf(m, tr[C + k]);
+    for (int k = lane; k < C; k += 32) m0 = fmaxf(m0, tr[k]);
+    m = warp_max(m);
+    m0 = warp_max(m0);
+    if (lane == 0) {
+      red[0] = (m == kNegInf) ? 0.f : m;
+      red[1] = (m0 == kNegInf) ? 0.f : m0;
+    }
+  }
+  for (int k = threadIdx.x; k < kWarps * 2 * kCP; k += blockDim.x) (&bcast[0][0][0])[k] = 0.f;
+  for (int k = threadIdx.x; k < kWarps * kCP; k += blockDim.x) (&xch[0][0])[k] = 0.f;
+  __syncthreads();
+  const float wmax = red[0], w0max = red[1];
+  if (b >= B) return;                       // both warps of the pair
+
+  float Wr[kCP], Wc[kCP];
+#pragma unroll
+  for (int j = 0; j < kCP; ++j) {
+    Wr[j] = (valid && j < C) ? __expf(tr[C + lane * C + j] - wmax) : 0.f;
+    Wc[j] = (valid && j < C) ? __expf(tr[C + j * C + lane] - wmax) : 0.f;
+  }
+  const float w0 = valid ? __expf(tr[lane] - w0max) : 0.f;
+  const float* Eb = E + (size_t)b * T * C;
+  float* hV = hist + (size_t)b * T * (C + 1);   // [T][C]: a^_t for t < Th (A), b^_t for t >= Th (B)
+  float* hC = hV + (size_t)T * C;               // [T] normalisers c_t of the alpha vectors
+  float* bc0 = bcast[warp][0];
+  float* bc1 = bcast[warp][1];
+  const int Th = T / 2;                          // >= 1 (launcher: T >= 2)
+  const float gs = sign * (grad_scale ? grad_scale[b] : 1.f);
+  float* gEb = gradE ? gradE + (size_t)b * T * C : nullptr;
+  float acc[kCP];
+#pragma unroll
+  for (int j = 0; j < kCP; ++j) acc[j] = 0.f;
+  double logz = 0.0;
+
+  if (role == 0) {
+    // ------------------------------------------------------------ A: alpha up over [0, Th)
+    logz = (double)w0max + (double)(Th - 1) * (double)wmax;
+    float ahat = 0.f;
+    float xn[kPF];
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) xn[k] = (valid && k < Th) ? __ldg(Eb + (size_t)k * C + lane) : kNegInf;
+    for (int t0 = 0; t0 < Th; t0 += kPF) {
+      float xc[kPF];
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        xc[k] = xn[k];
+        const int tn = t0 + kPF + k;
+        xn[k] = (valid && tn < Th) ? __ldg(Eb + (size_t)tn * C + lane) : kNegInf;
+      }
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        const int t = t0 + k;
+        if (t >= Th) break;
+        const float m = warp_max(xc[k]);
+        const float base = (m == kNegInf) ? 0.f : m;
+        const float p = valid ? __expf(xc[k] - base) : 0.f;
+        float av;
+        if (t == 0) {
+          av = p * w0;
+        } else {
+          bc0[lane] = ahat;
+          __syncwarp();
+          av = p * dot_row(Wr, bc0);
+          __syncwarp();
+        }
+        const float c = warp_max(av);
+        ahat = c > 0.f ? __fdividef(av, c) : 0.f;
+        logz += (double)base;
+        if (valid) hV[(size_t)t * C + lane] = ahat;
+        if (lane == 0) hC[t] = c;
+      }
+    }
+    xch[warp][lane] = ahat;                      // a^_{Th-1} for B
+    pair_sync(1 + pair);
+    float bhat = xch[warp + 1][lane];            // b^_{Th-1} from B
+    {
+      __syncwarp();
+      double lc = 0.0;
+      for (int t = lane; t < Th; t += 32) lc += (double)logf(hC[t]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lc += __shfl_xor_sync(kAll, lc, o);
+      logz += lc;
+    }
+    // ------------------------------------------------------------ A: beta down over [0, Th)
+    float acur = ahat;
+    float xq[kPF], aq[kPF], cq[kPF];
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      const int t = Th - 1 - k;
+      xq[k] = (valid && t >= 0) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+      aq[k] = (valid && t >= 1) ? hV[(size_t)(t - 1) * C + lane] : 0.f;
+      cq[k] = (t >= 0) ? hC[t] : 1.f;
+    }
+    for (int t0 = Th - 1; t0 >= 0; t0 -= kPF) {
+      float xc[kPF], ac[kPF], cc[kPF];
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        xc[k] = xq[k]; ac[k] = aq[k]; cc[k] = cq[k];
+        const int t = t0 - kPF - k;
+        xq[k] = (valid && t >= 0) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+        aq[k] = (valid && t >= 1) ? hV[(size_t)(t - 1) * C + lane] : 0.f;
+        cq[k] = (t >= 0) ? hC[t] : 1.f;
+      }
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        const int t = t0 - k;
+        if (t < 0) break;
+        const float m = warp_max(xc[k]);
+        const float base = (m == kNegInf) ? 0.f : m;
+        const float p = valid ? __expf(xc[k] - base) : 0.f;
+        const float gq = acur * bhat;
+        const float G = warp_sum(gq);
+        const float gamma = G > 0.f ? __fdividef(gq, G) : 0.f;
+        if (gEb && valid) {
+          float* dst = gEb + (size_t)t * C + lane;
+          *dst = accumulate ? *dst + gs * gamma : gs * gamma;
+        }
+        if (t == 0) {
+          if (gradTr && valid && gamma != 0.f) atomicAdd(&gradTr[lane], gs * gamma);
+          break;
+        }
+        const float r = p * bhat;
+        const float n = cc[k] * G;
+        const float rn = n > 0.f ? __fdividef(r, n) : 0.f;
+        bc0[lane] = ac[k];
+        bc1[lane] = r;
+        __syncwarp();
+        {
+          const float4* v = reinterpret_cast<const float4*>(bc0);
+#pragma unroll
+          for (int q = 0; q < kCP / 4; ++q) {
+            const float4 a4 = v[q];
+            acc[4 * q + 0] = fmaf(a4.x, rn, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(a4.y, rn, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(a4.z, rn, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(a4.w, rn, acc[4 * q + 3]);
+          }
+        }
+        const float bn = dot_row(Wc, bc1);
+        __syncwarp();
+        const float nb = warp_max(bn);
+        bhat = nb > 0.f ? __fdividef(bn, nb) : 0.f;
+        acur = ac[k];
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ B: beta down over [Th, T)
+    float bhat = valid ? 1.f : 0.f;
+    float xq[kPF];
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      const int t = T - 1 - k;
+      xq[k] = (valid && t >= Th) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+    }
+    for (int t0 = T - 1; t0 >= Th; t0 -= kPF) {
+      float xc[kPF];
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        xc[k] = xq[k];
+        const int t = t0 - kPF - k;
+        xq[k] = (valid && t >= Th) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+      }
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        const int t = t0 - k;
+        if (t < Th) break;
+        const float m = warp_max(xc[k]);
+        const float base = (m == kNegInf) ? 0.f : m;
+        const float p = valid ? __expf(xc[k] - base) : 0.f;
+        if (valid) hV[(size_t)t * C + lane] = bhat;          // b^_t
+        bc1[lane] = p * bhat;
+        __syncwarp();
+        const float bn = dot_row(Wc, bc1);
+        __syncwarp();
+        const float nb = warp_max(bn);
+        bhat = nb > 0.f ? __fdividef(bn, nb) : 0.f;           // b^_{t-1}
+      }
+    }
+    xch[warp][lane] = bhat;                      // b^_{Th-1} for A
+    pair_sync(1 + pair);
+    float ahat = xch[warp - 1][lane];            // a^_{Th-1} from A
+    // ------------------------------------------------------------ B: alpha up over [Th, T)
+    logz = (double)(T - Th) * (double)wmax;
+    float xn[kPF], bq[kPF];
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      const int t = Th + k;
+      xn[k] = (valid && t < T) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+      bq[k] = (valid && t < T) ? hV[(size_t)t * C + lane] : 0.f;
+    }
+    for (int t0 = Th; t0 < T; t0 += kPF) {
+      float xc[kPF], bcur[kPF];
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        xc[k] = xn[k]; bcur[k] = bq[k];
+        const int tn = t0 + kPF + k;
+        xn[k] = (valid && tn < T) ? __ldg(Eb + (size_t)tn * C + lane) : kNegInf;
+        bq[k] = (valid && tn < T) ? hV[(size_t)tn * C + lane] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < kPF; ++k) {
+        const int t = t0 + k;
+        if (t >= T) break;
+        const float m = warp_max(xc[k]);
+        const float base = (m == kNegInf) ? 0.f : m;
+        const float p = valid ? __expf(xc[k] - base) : 0.f;
+        bc0[lane] = ahat;                                   // a^_{t-1}
+        __syncwarp();
+        const float av = p * dot_row(Wr, bc0);
+        const float c = warp_max(av);
+        const float anew = c > 0.f ? __fdividef(av, c) : 0.f;
+        const float gq = anew * bcur[k];
+        const float G = warp_sum(gq);
+        const float gamma = G > 0.f ? __fdividef(gq, G) : 0.f;
+        if (gEb && valid) {
+          float* dst = gEb + (size_t)t * C + lane;
+          *dst = accumulate ? *dst + gs * gamma : gs * gamma;
+        }
+        const float n = c * G;
+        const float rn = n > 0.f ? __fdividef(p * bcur[k], n) : 0.f;
+        {
+          const float4* v = reinterpret_cast<const float4*>(bc0);
+#pragma unroll
+          for (int q = 0; q < kCP / 4; ++q) {
+            const float4 a4 = v[q];
+            acc[4 * q + 0] = fmaf(a4.x, rn, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(a4.y, rn, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(a4.z, rn, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(a4.w, rn, acc[4 * q + 3]);
+          }
+        }
+        __syncwarp();
+        ahat = anew;
+        logz += (double)base;
+        if (lane == 0) hC[t] = c;
+      }
+    }
+    {
+      __syncwarp();
+      double lc = 0.0;
+      for (int t = Th + lane; t < T; t += 32) lc += (double)logf(hC[t]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lc += __shfl_xor_sync(kAll, lc, o);
+      const float tail = warp_sum(ahat);
+      logz += lc + (double)logf(tail);
+    }
+  }
+  if (lane == 0) zpart[warp] = logz;
+  pair_sync(1 + pair);
+  if (role == 0 && lane == 0) scores[b] = (float)(zpart[warp] + zpart[warp + 1]);
+  if (gradTr && valid) {
+#pragma unroll
+    for (int j = 0; j < kCP; ++j) {
+      if (j < C) {
+        const float v = gs * Wr[j] * acc[j];
+        if (v != 0.f) atomicAdd(&gradTr[C + lane * C + j], v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Best path through emissions x the same bigram graph (ASG.viterbi, criterions/asg.py:217-226:
 // gtn.viterbi_path(gtn.intersect(g_em, g_tr))).  One warp per utterance, lane = label; the
 // lane's transition row in registers, the previous frame's scores broadcast through shared
@@ -313,13 +604,27 @@ int launch_asg_viterbi_dense(const float* E, const float* tr, int B, int T, int 
   return WFST_OK;
 }
 
+int g_asg_dense_single = 0;   // test hook (wfst_debug_force_generic_ctc(3)): one warp per utterance only
 bool asg_fcc_dense_eligible(int T, int C) { return T >= 1 && C >= 1 && C <= 32; }
 
 int launch_asg_fcc_dense(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
                          float sign, float* scores, float* gradE, int accumulate, float* gradTr,
                          float* hist, cudaStream_t st) {
-  asg_fcc_dense_kernel<<<(B + kWarps - 1) / kWarps, 32 * kWarps, 0, st>>>(
-      E, tr, B, T, C, grad_scale, sign, scores, gradE, accumulate, gradTr, hist);
+  // both kernels ask for the largest shared-memory carveout although they need little: an SM
+  // configured for them can then also host the lattice blocks that run next to them
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    cudaFuncSetAttribute(asg_fcc_dense_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(asg_fcc_dense_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    carveout_set = true;
+  }
+  // two warps per utterance that meet in the middle when gradients are wanted and T allows
+  if (T >= 8 && (gradE || gradTr) && !g_asg_dense_single)
+    asg_fcc_dense_split_kernel<<<(B + kWarps / 2 - 1) / (kWarps / 2), 32 * kWarps, 0, st>>>(
+        E, tr, B, T, C, grad_scale, sign, scores, gradE, accumulate, gradTr, hist);
+  else
+    asg_fcc_dense_kernel<<<(B + kWarps - 1) / kWarps, 32 * kWarps, 0, st>>>(
+        E, tr, B, T, C, grad_scale, sign, scores, gradE, accumulate, gradTr, hist);
   g_launches++;
   WFST_CUDA_CHECK(cudaGetLastError());
   return WFST_OK;

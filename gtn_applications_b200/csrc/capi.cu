@@ -53,10 +53,12 @@ extern "C" {
 const char* wfst_last_error(void) { return g_err; }
 int wfst_abi_version(void) { return WFST_ABI_VERSION; }
 int wfst_debug_force_generic_ctc(int on) {
-  // 0: default dispatch; 1: log-semiring kernel only; 2: no paired kernel
-  int old = g_force_generic ? 1 : g_force_generic_kind;
+  // 0: default dispatch; 1: log-semiring kernel only; 2: no paired kernel;
+  // 3: dense ASG full-connect kernel with one warp per utterance only (no two-warp split)
+  int old = g_force_generic ? 1 : (g_asg_dense_single ? 3 : g_force_generic_kind);
   g_force_generic = (on == 1);
   g_force_generic_kind = (on == 2) ? 2 : 0;
+  g_asg_dense_single = (on == 3);
   return old;
 }
 int wfst_debug_force_generic_lattice(int on) { return lattice_force_generic((on >= 1 && on <= 3) ? on : 0); }
@@ -342,15 +344,18 @@ int wfst_asg_forward_backward(const float* emissions, const float* transitions,
   if (rc != WFST_OK) return rc;
   WFST_CUDA_CHECK(cudaEventRecord(ev_fork, st));
   WFST_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_fork, 0));
-  // loss = Z_fcc - Z_fal (asg.py:111-115)
+  // loss = Z_fcc - Z_fal (asg.py:111-115).  The force-align kernel goes first: it needs 36 KB+
+  // of shared memory per block, and an SM that already runs the (static-shared-memory) dense
+  // kernel keeps that kernel's small carveout until it drains — launched second, the lattice
+  // blocks were confined to the SMs the dense kernel had left free (measured 0.77 -> 1.30 ms).
+  int rc2 = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
+                           grad_scale, -1.f, zfal, grad_emissions ? gfal : nullptr, 0, grad_transitions,
+                           hist_fal, s2);
   rc = (asg_fcc_dense_eligible(T, C) && !g_force_generic)
            ? launch_asg_fcc_dense(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
                                   grad_transitions, hist_fcc, st)
            : launch_asg_fcc(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
                             grad_transitions, hist_fcc, st);
-  int rc2 = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
-                           grad_scale, -1.f, zfal, grad_emissions ? gfal : nullptr, 0, grad_transitions,
-                           hist_fal, s2);
   // always join, also after a failed launch: the side stream must not stay forked
   cudaError_t e1 = cudaEventRecord(ev_join, s2);
   cudaError_t e2 = cudaStreamWaitEvent(st, ev_join, 0);

@@ -23,6 +23,7 @@ int launch_asg_fcc(const float* E, const float* tr, int B, int T, int C, const f
                    float* hist, cudaStream_t st);
 // dense full-connect ASG lattice, one warp per utterance (asg_dense.cu); C <= 32, T >= 1
 bool asg_fcc_dense_eligible(int T, int C);
+extern int g_asg_dense_single;   // test hook: 1 = never split an utterance over two warps
 int launch_asg_fcc_dense(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
                          float sign, float* scores, float* gradE, int accumulate, float* gradTr,
                          float* hist, cudaStream_t st);

@@ -52,8 +52,10 @@ extern "C" {
 /* thread-local message of the last error returned on this thread ("" if none) */
 WFST_API const char* wfst_last_error(void);
 WFST_API int wfst_abi_version(void);
-/* test hook: 1 = run CTC on the log-semiring lattice kernel only, 2 = skip the paired
- * scaled-probability kernel (use the single-utterance one), 0 = default (returns the old value) */
+/* test hook: 1 = run CTC on the log-semiring lattice kernel only (and ASG full-connect on the
+ * generic lattice kernel), 2 = skip the paired scaled-probability kernel (use the
+ * single-utterance one), 3 = dense ASG full-connect kernel with one warp per utterance only
+ * (no two-warp split), 0 = default (returns the old value) */
 WFST_API int wfst_debug_force_generic_ctc(int on);
 /* test hook: 1 = the acceptor lattice entry points (CSR, ASG force-align, CTC fallback) use the
  * generic global-memory kernel even when the acceptor fits the shared-memory ("lean") kernels,

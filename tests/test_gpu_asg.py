@@ -76,7 +76,8 @@ def test_module_replabels_garbage_and_checkpoint_names():
     assert_close_f32_fixture(crit.transitions.grad.cpu().numpy(), z["module_grad_transitions"])
 
 
-@pytest.mark.parametrize("B,T,C,lens", [(5, 77, 30, [20, 1, 33, 8, 40]), (2, 9, 3, [2, 4]), (3, 130, 32, [5, 60, 17])])
+@pytest.mark.parametrize("B,T,C,lens", [(5, 77, 30, [20, 1, 33, 8, 40]), (2, 9, 3, [2, 4]), (3, 130, 32, [5, 60, 17]),
+                                        (1, 8, 30, [3]), (3, 5, 7, [1, 2, 5])])
 def test_dense_and_generic_full_connect_kernels_agree(B, T, C, lens):
     """The dense warp-per-utterance full-connect kernel (C <= 32) and the generic lattice
     kernel compute the same loss and gradients (the generic path is forced with the CTC hook)."""
@@ -85,15 +86,18 @@ def test_dense_and_generic_full_connect_kernels_agree(B, T, C, lens):
     e = (rng.standard_normal((B, T, C)) * 2).astype(np.float32)
     tr = rng.standard_normal((C + 1, C)).astype(np.float32)
     tg = [rng.integers(0, C, size=n).tolist() for n in lens]
-    dense = run(e, tr, tg, "mean")
-    old = _lib.lib().wfst_debug_force_generic_ctc(1)
+    dense = run(e, tr, tg, "mean")           # two warps per utterance that meet in the middle (T >= 8)
+    old = _lib.lib().wfst_debug_force_generic_ctc(3)
     try:
+        single = run(e, tr, tg, "mean")      # one warp per utterance
+        _lib.lib().wfst_debug_force_generic_ctc(1)
         generic = run(e, tr, tg, "mean")
     finally:
         _lib.lib().wfst_debug_force_generic_ctc(old)
-    assert abs(dense[0] - generic[0]) <= 1e-5 * abs(generic[0])
-    assert_close(dense[1], generic[1])
-    assert_close(dense[2], generic[2])
+    for got in (dense, single):
+        assert abs(got[0] - generic[0]) <= 1e-5 * abs(generic[0])
+        assert_close(got[1], generic[1])
+        assert_close(got[2], generic[2])
 
 
 def test_full_size_properties_cfg3():

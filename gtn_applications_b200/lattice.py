@@ -22,7 +22,8 @@ def lattice_forward_backward(emissions, packed, grad_scale=None, want_grad_emiss
         g_e, acc = accumulate_into, 1
     else:
         g_e, acc = (torch.empty_like(emissions) if want_grad_emissions else None), 0
-    g_w = torch.zeros(packed.num_arcs, dtype=torch.float32, device=dev) if want_grad_weights else None
+    # an output of the call (the kernels / the C entry point clear what they accumulate into)
+    g_w = torch.empty(packed.num_arcs, dtype=torch.float32, device=dev) if want_grad_weights else None
     g_f = None
     if final_weights is not None and want_grad_weights:
         g_f = torch.zeros(final_weights.numel(), dtype=torch.float32, device=dev)

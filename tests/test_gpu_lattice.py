@@ -67,11 +67,12 @@ def test_ctc_chain_through_csr_matches_closed_form_kernel(lattice_kernel):
     torch.testing.assert_close(-gE / B, lp.grad, rtol=1e-4, atol=1e-7)
 
 
-def test_shared_graph_accumulates_weight_gradient(lattice_kernel):
+@pytest.mark.parametrize("T", [12, 200])          # 200 frames: several tiles, the two-block kernel applies
+def test_shared_graph_accumulates_weight_gradient(lattice_kernel, T):
     from gtn_applications_b200.packing import PackedAcceptors
     from gtn_applications_b200.lattice import lattice_forward_backward
     rng = np.random.default_rng(11)
-    B, T, C = 6, 12, 7
+    B, C = 6, 7
     g = random_acceptor(rng, 9, 40, C)
     E = rng.standard_normal((B, T, C)).astype(np.float32)
     packed = PackedAcceptors([g], "cuda")
@@ -85,3 +86,34 @@ def test_shared_graph_accumulates_weight_gradient(lattice_kernel):
         assert_close(gE[b].cpu().numpy(), rE)
         want += rW
     assert_close(gW.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("B,T,C,N,A", [(3, 150, 6, 30, 110), (2, 300, 1001, 200, 700)])
+def test_final_weights_and_weight_gradients_agree_across_kernels(B, T, C, N, A):
+    """Final weights (ABI 2) over many tiles: the two-block cluster kernel and the single-block
+    shared-memory kernel against the generic kernel (itself checked against the reference's
+    epsilon-graph fixtures in test_gpu_stc_transducer.py) — scores, emission, arc-weight and
+    final-weight gradients."""
+    from gtn_applications_b200 import _lib
+    from gtn_applications_b200.packing import PackedAcceptors
+    from gtn_applications_b200.lattice import lattice_forward_backward
+    rng = np.random.default_rng(T + C)
+    graphs = [random_acceptor(rng, N - b, A - 2 * b, C) for b in range(B)]
+    E = torch.tensor(rng.standard_normal((B, T, C)).astype(np.float32), device="cuda")
+    packed = PackedAcceptors(graphs, "cuda")
+    fw = torch.tensor(rng.standard_normal(packed.num_nodes).astype(np.float32), device="cuda")
+    gs = torch.tensor(rng.uniform(0.5, 2.0, B).astype(np.float32), device="cuda")
+    out = {}
+    for mode in (1, 2, 3):
+        old = _lib.lib().wfst_debug_force_generic_lattice(mode)
+        try:
+            out[mode] = [x.cpu().numpy() for x in lattice_forward_backward(
+                E, packed, grad_scale=gs, want_grad_weights=True, final_weights=fw)]
+        finally:
+            _lib.lib().wfst_debug_force_generic_lattice(old)
+    assert np.isfinite(out[1][0]).any()
+    for mode in (2, 3):
+        for ref, got in zip(out[1], out[mode]):
+            fin = np.isfinite(ref)
+            assert np.array_equal(fin, np.isfinite(got))
+            assert_close(got[fin], ref[fin])

@@ -6,6 +6,8 @@ import torch
 from . import _lib
 
 _workspaces = {}
+_rect_offsets = {}   # (device, B, L) -> int32 offsets of a rectangular [B, L] target tensor
+_rect_scales = {}    # (device, B, L, scale) -> float32 [B] vector of equal scales
 
 
 def require_cuda(t, name):
@@ -47,6 +49,30 @@ def pack_targets(targets, num_classes, device, scales=None):
     criterion call never waits for the stream."""
     import itertools
     import numpy as np
+    if torch.is_tensor(targets) and targets.dim() == 2 and targets.is_cuda:
+        # extension over the reference: a rectangular label tensor that already lives on the
+        # device is used in place — no host round trip and no H2D copy on the compute stream
+        # (a small copy there queues behind a loader's bulk H2D copies on the copy engine and
+        # delays the kernel).  Labels are not range-checked on the host; the kernels clamp them.
+        B, L = targets.shape
+        flat = targets.detach().to(device=device, dtype=torch.int32).contiguous().reshape(-1)
+        key = (str(device), int(B), int(L))
+        offs = _rect_offsets.get(key)
+        if offs is None:
+            offs = (torch.arange(B + 1, dtype=torch.int32, device=device) * L).contiguous()
+            _rect_offsets[key] = offs
+        out = (flat, offs, [L] * B, L)
+        if scales is not None:
+            skey = key + (float(scales[0]) if len(scales) else 0.0,)
+            gs = _rect_scales.get(skey)
+            if gs is None or any(s != scales[0] for s in scales):
+                gs = torch.tensor(scales, dtype=torch.float32, device=device)
+                if all(s == scales[0] for s in scales):
+                    if len(_rect_scales) > 64:
+                        _rect_scales.clear()
+                    _rect_scales[skey] = gs
+            out = out + (gs,)
+        return out
     if torch.is_tensor(targets) and targets.dim() == 2:
         # extension over the reference (which takes Python lists): a rectangular integer
         # tensor [B, L] skips the per-label Python work

@@ -131,6 +131,27 @@ def test_grad_output_scaling_and_cpu_input():
     torch.testing.assert_close(c.grad, a.grad.cpu())
 
 
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+@pytest.mark.parametrize("reduction", ["none", "mean"])
+def test_device_resident_rectangular_targets(dtype, reduction):
+    """A [B, L] label tensor that already lives on the device is used in place (no host round
+    trip): same loss and gradient as the list-of-lists call."""
+    from gtn_applications_b200.criterions.ctc import CTCLoss
+    torch.manual_seed(3)
+    B, T, C, L = 6, 90, 13, 17
+    lp0 = torch.log_softmax(torch.randn(B, T, C, device="cuda"), 2)
+    tg = torch.randint(C - 1, (B, L))
+    a = lp0.clone().requires_grad_(True)
+    la = CTCLoss(a, tg.tolist(), C - 1, reduction)
+    la.backward()
+    for _ in range(2):                      # second call: cached offsets / scales
+        b = lp0.clone().requires_grad_(True)
+        lb = CTCLoss(b, tg.to("cuda", dtype), C - 1, reduction)
+        lb.backward()
+        assert lb.item() == la.item()
+        assert torch.equal(a.grad, b.grad)
+
+
 def test_full_size_properties():
     """BASELINE configs[1] (B=256, T=1000, C=30, L=176): size-independent checks —
     every frame's posteriors sum to one (so grad rows sum to -scale/B), the

@@ -108,6 +108,10 @@ struct HostGraph {
   mutable std::vector<int32_t> out_off, out_il_flat, out_ol_flat;
   // for nodes whose out-list is olabel-sorted over a small dense label range: first position
   // of every label (lut_off[n] < 0: no table for node n; entry = position or -1)
+  // per arc {olabel, dst, ilabel, weight} in one 16-byte record (big graphs only): the composition
+  // touches all four for every move it makes, from four 4 MB arrays otherwise
+  struct ArcRec { int32_t ol, dst, il; float w; };
+  mutable std::vector<ArcRec> arc_rec;
   mutable std::vector<int64_t> lut_off;
   mutable std::vector<int32_t> lut;
   mutable int32_t lut_min = 0, lut_range = 0;
@@ -123,6 +127,8 @@ struct HostGraph {
       int32_t k = out_off[n];
       for (int32_t a : out[n]) { out_il_flat[k] = il[a]; out_ol_flat[k] = ol[a]; ++k; }
     }
+    arc_rec.resize(src.size());
+    for (size_t a = 0; a < src.size(); ++a) arc_rec[a] = {ol[a], dst[a], il[a], w[a]};
     lut_off.assign(out.size(), -1);
     lut.clear();
     if (ol_sorted && !ol.empty()) {
@@ -343,6 +349,11 @@ struct PairMatcher {
 
 std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B) {
   PairMatcher m(A, B);
+  const HostGraph::ArcRec* recA = m.cache_a ? A.arc_rec.data() : nullptr;   // hot fields of A's arcs, one cache line
+  auto a_ol = [&](int32_t i) { return recA ? recA[i].ol : A.ol[i]; };
+  auto a_dst = [&](int32_t i) { return recA ? recA[i].dst : A.dst[i]; };
+  auto a_il = [&](int32_t i) { return recA ? recA[i].il : A.il[i]; };
+  auto a_w = [&](int32_t i) { return recA ? recA[i].w : A.w[i]; };
   const size_t NA = (size_t)A.num_nodes();
   auto key = [NA](int a, int b) { return (size_t)a + NA * (size_t)b; };
   // Which state pairs can reach an accepting pair?  GTN answers this with a backward sweep
@@ -393,14 +404,15 @@ std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B
     mbeg.push_back((int32_t)moves.size());
     bool eps_pair = false;
     m.for_each(ca, cb, false, [&](int32_t i, int32_t j) {
-      eps_pair = eps_pair || A.ol[i] == kEpsilon;
-      if (dead_end(A.dst[i], B.dst[j])) return;
-      moves.push_back({i, j, visit(A.dst[i], B.dst[j])});
+      eps_pair = eps_pair || a_ol(i) == kEpsilon;
+      const int da = a_dst(i);
+      if (dead_end(da, B.dst[j])) return;
+      moves.push_back({i, j, visit(da, B.dst[j])});
     });
     if (eps_pair) continue;
     for (int32_t i : A.out[ca]) {
-      if (A.ol[i] != kEpsilon) { if (A.ol_sorted) break; else continue; }
-      moves.push_back({i, -1, visit(A.dst[i], cb)});
+      if (a_ol(i) != kEpsilon) { if (A.ol_sorted) break; else continue; }
+      moves.push_back({i, -1, visit(a_dst(i), cb)});
     }
     for (int32_t j : B.out[cb]) {
       if (B.il[j] != kEpsilon) { if (B.il_sorted) break; else continue; }
@@ -457,8 +469,8 @@ std::unique_ptr<HostGraph> compose_graphs(const HostGraph& A, const HostGraph& B
       const Move& mv = moves[e];
       const int d = node_for(mv.to);
       if (d < 0) continue;
-      if (mv.i >= 0 && mv.j >= 0) out->add_arc(cur, d, A.il[mv.i], B.ol[mv.j], A.w[mv.i] + B.w[mv.j]);
-      else if (mv.j < 0) out->add_arc(cur, d, A.il[mv.i], kEpsilon, A.w[mv.i]);
+      if (mv.i >= 0 && mv.j >= 0) out->add_arc(cur, d, a_il(mv.i), B.ol[mv.j], a_w(mv.i) + B.w[mv.j]);
+      else if (mv.j < 0) out->add_arc(cur, d, a_il(mv.i), kEpsilon, a_w(mv.i));
       else out->add_arc(cur, d, kEpsilon, B.ol[mv.j], B.w[mv.j]);
       out->prov1.push_back(mv.i);
       out->prov2.push_back(mv.j);

@@ -39,6 +39,13 @@ METRIC = "utterances/sec CTC fwd+bwd (B=256,T=1000,C=30)"
 ROT = 8
 
 
+def metric_name(workload):
+    B, T, C, L = WORKLOADS[workload]
+    if workload == "ctc_cfg2":
+        return METRIC
+    return "utterances/sec CTC fwd+bwd (B=%d per GPU,T=%d,C=%d)" % (B, T, C)
+
+
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -121,16 +128,37 @@ def synth(workload, device, seed):
 
 
 # ------------------------------------------------------------------ other BASELINE configs
+def reference_word_pieces():
+    """benchmarks/transducer_benchmark.py:19-23 on the committed copy of the reference's token list"""
+    with open(os.path.join(ROOT, "tests", "golden", "word_pieces_tokens_1000.txt"), "r") as fid:
+        tokens = sorted([l.strip() for l in fid])
+    graphemes = sorted(set(c for t in tokens for c in t))
+    return tokens, {t: i for i, t in enumerate(graphemes)}
+
+
+def roofline_of(alg_bytes, ms, traffic=None):
+    peak, src = measured_peak_hbm()
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": src, "algorithmic_bytes_per_step": alg_bytes, "ms": ms}
+
+
 def other_configs(dev):
-    """BASELINE.json configs[2] (ASG B=256,T=1000,C=30,L=176) and configs[3] (transducer, 1000 word
-    pieces, B=64, T=1000, 150 pieces per utterance): ms per fwd+bwd step through the Functions."""
+    """BASELINE.json configs[2] (ASG B=256,T=1000,C=30,L=176), configs[3] (transducer on the
+    reference's 1000-word-piece list, B=64, T=1000, 150 pieces per utterance) and the per-GPU shard
+    of configs[4] (CTC B=256,T=1500,C=80,L=264): ms per fwd+bwd step through the Functions
+    (time_utils.py:11-21 protocol + synchronise) and at the C ABI (CUDA events), each with its own
+    roofline (algorithmic bytes 8*T*C per utterance)."""
     import random
     import torch
+    from gtn_applications_b200 import _lib, _runtime as rt
     from gtn_applications_b200.criterions.asg import ASGLoss
     from gtn_applications_b200.criterions.transducer import Transducer
+    L_ = _lib.lib()
+    stream = torch.cuda.current_stream(dev)
 
-    def timed(fn, n):
-        for _ in range(2):
+    def timed(fn, n, warm=5):
+        for _ in range(warm):
             fn()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
@@ -139,59 +167,133 @@ def other_configs(dev):
         torch.cuda.synchronize(dev)
         return (time.perf_counter() - t0) / n
 
+    def event_timed(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n
+
+    out = {}
     g = torch.Generator().manual_seed(3)
     B, T, C, L = 256, 1000, 30, 176
-    e = torch.randn(B, T, C, generator=g).to(dev).requires_grad_(True)
+    es = [torch.randn(B, T, C, generator=g).to(dev).requires_grad_(True) for _ in range(5)]   # 154 MB > L2
     tr = torch.randn(C + 1, C, generator=g).to(dev).requires_grad_(True)
-    tg = [t for t in torch.randint(C, (B, L), generator=g)]
+    tgt = torch.randint(C, (B, L), generator=g)
+    tg = [t.tolist()[0] for t in tgt.split(1)]          # list of lists, as benchmarks/asg_benchmark.py:23-24
+    it = [0]
 
     def asg():
+        e = es[it[0] % 5]
+        it[0] += 1
         e.grad = None
         tr.grad = None
         ASGLoss(e, tr, tg, "mean").backward()
 
-    s3 = timed(asg, 10)
-    out = {"asg_cfg3": {"ms_per_step": s3 * 1e3, "utterances_per_s": B / s3,
-                        "what": "ASGLoss fwd+bwd, B=256 T=1000 C=30 L=176, randn emissions and transitions"}}
-    del e, tr
+    s3 = timed(asg, 20)
+    flat = tgt.reshape(-1).to(torch.int32).to(dev)
+    off = (torch.arange(B + 1, dtype=torch.int32) * L).to(dev)
+    gs = torch.full((B,), 1.0 / B, dtype=torch.float32, device=dev)
+    o3 = torch.empty(B + 1, dtype=torch.float32, device=dev)
+    ge, gt = torch.empty(B, T, C, device=dev), torch.empty(C + 1, C, device=dev)
+    ws = rt.workspace(dev, L_.wfst_asg_workspace_bytes(B, T, C, L))
+    trd = tr.detach()
+
+    def asg_abi():
+        ed = es[it[0] % 5].detach()
+        it[0] += 1
+        _lib.check(L_.wfst_asg_forward_backward(
+            ed.data_ptr(), trd.data_ptr(), flat.data_ptr(), off.data_ptr(), B, T, C, L, gs.data_ptr(),
+            o3.data_ptr(), o3[B:].data_ptr(), ge.data_ptr(), gt.data_ptr(), ws.data_ptr(), ws.numel(),
+            stream.cuda_stream))
+
+    a3 = event_timed(asg_abi, 20)
+    alg3 = 8.0 * T * C * B + 8.0 * (C + 1) * C
+    out["asg_cfg3"] = {"ms_per_step": s3 * 1e3, "utterances_per_s": B / s3, "abi_ms_per_step": a3,
+                       "roofline": roofline_of(alg3, a3), "roofline_function_path": roofline_of(alg3, s3 * 1e3),
+                       "what": "ASGLoss(inputs, transitions, list_of_lists, 'mean').backward() (benchmarks/"
+                               "asg_benchmark.py:26-30), B=256 T=1000 C=30 L=176, randn emissions and "
+                               "transitions; abi = wfst_asg_forward_backward, CUDA events"}
+    del es, tr, ge
+    # ---- configs[3]
+    tokens, g2i = reference_word_pieces()
     rnd = random.Random(0)
-    letters = "abcdefghijklmnopqrstuvwxyz"
-    pieces = sorted({"".join(rnd.choice(letters) for _ in range(rnd.randint(1, 4))) for _ in range(1400)})[:1000]
-    pieces = sorted(set(pieces) | set(letters))
-    g2i = {ch: i for i, ch in enumerate(letters)}
     Bt, NP = 64, 150
-    crit = Transducer(pieces, g2i, blank="optional", allow_repeats=False, reduction="mean")
-    x = torch.randn(Bt, T, len(pieces) + 1, generator=g).to(dev).requires_grad_(True)
-    targets = [torch.tensor([g2i[c] for c in "".join(rnd.choice(pieces) for _ in range(NP))]) for _ in range(Bt)]
+    crit = Transducer(tokens, g2i, blank="optional", allow_repeats=False, reduction="mean")
+    Ct = len(tokens) + 1
+    x = torch.randn(Bt, T, Ct, generator=g).to(dev).requires_grad_(True)
+    targets = [torch.tensor([g2i[l] for wp in (rnd.choice(tokens) for _ in range(NP)) for l in wp])
+               for _ in range(Bt)]
 
     def tdc():
         x.grad = None
         crit(x, targets).backward()
 
-    s4 = timed(tdc, 3)
+    s4 = timed(tdc, 5, warm=2)
+    alg4 = 8.0 * T * Ct * Bt
     out["transducer_cfg4"] = {"ms_per_step": s4 * 1e3, "utterances_per_s": Bt / s4,
-                              "what": "Transducer module fwd+bwd (log_softmax + alignment graphs on host threads + "
-                                      "lattice kernel), B=64 T=1000, %d word pieces (synthetic list), 150 pieces per "
-                                      "utterance, blank optional, no repeats" % len(pieces)}
+                              "roofline": roofline_of(alg4, s4 * 1e3, ncu_traffic("transducer_cfg4")),
+                              "what": "Transducer module fwd+bwd (log_softmax + alignment graphs on host "
+                                      "threads + lattice kernel), B=64 T=1000, the reference's %d word pieces "
+                                      "(benchmarks/word_pieces_tokens_1000.txt), 150 pieces per utterance, blank "
+                                      "optional, no repeats (transducer_benchmark.py:19-44)" % len(tokens)}
+    del x
+    # ---- configs[4], one GPU's shard
+    B5, T5, C5, L5 = WORKLOADS["ctc_cfg5"]
+    lp5, tg5 = synth("ctc_cfg5", dev, 7)
+    flat5 = tg5.reshape(-1).to(torch.int32).to(dev)
+    off5 = (torch.arange(B5 + 1, dtype=torch.int32) * L5).to(dev)
+    gs5 = torch.full((B5,), 1.0 / B5, dtype=torch.float32, device=dev)
+    o5 = torch.empty(B5 + 1, dtype=torch.float32, device=dev)
+    g5 = torch.empty(B5, T5, C5, device=dev)
+    ws5 = rt.workspace(dev, L_.wfst_ctc_workspace_bytes(B5, T5, C5, L5))
+
+    def cfg5():
+        _lib.check(L_.wfst_ctc_forward_backward(
+            lp5.data_ptr(), flat5.data_ptr(), off5.data_ptr(), B5, T5, C5, C5 - 1, L5, gs5.data_ptr(),
+            o5.data_ptr(), o5[B5:].data_ptr(), g5.data_ptr(), ws5.data_ptr(), ws5.numel(), stream.cuda_stream))
+
+    a5 = event_timed(cfg5, 20)
+    out["ctc_cfg5_shard"] = {"ms_per_step": a5, "utterances_per_s": B5 / (a5 * 1e-3),
+                             "roofline": roofline_of(8.0 * T5 * C5 * B5, a5, ncu_traffic("ctc_cfg5")),
+                             "what": "wfst_ctc_forward_backward on one GPU's shard of configs[4] (B=256 of 2048, "
+                                     "T=1500, C=80, L=264), CUDA events; the 8-GPU run is `torchrun ... bench.py "
+                                     "--gpus 8 --workload ctc_cfg5`"}
     return out
 
 
 # ------------------------------------------------------------------ CPU baseline
-def cpu_baseline_run(workload, budget_s, steps=None, warmup=1):
+def cpu_baseline_run(workload, budget_s, steps=None, warmup=1, full_batch=False):
     """Times the oracle — the C++ restatement of the GTN CPU algorithm (materialised
     intersect + Kahn forward_score + tape backward) driven like criterions/ctc.py:31-94,
-    batch-parallel on all host cores like gtn.parallel_for — on a bounded sample of the
-    workload.  Returns utterances/sec and a description."""
+    batch-parallel on all host cores like gtn.parallel_for.  With full_batch each pass is the
+    workload's whole batch (the reference arm: same config as the GPU arm); otherwise a bounded
+    sample of it (the cpu_baseline leg of the GPU line).  Returns utterances/sec and a description."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gtn
     import _gtn_oracle
     import ref_criterions as rc
     B, T, C, L = WORKLOADS[workload]
     cores = _gtn_oracle.pool_size()
-    n = min(B, max(cores, 8))
+    n = B if full_batch else min(B, max(cores, 8))
     lp, tg = synth(workload, None, 0)
     e = lp[:n].numpy()
     t = tg[:n].tolist()
+    if full_batch and steps is not None:
+        # keep the whole --steps K run within a few minutes: time one pass over a core-sized
+        # sample first and shrink the per-step batch only if K full batches would not fit
+        k = min(B, max(cores, 8))
+        t0 = time.perf_counter()
+        rc.ctc(gtn, e[:k], t[:k], C - 1, "none")
+        est = (time.perf_counter() - t0) * B / k
+        if est * (steps + warmup) > 360.0:
+            n = max(k, int(B * 360.0 / (est * (steps + warmup))) // k * k)
+            e, t = e[:n], t[:n]
     for _ in range(warmup):
         rc.ctc(gtn, e, t, C - 1, "none")
     times = []
@@ -214,24 +316,61 @@ def cpu_baseline_run(workload, budget_s, steps=None, warmup=1):
     }, mean, n
 
 
+def torch_ctc_cpu(workload, budget_s=8.0):
+    """The reference's other sanctioned CPU path (CTC(use_pt=True), criterions/ctc.py:109-121):
+    log_softmax + torch.nn.functional.ctc_loss + backward on the host cores, whole batch."""
+    import torch
+    B, T, C, L = WORKLOADS[workload]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, T, C, generator=g).requires_grad_(True)
+    tg = torch.randint(C - 2, (B, L), generator=g)
+
+    def step():
+        x.grad = None
+        lp = torch.nn.functional.log_softmax(x, dim=2)
+        loss = torch.nn.functional.ctc_loss(lp.permute(1, 0, 2), tg.reshape(-1), [T] * B, [L] * B, blank=C - 1,
+                                            zero_infinity=True)
+        loss.backward()
+
+    step()
+    times = []
+    t_start = time.perf_counter()
+    while time.perf_counter() - t_start < budget_s and len(times) < 10:
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return {"value": B / mean, "unit": "utterances/s", "ms_per_step": mean * 1e3, "threads": torch.get_num_threads(),
+            "what": "log_softmax + torch.nn.functional.ctc_loss + backward on the host (the reference's use_pt "
+                    "path, ctc.py:109-121), B=%d T=%d C=%d L=%d, %d passes" % (B, T, C, L, len(times))}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, mean, n = cpu_baseline_run(args.workload, 0, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    base, mean, n = cpu_baseline_run(args.workload, 0, steps=args.steps, warmup=max(1, min(args.warmup, 2)),
+                                     full_batch=True)
     B, T, C, L = WORKLOADS[args.workload]
     line = {
-        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "utterances/s",
+        "impl": "reference", "metric": metric_name(args.workload), "value": base["value"], "unit": "utterances/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "%s: CTC fwd+bwd B=%d T=%d C=%d L=%d; each step = %d utterances on the "
-                               "host cores" % (args.workload, B, T, C, L, n)},
+        "config": {"workload": "%s: CTC fwd+bwd B=%d T=%d C=%d L=%d; each step = %d utterances (%s) on the "
+                               "host cores" % (args.workload, B, T, C, L, n,
+                                               "the whole batch" if n == B else "a bounded sample of the batch"),
+                   "same_config_as_gpu_arm": n == B},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "utterances/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_torch_cpu:
+        try:
+            line["torch_ctc_loss_cpu"] = torch_ctc_cpu(args.workload)
+        except Exception as exc:
+            line["torch_ctc_loss_cpu"] = {"error": repr(exc)[:200]}
     print(json.dumps(line), flush=True)
 
 
@@ -327,6 +466,96 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kern_ms = float(t[0]), float(t[1])
     loss_value = float(outs[(args.steps - 1) % NOUT][B].item())
+
+    # ---- fallback rate of the timed batches: utterances the scaled kernel flagged and the
+    # log-semiring kernel recomputed (outside the timed region: one more step per batch + flag read)
+    import numpy as np
+    flagged = 0
+    for r in range(ROT):
+        step(r)
+        drain()
+        torch.cuda.synchronize(dev)
+        fl = np.zeros(B, dtype=np.int32)
+        _lib.check(L_.wfst_debug_ctc_hazards(ws.data_ptr(), B, T, C, L, fl.ctypes.data))
+        flagged += int((fl > 0).sum())
+    fallback_rate = flagged / float(ROT * B)
+
+    # ---- function path: the reference benchmark's own call (benchmarks/ctc_benchmark.py:23-29,
+    # time_utils.py:11-21): device-resident emissions, targets as a Python list of lists,
+    # CTCLoss(inputs, tgt, N - 1).backward(), 5 warm-ups, wall clock over the iterations with a
+    # synchronise at both ends (the path is asynchronous)
+    fp_inputs = [b[0].clone().requires_grad_(True) for b in batches[:5]]     # 154 MB > L2
+    fp_tgt = [t.tolist()[0] for t in batches[0][3].split(1)]
+
+    def fp_func(i):
+        x = fp_inputs[i % 5]
+        x.grad = None
+        op = CTCLoss(x, fp_tgt, C - 1)
+        op.backward()
+
+    for i in range(5):
+        fp_func(i)
+    torch.cuda.synchronize(dev)
+    fp_iters = max(5, min(args.steps, 100))
+    t0 = time.perf_counter()
+    for i in range(fp_iters):
+        fp_func(i)
+    torch.cuda.synchronize(dev)
+    fp_s = (time.perf_counter() - t0) / fp_iters
+    t = torch.tensor([fp_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fp_s = float(t[0])
+    del fp_inputs
+
+    # ---- the existing GPU kernel on the same box: torch.nn.functional.ctc_loss, the reference's
+    # use_pt path (criterions/ctc.py:109-121), forward + backward on the same shapes, CUDA events
+    torch_gpu = None
+    if world == 1 and not args.no_comparators:
+        try:
+            xs_t = [torch.randn(B, T, C, device=dev, generator=torch.Generator(device=dev).manual_seed(70 + r))
+                    .requires_grad_(True) for r in range(5)]
+            lps_t = [b[0].clone().requires_grad_(True) for b in batches[:5]]
+            tgt_t = batches[0][3].to(dev)
+            ilen, tlen = [T] * B, [L] * B
+
+            def pt_logits(i):      # what CTC(use_pt=True).forward + backward run (ctc.py:107,114-121)
+                x = xs_t[i % 5]
+                x.grad = None
+                lp = torch.nn.functional.log_softmax(x, dim=2)
+                torch.nn.functional.ctc_loss(lp.permute(1, 0, 2), tgt_t, ilen, tlen, blank=C - 1,
+                                             zero_infinity=True).backward()
+
+            def pt_logprobs(i):    # the criterion alone on log-probabilities (the headline's inputs)
+                lp = lps_t[i % 5]
+                lp.grad = None
+                torch.nn.functional.ctc_loss(lp.permute(1, 0, 2), tgt_t, ilen, tlen, blank=C - 1,
+                                             zero_infinity=True).backward()
+
+            def ev_time(fn, n):
+                for i in range(3):
+                    fn(i)
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for i in range(n):
+                    fn(i)
+                b.record(stream)
+                torch.cuda.synchronize(dev)
+                return a.elapsed_time(b) / n
+
+            n_pt = max(3, min(args.steps, 20))
+            ms_lp, ms_x = ev_time(pt_logprobs, n_pt), ev_time(pt_logits, n_pt)
+            torch_gpu = {"from_log_probs_ms_per_step": ms_lp, "from_logits_ms_per_step": ms_x,
+                         "utterances_per_s_from_log_probs": B / (ms_lp * 1e-3),
+                         "utterances_per_s_from_logits": B / (ms_x * 1e-3), "steps": n_pt,
+                         "what": "torch.nn.functional.ctc_loss fwd+bwd on this GPU (native CUDA kernel; cuDNN's "
+                                 "needs blank=0), reduction='mean', zero_infinity=True as criterions/ctc.py:114-121; "
+                                 "from_logits adds log_softmax and its backward (ctc.py:107); CUDA events, inputs "
+                                 "rotate over 5 batches"}
+            del xs_t, lps_t
+        except Exception as exc:
+            torch_gpu = {"error": repr(exc)[:200]}
 
     # ---- e2e: the user-facing call with HOST inputs (pinned), copies inside the timed region.
     # Like a training loop with a prefetching loader, the copies of the next steps' emissions are
@@ -449,7 +678,7 @@ def run_gpu(args):
         alg_bytes = 8.0 * T * C * B            # read E once + write grad once
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": B * world * args.steps / (total_ms * 1e-3),
+            "metric": metric_name(args.workload), "value": B * world * args.steps / (total_ms * 1e-3),
             "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -467,12 +696,21 @@ def run_gpu(args):
                     "d2h_bytes_per_step": 4,
                     "path": "CTCLoss(emissions, targets).backward() with both copied pinned host -> cuda on a copy stream every step (two steps in flight); every step's loss copied to pinned host memory and read by the host one step later"},
             "gpu_launches": int(launches),
+            "fallback_rate": fallback_rate,
+            "function_path": {
+                "ms_per_step": fp_s * 1e3, "value": B * world / fp_s, "unit": "utterances/s", "iterations": fp_iters,
+                "what": "CTCLoss(inputs, list_of_lists, C-1).backward() exactly as benchmarks/ctc_benchmark.py:"
+                        "23-29 with device-resident emissions (5 batches in rotation), time_utils.py protocol "
+                        "(5 warm-ups, wall clock) + synchronise; includes walking the %d Python ints of the "
+                        "targets every call (csrc/pytargets.c)" % (B * L)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": kern_ms},
         }
+        if torch_gpu is not None:
+            line["torch_ctc_loss_gpu"] = torch_gpu
         if module_line is not None:
             line["ctc_module_on_logits"] = module_line
         if other is not None:
@@ -480,6 +718,11 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu_baseline:
             base, _, _ = cpu_baseline_run(args.workload, args.cpu_seconds)
             line["cpu_baseline"] = base
+            if not args.no_torch_cpu:
+                try:
+                    line["torch_ctc_loss_cpu"] = torch_ctc_cpu(args.workload, 6.0)
+                except Exception as exc:
+                    line["torch_ctc_loss_cpu"] = {"error": repr(exc)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -495,6 +738,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-torch-cpu", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

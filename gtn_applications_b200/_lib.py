@@ -92,6 +92,28 @@ SIGNATURES = {
 
 _lock = threading.Lock()
 _lib = None
+_pytargets = None
+PYTARGETS_PATH = os.path.join(_HERE, "lib", "lib_wfst_pytargets.so")
+
+
+def pytargets():
+    """The Python-list walker (csrc/pytargets.c), loaded with PyDLL (GIL held, borrowed
+    references).  Built together with libwfst_b200.so; raises if it is missing."""
+    global _pytargets
+    if _pytargets is None:
+        with _lock:
+            if _pytargets is None:
+                if not os.path.exists(PYTARGETS_PATH):
+                    raise WfstError("lib_wfst_pytargets.so is not built (%s); run `make -C "
+                                    "gtn_applications_b200/csrc`" % PYTARGETS_PATH)
+                h = ctypes.PyDLL(PYTARGETS_PATH)
+                h.wfst_pytargets_lengths.restype = ctypes.c_longlong
+                h.wfst_pytargets_lengths.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_longlong]
+                h.wfst_pytargets_fill.restype = ctypes.c_longlong
+                h.wfst_pytargets_fill.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_longlong,
+                                                  ctypes.c_void_p]
+                _pytargets = h
+    return _pytargets
 
 
 class WfstError(RuntimeError):

@@ -141,6 +141,9 @@ class ASGLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
+        if ctx.grads is None:
+            raise RuntimeError("ASGLoss: backward called twice on the same forward (the gradient buffers are single "
+                               "use; retain_graph is not supported, as in the reference)")
         g_e, g_t = ctx.grads
         ctx.grads = None
         L = _lib.lib()

@@ -69,8 +69,14 @@ class CTCLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
+        if getattr(ctx, "consumed", False):
+            # gtn.backward(..., retain_graph=False) frees the tape (ctc.py:78): a second backward
+            # through the same forward is an error there too (skipped test gtn_ctc_test.py:82)
+            raise RuntimeError("CTCLoss: backward called twice on the same forward (the gradient buffer is "
+                               "single use; retain_graph is not supported, as in the reference)")
         grad = ctx.grad
-        ctx.grad = None  # single use, like gtn.backward(retain_graph=False) (ctc.py:78)
+        ctx.grad = None
+        ctx.consumed = True
         if grad is None:
             return None, None, None, None
         go = grad_output.detach().to(device=grad.device, dtype=torch.float32).reshape(1)
@@ -99,6 +105,8 @@ class CTCLogitsLossFunction(torch.autograd.Function):
         if not (inputs.is_cuda and inputs.dtype == torch.float32 and inputs.dim() == 3):
             return False
         B, T, C = inputs.shape
+        if inputs.is_contiguous() and inputs.data_ptr() % 16 != 0:
+            return False        # the fused kernel moves tiles with 16-byte bulk copies
         max_len = max(rt.target_lengths(targets), default=0)
         return bool(_lib.lib().wfst_ctc_logits_supported(B, T, C, max_len))
 

@@ -84,8 +84,12 @@ class STCLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("STCLoss: backward called twice on the same forward (the gradient buffers are single "
+                               "use; retain_graph is not supported, as in the reference)")
         grad = ctx.grad
         ctx.grad = None
+        ctx.consumed = True
         if grad is None:
             return None, None, None, None
         grad = rt.scale_by(grad, grad_output)

@@ -271,6 +271,9 @@ class TransducerLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
+        if ctx.grads is None:
+            raise RuntimeError("TransducerLoss: backward called twice on the same forward (the gradient buffers are single "
+                               "use; retain_graph is not supported, as in the reference)")
         g_e, g_tp = ctx.grads
         ctx.grads = None
         if g_e is not None:
@@ -421,12 +424,17 @@ class ConvTransduce1DFunction(torch.autograd.Function):
                 gs = deltas[:, i].contiguous()
                 if viterbi:
                     # d viterbi_score / d weights = indicator of the best path's arcs
+                    # (a window with no accepting path has score -inf and labels / arcs of -1:
+                    # it contributes nothing — the indices are clamped and the values masked)
                     labels, arcs = paths[i]
+                    valid = (labels >= 0).to(torch.float32)                 # [B*T', ks]
+                    vals = gs.view(-1, 1) * valid
                     if need_in:
-                        gwin.scatter_add_(2, labels.long().unsqueeze(2), gs.view(-1, 1, 1).expand(-1, ks, 1).contiguous())
+                        gwin.scatter_add_(2, labels.clamp_min(0).long().unsqueeze(2), vals.unsqueeze(2).contiguous())
                     if need_k:
                         kg = torch.zeros(narcs[i], dtype=torch.float32, device=dev)
-                        kg.index_add_(0, arcs.long().reshape(-1), gs.view(-1, 1).expand(-1, ks).reshape(-1))
+                        if narcs[i] > 0:
+                            kg.index_add_(0, arcs.clamp_min(0).long().reshape(-1), vals.reshape(-1))
                         kgrads.append(kg)
                 else:
                     _, _, g_w = lattice_forward_backward(

@@ -15,6 +15,7 @@
 //   dZ/dtr[i,j]  = W[i,j] * sum_t a^_{t-1}[j] p_t[i] b^_t[i] / (c_t sum_i a^_t[i] b^_t[i])
 // The forward vectors go to the caller's workspace ([T, C] per utterance, written and read
 // once, coalesced).  Handles C <= 32 and T >= 1; other shapes use the generic lattice kernel.
+#include <atomic>
 #include "common.cuh"
 #include "launchers.h"
 
@@ -612,11 +613,15 @@ int launch_asg_fcc_dense(const float* E, const float* tr, int B, int T, int C, c
                          float* hist, cudaStream_t st) {
   // both kernels ask for the largest shared-memory carveout although they need little: an SM
   // configured for them can then also host the lattice blocks that run next to them
-  static bool carveout_set = false;
-  if (!carveout_set) {
+  // (function attributes are per device: remember which devices have been configured)
+  static std::atomic<unsigned long long> carveout_set{0};
+  int devi = 0;
+  cudaGetDevice(&devi);
+  const unsigned long long bit = 1ull << (devi & 63);
+  if (!(carveout_set.load() & bit)) {
     cudaFuncSetAttribute(asg_fcc_dense_split_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(asg_fcc_dense_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    carveout_set = true;
+    carveout_set.fetch_or(bit);
   }
   // two warps per utterance that meet in the middle when gradients are wanted and T allows
   if (T >= 8 && (gradE || gradTr) && !g_asg_dense_single)

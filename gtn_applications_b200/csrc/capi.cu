@@ -21,7 +21,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// grow-only device scratch used by the *_host entry points
+// grow-only device scratch used by the *_host entry points, one per CUDA device (a buffer or
+// a stream created under one device must not be used under another)
 struct HostPathBuffers {
   std::mutex mu;
   void* dev = nullptr;
@@ -38,7 +39,13 @@ struct HostPathBuffers {
     return WFST_OK;
   }
 };
-static HostPathBuffers g_host;
+static constexpr int kMaxHostPathDevices = 64;
+static HostPathBuffers g_host_per_device[kMaxHostPathDevices];
+static HostPathBuffers& host_buffers() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return g_host_per_device[(d >= 0 && d < kMaxHostPathDevices) ? d : 0];
+}
 // test hook: route CTC through the log-semiring kernel only
 static int g_force_generic = 0;
 // test hook: 2 = skip the paired kernel (exercise the single-utterance scaled kernel)
@@ -216,6 +223,7 @@ int wfst_ctc_forward_backward_host(const float* emissions, const int32_t* target
   }
   for (int k = 0; k < total; ++k)
     WFST_REQUIRE(targets[k] >= 0 && targets[k] < C, "target label %d outside [0,%d)", targets[k], C);
+  HostPathBuffers& g_host = host_buffers();
   std::lock_guard<std::mutex> lk(g_host.mu);
   size_t nE = align_up((size_t)B * T * C * 4, 256), nT = align_up((size_t)(total + 1) * 4, 256),
          nO = align_up((size_t)(B + 1) * 4, 256), nS = align_up((size_t)B * 4, 256);

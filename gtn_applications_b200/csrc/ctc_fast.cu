@@ -981,12 +981,16 @@ __global__ void __launch_bounds__(224, (K <= 12) ? 2 : 1) ctc_fast_kernel(CtcFas
   __syncthreads();
   int has_blank = 0;
   for (int n = threadIdx.x; n < L; n += NT) {
-    atomicAdd(&sm.hist[y[n]], 1);
-    has_blank |= (y[n] == a.blank);
+    const int yy = y[n];
+    // a label outside [0, C) (device-resident targets are not validated on the host) must not
+    // index the histogram or a p tile: flag the utterance, the log-semiring kernel clamps it
+    if (yy < 0 || yy >= C) { has_blank = 1; continue; }
+    atomicAdd(&sm.hist[yy], 1);
+    has_blank |= (yy == a.blank);
   }
   if (__syncthreads_or(has_blank)) {
     // a target that contains the blank label shares a gradient column between a label state
-    // and the blank states: leave it to the log-semiring kernel
+    // and the blank states: leave it to the log-semiring kernel (so are out-of-range labels)
     if (threadIdx.x == 0) a.hazard[cx.b] = 1;   // reason 1
     return;
   }

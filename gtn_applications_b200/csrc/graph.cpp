@@ -878,51 +878,83 @@ int wfst_graph_savetxt(int32_t h, const char* path) {
   return WFST_OK;
 }
 
-// binary: int32 {num_nodes, num_start, num_accept, num_arcs}, start ids, accept ids, then
-// per arc {src, dst, ilabel, olabel} int32 + weight float32
+// binary (gtn.save / gtn.load, utils.py:261): the layout of GTN's saveGraph as recalled from
+// its public source (GTN is not in the build container; INTEGRATION.md says how to check it
+// against a file written by the real library): int32 num_nodes, num_start, num_accept; the
+// start ids; the accept ids; int32 num_arcs; then per arc {src, dst, ilabel, olabel} int32 +
+// weight float32.  The loader also accepts the round-1 layout of this library (num_arcs as
+// the fourth header word): both have the same length, the position of num_arcs tells them apart.
 int wfst_graph_save(int32_t h, const char* path) {
   GRAPH_OR_FAIL(g, h);
+  if (!path) { set_error("save: null path"); return WFST_ERR_INVALID; }
   FILE* f = std::fopen(path, "wb");
   if (!f) { set_error("save: cannot open %s", path); return WFST_ERR_INVALID; }
-  int32_t hdr[4] = {g->num_nodes(), (int32_t)g->starts.size(), (int32_t)g->accepts.size(), g->num_arcs()};
-  std::fwrite(hdr, 4, 4, f);
-  std::fwrite(g->starts.data(), 4, g->starts.size(), f);
-  std::fwrite(g->accepts.data(), 4, g->accepts.size(), f);
-  for (int a = 0; a < g->num_arcs(); ++a) {
+  int32_t hdr[3] = {g->num_nodes(), (int32_t)g->starts.size(), (int32_t)g->accepts.size()};
+  int32_t narcs = g->num_arcs();
+  bool ok = std::fwrite(hdr, 4, 3, f) == 3;
+  ok = ok && std::fwrite(g->starts.data(), 4, g->starts.size(), f) == g->starts.size();
+  ok = ok && std::fwrite(g->accepts.data(), 4, g->accepts.size(), f) == g->accepts.size();
+  ok = ok && std::fwrite(&narcs, 4, 1, f) == 1;
+  for (int a = 0; ok && a < narcs; ++a) {
     int32_t rec[4] = {g->src[a], g->dst[a], g->il[a], g->ol[a]};
-    std::fwrite(rec, 4, 4, f);
-    std::fwrite(&g->w[a], 4, 1, f);
+    ok = std::fwrite(rec, 4, 4, f) == 4 && std::fwrite(&g->w[a], 4, 1, f) == 1;
   }
-  std::fclose(f);
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) { set_error("save: write to %s failed", path); return WFST_ERR_INVALID; }
   return WFST_OK;
 }
 
 int32_t wfst_graph_load(const char* path) {
+  if (!path) { set_error("load: null path"); return WFST_ERR_INVALID; }
   FILE* f = std::fopen(path, "rb");
   if (!f) { set_error("load: cannot open %s", path); return WFST_ERR_INVALID; }
-  int32_t hdr[4];
-  if (std::fread(hdr, 4, 4, f) != 4) { std::fclose(f); set_error("load: truncated"); return WFST_ERR_INVALID; }
-  std::vector<int32_t> st(hdr[1]), ac(hdr[2]);
-  bool ok = std::fread(st.data(), 4, st.size(), f) == st.size() &&
-            std::fread(ac.data(), 4, ac.size(), f) == ac.size();
-  std::vector<uint8_t> fl(hdr[0], 0);
-  for (int s : st) if (s >= 0 && s < hdr[0]) fl[s] |= 1;
-  for (int s : ac) if (s >= 0 && s < hdr[0]) fl[s] |= 2;
-  auto g = std::make_unique<HostGraph>();
-  g->calc_grad = true;
-  for (int n = 0; n < hdr[0]; ++n) g->add_node(fl[n] & 1, fl[n] & 2);
-  for (int a = 0; ok && a < hdr[3]; ++a) {
-    int32_t rec[4];
-    float w;
-    ok = std::fread(rec, 4, 4, f) == 4 && std::fread(&w, 4, 1, f) == 1;
-    if (ok) {
-      if (rec[0] < 0 || rec[1] < 0 || rec[0] >= hdr[0] || rec[1] >= hdr[0]) { ok = false; break; }
-      g->add_arc(rec[0], rec[1], rec[2], rec[3], w);
-    }
+  std::vector<int32_t> words;
+  {
+    int32_t buf[4096];
+    size_t n;
+    while ((n = std::fread(buf, 4, 4096, f)) > 0) words.insert(words.end(), buf, buf + n);
   }
   std::fclose(f);
-  if (!ok) { set_error("load: %s is truncated or corrupt", path); return WFST_ERR_INVALID; }
-  return put(std::move(g));
+  auto fail = [&]() { set_error("load: %s is truncated or corrupt", path); return (int32_t)WFST_ERR_INVALID; };
+  const size_t nw = words.size();
+  if (nw < 4) return fail();
+  const int64_t nn = words[0], ns = words[1], na = words[2];
+  if (nn < 0 || ns < 0 || na < 0 || ns > nn || na > nn) return fail();
+  // both layouts: 4 header words in total + ns + na + 5 * narcs
+  if ((int64_t)nw < 4 + ns + na || ((int64_t)nw - 4 - ns - na) % 5 != 0) return fail();
+  const int64_t narcs = ((int64_t)nw - 4 - ns - na) / 5;
+  size_t ids;            // first start id
+  if (words[3 + ns + na] == narcs) ids = 3;          // GTN layout
+  else if (words[3] == narcs) ids = 4;               // round-1 layout of this library
+  else return fail();
+  const size_t arcs0 = 4 + (size_t)ns + (size_t)na;
+  try {
+    std::vector<uint8_t> fl((size_t)nn, 0);
+    for (int64_t k = 0; k < ns; ++k) {
+      const int32_t s = words[ids + k];
+      if (s < 0 || s >= nn) return fail();
+      fl[s] |= 1;
+    }
+    for (int64_t k = 0; k < na; ++k) {
+      const int32_t s = words[ids + ns + k];
+      if (s < 0 || s >= nn) return fail();
+      fl[s] |= 2;
+    }
+    auto g = std::make_unique<HostGraph>();
+    g->calc_grad = true;
+    for (int64_t n = 0; n < nn; ++n) g->add_node(fl[n] & 1, fl[n] & 2);
+    for (int64_t a = 0; a < narcs; ++a) {
+      const int32_t* rec = &words[arcs0 + 5 * (size_t)a];
+      if (rec[0] < 0 || rec[1] < 0 || rec[0] >= nn || rec[1] >= nn) return fail();
+      float w;
+      std::memcpy(&w, rec + 4, 4);
+      g->add_arc(rec[0], rec[1], rec[2], rec[3], w);
+    }
+    return put(std::move(g));
+  } catch (const std::exception& e) {   // bad_alloc on an absurd header: never across the C boundary
+    set_error("load: %s: %s", path, e.what());
+    return WFST_ERR_INVALID;
+  }
 }
 
 // Kahn-order tropical shortest path with back-pointers; ties keep the first maximum in

@@ -152,3 +152,88 @@ def asg(E, transitions, targets, reduction="none"):
         gT_all[b] = gt.reshape(tr.shape) * scale
     return {"loss": losses.mean(), "losses": losses, "grad": gE_all,
             "grad_transitions": gT_all.mean(0)}
+
+
+# ---- CTC without an arc list: the three-term recursion over states (Appendix B) ----
+def ctc_dense_one(E, target, blank):
+    """One utterance: E [T, C] float64 -> (log Z, dZ/dE [T, C]).  Same recursion as
+    acceptor_forward_backward(E, *ctc_acceptor(target, blank)), vectorised over the 2L+1
+    states (shifted copies instead of an arc list), so that full BASELINE-size batches
+    (256 x T=1000 x S=353) finish in seconds."""
+    E = np.asarray(E, dtype=np.float64)
+    T, C = E.shape
+    y = np.asarray(list(target), dtype=np.int64)
+    L = len(y)
+    S = 2 * L + 1
+    lab = np.full(S, blank, dtype=np.int64)
+    lab[1::2] = y
+    skip = np.zeros(S, dtype=bool)
+    if L > 1:
+        skip[3::2] = y[1:] != y[:-1]
+    if T == 0:
+        return (0.0 if L == 0 else NEG), np.zeros((T, C))
+    Es = E[:, lab]                                            # [T, S]
+    def shift_right(v, k):      # out[s] = v[s - k]
+        out = np.full(S, NEG)
+        if k < S:
+            out[k:] = v[:S - k]
+        return out
+
+    def shift_left(v, k):       # out[s] = v[s + k]
+        out = np.full(S, NEG)
+        if k < S:
+            out[:S - k] = v[k:]
+        return out
+
+    def lse3(a, b, c):
+        m = np.maximum(np.maximum(a, b), c)
+        safe = np.where(np.isfinite(m), m, 0.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = safe + np.log(np.exp(a - safe) + np.exp(b - safe) + np.exp(c - safe))
+        return np.where(np.isfinite(m), out, NEG)
+
+    alpha = np.full((T, S), NEG)
+    alpha[0, 0] = Es[0, 0]
+    if S > 1:
+        alpha[0, 1] = Es[0, 1]
+    for t in range(1, T):
+        a = alpha[t - 1]
+        a1 = shift_right(a, 1)
+        a2 = np.where(skip, shift_right(a, 2), NEG)
+        alpha[t] = lse3(a, a1, a2) + Es[t]
+    fin = alpha[T - 1, max(S - 2, 0):]
+    if not np.isfinite(fin.max()):
+        return NEG, np.zeros((T, C))
+    Z = fin.max() + np.log(np.exp(fin - fin.max()).sum())
+    # beta[t, s]: log mass of completing from state s after frame t (emission of t excluded)
+    beta = np.full((T, S), NEG)
+    beta[T - 1, max(S - 2, 0):] = 0.0
+    skip_out = np.zeros(S, dtype=bool)                                # arc s -> s+2 exists
+    if S > 2:
+        skip_out[:S - 2] = skip[2:]
+    for t in range(T - 2, -1, -1):
+        x = beta[t + 1] + Es[t + 1]
+        x1 = shift_left(x, 1)
+        x2 = np.where(skip_out, shift_left(x, 2), NEG)
+        beta[t] = lse3(x, x1, x2)
+    with np.errstate(invalid="ignore"):
+        post = np.exp(alpha + beta - Z)
+    post = np.where(np.isfinite(alpha) & np.isfinite(beta), post, 0.0)
+    onehot = np.zeros((S, C))
+    onehot[np.arange(S), lab] = 1.0
+    return Z, post @ onehot
+
+
+def ctc_dense(E, targets, blank, reduction="none"):
+    """ctc() on the vectorised recursion (same return value)."""
+    E = np.asarray(E, dtype=np.float64)
+    B = E.shape[0]
+    losses = np.zeros(B)
+    grad = np.zeros_like(E)
+    for b in range(B):
+        Z, gE = ctc_dense_one(E[b], targets[b], blank)
+        L = len(targets[b])
+        scale = (1.0 / L if L > 0 else 1.0) if reduction == "mean" else 1.0
+        losses[b] = -Z * scale
+        grad[b] = -gE * scale / B
+    return {"loss": losses.mean(), "losses": losses, "grad": grad}

@@ -908,17 +908,19 @@ void saveTxt(std::ostream& out, const GraphT<R>& g) {
         << g.olabel(a) << " " << g.weight(a) << "\n";
 }
 
-// binary: int32 {numNodes, numStart, numAccept, numArcs}, start ids, accept
-// ids, then per arc {src, dst, ilabel, olabel} int32 and weight float32.
+// binary, as recalled from gtn/utils.cpp saveGraph / loadGraph (GTN is not in the
+// container, so the field order is "parity unpinned"): int32 numNodes, numStart,
+// numAccept; the start ids; the accept ids; int32 numArcs; then per arc
+// {src, dst, ilabel, olabel} int32 and weight float32.
 template <typename R>
 void saveBin(std::ostream& out, const GraphT<R>& g) {
   auto wi = [&](int v) { out.write(reinterpret_cast<const char*>(&v), 4); };
   wi(g.numNodes());
   wi((int)g.start().size());
   wi((int)g.accept().size());
-  wi(g.numArcs());
   for (int s : g.start()) wi(s);
   for (int s : g.accept()) wi(s);
+  wi(g.numArcs());
   for (int a = 0; a < g.numArcs(); ++a) {
     wi(g.srcNode(a));
     wi(g.dstNode(a));
@@ -937,16 +939,20 @@ GraphT<R> loadBin(std::istream& in) {
     if (!in) throw std::invalid_argument("[load] truncated graph file");
     return v;
   };
-  int nn = ri(), ns = ri(), na = ri(), narcs = ri();
+  int nn = ri(), ns = ri(), na = ri();
+  if (nn < 0 || ns < 0 || na < 0 || ns > nn || na > nn) throw std::invalid_argument("[load] corrupt header");
   std::vector<char> isS(nn, 0), isA(nn, 0);
   for (int i = 0; i < ns; ++i) isS.at(ri()) = 1;
   for (int i = 0; i < na; ++i) isA.at(ri()) = 1;
+  int narcs = ri();
+  if (narcs < 0) throw std::invalid_argument("[load] corrupt header");
   GraphT<R> g;
   for (int n = 0; n < nn; ++n) g.addNode(isS[n], isA[n]);
   for (int a = 0; a < narcs; ++a) {
     int s = ri(), d = ri(), il = ri(), ol = ri();
     float w;
     in.read(reinterpret_cast<char*>(&w), 4);
+    if (!in) throw std::invalid_argument("[load] truncated graph file");
     g.addArc(s, d, il, ol, (R)w);
   }
   return g;

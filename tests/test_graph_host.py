@@ -128,6 +128,23 @@ def test_compose_with_epsilon_transitions_and_provenance(gtn32, tmp_path):
     assert G.equal(G.load(p), g)
     gtn32.save(os.path.join(tmp_path, "o.bin"), og)
     assert G.equal(G.load(os.path.join(tmp_path, "o.bin")), g)   # same binary format as the oracle's
+    # layout (as recalled from GTN's saveGraph): num_arcs follows the start / accept id lists
+    raw = np.fromfile(p, dtype=np.int32)
+    a = g.arrays()
+    ns, na = int(a["start"].sum()), int(a["accept"].sum())
+    assert raw[0] == g.num_nodes() and raw[1] == ns and raw[2] == na and raw[3 + ns + na] == g.num_arcs()
+    # files written by round 1 of this library (num_arcs as the 4th header word) still load
+    old = np.concatenate((raw[:3], [g.num_arcs()], raw[3:3 + ns + na], raw[4 + ns + na:])).astype(np.int32)
+    p1 = os.path.join(tmp_path, "round1.bin")
+    old.tofile(p1)
+    assert G.equal(G.load(p1), g)
+    # corrupt headers are rejected with an error (nothing may throw across the C boundary)
+    for bad in (np.array([-5, 1, 1, 0], np.int32), np.array([3, -1, 0, 0], np.int32),
+                np.array([2, 1, 1, 0, 1, 7, 0, 0, 0, 0, 0], np.int32), raw[:-2], np.array([1], np.int32)):
+        pb = os.path.join(tmp_path, "bad.bin")
+        bad.tofile(pb)
+        with pytest.raises((ValueError, RuntimeError)):
+            G.load(pb)
 
 
 def test_isomorphic_equal_and_viterbi_path(gtn32):

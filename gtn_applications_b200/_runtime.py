@@ -122,7 +122,24 @@ def pack_targets(targets, num_classes, device, scales=None):
     return out
 
 
-def _pack_list_of_lists(targets, num_classes, device, scales):
+def pack_targets_reduction(targets, num_classes, device, reduction, batch):
+    """pack_targets + reduction_scales in one step: returns (flat, offsets, max_len, gscale) where
+    gscale[b] = scale_b / batch (ctc.py:53-56,81,87).  For the reference's list-of-lists argument
+    the lengths come out of the C walker and the scales are formed vectorised — no per-utterance
+    Python work on the call path (the Function is host-bound at BASELINE sizes otherwise)."""
+    import numpy as np
+    if reduction not in ("none", "mean"):
+        raise ValueError("invalid value for reduction '" + str(reduction) + "'")
+    if isinstance(targets, (list, tuple)) and targets and isinstance(targets[0], (list, tuple)):
+        fast = _pack_list_of_lists(targets, num_classes, device, None, (reduction, batch))
+        if fast is not None:
+            return fast
+    scales = reduction_scales(reduction, target_lengths(targets))
+    flat, offsets, _, max_len, gscale = pack_targets(targets, num_classes, device, [x / batch for x in scales])
+    return flat, offsets, max_len, gscale
+
+
+def _pack_list_of_lists(targets, num_classes, device, scales, reduction=None):
     """The reference's own argument type — a Python list of lists of ints (ctc.py:32,
     benchmarks/ctc_benchmark.py:23-24) — walked in C (csrc/pytargets.c) straight into the pinned
     staging buffer: 0.1 ms instead of 1.6 ms of per-label interpreter work at B=256, L=176.
@@ -136,7 +153,7 @@ def _pack_list_of_lists(targets, num_classes, device, scales):
     total = pt.wfst_pytargets_lengths(targets, lens.ctypes.data, nb)
     if total < 0:
         return None
-    ns = nb if scales is not None else 0
+    ns = nb if (scales is not None or reduction is not None) else 0
     host = torch.empty(total + nb + 1 + ns, dtype=torch.int32, pin_memory=torch.cuda.is_available())
     mm = np.zeros(2, dtype=np.int32)
     if pt.wfst_pytargets_fill(targets, host.data_ptr(), total, mm.ctypes.data) != total:
@@ -146,10 +163,20 @@ def _pack_list_of_lists(targets, num_classes, device, scales):
     buf = host.numpy()
     buf[total] = 0
     np.cumsum(lens, out=buf[total + 1:total + nb + 1])
-    if ns:
+    if reduction is not None:
+        kind, batch = reduction
+        sc = buf[total + nb + 1:].view(np.float32)
+        if kind == "mean":
+            np.divide(1.0 / batch, np.maximum(lens, 1), out=sc)
+        else:
+            sc[:] = 1.0 / batch
+    elif ns:
         buf[total + nb + 1:].view(np.float32)[:] = scales
     dev = host.to(device, non_blocking=True)
-    out = (dev[:total], dev[total:total + nb + 1], lens.tolist(), int(lens.max()) if nb else 0)
+    max_len = int(lens.max()) if nb else 0
+    if reduction is not None:
+        return dev[:total], dev[total:total + nb + 1], max_len, dev[total + nb + 1:].view(torch.float32)
+    out = (dev[:total], dev[total:total + nb + 1], lens.tolist(), max_len)
     if scales is not None:
         out = out + (dev[total + nb + 1:].view(torch.float32),)
     return out

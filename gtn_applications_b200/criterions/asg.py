@@ -116,12 +116,13 @@ class ASGLossFunction(torch.autograd.Function):
         rt.require_cuda(inputs, "inputs")
         rt.require_cuda(transitions, "transitions")
         assert transitions.shape == (C + 1, C)
-        scales = rt.reduction_scales(reduction, [len(t) for t in targets])
+        if reduction not in ("none", "mean"):
+            raise ValueError("invalid value for reduction '" + str(reduction) + "'")
         e = rt.to_device(inputs.detach())
         dev = e.device
         with torch.cuda.device(dev):
             tr = transitions.detach().to(dev).contiguous()
-            flat, offsets, _, max_len, gscale = rt.pack_targets(targets, C, dev, [s / B for s in scales])
+            flat, offsets, max_len, gscale = rt.pack_targets_reduction(targets, C, dev, reduction, B)
             out = torch.empty(B + 1, dtype=torch.float32, device=dev)
             need_e, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
             g_e = torch.empty_like(e) if need_e else None

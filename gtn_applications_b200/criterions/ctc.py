@@ -41,7 +41,8 @@ class CTCLossFunction(torch.autograd.Function):
             raise ValueError("log_probs must be [B, T, C]")
         B, T, C = log_probs.shape
         rt.require_cuda(log_probs, "log_probs")
-        scales = rt.reduction_scales(reduction, rt.target_lengths(targets))
+        if reduction not in ("none", "mean"):
+            raise ValueError("invalid value for reduction '" + str(reduction) + "'")
         if len(targets) != B:
             raise ValueError("need one target sequence per batch entry")
         if not 0 <= blank_idx < C:
@@ -49,7 +50,7 @@ class CTCLossFunction(torch.autograd.Function):
         e = rt.to_device(log_probs.detach())
         dev = e.device
         with torch.cuda.device(dev):
-            flat, offsets, _, max_len, gscale = rt.pack_targets(targets, C, dev, [s / B for s in scales])
+            flat, offsets, max_len, gscale = rt.pack_targets_reduction(targets, C, dev, reduction, B)
             out = torch.empty(B + 1, dtype=torch.float32, device=dev)
             need_grad = log_probs.requires_grad
             grad = torch.empty_like(e) if need_grad else None
@@ -116,7 +117,8 @@ class CTCLogitsLossFunction(torch.autograd.Function):
             raise ValueError("inputs must be [B, T, C]")
         B, T, C = inputs.shape
         rt.require_cuda(inputs, "inputs")
-        scales = rt.reduction_scales(reduction, rt.target_lengths(targets))
+        if reduction not in ("none", "mean"):
+            raise ValueError("invalid value for reduction '" + str(reduction) + "'")
         if len(targets) != B:
             raise ValueError("need one target sequence per batch entry")
         if not 0 <= blank_idx < C:
@@ -124,7 +126,7 @@ class CTCLogitsLossFunction(torch.autograd.Function):
         e = rt.to_device(inputs.detach())
         dev = e.device
         with torch.cuda.device(dev):
-            flat, offsets, _, max_len, gscale = rt.pack_targets(targets, C, dev, [s / B for s in scales])
+            flat, offsets, max_len, gscale = rt.pack_targets_reduction(targets, C, dev, reduction, B)
             L = _lib.lib()
             if not L.wfst_ctc_logits_supported(B, T, C, max_len):
                 raise NotImplementedError("fused logits CTC does not handle this shape; use log_softmax + CTCLoss")

@@ -50,6 +50,8 @@ static HostPathBuffers& host_buffers() {
 static int g_force_generic = 0;
 // test hook: 2 = skip the paired kernel (exercise the single-utterance scaled kernel)
 static int g_force_generic_kind = 0;
+// test hook: 1 = skip the chain-split kernel (exercise the paired kernel)
+static int g_no_chain = 0;
 
 }  // namespace wfst
 
@@ -62,9 +64,11 @@ int wfst_abi_version(void) { return WFST_ABI_VERSION; }
 int wfst_debug_force_generic_ctc(int on) {
   // 0: default dispatch; 1: log-semiring kernel only; 2: no paired kernel;
   // 3: dense ASG full-connect kernel with one warp per utterance only (no two-warp split)
-  int old = g_force_generic ? 1 : (g_asg_dense_single ? 3 : g_force_generic_kind);
+  // 4: no chain-split CTC kernel (paired / single-utterance kernels as before)
+  int old = g_force_generic ? 1 : (g_asg_dense_single ? 3 : (g_no_chain ? 4 : g_force_generic_kind));
   g_force_generic = (on == 1);
   g_force_generic_kind = (on == 2) ? 2 : 0;
+  g_no_chain = (on == 4 || on == 2);
   g_asg_dense_single = (on == 3);
   return old;
 }
@@ -72,17 +76,23 @@ int wfst_debug_force_generic_lattice(int on) { return lattice_force_generic((on 
 unsigned long long wfst_launch_count(void) { return g_launches.load(); }
 
 // --------------------------------------------------------------------- CTC
-// scaled-probability kernels, in order of preference: paired (two utterances per block,
-// packed FP32), single (larger targets), none (log-semiring kernel only)
+// scaled-probability kernels, in order of preference: chain-split (one utterance per block, both
+// time directions packed, chain split over warps), paired (two utterances per block), single
+// (larger targets), none (log-semiring kernel only)
 static int ctc_scaled_kind(int T, int C, int max_target_len) {
   if (g_force_generic) return 0;
+  if (!g_no_chain && ctc_chain_eligible(T, C, max_target_len)) return 3;
   if (g_force_generic_kind != 2 && ctc_pair_eligible(T, C, max_target_len)) return 2;
   if (ctc_fast_eligible(T, C, max_target_len)) return 1;
   return 0;
 }
 static size_t ctc_scaled_workspace_bytes(int B, int T, int C, int max_target_len) {
   size_t n = 0;
-  if (ctc_pair_eligible(T, C, max_target_len)) n = ctc_pair_workspace_bytes(B, T, max_target_len);
+  if (ctc_chain_eligible(T, C, max_target_len)) n = ctc_chain_workspace_bytes(B, T, max_target_len);
+  if (ctc_pair_eligible(T, C, max_target_len)) {
+    size_t m = ctc_pair_workspace_bytes(B, T, max_target_len);
+    if (m > n) n = m;
+  }
   if (ctc_fast_eligible(T, C, max_target_len)) {
     size_t m = ctc_fast_workspace_bytes(B, T, max_target_len);
     if (m > n) n = m;
@@ -121,10 +131,12 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
     // scaled-probability kernel; utterances it flags are redone by the log-semiring kernel
     int* hazard = nullptr;
     void* fws = (char*)workspace + hb + align_up((size_t)B * sizeof(float), 256);
-    rc = kind == 2 ? launch_ctc_pair(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
-                                     grad_scale, z, grad, fws, &hazard, 0, st)
-                   : launch_ctc_fast(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
-                                     grad_scale, z, grad, fws, &hazard, st);
+    rc = kind == 3 ? launch_ctc_chain(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+                                      grad_scale, z, grad, fws, &hazard, st)
+         : kind == 2 ? launch_ctc_pair(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+                                       grad_scale, z, grad, fws, &hazard, 0, st)
+                     : launch_ctc_fast(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+                                       grad_scale, z, grad, fws, &hazard, st);
     if (rc != WFST_OK) return rc;
     rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
                     z, grad, hist, hazard, st);
@@ -202,7 +214,8 @@ int wfst_debug_ctc_hazards(const void* workspace, int B, int T, int C, int max_t
   const int kind = ctc_scaled_kind(T, C, max_target_len);
   if (kind == 0) return WFST_OK;
   size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
-  size_t fb = kind == 2 ? ctc_pair_workspace_bytes(B, T, max_target_len) : ctc_fast_workspace_bytes(B, T, max_target_len);
+  size_t fb = kind == 3 ? ctc_chain_workspace_bytes(B, T, max_target_len)
+              : kind == 2 ? ctc_pair_workspace_bytes(B, T, max_target_len) : ctc_fast_workspace_bytes(B, T, max_target_len);
   const char* hz = (const char*)workspace + hb + fb - align_up((size_t)B * sizeof(int), 256);
   WFST_CUDA_CHECK(cudaDeviceSynchronize());
   WFST_CUDA_CHECK(cudaMemcpy(host_flags, hz, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost));

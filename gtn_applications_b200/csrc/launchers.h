@@ -51,6 +51,13 @@ size_t ctc_pair_workspace_bytes(int B, int T, int max_target_len);
 int launch_ctc_pair(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                     int blank, int max_target_len, const float* grad_scale, float* z_out,
                     float* gradE, void* workspace, int** hazard_out, int fused, cudaStream_t st);
+// chain-split scaled CTC (ctc_chain.cu): one utterance per block, both time directions packed
+// in FP32 pairs, the chain split over W warps skewed by one 8-frame step
+bool ctc_chain_eligible(int T, int C, int max_target_len);
+size_t ctc_chain_workspace_bytes(int B, int T, int max_target_len);
+int launch_ctc_chain(const float* E, const int* targets, const int* offsets, int B, int T, int C,
+                     int blank, int max_target_len, const float* grad_scale, float* z_out,
+                     float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
 // log_softmax rows / its backward for the utterances with active[b] != 0 (lsm.cu): the
 // fallback of the fused mode
 int launch_lsm_rows(const float* x, const int* active, int B, int T, int C, float* out, cudaStream_t st);

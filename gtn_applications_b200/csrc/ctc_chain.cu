@@ -53,6 +53,14 @@ namespace chaink {
 
 typedef unsigned long long p2;   // two packed floats: low = direction 0, high = direction 1
 
+#ifdef WFST_PROFILE
+#define PROF_DECL long long pf_t0 = clock64(), pf_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(i) do { long long pf_t1 = clock64(); pf_acc[i] += pf_t1 - pf_t0; pf_t0 = pf_t1; } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#endif
+
 constexpr int kSeg = 8;               // frames per step / tile
 constexpr int kEventEvery = 2;        // lanes are renormalised every kEventEvery steps
 constexpr int kUndef = -(1 << 19);    // "no exponent": lane holds only zeros
@@ -61,7 +69,7 @@ constexpr int kNR = 3;                // raw (TMA) staging slots per producer wa
 constexpr int kRD = 4;                // depth of the warp-to-warp chain rings
 constexpr int kMaxAB = 8;             // step buffers (abar / products), at most
 constexpr int kMaxNB = 12;            // p tiles, at most
-constexpr int kMaxList = 48;          // reduction table: sum over class rounds of the longest list
+constexpr int kMaxList = 32;          // reduction table: sum over class rounds of the longest list
 constexpr int kMaxW = 4;
 constexpr int kRingPairs = 10;        // ring entry: 9 boundary pairs + {e0, e1}
 
@@ -206,12 +214,14 @@ struct Geo {
   static constexpr int NL = 32 * W;            // lanes of the chain
   static constexpr int Sp = K * NL;            // slots
   static constexpr int HL = K / 2;             // label slots per lane
-  static constexpr int SA = (HL & 1) ? HL : HL + 1;     // abar row: pairs per lane (odd: conflict-free 64-bit accesses)
-  static constexpr int PADA = 4;               // zero pairs in front of an abar row
-  static constexpr int ROWP = PADA + SA * NL + 2;
+  // an abar row is two planes (direction 0, direction 1) of PADA zero words + SA words per lane
+  static constexpr int SA = (HL & 1) ? HL : HL + 1;     // odd: conflict-free 32-bit accesses
+  static constexpr int PADA = 4;
+  static constexpr int ROWP = PADA + SA * NL + 4;       // words per plane
+  static constexpr uint32_t PLANEB = 4u * ROWP;
   static constexpr uint32_t ROWB = 8u * ROWP;
-  static constexpr uint32_t EXTB = 8u * (SA - HL + 1);  // distance from a lane block back to the previous block's last label
-  static constexpr int SB = K + 1;             // boundary row: pairs per lane (odd)
+  static constexpr uint32_t EXTB = 4u * (SA - HL + 1);  // distance from a lane block back to the previous block's last label
+  static constexpr int SB = K;                 // boundary row: pairs per lane (touched once per step: bank conflicts do not matter)
   static constexpr int BNDP = 4 + SB * NL + 2;
   static constexpr uint32_t BNDB = 8u * BNDP;
   static constexpr int CKF = 2 * K + 4;        // checkpoint floats per lane
@@ -233,7 +243,7 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
   size_t p = 0;
   L.raw = p;    p += 2 * (size_t)kNR * rawsz + 32;                  // [d][slot][8*C] (+ slack)
   L.out = p;    p += 2 * 2 * rawsz;                                 // [d][ob][8*C]
-  L.abuf = p;   p += (size_t)NAB * kSeg * G::ROWP * 2;              // [buf][row][pair]
+  L.abuf = p;   p += (size_t)NAB * kSeg * G::ROWP * 2;              // [buf][row][plane][word]
   L.bnd = p;    p += (size_t)NAB * G::BNDP * 2;                     // [buf][pair]: live state at the step boundary
   L.lexp = p;   p += (size_t)NAB * 2 * G::NL;                       // [buf][d][gl] (int)
   L.cert = p;   p += (size_t)NAB * W * 2;                           // [buf][w] (pair)
@@ -381,6 +391,12 @@ __device__ __forceinline__ p2 left_in(p2 last, uint32_t ring_addr, int lane, p2 
   if (lane == 0) left = bv;
   return mul2(left, f);
 }
+// same with the ring value already in a register
+__device__ __forceinline__ p2 left_in_reg(p2 last, p2 bv, int lane, p2 f) {
+  p2 left = shfl_up2(last);
+  if (lane == 0) left = bv;
+  return mul2(left, f);
+}
 
 // Event: renormalise the lane (max mantissa in [1,2)) and make the lane exponents
 // consistent from left to right (the direction mass flows):
@@ -390,9 +406,8 @@ __device__ __forceinline__ p2 left_in(p2 last, uint32_t ring_addr, int lane, p2 
 //     small enough that a wave crossing several lanes inside one 16-frame window cannot
 //     overflow: D * (lanes crossed) + log2(3^16) < 127.
 // This is the prefix composition of the maps x -> max(c, x - d) with (c, d) = (own
-// exponent, D) or (undefined, 0), which is associative: a 5-step warp scan, applied to the
-// exponent Ein of the previous warp's last lane (undefined for the first warp).  "Undefined" is
-// any value below kUndef / 2; (c, d) travel in one shuffle as c * 2048 + d (d < 2048).
+// exponent, D) or (undefined, 0), applied to the exponent Ein of the previous warp's last lane
+// (undefined for the first warp).  "Undefined" is any value below kUndef / 2.
 template <int K>
 __device__ __forceinline__ void event2(p2 (&v)[K], int (&e)[2], p2& f, int lane, const int (&Ein)[2]) {
   constexpr int kChain = (2 * kSeg * kEventEvery + K - 1) / K + 1;   // lanes a wave can cross in a window
@@ -403,39 +418,29 @@ __device__ __forceinline__ void event2(p2 (&v)[K], int (&e)[2], p2& f, int lane,
     m[0] = fmaxf(m[0], lo(v[i]));
     m[1] = fmaxf(m[1], hi(v[i]));
   }
-  int ex[2], eown[2], c[2], d[2];
+  // With m_l = number of lanes 0..l that hold mass, the composition collapses to a prefix
+  // maximum:  E_l = max( max_{l' <= l, mass} (eown_l' + D m_l'),  Ein ) - D m_l .
+  int ex[2], eown[2], val[2], dm[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     ex[u] = min(max((int)((__float_as_uint(m[u]) >> 23) & 0xffu) - 127, -126), 126);
     const bool has = m[u] > 0.f;
     if (!has) ex[u] = 0;
     eown[u] = has ? (defined_exp(e[u]) ? e[u] : 0) + ex[u] : kUndef;
-    c[u] = eown[u];
-    d[u] = has ? D : 0;
+    dm[u] = D * __popc(__ballot_sync(kFull, has) & (0xffffffffu >> (31 - lane)));
+    val[u] = has ? eown[u] + dm[u] : 2 * kUndef;
   }
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int pc[2], pd[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int packed = __shfl_up_sync(kFull, c[u] * 2048 + d[u], o);
-      pd[u] = packed & 2047;
-      pc[u] = packed >> 11;            // arithmetic shift: floor((c * 2048 + d) / 2048) = c
-    }
-    if (lane >= o) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        c[u] = max(c[u], max(pc[u], kUndef) - d[u]);
-        d[u] += pd[u];
-      }
-    }
+    for (int u = 0; u < 2; ++u) val[u] = max(val[u], __shfl_up_sync(kFull, val[u], o));   // lanes < o get their own value back
   }
   int t[2];           // total power-of-two shift applied to the lane
   float fv[2];
   bool deep = false;
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    const int cin = max(c[u], max(Ein[u], kUndef) - d[u]);
+    const int cin = max(val[u], defined_exp(Ein[u]) ? Ein[u] : 2 * kUndef) - dm[u];
     const int E = defined_exp(cin) ? cin : kUndef;
     t[u] = -ex[u] + ((defined_exp(E) && defined_exp(eown[u])) ? eown[u] - E : 0);   // second term <= 0
     e[u] = E;
@@ -481,15 +486,23 @@ __device__ __forceinline__ void ckpt_load_swapped(const float* base, p2 (&v)[K],
   e[1] = __float_as_int(lo(q.x));
 }
 
-// p-tile ring, as seen by a consumer warp: use number kt of buffer kt % NB
-__device__ __forceinline__ uint32_t ptile_wait(const Smem& sm, const Ctx& cx, int kt) {
-  const int buf = kt % cx.NB;
-  bar_wait(sm.bars, kBarPFull + buf, (uint32_t)(kt / cx.NB) & 1u);
-  return sm.ptile + 4u * (uint32_t)(buf * 2 * cx.CP * 9);
+// p-tile ring, as seen by a consumer warp that takes every tile from `first` on
+struct PRing {
+  int buf;
+  uint32_t par;
+  __device__ __forceinline__ void init(int first, int NB) { buf = first % NB; par = (uint32_t)(first / NB) & 1u; }
+  __device__ __forceinline__ void next(int NB) {
+    if (++buf == NB) { buf = 0; par ^= 1u; }
+  }
+};
+__device__ __forceinline__ uint32_t ptile_wait(const Smem& sm, const Ctx& cx, const PRing& r) {
+  bar_wait(sm.bars, kBarPFull + r.buf, r.par);
+  return sm.ptile + 4u * (uint32_t)(r.buf * 2 * cx.CP * 9);
 }
-__device__ __forceinline__ void ptile_release(const Smem& sm, const Ctx& cx, int kt, uint32_t count) {
+__device__ __forceinline__ void ptile_release(const Smem& sm, const Ctx& cx, PRing& r, uint32_t count) {
   __syncwarp();
-  if (cx.lane == 0) bar_arrive(sm.bars, kBarPEmpty + kt % cx.NB, count);
+  if (cx.lane == 0) bar_arrive(sm.bars, kBarPEmpty + r.buf, count);
+  r.next(cx.NB);
 }
 
 // ---------------------------------------------------------------------------
@@ -499,6 +512,8 @@ __device__ __forceinline__ void ptile_release(const Smem& sm, const Ctx& cx, int
 struct ProducerState {
   int fetched, converted;
   uint32_t tma_phase, tma_used;
+  int pbuf;            // p-tile buffer of the next tile
+  uint32_t ppar;       // parity of its "empty" barrier
   double msum;
 };
 
@@ -511,12 +526,13 @@ __device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, con
   const int c0 = (C * part) / 4, c1 = (C * (part + 1)) / 4;
   const uint32_t raw0 = sm.raw + 4u * (uint32_t)(c * kNR) * rawsz;
   const int tbar = kBarTma + c * kNR;
+  const float* Eb = a.E + (size_t)cx.b * T * C;
   auto issue_raw = [&](int kt) {
     int lo_, rows;
     comp_seg(cx, c, kt, lo_, rows);
     const int slot = ps.fetched % kNR;
     const uint32_t bytes = (uint32_t)rows * C * 4u;
-    const float* src = a.E + ((size_t)cx.b * T + (size_t)lo_) * C;
+    const float* src = Eb + (size_t)lo_ * C;
     const uint32_t dst = raw0 + 4u * (uint32_t)slot * rawsz;
     const bool tma = rows > 0 && (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     if (tma) {
@@ -536,41 +552,71 @@ __device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, con
     ++ps.fetched;
   };
   int kf = 0;   // next entry to fetch (relative)
+  PROF_DECL;
   for (int i = 0; i < kcnt; ++i) {
+    PROF_MARK(2);
     while (kf < kcnt && ps.fetched < ps.converted + kNR) issue_raw(kbeg + kf++);
+    PROF_MARK(3);
     const int kt = kbeg + i;
     const int slot = ps.converted % kNR;
     int lo_, rows;
     comp_seg(cx, c, kt, lo_, rows);
-    const int buf = kt % cx.NB;
-    if (kt >= cx.NB)   // wait until the consumers have released this p-tile buffer
-      bar_wait(sm.bars, kBarPEmpty + buf, (uint32_t)(kt / cx.NB - 1) & 1u);
+    const int buf = ps.pbuf;
+    if (kt >= cx.NB) {  // wait until the consumers have released this p-tile buffer
+      bar_wait(sm.bars, kBarPEmpty + buf, ps.ppar);
+    }
+    if (++ps.pbuf == cx.NB) { ps.pbuf = 0; if (kt >= cx.NB) ps.ppar ^= 1u; }
+    PROF_MARK(0);
     if ((ps.tma_used >> slot) & 1u) {
       bar_wait(sm.bars, tbar + slot, (ps.tma_phase >> slot) & 1u);
       ps.tma_phase ^= 1u << slot;
     }
+    PROF_MARK(1);
     const bool live = fr < rows;
     const uint32_t er = raw0 + 4u * ((uint32_t)slot * rawsz + (uint32_t)(fr * C));
     // tile row = the step at which component c consumes frame fr (c = 0 ascends, c = 1 descends)
     const int trow = c == 0 ? fr : rows - 1 - fr;
     const uint32_t pt = sm.ptile + 4u * (uint32_t)((buf * 2 + c) * cx.CP * 9) + 4u * (uint32_t)(live ? trow : 0);
-    float mx = kNegInf;
-    if (live)
-      for (int cc = c0; cc < c1; ++cc) mx = fmaxf(mx, lds(er + 4u * cc));
-    mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 8));
-    mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 16));
     // a row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface through
     // the certificate
-    const float base = (mx == kNegInf) ? 0.f : mx;
-    const float nb = -base * 1.4426950408889634f;
-    if (live)
-      for (int cc = c0; cc < c1; ++cc)
-        sts(pt + 36u * (uint32_t)cc, ex2_fast(fmaf(lds(er + 4u * cc), 1.4426950408889634f, nb)));
+    float base;
+    if (c1 - c0 <= 8) {
+      // the lane's quarter of the row stays in registers between the two passes
+      float ev[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ev[q] = (live && c0 + q < c1) ? lds(er + 4u * (uint32_t)(c0 + q)) : kNegInf;
+      float mx = fmaxf(fmaxf(fmaxf(ev[0], ev[1]), fmaxf(ev[2], ev[3])), fmaxf(fmaxf(ev[4], ev[5]), fmaxf(ev[6], ev[7])));
+      mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 16));
+      base = (mx == kNegInf) ? 0.f : mx;
+      const float nb = -base * 1.4426950408889634f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (live && c0 + q < c1) sts(pt + 36u * (uint32_t)(c0 + q), ex2_fast(fmaf(ev[q], 1.4426950408889634f, nb)));
+    } else {
+      float mx = kNegInf;
+      if (live)
+        for (int cc = c0; cc < c1; ++cc) mx = fmaxf(mx, lds(er + 4u * cc));
+      mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, 16));
+      base = (mx == kNegInf) ? 0.f : mx;
+      const float nb = -base * 1.4426950408889634f;
+      if (live) {
+#pragma unroll 4
+        for (int cc = c0; cc < c1; ++cc)
+          sts(pt + 36u * (uint32_t)cc, ex2_fast(fmaf(lds(er + 4u * cc), 1.4426950408889634f, nb)));
+      }
+    }
     if (live && part == 0 && phase1) ps.msum += (double)base;
     __syncwarp();
     if (lane == 0) bar_arrive(sm.bars, kBarPFull + buf);
     ++ps.converted;
   }
+  PROF_MARK(2);
+#ifdef WFST_PROFILE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("P%d (phase1 %d) cycles: wait_pempty %lld wait_tma %lld convert %lld issue %lld\n", c, (int)phase1, pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3]);
+#endif
 }
 
 template <int W>
@@ -578,6 +624,7 @@ __device__ __forceinline__ void role_producer(const Args& a, const Smem& sm, con
   const int lane = cx.lane, nsd = cx.nsd;
   ProducerState ps;
   ps.fetched = 0; ps.converted = 0; ps.tma_phase = 0u; ps.tma_used = 0u;
+  ps.pbuf = 0; ps.ppar = 0u;
   ps.msum = 0.0;
   produce_range<W>(a, sm, cx, ps, c, 0, nsd, true);
   // loss: log Z = log(Zm) + eZ ln2 + sum_t max_t; the two producers each hold the row maxima
@@ -631,20 +678,28 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   const uint32_t ring_in0 = sm.ringL + 8u * (uint32_t)(w * kRD * kRingPairs);
   const uint32_t ring_out0 = sm.ringL + 8u * (uint32_t)((w + 1) * kRD * kRingPairs);
   uint32_t rin = ring_in0, rout = ring_out0;
+  PRing pr;
+  pr.init(0, cx.NB);
+  const bool has_partial = nsd > cx.nfull;
 
   // start of global step g: take the left warp's ring entry, renormalise if due, open my own entry
+  PROF_DECL;
   auto step_begin = [&](int g, bool ev) {
     const int slot = g % kRD;
     rin = ring_in0 + 8u * (uint32_t)(slot * kRingPairs);
     rout = ring_out0 + 8u * (uint32_t)(slot * kRingPairs);
+    PROF_MARK(0);
     if (w > 0) bar_wait(sm.bars, kBarLFull + w * kRD + slot, (uint32_t)(g / kRD) & 1u);
+    PROF_MARK(1);
     if (ev) {
       int Ein[2] = {kUndef, kUndef};
       if (w > 0) { Ein[0] = ldsi(rin + 72u); Ein[1] = ldsi(rin + 76u); }
       event2<K>(v, e, f, lane, Ein);
     }
+    PROF_MARK(2);
     if (w < W - 1) {
       if (g >= kRD) bar_wait(sm.bars, kBarLEmpty + (w + 1) * kRD + slot, (uint32_t)(g / kRD - 1) & 1u);
+      PROF_MARK(3);
       if (lane == 31) {
         sts64(rout, v[K - 1]);
         stsi(rout + 72u, e[0]);
@@ -676,7 +731,10 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
       for (int i = 0; i < K; ++i) v[i] = pk(kx ? lo(v[i]) : lo(old[i]), ky ? hi(v[i]) : hi(old[i]));
       if (want_abar) {
 #pragma unroll
-        for (int q = 0; q < HL; ++q) sts64(ar + (uint32_t)it * G::ROWB + 8u * q, abar[q]);
+        for (int q = 0; q < HL; ++q) {
+          sts(ar + (uint32_t)it * G::ROWB + 4u * q, lo(abar[q]));
+          sts(ar + G::PLANEB + (uint32_t)it * G::ROWB + 4u * q, hi(abar[q]));
+        }
       }
       if (lane == 31) sts64(rout + 8u * (uint32_t)(it + 1), v[K - 1]);
     }
@@ -686,32 +744,42 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   for (int g = 0; g < nsd; ++g) {
     step_begin(g, g % kEventEvery == 0);
     ckpt_store<K>(ck + (size_t)g * NL * G::CKF, v, e);
-    const int rx = seg_rows(cx, 0, g), ry = seg_rows(cx, 1, g);
-    const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, g));
-    if (rx == kSeg && ry == kSeg) {
+    const bool partial = has_partial && g == cx.nfull;
+    PROF_MARK(0);
+    const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, pr));
+    PROF_MARK(4);
+    if (!partial) {
       PRow<K> nx = load_prow<K>(ta, 0);
+      p2 bvn = lds64(rin);
 #pragma unroll
       for (int it = 0; it < kSeg; ++it) {
         const PRow<K> cur = nx;
-        if (it + 1 < kSeg) nx = load_prow<K>(ta, it + 1);
-        const p2 in1 = left_in(v[K - 1], rin + 8u * it, lane, f);
+        const p2 bv = bvn;
+        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); bvn = lds64(rin + 8u * (it + 1)); }
+        const p2 in1 = left_in_reg(v[K - 1], bv, lane, f);
         step<K, false>(v, abar, tp, cur, in1);
         if (lane == 31) sts64(rout + 8u * (it + 1), v[K - 1]);
       }
     } else {
-      slow_frames(ta, rx, ry, 0u, false);
+      slow_frames(ta, cx.r0, cx.r1, 0u, false);
     }
-    ptile_release(sm, cx, g, 2);   // no recompute warp reads phase-1 tiles
+    ptile_release(sm, cx, pr, 2);   // no recompute warp reads phase-1 tiles
     step_end(g);
   }
 
+  PROF_MARK(0);
+#ifdef WFST_PROFILE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("L%d phase 1 cycles: work %lld wait_ring %lld event %lld wait_ring_empty %lld wait_ptile %lld\n", w, pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3], pf_acc[4]);
+  for (int i = 0; i < 8; ++i) pf_acc[i] = 0;
+#endif
   // ------------------------------------------------------------------ meeting: Z
   // every live warp renormalises (consistent exponents for the successor sums below) and
   // publishes its state in the layout of a boundary row (buffer 0); then
   //   Z = sum over y-slots of (successor sum of beta~)(slot) * alpha(partner slot).
   step_begin(nsd, true);
   const uint32_t mybnd = 8u * (uint32_t)(4 + gl * G::SB);       // my slots in a boundary row
-  const uint32_t myabar = 8u * (uint32_t)(G::PADA + gl * G::SA);
+  const uint32_t myabar = 4u * (uint32_t)(G::PADA + gl * G::SA);
   {
 #pragma unroll
     for (int i = 0; i < K; ++i) sts64(sm.bnd + mybnd + 8u * i, v[i]);
@@ -741,7 +809,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     float pm = 0.f;
 #pragma unroll
     for (int i = 0; i <= K - 2; ++i) pm = fmaf(hi(bb[i]), lo(lds64(pblock + 8u * (K - 2 - i))), pm);
-    const float px = hi(bb[K - 1]) * lo(lds64(pblock - 16u));
+    const float px = hi(bb[K - 1]) * lo(lds64(pblock - 8u));
     const int ea = ldsi(sm.lexp + 4u * (uint32_t)pl);
     const int eb = pl > 0 ? ldsi(sm.lexp + 4u * (uint32_t)(pl - 1)) : kUndef;
     int Em = kUndef, Ex = kUndef;
@@ -788,10 +856,13 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   if (!cx.want_grad || !okz) return;
 
   // ------------------------------------------------------------------ phase 2
-  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, buf = (buf + 1 == NAB) ? 0 : buf + 1) {
-    const int g = nsd + 1 + k2, kt = nsd + k2;
+  uint32_t rpar = 0u;   // (k2 / NAB) & 1
+  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, rpar ^= (buf + 1 == NAB), buf = (buf + 1 == NAB) ? 0 : buf + 1) {
+    const int g = nsd + 1 + k2;
     step_begin(g, g % kEventEvery == 0);
-    if (k2 >= NAB) bar_wait(sm.bars, kBarAEmpty + buf, (uint32_t)(k2 / NAB - 1) & 1u);
+    PROF_MARK(0);
+    if (k2 >= NAB) bar_wait(sm.bars, kBarAEmpty + buf, rpar ^ 1u);
+    PROF_MARK(5);
     {
       const uint32_t le = sm.lexp + 4u * (uint32_t)(buf * 2 * NL + gl);
       stsi(le, e[0]);
@@ -801,31 +872,42 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
 #pragma unroll
       for (int i = 0; i < K; ++i) sts64(bb + 8u * i, v[i]);
     }
-    int lox, loy, rx, ry;
-    comp_seg(cx, 0, kt, lox, rx);
-    comp_seg(cx, 1, kt, loy, ry);
-    const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, kt));
+    // component c continues through the other direction's steps, last one (the partial one) first
+    const bool partial = has_partial && k2 == 0;
+    PROF_MARK(0);
+    const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, pr));
+    PROF_MARK(4);
     const uint32_t ar = sm.abuf + (uint32_t)(buf * kSeg) * G::ROWB + myabar;
-    if (rx == kSeg && ry == kSeg) {
+    if (!partial) {
       PRow<K> nx = load_prow<K>(ta, 0);
+      p2 bvn = lds64(rin);
 #pragma unroll
       for (int it = 0; it < kSeg; ++it) {
         const PRow<K> cur = nx;
-        if (it + 1 < kSeg) nx = load_prow<K>(ta, it + 1);
-        const p2 in1 = left_in(v[K - 1], rin + 8u * it, lane, f);
+        const p2 bv = bvn;
+        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); bvn = lds64(rin + 8u * (it + 1)); }
+        const p2 in1 = left_in_reg(v[K - 1], bv, lane, f);
         step<K, true>(v, abar, tp, cur, in1);
 #pragma unroll
-        for (int q = 0; q < HL; ++q) sts64(ar + (uint32_t)it * G::ROWB + 8u * q, abar[q]);
+        for (int q = 0; q < HL; ++q) {
+          sts(ar + (uint32_t)it * G::ROWB + 4u * q, lo(abar[q]));
+          sts(ar + G::PLANEB + (uint32_t)it * G::ROWB + 4u * q, hi(abar[q]));
+        }
         if (lane == 31) sts64(rout + 8u * (it + 1), v[K - 1]);
       }
     } else {
-      slow_frames(ta, rx, ry, ar, true);
+      slow_frames(ta, cx.r1, cx.r0, ar, true);
     }
     __syncwarp();
     if (lane == 0) bar_arrive(sm.bars, kBarAFull + buf);
-    ptile_release(sm, cx, kt, 1);
+    ptile_release(sm, cx, pr, 1);
     step_end(g);
   }
+  PROF_MARK(0);
+#ifdef WFST_PROFILE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("L%d phase 2 cycles: work %lld wait_ring %lld event %lld wait_ring_empty %lld wait_ptile %lld wait_aempty %lld\n", w, pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3], pf_acc[4], pf_acc[5]);
+#endif
   // certificate, last leg: the sweep must arrive with total mass Z on the two slots that end the
   // chain in each orientation (the recompute warps check every earlier step boundary)
   {
@@ -862,17 +944,23 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
 // ---------------------------------------------------------------------------
 template <int K>
 __device__ __forceinline__ void rc_frame(p2 (&w)[K], const Topo<K>& tp, const PRow<K>& cur, p2 in1, p2 h2, uint32_t arow,
-                                         uint32_t extb) {
+                                         uint32_t extb, uint32_t planeb) {
   // partner of my odd slot i (<= K-3) is label slot (K-3-i)/2 of the partner block; of my slot
   // K-1, the last label slot of the block before it
   p2 av[K / 2], dummy[K / 2];
 #pragma unroll
-  for (int q = 0; q < K / 2 - 1; ++q) av[q] = lds64(arow + 8u * q);
-  const p2 ext = lds64(arow - extb);
+  for (int q = 0; q < K / 2 - 1; ++q) av[q] = pk(lds(arow + 4u * q), lds(arow + planeb + 4u * q));
+  const p2 ext = pk(lds(arow - extb), lds(arow + planeb - extb));
   step<K, false>(w, dummy, tp, cur, in1);
 #pragma unroll
-  for (int q = 0; q < K / 2 - 1; ++q) sts64(arow + 8u * q, mul2(w[K - 3 - 2 * q], av[q]));
-  sts64(arow - extb, mul2(mul2(w[K - 1], ext), h2));
+  for (int q = 0; q < K / 2 - 1; ++q) {
+    const p2 pr = mul2(w[K - 3 - 2 * q], av[q]);
+    sts(arow + 4u * q, lo(pr));
+    sts(arow + planeb + 4u * q, hi(pr));
+  }
+  const p2 pe = mul2(mul2(w[K - 1], ext), h2);
+  sts(arow - extb, lo(pe));
+  sts(arow + planeb - extb, hi(pe));
 }
 
 template <int K, int W>
@@ -888,7 +976,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   build_topo<K, W>(tp, cx, sm.ytab, gl, true, a.blank);
   const float* ck = a.ckpt + ((size_t)cx.b * nsd * NL + gl) * G::CKF;
   const int pl = NL - 1 - gl;
-  const uint32_t pabar = 8u * (uint32_t)(G::PADA + pl * G::SA);   // partner block in an abar row
+  const uint32_t pabar = 4u * (uint32_t)(G::PADA + pl * G::SA);   // partner block in a plane of an abar row
   const uint32_t pbnd = 8u * (uint32_t)(4 + pl * G::SB);          // partner block in a boundary row
   const uint32_t ring_in0 = sm.ringR + 8u * (uint32_t)(w * kRD * kRingPairs);
   const uint32_t ring_out0 = sm.ringR + 8u * (uint32_t)((w + 1) * kRD * kRingPairs);
@@ -896,14 +984,20 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   p2 wv[K];
   int ew[2];
   ckpt_load_swapped<K>(ck + (size_t)(nsd - 1) * NL * G::CKF, wv, ew);
-  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, buf = (buf + 1 == NAB) ? 0 : buf + 1) {
-    const int kt = nsd + k2, slot = k2 % kRD;
+  PRing pr;
+  pr.init(nsd, cx.NB);
+  const bool has_partial = nsd > cx.nfull;
+  PROF_DECL;
+  uint32_t rpar = 0u;   // (k2 / NAB) & 1
+  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, rpar ^= (buf + 1 == NAB), buf = (buf + 1 == NAB) ? 0 : buf + 1) {
+    const int slot = k2 % kRD;
     const uint32_t rin = ring_in0 + 8u * (uint32_t)(slot * kRingPairs);
     const uint32_t rout = ring_out0 + 8u * (uint32_t)(slot * kRingPairs);
-    int lox, loy, rx, ry;
-    comp_seg(cx, 0, kt, lox, rx);
-    comp_seg(cx, 1, kt, loy, ry);
-    bar_wait(sm.bars, kBarAFull + buf, (uint32_t)(k2 / NAB) & 1u);
+    const bool partial = has_partial && k2 == 0;
+    const int rx = partial ? cx.r1 : kSeg, ry = partial ? cx.r0 : kSeg;
+    PROF_MARK(0);
+    bar_wait(sm.bars, kBarAFull + buf, rpar);
+    PROF_MARK(1);
     // scales
     float gsc[2], hsc[2], frs[2];
 #pragma unroll
@@ -930,23 +1024,28 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     }
     const p2 f2 = pk(frs[0], frs[1]), h2 = pk(hsc[0], hsc[1]);
     // chain ring: my left neighbour's entry of this step; open my own
+    PROF_MARK(0);
     if (w > 0) bar_wait(sm.bars, kBarRFull + w * kRD + slot, (uint32_t)(k2 / kRD) & 1u);
     if (w < W - 1) {
       if (k2 >= kRD) bar_wait(sm.bars, kBarREmpty + (w + 1) * kRD + slot, (uint32_t)(k2 / kRD - 1) & 1u);
       if (lane == 31) sts64(rout, wv[K - 1]);
     }
-    const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, kt));
+    PROF_MARK(2);
+    const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, pr));
+    PROF_MARK(3);
     const uint32_t ar = sm.abuf + (uint32_t)(buf * kSeg) * G::ROWB + pabar;
     const int nfr = max(rx, ry);
-    if (rx == kSeg && ry == kSeg) {
+    if (!partial) {
       // against the live step order
       PRow<K> nx = load_prow<K>(ta, kSeg - 1);
+      p2 bvn = lds64(rin);
 #pragma unroll
       for (int it = kSeg - 1; it >= 0; --it) {
         const PRow<K> cur = nx;
-        if (it > 0) nx = load_prow<K>(ta, it - 1);
-        const p2 in1 = left_in(wv[K - 1], rin + 8u * (kSeg - 1 - it), lane, f2);
-        rc_frame<K>(wv, tp, cur, in1, h2, ar + (uint32_t)it * G::ROWB, G::EXTB);
+        const p2 bv = bvn;
+        if (it > 0) { nx = load_prow<K>(ta, it - 1); bvn = lds64(rin + 8u * (kSeg - it)); }
+        const p2 in1 = left_in_reg(wv[K - 1], bv, lane, f2);
+        rc_frame<K>(wv, tp, cur, in1, h2, ar + (uint32_t)it * G::ROWB, G::EXTB, G::PLANEB);
         if (lane == 31) sts64(rout + 8u * (kSeg - it), wv[K - 1]);
       }
     } else {
@@ -957,7 +1056,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
 #pragma unroll
         for (int i = 0; i < K; ++i) old[i] = wv[i];
         const p2 in1 = left_in(wv[K - 1], rin + 8u * (uint32_t)(nfr - 1 - it), lane, f2);
-        rc_frame<K>(wv, tp, cur, in1, h2, ar + (uint32_t)it * G::ROWB, G::EXTB);
+        rc_frame<K>(wv, tp, cur, in1, h2, ar + (uint32_t)it * G::ROWB, G::EXTB, G::PLANEB);
         const bool kx = it < rx, ky = it < ry;
 #pragma unroll
         for (int i = 0; i < K; ++i) wv[i] = pk(kx ? lo(wv[i]) : lo(old[i]), ky ? hi(wv[i]) : hi(old[i]));
@@ -978,7 +1077,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
           const p2 a2 = (i >= 2) ? wv[i - 2] : in1;
           sx = fma2(tp.skipm[i >> 1], a2, sx);
         }
-        if (i == K - 1) acc = fma2(mul2(sx, h2), lds64(bb - 16u), acc);
+        if (i == K - 1) acc = fma2(mul2(sx, h2), lds64(bb - 8u), acc);
         else acc = fma2(sx, lds64(bb + 8u * (K - 2 - i)), acc);
       }
       const float t0 = warp_sum(lo(acc)), t1 = warp_sum(hi(acc));
@@ -992,8 +1091,13 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
       if (w < W - 1) bar_arrive(sm.bars, kBarRFull + (w + 1) * kRD + slot);
       if (w > 0) bar_arrive(sm.bars, kBarREmpty + w * kRD + slot);
     }
-    ptile_release(sm, cx, kt, 1);
+    ptile_release(sm, cx, pr, 1);
   }
+  PROF_MARK(0);
+#ifdef WFST_PROFILE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("RC%d cycles: work %lld wait_afull %lld wait_ring %lld wait_ptile %lld\n", w, pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3]);
+#endif
   bad = __reduce_or_sync(kFull, (unsigned)bad);
   if (bad && lane == 0) atomicOr(&a.hazard[cx.b], bad);
 }
@@ -1003,28 +1107,79 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
 // Lane = class (classes beyond 32 in further rounds); entry i of a round holds, per lane, the
 // row offset of the i-th occurrence of the lane's class (or of a zero pad).
 // ---------------------------------------------------------------------------
+constexpr int kRegList = 16;   // entries of a class list the reduction keeps in registers
+
 template <int K, int W>
 __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const Ctx& cx, const int c) {
   using G = Geo<K, W>;
   const int lane = cx.lane, nsd = cx.nsd, T = cx.T, C = cx.C, NAB = cx.NAB;
+  const int rounds = (C + 31) >> 5;
+  const int* rinfo = sm.hist + C;   // per round {nmax, base}
+  // One round of classes: the lane's list of row offsets lives in registers, ordered (while
+  // phase 1 runs) so that, slot by slot, the lanes of the warp read distinct banks: every slot
+  // each lane proposes one of its next three entries, the lowest lane wins a contested bank.
+  const int nmax0 = rinfo[0];
+  bool reg_lists = rounds == 1;
+  uint32_t offs[kRegList];
+  int nslots = 0;
+  if (reg_lists) {
+    const uint32_t tb = sm.xtab + 2u * (uint32_t)(c * kMaxList * 32 + lane);   // entry k at tb + 64 k
+    const int n = lane < C ? sm.hist[lane] : 0;
+    int done = 0;
+#pragma unroll
+    for (int sl = 0; sl < kRegList; ++sl) {
+      uint32_t taken = 0u, mine = 0xffffu;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int k = done + t;
+        const bool cand = mine == 0xffffu && k < n;
+        const uint32_t off = cand ? lds_u16(tb + 64u * (uint32_t)k) : 0u;
+        const uint32_t bank = (off >> 2) & 31u;
+        const bool okb = cand && !((taken >> bank) & 1u);
+        const unsigned peers = __match_any_sync(kFull, okb ? bank : 32u + (uint32_t)lane);
+        const bool win = okb && (__ffs(peers) - 1) == lane;
+        if (win) {
+          mine = off;
+          if (t > 0) {   // keep the entries still to be placed contiguous
+            const uint32_t first = lds_u16(tb + 64u * (uint32_t)done);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(tb + 64u * (uint32_t)k), "h"((unsigned short)first) : "memory");
+          }
+        }
+        taken |= __reduce_or_sync(kFull, win ? (1u << bank) : 0u);
+      }
+      if (mine != 0xffffu) ++done;
+      offs[sl] = mine;
+      if (__any_sync(kFull, mine != 0xffffu)) nslots = sl + 1;
+    }
+    reg_lists = __all_sync(kFull, done == n);   // else: the table (a permutation of itself) is walked from shared memory
+  } else {
+#pragma unroll
+    for (int i = 0; i < kRegList; ++i) offs[i] = 0xffffu;
+  }
+  (void)nmax0;
   bar_wait(sm.bars, kBarZ, 0u);
   const bool ok = lds(sm.zx + 8u) != 0.f;
   if (!cx.want_grad || !ok) return;
   const uint32_t rawsz = cx.rawsz;
   const float Zm = lds(sm.zx);
   const float kappa = -(a.grad_scale ? a.grad_scale[cx.b] : 1.f) / Zm;
-  const int rounds = (C + 31) >> 5;
-  const int* rinfo = sm.hist + C;   // per round {nmax, base}
+  const bool has_partial = nsd > cx.nfull;
   int bad = 0;
   float* gE = a.gradE + (size_t)cx.b * T * C;
-  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, buf = (buf + 1 == NAB) ? 0 : buf + 1) {
-    const int kt = nsd + k2;
-    int lo_, rows;
-    comp_seg(cx, c, kt, lo_, rows);
+  PROF_DECL;
+  uint32_t rpar = 0u;
+  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, rpar ^= (buf + 1 == NAB), buf = (buf + 1 == NAB) ? 0 : buf + 1) {
+    // component c works through the other direction's steps, the partial one first
+    const int kk = nsd - 1 - k2;
+    const int rows = (has_partial && k2 == 0) ? (c == 0 ? cx.r1 : cx.r0) : kSeg;
+    const int lo_ = seg_lo(cx, 1 - c, kk);
     const int ob = k2 & 1;
-    bar_wait(sm.bars, kBarXFull + buf, (uint32_t)(k2 / NAB) & 1u);
+    PROF_MARK(0);
+    bar_wait(sm.bars, kBarXFull + buf, rpar);
+    PROF_MARK(1);
     {
       float tot = 0.f;
+#pragma unroll
       for (int i = 0; i < W; ++i) {
         const p2 t = lds64(sm.cert + 8u * (uint32_t)(buf * W + i));
         tot += c ? hi(t) : lo(t);
@@ -1033,37 +1188,65 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
     }
     if (lane == 0) bulk_wait_read<1>();   // the store that last read this out buffer is done
     __syncwarp();
-    const uint32_t ab = sm.abuf + (uint32_t)(buf * kSeg) * G::ROWB + 4u * (uint32_t)c;
+    const uint32_t ab = sm.abuf + (uint32_t)(buf * kSeg) * G::ROWB + (uint32_t)c * G::PLANEB;
     const uint32_t ot = sm.out + 4u * (uint32_t)((c * 2 + ob) * rawsz);
     // buffer row j holds the frame of step j: frame row r = j (c = 0) or rows-1-j (c = 1)
     const int rsign = c == 0 ? 1 : -1, rbase = c == 0 ? 0 : rows - 1;
     float rs[kSeg];     // per-row sum of the label posteriors of this lane's classes
+    if (reg_lists) {
 #pragma unroll
-    for (int j = 0; j < kSeg; ++j) rs[j] = 0.f;
-    for (int r = 0; r < rounds; ++r) {
-      const int nmax = rinfo[2 * r], base = rinfo[2 * r + 1];
-      const int cls = 32 * r + lane;
-      float acc[kSeg];
+      for (int j = 0; j < kSeg; ++j) rs[j] = 0.f;
 #pragma unroll
-      for (int j = 0; j < kSeg; ++j) acc[j] = 0.f;
-      uint32_t xt = sm.xtab + 2u * (uint32_t)((c * kMaxList + base) * 32 + lane);
-#pragma unroll 2
-      for (int i = 0; i < nmax; ++i, xt += 64u) {
-        const uint32_t o = ab + lds_u16(xt);
+      for (int i0 = 0; i0 < kRegList; i0 += 4) {
+        if (i0 < nslots) {   // warp-uniform; lanes without an entry in a slot read the zero word in front of the plane
+          float t[4][kSeg];
 #pragma unroll
-        for (int j = 0; j < kSeg; ++j) acc[j] += lds(o + (uint32_t)j * G::ROWB);   // rows >= `rows` hold finite stale data; never stored
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t o = ab + (offs[i0 + i] != 0xffffu ? offs[i0 + i] : 0u);
+#pragma unroll
+            for (int j = 0; j < kSeg; ++j) t[i][j] = lds(o + (uint32_t)j * G::ROWB);   // rows >= `rows` hold finite stale data; never stored
+          }
+#pragma unroll
+          for (int j = 0; j < kSeg; ++j) rs[j] += (t[0][j] + t[1][j]) + (t[2][j] + t[3][j]);
+        }
       }
-      if (cls < C && cls != a.blank) {
-        uint32_t dsto = ot + 4u * (uint32_t)(cls + rbase * C);
+      if (lane < C && lane != a.blank) {
+        uint32_t dsto = ot + 4u * (uint32_t)(lane + rbase * C);
         const int32_t dstep = 4 * rsign * C;
 #pragma unroll
         for (int j = 0; j < kSeg; ++j) {
-          if (j < rows) sts(dsto, acc[j] * kappa);
+          if (j < rows) sts(dsto, rs[j] * kappa);
           dsto += dstep;
         }
       }
+    } else {
 #pragma unroll
-      for (int j = 0; j < kSeg; ++j) rs[j] += acc[j];
+      for (int j = 0; j < kSeg; ++j) rs[j] = 0.f;
+      for (int r = 0; r < rounds; ++r) {
+        const int nmax = rinfo[2 * r], base = rinfo[2 * r + 1];
+        const int cls = 32 * r + lane;
+        float acc[kSeg];
+#pragma unroll
+        for (int j = 0; j < kSeg; ++j) acc[j] = 0.f;
+        uint32_t xt = sm.xtab + 2u * (uint32_t)((c * kMaxList + base) * 32 + lane);
+#pragma unroll 2
+        for (int i = 0; i < nmax; ++i, xt += 64u) {
+          const uint32_t o = ab + lds_u16(xt);
+#pragma unroll
+          for (int j = 0; j < kSeg; ++j) acc[j] += lds(o + (uint32_t)j * G::ROWB);
+        }
+        if (cls < C && cls != a.blank) {
+          uint32_t dsto = ot + 4u * (uint32_t)(cls + rbase * C);
+          const int32_t dstep = 4 * rsign * C;
+#pragma unroll
+          for (int j = 0; j < kSeg; ++j) {
+            if (j < rows) sts(dsto, acc[j] * kappa);
+            dsto += dstep;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kSeg; ++j) rs[j] += acc[j];
+      }
     }
     // blank posterior of a frame = Zm - (sum of its label posteriors): the posteriors of a frame
     // sum to Zm, which the recompute warps certify at every step boundary.  Transposed
@@ -1113,6 +1296,10 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
     if (lane == 0) bulk_commit();   // one group per step (possibly empty)
     __syncwarp();
   }
+  PROF_MARK(0);
+#ifdef WFST_PROFILE
+  if (blockIdx.x == 0 && lane == 0) printf("X%d cycles: work %lld wait_xfull %lld\n", c, pf_acc[0], pf_acc[1]);
+#endif
   if (lane == 0) bulk_wait_all<0>();
   bad = __reduce_or_sync(kFull, (unsigned)bad);
   if (bad && lane == 0) atomicOr(&a.hazard[cx.b], 8);
@@ -1124,6 +1311,9 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
 template <int K, int W>
 __global__ void __launch_bounds__(Geo<K, W>::NT, (W <= 2 ? 2 : 1)) ctc_chain_kernel(Args a) {
   extern __shared__ __align__(16) float smem_raw[];
+#ifdef WFST_PROFILE
+  const long long pf_setup0 = clock64();
+#endif
   using G = Geo<K, W>;
   constexpr int NT = G::NT;
   const int warp = threadIdx.x >> 5;
@@ -1195,12 +1385,10 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (W <= 2 ? 2 : 1)) ctc_chain_ker
     if (2 * cx.L + 1 > G::Sp - 1) flag = 1;
   }
   if (!flag) {
-    // per-class counts (deterministic: one thread per class walks the target)
-    for (int cc = threadIdx.x; cc < C; cc += NT) {
-      int cnt = 0;
-      for (int n = 0; n < cx.L; ++n) cnt += (sm.ytab[n] == cc);
-      sm.hist[cc] = cnt;
-    }
+    // per-class counts (integer atomics: order independent)
+    for (int cc = threadIdx.x; cc < C + 16; cc += NT) sm.hist[cc] = 0;
+    __syncthreads();
+    for (int n = threadIdx.x; n < cx.L; n += NT) atomicAdd(&sm.hist[sm.ytab[n]], 1);
     __syncthreads();
     const int rounds = (C + 31) >> 5;
     if (warp == 0) {
@@ -1217,24 +1405,26 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (W <= 2 ? 2 : 1)) ctc_chain_ker
     // tables the reduction cannot hold go to the log-semiring kernel (reason 16)
     if (sm.hist[C + 2 * rounds] > kMaxList) flag = 16;
     if (!flag) {
+      // position n becomes entry (number of earlier positions with the same label) of its class:
+      // a deterministic order, so the sums of the reduction do not depend on scheduling
+      for (int n = threadIdx.x; n < cx.L; n += NT) {
+        const int cc = sm.ytab[n];
+        int rank = 0;
+#pragma unroll 4
+        for (int m = 0; m < n; ++m) rank += (sm.ytab[m] == cc);
+        const int base = sm.hist[C + 2 * (cc >> 5) + 1], ln = cc & 31;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const int j = d == 0 ? 2 * n + 1 : G::Sp - 3 - 2 * n;
+          const int off = 4 * (G::PADA + (j / K) * G::SA + (j % K) / 2);
+          sm.xtab_gen[(d * kMaxList + base + rank) * 32 + ln] = (unsigned short)off;
+        }
+      }
       for (int cc = threadIdx.x; cc < 32 * rounds; cc += NT) {
         const int r = cc >> 5, ln = cc & 31;
         const int nm = sm.hist[C + 2 * r], base = sm.hist[C + 2 * r + 1];
-        int i = 0;
-        if (cc < C) {
-          for (int n = 0; n < cx.L; ++n) {
-            if (sm.ytab[n] != cc) continue;
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-              const int j = d == 0 ? 2 * n + 1 : G::Sp - 3 - 2 * n;
-              const int off = 8 * (G::PADA + (j / K) * G::SA + (j % K) / 2);
-              sm.xtab_gen[(d * kMaxList + base + i) * 32 + ln] = (unsigned short)off;
-            }
-            ++i;
-          }
-        }
-        for (; i < nm; ++i) {
-          sm.xtab_gen[(base + i) * 32 + ln] = 0;                 // pair 0 of a row is always zero
+        for (int i = cc < C ? sm.hist[cc] : 0; i < nm; ++i) {
+          sm.xtab_gen[(base + i) * 32 + ln] = 0;                 // word 0 of a plane is always zero
           sm.xtab_gen[(kMaxList + base + i) * 32 + ln] = 0;
         }
       }
@@ -1243,6 +1433,9 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (W <= 2 ? 2 : 1)) ctc_chain_ker
   if (flag && threadIdx.x == 0) atomicOr(&a.hazard[cx.b], flag);
   __syncthreads();
   if (flag) return;
+#ifdef WFST_PROFILE
+  if (blockIdx.x == 0 && threadIdx.x == 0) printf("setup cycles: %lld\n", clock64() - pf_setup0);
+#endif
 
   // warp -> scheduler partition is warp % 4
   if (warp < W) role_live<K, W>(a, sm, cx, warp);
@@ -1280,8 +1473,9 @@ static bool pick_bufs(int C, int& NAB, int& NB, size_t& bytes) {
   const size_t two = (size_t)(113 * 1024), one = (size_t)(227 * 1024);
   for (int pass = 0; pass < 2; ++pass) {
     const size_t lim = (pass == 0 && W <= 2) ? two : one;
-    for (int nab = nab_want; nab >= (pass == 0 ? nab_want - 1 : 3); --nab) {
-      for (int nb = nb_want; nb >= (pass == 0 ? nb_want - 1 : W + 2); --nb) {
+    const int nab_min = pass == 0 ? nab_want - 1 : 3, nb_min = pass == 0 ? nb_want - 2 : W + 2;
+    for (int nab = nab_want; nab >= nab_min; --nab) {
+      for (int nb = nb_want; nb >= nb_min; --nb) {
         const size_t b = make_layout<kK, W>(C, nab, nb).total * sizeof(float);
         if (b <= lim) { NAB = nab; NB = nb; bytes = b; return true; }
       }

@@ -967,6 +967,70 @@ int32_t wfst_graph_viterbi_path(int32_t h) {
   return put(std::move(out));
 }
 
+// Shortest distance of an acyclic graph from its start to its accept nodes, and its gradient
+// with respect to the arc weights: gtn.forward_score (log semiring; the gradient is the arc
+// posterior) or gtn.viterbi_score (tropical != 0; the gradient marks the arcs of the best path,
+// ties as in viterbi_path), followed by gtn.backward of the scalar.  Host graphs only: this is
+// the graph-building API's scoring (tests, small graphs), not the batched GPU path.
+// arc_grad may be null; otherwise num_arcs floats.
+int wfst_graph_score(int32_t h, int tropical, float* score, float* arc_grad) {
+  GRAPH_OR_FAIL(g, h);
+  if (!score) { set_error("null score pointer"); return WFST_ERR_INVALID; }
+  const int N = g->num_nodes(), A = g->num_arcs();
+  const double NEG = -INFINITY;
+  std::vector<double> alpha(N, NEG);
+  std::vector<int32_t> deg(N), order, best(N, -1);
+  order.reserve(N);
+  for (int n = 0; n < N; ++n) { deg[n] = (int)g->in[n].size(); if (!deg[n]) order.push_back(n); }
+  auto lse = [](double a, double b) {
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    const double m = a > b ? a : b;
+    return m + std::log(std::exp(a - m) + std::exp(b - m));
+  };
+  for (size_t k = 0; k < order.size(); ++k) {
+    const int n = order[k];
+    double m = (g->flags[n] & 1) ? 0.0 : NEG;
+    if (tropical) {
+      for (int32_t a : g->in[n]) {
+        const double v = alpha[g->src[a]] + (double)g->w[a];
+        if (v > m) { m = v; best[n] = a; }
+      }
+    } else {
+      for (int32_t a : g->in[n]) m = lse(m, alpha[g->src[a]] + (double)g->w[a]);
+    }
+    alpha[n] = m;
+    for (int32_t a : g->out[n]) if (--deg[g->dst[a]] == 0) order.push_back(g->dst[a]);
+  }
+  if ((int)order.size() != N) { set_error("score: graph has a cycle"); return WFST_ERR_INVALID; }
+  double z = NEG;
+  int end = -1;
+  for (int n : g->accepts) {
+    if (tropical) { if (alpha[n] > z) { z = alpha[n]; end = n; } }
+    else z = lse(z, alpha[n]);
+  }
+  *score = (float)z;
+  if (!arc_grad) return WFST_OK;
+  for (int a = 0; a < A; ++a) arc_grad[a] = 0.f;
+  if (z == NEG) return WFST_OK;
+  if (tropical) {
+    for (int n = end; n >= 0 && best[n] >= 0; n = g->src[best[n]]) arc_grad[best[n]] = 1.f;
+    return WFST_OK;
+  }
+  std::vector<double> beta(N, NEG);
+  for (int k = N - 1; k >= 0; --k) {
+    const int n = order[k];
+    double m = (g->flags[n] & 2) ? 0.0 : NEG;
+    for (int32_t a : g->out[n]) m = lse(m, (double)g->w[a] + beta[g->dst[a]]);
+    beta[n] = m;
+  }
+  for (int a = 0; a < A; ++a) {
+    const double v = alpha[g->src[a]] + (double)g->w[a] + beta[g->dst[a]] - z;
+    arc_grad[a] = v == NEG ? 0.f : (float)std::exp(v);
+  }
+  return WFST_OK;
+}
+
 // Alignment -> token sequence for a batch of best alignments (Transducer.viterbi,
 // criterions/transducer.py:223-233): per utterance a chain of the T frame labels is composed
 // with the token graph, the best path taken, projected on its output labels and epsilons

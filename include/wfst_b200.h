@@ -285,6 +285,13 @@ WFST_API int wfst_asg_viterbi(const float* emissions, const float* transitions, 
  * best path, first maximum in in-list order on ties (GTN's traversal order). */
 WFST_API int32_t wfst_graph_viterbi_path(int32_t graph);
 
+/* Host-side scoring of an acyclic graph: gtn.forward_score (tropical = 0) or gtn.viterbi_score
+ * (tropical != 0) and, if arc_grad != NULL (num_arcs floats), the gradient gtn.backward would
+ * leave on its arcs (arc posteriors / indicator of the best path).  This serves the
+ * graph-building API (the reference's tests build expected values this way,
+ * tests/transducer_test.py:218-273); batched scoring of emissions runs on the GPU. */
+WFST_API int wfst_graph_score(int32_t graph, int tropical, float* score, float* arc_grad);
+
 /* Multiplies x[0..n) in place by *scale (a device scalar); returns immediately on
  * the device when *scale == 1 (the common loss.backward() case), so autograd's
  * grad_output costs no pass over the [B,T,C] gradient (ctc.py:87, asg.py:174). */

@@ -86,6 +86,15 @@ static int ctc_scaled_kind(int T, int C, int max_target_len) {
   if (ctc_fast_eligible(T, C, max_target_len)) return 1;
   return 0;
 }
+// alpha history: the float32 lattice kernels' [B, T+1, S] or, larger, the float64 fallback's [B, T, S]
+static size_t ctc_hist_bytes(int B, int T, int C, int max_target_len) {
+  size_t n = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1);
+  if (ctc_exact_eligible(T, C, max_target_len)) {
+    const size_t m = ctc_exact_hist_bytes(B, T, max_target_len);
+    if (m > n) n = m;
+  }
+  return n;
+}
 static size_t ctc_scaled_workspace_bytes(int B, int T, int C, int max_target_len) {
   size_t n = 0;
   if (ctc_chain_eligible(T, C, max_target_len)) n = ctc_chain_workspace_bytes(B, T, max_target_len);
@@ -101,7 +110,7 @@ static size_t ctc_scaled_workspace_bytes(int B, int T, int C, int max_target_len
 }
 // workspace: [alpha history of the log-semiring kernel][scores B][fast-path checkpoints + hazard]
 size_t wfst_ctc_workspace_bytes(int B, int T, int C, int max_target_len) {
-  size_t n = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
+  size_t n = ctc_hist_bytes(B, T, C, max_target_len) + align_up((size_t)B * sizeof(float), 256);
   n += ctc_scaled_workspace_bytes(B, T, C, max_target_len);
   return n;
 }
@@ -123,7 +132,7 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* hist = (float*)workspace;
-  size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1);
+  size_t hb = ctc_hist_bytes(B, T, C, max_target_len);
   float* z = (float*)((char*)workspace + hb);
   int rc;
   const int kind = ctc_scaled_kind(T, C, max_target_len);
@@ -138,8 +147,12 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
                      : launch_ctc_fast(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
                                        grad_scale, z, grad, fws, &hazard, st);
     if (rc != WFST_OK) return rc;
-    rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
-                    z, grad, hist, hazard, st);
+    // flagged utterances: float64 log-semiring kernel (the float32 one beyond its limits)
+    rc = ctc_exact_eligible(T, C, max_target_len)
+             ? launch_ctc_exact(emissions, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
+                                z, grad, hist, hazard, st)
+             : launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
+                          z, grad, hist, hazard, st);
   } else {
     rc = launch_ctc(emissions, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale,
                     z, grad, hist, nullptr, st);
@@ -183,7 +196,7 @@ int wfst_ctc_logits_forward_backward(const float* logits, const int32_t* targets
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* hist = (float*)workspace;
-  const size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1);
+  const size_t hb = ctc_hist_bytes(B, T, C, max_target_len);
   float* z = (float*)((char*)workspace + hb);
   void* fws = (char*)workspace + hb + align_up((size_t)B * sizeof(float), 256);
   const size_t nE = align_up((size_t)B * T * C * sizeof(float), 256);
@@ -197,8 +210,11 @@ int wfst_ctc_logits_forward_backward(const float* logits, const int32_t* targets
   // log-semiring kernel on them, chain back to logits (blocks of unflagged utterances exit at once)
   rc = launch_lsm_rows(logits, hazard, B, T, C, lsm, st);
   if (rc != WFST_OK) return rc;
-  rc = launch_ctc(lsm, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale, z,
-                  grad ? glp : nullptr, hist, hazard, st);
+  rc = ctc_exact_eligible(T, C, max_target_len)
+           ? launch_ctc_exact(lsm, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale, z,
+                              grad ? glp : nullptr, hist, hazard, st)
+           : launch_ctc(lsm, targets, target_offsets, B, T, C, blank, max_target_len, grad_scale, z,
+                        grad ? glp : nullptr, hist, hazard, st);
   if (rc != WFST_OK) return rc;
   if (grad) {
     rc = launch_lsm_backward(lsm, glp, hazard, B, T, C, grad, st);
@@ -213,7 +229,7 @@ int wfst_debug_ctc_hazards(const void* workspace, int B, int T, int C, int max_t
   for (int b = 0; b < B; ++b) host_flags[b] = -1;
   const int kind = ctc_scaled_kind(T, C, max_target_len);
   if (kind == 0) return WFST_OK;
-  size_t hb = lattice_hist_bytes(B, T, C, 2 * max_target_len + 1) + align_up((size_t)B * sizeof(float), 256);
+  size_t hb = ctc_hist_bytes(B, T, C, max_target_len) + align_up((size_t)B * sizeof(float), 256);
   size_t fb = kind == 3 ? ctc_chain_workspace_bytes(B, T, max_target_len)
               : kind == 2 ? ctc_pair_workspace_bytes(B, T, max_target_len) : ctc_fast_workspace_bytes(B, T, max_target_len);
   const char* hz = (const char*)workspace + hb + fb - align_up((size_t)B * sizeof(int), 256);

@@ -72,7 +72,7 @@ constexpr int kMaxAB = 8;             // step buffers (abar / products), at most
 constexpr int kMaxNB = 12;            // p tiles, at most
 constexpr int kMaxList = 32;          // reduction table: sum over class rounds of the longest list
 constexpr int kMaxW = 4;
-constexpr int kRingEnt = 10;          // ring slot of a step: 9 boundary values + a header, 16 bytes each {lo, hi, tag, -}
+constexpr int kRingPairs = 10;        // ring entry: 9 boundary pairs + {e0, e1}
 
 struct Args {
   const float* E;
@@ -175,8 +175,10 @@ __device__ __forceinline__ float pow2c(int d) { return (d < -126) ? 0.f : pow2i(
 constexpr int kBarPFull = 0;                              // [kMaxNB]       p tile ready (P0 + P1 -> live, RC)
 constexpr int kBarPEmpty = kBarPFull + kMaxNB;            // [kMaxNB]       p tile released (count 2W)
 constexpr int kBarTma = kBarPEmpty + kMaxNB;              // [2][kNR]       raw tiles landed
-constexpr int kBarLEmpty = kBarTma + 2 * kNR;             // [kMaxW][kRD]   live chain ring slot consumed (w -> w-1)
-constexpr int kBarREmpty = kBarLEmpty + kMaxW * kRD;      // [kMaxW][kRD]   recompute chain ring slot consumed
+constexpr int kBarLFull = kBarTma + 2 * kNR;              // [kMaxW][kRD]   live chain ring entry written (w-1 -> w)
+constexpr int kBarLEmpty = kBarLFull + kMaxW * kRD;       // [kMaxW][kRD]   ... consumed
+constexpr int kBarRFull = kBarLEmpty + kMaxW * kRD;       // [kMaxW][kRD]   recompute chain ring
+constexpr int kBarREmpty = kBarRFull + kMaxW * kRD;
 constexpr int kBarAFull = kBarREmpty + kMaxW * kRD;       // [kMaxAB]       abar rows of a step stored (count W; live -> RC)
 constexpr int kBarXFull = kBarAFull + kMaxAB;             // [kMaxAB]       products ready (count W; RC -> X)
 constexpr int kBarAEmpty = kBarXFull + kMaxAB;            // [kMaxAB]       step buffer free (count 2; X -> live)
@@ -248,8 +250,8 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
   L.cert = p;   p += (size_t)NAB * W * 2;                           // [buf][w] (pair)
   L.ptile = p;  p += (size_t)NB * 2 * CP * 9 + 8;                   // [buf][d][col][9]
   p = (p + 3) & ~(size_t)3;
-  L.ringL = p;  p += (size_t)(W + 1) * kRD * kRingEnt * 4;          // [w][slot][entry]{lo, hi, tag, -}
-  L.ringR = p;  p += (size_t)(W + 1) * kRD * kRingEnt * 4;
+  L.ringL = p;  p += (size_t)(W + 1) * kRD * kRingPairs * 2;        // [w][slot]{9 boundary pairs, e0, e1}
+  L.ringR = p;  p += (size_t)(W + 1) * kRD * kRingPairs * 2;
   p = (p + 3) & ~(size_t)3;
   L.zero_end = p;
   L.bars = p;   p += 2 * kNumBars;
@@ -383,36 +385,18 @@ __device__ __forceinline__ void step(p2 (&v)[K], p2 (&abar)[K / 2], const Topo<K
 }
 
 // the left neighbour's last slot: by shuffle, lane 0 takes the value the previous warp of the
-// chain left in the ring (zero for the first warp)
+// chain left in the ring (zero for the first warp: its ring is never written)
+__device__ __forceinline__ p2 left_in(p2 last, uint32_t ring_addr, int lane, p2 f) {
+  p2 left = shfl_up2(last);
+  const p2 bv = lds64(ring_addr);
+  if (lane == 0) left = bv;
+  return mul2(left, f);
+}
+// same with the ring value already in a register
 __device__ __forceinline__ p2 left_in_reg(p2 last, p2 bv, int lane, p2 f) {
   p2 left = shfl_up2(last);
   if (lane == 0) left = bv;
   return mul2(left, f);
-}
-
-// Warp-to-warp chain ring.  The left warp of the chain leaves the value of its last slot after
-// every frame as one 16-byte entry {lo, hi, tag, -}; the tag names the (step, frame) it belongs to,
-// so the right warp follows ONE FRAME behind by polling the entry it needs (all lanes read the
-// same address; a 16-byte store of one lane is seen whole or not at all).  Slots are recycled
-// every kRD steps under an mbarrier the consumer arrives on.
-struct RingEnt {
-  uint32_t a, b, tag, pad;
-};
-__device__ __forceinline__ uint32_t ring_tag(int step, int i) { return ((uint32_t)step << 4) | (uint32_t)(i + 1); }
-__device__ __forceinline__ void ring_put(uint32_t addr, p2 v, uint32_t tag) {
-  asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(__float_as_uint(lo(v))),
-               "r"(__float_as_uint(hi(v))), "r"(tag), "r"(0u)
-               : "memory");
-}
-__device__ __forceinline__ RingEnt ring_peek(uint32_t addr) {
-  RingEnt q;
-  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.a), "=r"(q.b), "=r"(q.tag), "=r"(q.pad) : "r"(addr) : "memory");
-  return q;
-}
-// the entry peeked earlier, re-read until it carries the expected tag
-__device__ __forceinline__ p2 ring_take(RingEnt q, uint32_t addr, uint32_t tag) {
-  while (q.tag != tag) q = ring_peek(addr);
-  return pk(__uint_as_float(q.a), __uint_as_float(q.b));
 }
 
 // Event: renormalise the lane (max mantissa in [1,2)) and make the lane exponents
@@ -692,11 +676,9 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
 #pragma unroll
     for (int i = 0; i < K; ++i) v[i] = pk(x[0][i], x[1][i]);
   }
-  const uint32_t ring_in0 = sm.ringL + 16u * (uint32_t)(w * kRD * kRingEnt);
-  const uint32_t ring_out0 = sm.ringL + 16u * (uint32_t)((w + 1) * kRD * kRingEnt);
+  const uint32_t ring_in0 = sm.ringL + 8u * (uint32_t)(w * kRD * kRingPairs);
+  const uint32_t ring_out0 = sm.ringL + 8u * (uint32_t)((w + 1) * kRD * kRingPairs);
   uint32_t rin = ring_in0, rout = ring_out0;
-  int gcur = 0;          // the global step the ring addresses belong to
-  const bool has_left = w > 0;
   PRing pr;
   pr.init(0, cx.NB);
   const bool has_partial = nsd > cx.nfull;
@@ -705,18 +687,14 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   PROF_DECL;
   auto step_begin = [&](int g, bool ev) {
     const int slot = g % kRD;
-    gcur = g;
-    rin = ring_in0 + 16u * (uint32_t)(slot * kRingEnt);
-    rout = ring_out0 + 16u * (uint32_t)(slot * kRingEnt);
+    rin = ring_in0 + 8u * (uint32_t)(slot * kRingPairs);
+    rout = ring_out0 + 8u * (uint32_t)(slot * kRingPairs);
     PROF_MARK(0);
+    if (w > 0) bar_wait(sm.bars, kBarLFull + w * kRD + slot, (uint32_t)(g / kRD) & 1u);
+    PROF_MARK(1);
     if (ev) {
       int Ein[2] = {kUndef, kUndef};
-      if (has_left) {   // the left warp's exponents after ITS event of this step (header entry)
-        const p2 h = ring_take(ring_peek(rin + 16u * 9u), rin + 16u * 9u, ring_tag(g, 9));
-        Ein[0] = __float_as_int(lo(h));
-        Ein[1] = __float_as_int(hi(h));
-      }
-      PROF_MARK(1);
+      if (w > 0) { Ein[0] = ldsi(rin + 72u); Ein[1] = ldsi(rin + 76u); }
       event2<K>(v, e, f, lane, Ein);
     }
     PROF_MARK(2);
@@ -724,26 +702,19 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
       if (g >= kRD) bar_wait(sm.bars, kBarLEmpty + (w + 1) * kRD + slot, (uint32_t)(g / kRD - 1) & 1u);
       PROF_MARK(3);
       if (lane == 31) {
-        ring_put(rout + 16u * 9u, pk(__int_as_float(e[0]), __int_as_float(e[1])), ring_tag(g, 9));
-        ring_put(rout, v[K - 1], ring_tag(g, 0));
+        sts64(rout, v[K - 1]);
+        stsi(rout + 72u, e[0]);
+        stsi(rout + 76u, e[1]);
       }
     }
   };
   auto step_end = [&](int g) {
     const int slot = g % kRD;
     __syncwarp();
-    if (lane == 0 && has_left) bar_arrive(sm.bars, kBarLEmpty + w * kRD + slot);
-  };
-  // the left neighbour's last slot before frame `it` of the current step (zero for the first warp)
-  auto ring_in_peek = [&](int it) -> RingEnt {
-    RingEnt q;
-    q.a = 0u; q.b = 0u; q.tag = 0u; q.pad = 0u;
-    if (has_left) q = ring_peek(rin + 16u * (uint32_t)it);
-    return q;
-  };
-  auto ring_in_take = [&](RingEnt q, int it) -> p2 {
-    if (!has_left) return pk(0.f, 0.f);
-    return ring_take(q, rin + 16u * (uint32_t)it, ring_tag(gcur, it));
+    if (lane == 0) {
+      if (w < W - 1) bar_arrive(sm.bars, kBarLFull + (w + 1) * kRD + slot);
+      if (w > 0) bar_arrive(sm.bars, kBarLEmpty + w * kRD + slot);
+    }
   };
   // frames of a partial step: component c is frozen from frame rows_c on
   auto slow_frames = [&](const TileAddr<K>& ta, int rx, int ry, uint32_t ar, bool want_abar) {
@@ -754,7 +725,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
       p2 old[K];
 #pragma unroll
       for (int i = 0; i < K; ++i) old[i] = v[i];
-      const p2 in1 = left_in_reg(v[K - 1], ring_in_take(ring_in_peek(it), it), lane, f);
+      const p2 in1 = left_in(v[K - 1], rin + 8u * (uint32_t)it, lane, f);
       step<K, true>(v, abar, tp, cur, in1);
       const bool kx = it < rx, ky = it < ry;
 #pragma unroll
@@ -766,7 +737,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
           sts(ar + G::PLANEB + (uint32_t)it * G::ROWB + 4u * q, hi(abar[q]));
         }
       }
-      if (lane == 31) ring_put(rout + 16u * (uint32_t)(it + 1), v[K - 1], ring_tag(gcur, it + 1));
+      if (lane == 31) sts64(rout + 8u * (uint32_t)(it + 1), v[K - 1]);
     }
   };
 
@@ -780,15 +751,15 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     PROF_MARK(4);
     if (!partial) {
       PRow<K> nx = load_prow<K>(ta, 0);
-      RingEnt qn = ring_in_peek(0);
+      p2 bvn = lds64(rin);
 #pragma unroll
       for (int it = 0; it < kSeg; ++it) {
         const PRow<K> cur = nx;
-        const p2 bv = ring_in_take(qn, it);
-        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); qn = ring_in_peek(it + 1); }
+        const p2 bv = bvn;
+        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); bvn = lds64(rin + 8u * (it + 1)); }
         const p2 in1 = left_in_reg(v[K - 1], bv, lane, f);
         step<K, false>(v, abar, tp, cur, in1);
-        if (lane == 31) ring_put(rout + 16u * (it + 1), v[K - 1], ring_tag(gcur, it + 1));
+        if (lane == 31) sts64(rout + 8u * (it + 1), v[K - 1]);
       }
     } else {
       slow_frames(ta, cx.r0, cx.r1, 0u, false);
@@ -821,7 +792,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   {
     p2 bb[K];
     {
-      const p2 in1 = left_in_reg(v[K - 1], ring_in_take(ring_in_peek(0), 0), lane, f);
+      const p2 in1 = left_in(v[K - 1], rin, lane, f);
 #pragma unroll
       for (int i = K - 1; i >= 0; --i) {
         const p2 a1 = (i >= 1) ? v[i - 1] : in1;
@@ -910,12 +881,12 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     const uint32_t ar = sm.abuf + (uint32_t)(buf * kSeg) * G::ROWB + myabar;
     if (!partial) {
       PRow<K> nx = load_prow<K>(ta, 0);
-      RingEnt qn = ring_in_peek(0);
+      p2 bvn = lds64(rin);
 #pragma unroll
       for (int it = 0; it < kSeg; ++it) {
         const PRow<K> cur = nx;
-        const p2 bv = ring_in_take(qn, it);
-        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); qn = ring_in_peek(it + 1); }
+        const p2 bv = bvn;
+        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); bvn = lds64(rin + 8u * (it + 1)); }
         const p2 in1 = left_in_reg(v[K - 1], bv, lane, f);
         step<K, true>(v, abar, tp, cur, in1);
 #pragma unroll
@@ -923,7 +894,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
           sts(ar + (uint32_t)it * G::ROWB + 4u * q, lo(abar[q]));
           sts(ar + G::PLANEB + (uint32_t)it * G::ROWB + 4u * q, hi(abar[q]));
         }
-        if (lane == 31) ring_put(rout + 16u * (it + 1), v[K - 1], ring_tag(gcur, it + 1));
+        if (lane == 31) sts64(rout + 8u * (it + 1), v[K - 1]);
       }
     } else {
       slow_frames(ta, cx.r1, cx.r0, ar, true);
@@ -1008,9 +979,8 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   const int pl = NL - 1 - gl;
   const uint32_t pabar = 4u * (uint32_t)(G::PADA + pl * G::SA);   // partner block in a plane of an abar row
   const uint32_t pbnd = 8u * (uint32_t)(4 + pl * G::SB);          // partner block in a boundary row
-  const uint32_t ring_in0 = sm.ringR + 16u * (uint32_t)(w * kRD * kRingEnt);
-  const uint32_t ring_out0 = sm.ringR + 16u * (uint32_t)((w + 1) * kRD * kRingEnt);
-  const bool has_left = w > 0;
+  const uint32_t ring_in0 = sm.ringR + 8u * (uint32_t)(w * kRD * kRingPairs);
+  const uint32_t ring_out0 = sm.ringR + 8u * (uint32_t)((w + 1) * kRD * kRingPairs);
   int bad = 0;   // reason 4: scale overflow when pairing live and recomputed values
   p2 wv[K];
   int ew[2];
@@ -1022,19 +992,8 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   uint32_t rpar = 0u;   // (k2 / NAB) & 1
   for (int k2 = 0, buf = 0; k2 < nsd; ++k2, rpar ^= (buf + 1 == NAB), buf = (buf + 1 == NAB) ? 0 : buf + 1) {
     const int slot = k2 % kRD;
-    const uint32_t rin = ring_in0 + 16u * (uint32_t)(slot * kRingEnt);
-    const uint32_t rout = ring_out0 + 16u * (uint32_t)(slot * kRingEnt);
-    // the left neighbour's last slot before the i-th frame of this step (zero for the first warp)
-    auto ring_in_peek = [&](int i) -> RingEnt {
-      RingEnt q;
-      q.a = 0u; q.b = 0u; q.tag = 0u; q.pad = 0u;
-      if (has_left) q = ring_peek(rin + 16u * (uint32_t)i);
-      return q;
-    };
-    auto ring_in_take = [&](RingEnt q, int i) -> p2 {
-      if (!has_left) return pk(0.f, 0.f);
-      return ring_take(q, rin + 16u * (uint32_t)i, ring_tag(k2, i));
-    };
+    const uint32_t rin = ring_in0 + 8u * (uint32_t)(slot * kRingPairs);
+    const uint32_t rout = ring_out0 + 8u * (uint32_t)(slot * kRingPairs);
     const bool partial = has_partial && k2 == 0;
     const int rx = partial ? cx.r1 : kSeg, ry = partial ? cx.r0 : kSeg;
     PROF_MARK(0);
@@ -1067,9 +1026,10 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     const p2 f2 = pk(frs[0], frs[1]), h2 = pk(hsc[0], hsc[1]);
     // chain ring: my left neighbour's entry of this step; open my own
     PROF_MARK(0);
+    if (w > 0) bar_wait(sm.bars, kBarRFull + w * kRD + slot, (uint32_t)(k2 / kRD) & 1u);
     if (w < W - 1) {
       if (k2 >= kRD) bar_wait(sm.bars, kBarREmpty + (w + 1) * kRD + slot, (uint32_t)(k2 / kRD - 1) & 1u);
-      if (lane == 31) ring_put(rout, wv[K - 1], ring_tag(k2, 0));
+      if (lane == 31) sts64(rout, wv[K - 1]);
     }
     PROF_MARK(2);
     const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, pr));
@@ -1079,15 +1039,15 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     if (!partial) {
       // against the live step order
       PRow<K> nx = load_prow<K>(ta, kSeg - 1);
-      RingEnt qn = ring_in_peek(0);
+      p2 bvn = lds64(rin);
 #pragma unroll
       for (int it = kSeg - 1; it >= 0; --it) {
         const PRow<K> cur = nx;
-        const p2 bv = ring_in_take(qn, kSeg - 1 - it);
-        if (it > 0) { nx = load_prow<K>(ta, it - 1); qn = ring_in_peek(kSeg - it); }
+        const p2 bv = bvn;
+        if (it > 0) { nx = load_prow<K>(ta, it - 1); bvn = lds64(rin + 8u * (kSeg - it)); }
         const p2 in1 = left_in_reg(wv[K - 1], bv, lane, f2);
         rc_frame<K>(wv, tp, cur, in1, h2, ar + (uint32_t)it * G::ROWB, G::EXTB, G::PLANEB);
-        if (lane == 31) ring_put(rout + 16u * (kSeg - it), wv[K - 1], ring_tag(k2, kSeg - it));
+        if (lane == 31) sts64(rout + 8u * (kSeg - it), wv[K - 1]);
       }
     } else {
 #pragma unroll 1
@@ -1096,18 +1056,18 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
         p2 old[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) old[i] = wv[i];
-        const p2 in1 = left_in_reg(wv[K - 1], ring_in_take(ring_in_peek(nfr - 1 - it), nfr - 1 - it), lane, f2);
+        const p2 in1 = left_in(wv[K - 1], rin + 8u * (uint32_t)(nfr - 1 - it), lane, f2);
         rc_frame<K>(wv, tp, cur, in1, h2, ar + (uint32_t)it * G::ROWB, G::EXTB, G::PLANEB);
         const bool kx = it < rx, ky = it < ry;
 #pragma unroll
         for (int i = 0; i < K; ++i) wv[i] = pk(kx ? lo(wv[i]) : lo(old[i]), ky ? hi(wv[i]) : hi(old[i]));
-        if (lane == 31) ring_put(rout + 16u * (uint32_t)(nfr - it), wv[K - 1], ring_tag(k2, nfr - it));
+        if (lane == 31) sts64(rout + 8u * (uint32_t)(nfr - it), wv[K - 1]);
       }
     }
     {
       // certificate: sum_s v_live(s) * (successor sum of w)(s) at the step boundary must be Z
       // (float32 range can only be exceeded by losing mass or producing inf / NaN)
-      const p2 in1 = left_in_reg(wv[K - 1], ring_in_take(ring_in_peek(nfr), nfr), lane, f2);
+      const p2 in1 = left_in(wv[K - 1], rin + 8u * (uint32_t)nfr, lane, f2);
       const uint32_t bb = sm.bnd + (uint32_t)buf * G::BNDB + pbnd;
       p2 acc = pk(0.f, 0.f);
 #pragma unroll
@@ -1129,7 +1089,8 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     __syncwarp();
     if (lane == 0) {
       bar_arrive(sm.bars, kBarXFull + buf);
-      if (has_left) bar_arrive(sm.bars, kBarREmpty + w * kRD + slot);
+      if (w < W - 1) bar_arrive(sm.bars, kBarRFull + (w + 1) * kRD + slot);
+      if (w > 0) bar_arrive(sm.bars, kBarREmpty + w * kRD + slot);
     }
     ptile_release(sm, cx, pr, 1);
   }
@@ -1180,9 +1141,10 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
         const bool win = okb && (__ffs(peers) - 1) == lane;
         if (win) {
           mine = off;
-          if (t > 0) {   // keep the entries still to be placed contiguous
+          if (t > 0) {   // swap it with the first entry still to be placed: those stay contiguous, the table a permutation
             const uint32_t first = lds_u16(tb + 64u * (uint32_t)done);
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(tb + 64u * (uint32_t)k), "h"((unsigned short)first) : "memory");
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(tb + 64u * (uint32_t)done), "h"((unsigned short)off) : "memory");
           }
         }
         taken |= __reduce_or_sync(kFull, win ? (1u << bank) : 0u);
@@ -1488,8 +1450,11 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 384 ? 2 : 1))
 // (slots per lane, warps per chain) by target length: short per-frame work per warp first
 struct Cfg {
   int K, W;
+  bool automatic;   // false: only when forced (WFST_CHAIN_CFG)
 };
-static const Cfg kCfgs[] = {{4, 1}, {4, 2}, {4, 3}, {4, 4}, {6, 3}, {6, 4}, {6, 2}};
+// the chain warps are skewed by a whole step, so few warps with more slots win once the chain
+// needs more than two warps
+static const Cfg kCfgs[] = {{4, 1, true}, {4, 2, true}, {4, 3, false}, {4, 4, false}, {6, 3, true}, {6, 4, true}, {6, 2, true}};
 constexpr int kNumCfgs = (int)(sizeof(kCfgs) / sizeof(kCfgs[0]));
 
 // test / tuning hook: WFST_CHAIN_CFG="K,W" forces a configuration for targets it can hold
@@ -1510,8 +1475,9 @@ static int pick_cfg(int max_target_len) {
   int first = -1;
   for (int i = 0; i < kNumCfgs; ++i) {
     if (32 * kCfgs[i].K * kCfgs[i].W - 1 < S) continue;
-    if (first < 0) first = i;
     if (kCfgs[i].K == g_force_k && kCfgs[i].W == g_force_w) return i;
+    if (!kCfgs[i].automatic) continue;
+    if (first < 0 || 32 * kCfgs[i].K * kCfgs[i].W < 32 * kCfgs[first].K * kCfgs[first].W) first = i;   // smallest chain that holds the target
   }
   return first;
 }
@@ -1520,11 +1486,11 @@ template <int K, int W>
 static bool pick_bufs(int C, int& NAB, int& NB, size_t& bytes) {
   // step buffers for the live -> recompute -> reduce pipeline and p tiles for live + recompute;
   // two blocks per SM when that fits, else what fits in one
-  const int nab_want = 5, nb_want = 7;
+  const int nab_want = min(2 * W + 1, kMaxAB), nb_want = min(2 * W + 3, kMaxNB);
   const size_t two = (size_t)(113 * 1024), one = (size_t)(227 * 1024);
   for (int pass = 0; pass < 2; ++pass) {
     const size_t lim = pass == 0 ? two : one;
-    const int nab_min = pass == 0 ? 4 : 3, nb_min = pass == 0 ? 5 : 4;
+    const int nab_min = pass == 0 ? max(nab_want - 1, 3) : 3, nb_min = pass == 0 ? max(nb_want - 2, 4) : 4;
     for (int nab = nab_want; nab >= nab_min; --nab) {
       for (int nb = nb_want; nb >= nb_min; --nb) {
         const size_t b = make_layout<K, W>(C, nab, nb).total * sizeof(float);

@@ -58,6 +58,12 @@ size_t ctc_chain_workspace_bytes(int B, int T, int max_target_len);
 int launch_ctc_chain(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                      int blank, int max_target_len, const float* grad_scale, float* z_out,
                      float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
+// float64 log-semiring CTC (ctc_exact.cu): recomputes the utterances the scaled kernels flag
+bool ctc_exact_eligible(int T, int C, int max_target_len);
+size_t ctc_exact_hist_bytes(int B, int T, int max_target_len);
+int launch_ctc_exact(const float* E, const int* targets, const int* offsets, int B, int T, int C,
+                     int blank, int max_target_len, const float* grad_scale, float* scores,
+                     float* gradE, void* hist, const int* active, cudaStream_t st);
 // log_softmax rows / its backward for the utterances with active[b] != 0 (lsm.cu): the
 // fallback of the fused mode
 int launch_lsm_rows(const float* x, const int* active, int B, int T, int C, float* out, cudaStream_t st);

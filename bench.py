@@ -544,6 +544,39 @@ def run_gpu(args):
         flagged += int((fl > 0).sum())
     fallback_rate = flagged / float(ROT * B)
 
+    # ---- steep emissions: log_softmax(s * randn) with targets unrelated to the scores is outside
+    # float32's range for the scaled kernel at s >= 2; those utterances are recomputed by the
+    # float64 log-semiring kernel (ctc_exact.cu).  What that costs, reported beside the headline.
+    steep = None
+    if world == 1 and not args.no_comparators:
+        steep = {}
+        for sc in (2.0, 4.0):
+            g = torch.Generator(device="cpu").manual_seed(77)
+            lp_s = torch.log_softmax(torch.randn(B, T, C, generator=g).to(dev) * sc, 2).contiguous()
+            flat, off = batches[0][1], batches[0][2]
+
+            def steep_step():
+                _lib.check(L_.wfst_ctc_forward_backward(
+                    lp_s.data_ptr(), flat.data_ptr(), off.data_ptr(), B, T, C, C - 1, L, gscale.data_ptr(),
+                    out.data_ptr(), out[B:].data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), stream.cuda_stream))
+            for _ in range(3):
+                steep_step()
+            torch.cuda.synchronize(dev)
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(10):
+                steep_step()
+            b2.record(stream)
+            torch.cuda.synchronize(dev)
+            fl = np.zeros(B, dtype=np.int32)
+            _lib.check(L_.wfst_debug_ctc_hazards(ws.data_ptr(), B, T, C, L, fl.ctypes.data))
+            ms_s = a.elapsed_time(b2) / 10
+            steep["scale_%g" % sc] = {"ms_per_step": ms_s, "utterances_per_s": B / (ms_s * 1e-3),
+                                       "fallback_rate": float((fl > 0).mean())}
+            del lp_s
+        steep["what"] = ("wfst_ctc_forward_backward on log_softmax(scale * randn) emissions with unrelated targets "
+                         "(same B, T, C, L): scaled kernel + float64 fallback kernel for the flagged utterances; CUDA events")
+
     # ---- function path: the reference benchmark's own call (benchmarks/ctc_benchmark.py:23-29,
     # time_utils.py:11-21): device-resident emissions, targets as a Python list of lists,
     # CTCLoss(inputs, tgt, N - 1).backward(), 5 warm-ups, wall clock over the iterations with a
@@ -698,6 +731,8 @@ def run_gpu(args):
                     "path": "CTCLoss(emissions, targets).backward() with both copied pinned host -> cuda on a copy stream every step (two steps in flight); every step's loss copied to pinned host memory and read by the host one step later"},
             "gpu_launches": int(launches),
             "fallback_rate": fallback_rate,
+            "kernel": "ctc_chain_kernel (csrc/ctc_chain.cu): one block per utterance, both time directions packed in "
+                      "FP32 pairs, chain split over warps; flagged utterances -> ctc_exact_kernel (float64)",
             "function_path": {
                 "ms_per_step": fp_s * 1e3, "value": B * world / fp_s, "unit": "utterances/s", "iterations": fp_iters,
                 "what": "CTCLoss(inputs, list_of_lists, C-1).backward() exactly as benchmarks/ctc_benchmark.py:"
@@ -710,6 +745,8 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": kern_ms},
         }
+        if steep is not None:
+            line["steep_emissions"] = steep
         if torch_gpu is not None:
             line["torch_ctc_loss_gpu"] = torch_gpu
         if module_line is not None:

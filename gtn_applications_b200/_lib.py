@@ -37,6 +37,7 @@ SIGNATURES = {
     "wfst_abi_version": (_I, []),
     "wfst_launch_count": (ctypes.c_ulonglong, []),
     "wfst_debug_force_generic_ctc": (_I, [_I]),
+    "wfst_debug_ctc_chain_config": (_I, [_I, _I]),
     "wfst_debug_force_generic_lattice": (_I, [_I]),
     "wfst_asg_viterbi_supported": (_I, [_I, _I]),
     "wfst_asg_viterbi": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),

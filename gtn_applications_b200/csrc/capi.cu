@@ -52,6 +52,8 @@ static int g_force_generic = 0;
 static int g_force_generic_kind = 0;
 // test hook: 1 = skip the chain-split kernel (exercise the paired kernel)
 static int g_no_chain = 0;
+// test hook: 1 = chain-split kernel first, whatever else is eligible
+static int g_chain_first = 0;
 
 }  // namespace wfst
 
@@ -65,24 +67,29 @@ int wfst_debug_force_generic_ctc(int on) {
   // 0: default dispatch; 1: log-semiring kernel only; 2: no paired kernel;
   // 3: dense ASG full-connect kernel with one warp per utterance only (no two-warp split)
   // 4: no chain-split CTC kernel (paired / single-utterance kernels as before)
-  int old = g_force_generic ? 1 : (g_asg_dense_single ? 3 : (g_no_chain ? 4 : g_force_generic_kind));
+  // 5: chain-split CTC kernel first (default: paired kernel where it is eligible, chain-split otherwise)
+  int old = g_force_generic ? 1 : (g_asg_dense_single ? 3 : (g_chain_first ? 5 : (g_no_chain ? 4 : g_force_generic_kind)));
   g_force_generic = (on == 1);
   g_force_generic_kind = (on == 2) ? 2 : 0;
   g_no_chain = (on == 4 || on == 2);
+  g_chain_first = (on == 5);
   g_asg_dense_single = (on == 3);
   return old;
 }
 int wfst_debug_force_generic_lattice(int on) { return lattice_force_generic((on >= 1 && on <= 3) ? on : 0); }
 unsigned long long wfst_launch_count(void) { return g_launches.load(); }
+int wfst_debug_ctc_chain_config(int K, int W) { return ctc_chain_force_config(K, W); }
 
 // --------------------------------------------------------------------- CTC
-// scaled-probability kernels, in order of preference: chain-split (one utterance per block, both
-// time directions packed, chain split over warps), paired (two utterances per block), single
-// (larger targets), none (log-semiring kernel only)
+// scaled-probability kernels, in order of preference: paired (two utterances per block: 4 %
+// faster at cfg2 than the chain-split one, 0.213 vs 0.221 ms in bench.py), chain-split (one
+// utterance per block, both time directions packed, chain split over warps: everything the
+// paired layout cannot hold, e.g. cfg5), single (the rest), none (log-semiring kernels only)
 static int ctc_scaled_kind(int T, int C, int max_target_len) {
   if (g_force_generic) return 0;
-  if (!g_no_chain && ctc_chain_eligible(T, C, max_target_len)) return 3;
+  if (g_chain_first && ctc_chain_eligible(T, C, max_target_len)) return 3;
   if (g_force_generic_kind != 2 && ctc_pair_eligible(T, C, max_target_len)) return 2;
+  if (!g_no_chain && ctc_chain_eligible(T, C, max_target_len)) return 3;
   if (ctc_fast_eligible(T, C, max_target_len)) return 1;
   return 0;
 }

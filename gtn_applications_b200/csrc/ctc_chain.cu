@@ -68,9 +68,10 @@ constexpr int kUndef = -(1 << 19);    // "no exponent": lane holds only zeros
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNR = 3;                // raw (TMA) staging slots per producer warp
 constexpr int kRD = 4;                // depth of the warp-to-warp chain rings
+constexpr int kRS = 1;                // recompute warp sets: set r takes the steps k2 = r (mod kRS)
 constexpr int kMaxAB = 8;             // step buffers (abar / products), at most
 constexpr int kMaxNB = 12;            // p tiles, at most
-constexpr int kMaxList = 32;          // reduction table: sum over class rounds of the longest list
+constexpr int kMaxList = 48;          // reduction table: sum over class rounds of the longest list
 constexpr int kMaxW = 4;
 constexpr int kRingPairs = 10;        // ring entry: 9 boundary pairs + {e0, e1}
 
@@ -177,9 +178,9 @@ constexpr int kBarPEmpty = kBarPFull + kMaxNB;            // [kMaxNB]       p ti
 constexpr int kBarTma = kBarPEmpty + kMaxNB;              // [2][kNR]       raw tiles landed
 constexpr int kBarLFull = kBarTma + 2 * kNR;              // [kMaxW][kRD]   live chain ring entry written (w-1 -> w)
 constexpr int kBarLEmpty = kBarLFull + kMaxW * kRD;       // [kMaxW][kRD]   ... consumed
-constexpr int kBarRFull = kBarLEmpty + kMaxW * kRD;       // [kMaxW][kRD]   recompute chain ring
-constexpr int kBarREmpty = kBarRFull + kMaxW * kRD;
-constexpr int kBarAFull = kBarREmpty + kMaxW * kRD;       // [kMaxAB]       abar rows of a step stored (count W; live -> RC)
+constexpr int kBarRFull = kBarLEmpty + kMaxW * kRD;       // [kRS][kMaxW][kRD]   recompute chain rings
+constexpr int kBarREmpty = kBarRFull + kRS * kMaxW * kRD;
+constexpr int kBarAFull = kBarREmpty + kRS * kMaxW * kRD;       // [kMaxAB]       abar rows of a step stored (count W; live -> RC)
 constexpr int kBarXFull = kBarAFull + kMaxAB;             // [kMaxAB]       products ready (count W; RC -> X)
 constexpr int kBarAEmpty = kBarXFull + kMaxAB;            // [kMaxAB]       step buffer free (count 2; X -> live)
 constexpr int kBarZ = kBarAEmpty + kMaxAB;                // Z published
@@ -226,7 +227,7 @@ struct Geo {
   static constexpr int BNDP = 4 + SB * NL + 2;
   static constexpr uint32_t BNDB = 8u * BNDP;
   static constexpr int CKF = 2 * K + 4;        // checkpoint floats per lane
-  static constexpr int NWARPS = 2 * W + 4;     // live, recompute, X0 X1, P0 P1
+  static constexpr int NWARPS = W + kRS * W + 4;   // live, recompute sets, X0 X1, P0 P1
   static constexpr int NT = 32 * NWARPS;
 };
 
@@ -251,7 +252,7 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
   L.ptile = p;  p += (size_t)NB * 2 * CP * 9 + 8;                   // [buf][d][col][9]
   p = (p + 3) & ~(size_t)3;
   L.ringL = p;  p += (size_t)(W + 1) * kRD * kRingPairs * 2;        // [w][slot]{9 boundary pairs, e0, e1}
-  L.ringR = p;  p += (size_t)(W + 1) * kRD * kRingPairs * 2;
+  L.ringR = p;  p += (size_t)kRS * (W + 1) * kRD * kRingPairs * 2;
   p = (p + 3) & ~(size_t)3;
   L.zero_end = p;
   L.bars = p;   p += 2 * kNumBars;
@@ -965,7 +966,7 @@ __device__ __forceinline__ void rc_frame(p2 (&w)[K], const Topo<K>& tp, const PR
 }
 
 template <int K, int W>
-__device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx& cx, const int w) {
+__device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx& cx, const int w, const int set) {
   using G = Geo<K, W>;
   constexpr int NL = G::NL;
   const int lane = cx.lane, gl = 32 * w + lane, nsd = cx.nsd, NAB = cx.NAB;
@@ -979,19 +980,22 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   const int pl = NL - 1 - gl;
   const uint32_t pabar = 4u * (uint32_t)(G::PADA + pl * G::SA);   // partner block in a plane of an abar row
   const uint32_t pbnd = 8u * (uint32_t)(4 + pl * G::SB);          // partner block in a boundary row
-  const uint32_t ring_in0 = sm.ringR + 8u * (uint32_t)(w * kRD * kRingPairs);
-  const uint32_t ring_out0 = sm.ringR + 8u * (uint32_t)((w + 1) * kRD * kRingPairs);
+  const uint32_t ring_in0 = sm.ringR + 8u * (uint32_t)((set * (W + 1) + w) * kRD * kRingPairs);
+  const uint32_t ring_out0 = sm.ringR + 8u * (uint32_t)((set * (W + 1) + w + 1) * kRD * kRingPairs);
+  const int rbar = set * kMaxW * kRD;   // this set's chain barriers
   int bad = 0;   // reason 4: scale overflow when pairing live and recomputed values
   p2 wv[K];
   int ew[2];
-  ckpt_load_swapped<K>(ck + (size_t)(nsd - 1) * NL * G::CKF, wv, ew);
+  if (set < nsd) ckpt_load_swapped<K>(ck + (size_t)(nsd - 1 - set) * NL * G::CKF, wv, ew);
   PRing pr;
-  pr.init(nsd, cx.NB);
+  pr.init(nsd + set, cx.NB);
   const bool has_partial = nsd > cx.nfull;
   PROF_DECL;
-  uint32_t rpar = 0u;   // (k2 / NAB) & 1
-  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, rpar ^= (buf + 1 == NAB), buf = (buf + 1 == NAB) ? 0 : buf + 1) {
-    const int slot = k2 % kRD;
+  // this set's j-th step is k2 = set + kRS j
+  int buf = set % NAB;
+  uint32_t rpar = (uint32_t)(set / NAB) & 1u;   // (k2 / NAB) & 1
+  for (int k2 = set, j = 0; k2 < nsd; k2 += kRS, ++j) {
+    const int slot = j % kRD;
     const uint32_t rin = ring_in0 + 8u * (uint32_t)(slot * kRingPairs);
     const uint32_t rout = ring_out0 + 8u * (uint32_t)(slot * kRingPairs);
     const bool partial = has_partial && k2 == 0;
@@ -1026,9 +1030,9 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     const p2 f2 = pk(frs[0], frs[1]), h2 = pk(hsc[0], hsc[1]);
     // chain ring: my left neighbour's entry of this step; open my own
     PROF_MARK(0);
-    if (w > 0) bar_wait(sm.bars, kBarRFull + w * kRD + slot, (uint32_t)(k2 / kRD) & 1u);
+    if (w > 0) bar_wait(sm.bars, kBarRFull + rbar + w * kRD + slot, (uint32_t)(j / kRD) & 1u);
     if (w < W - 1) {
-      if (k2 >= kRD) bar_wait(sm.bars, kBarREmpty + (w + 1) * kRD + slot, (uint32_t)(k2 / kRD - 1) & 1u);
+      if (j >= kRD) bar_wait(sm.bars, kBarREmpty + rbar + (w + 1) * kRD + slot, (uint32_t)(j / kRD - 1) & 1u);
       if (lane == 31) sts64(rout, wv[K - 1]);
     }
     PROF_MARK(2);
@@ -1085,14 +1089,18 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
       if (lane == 0) sts64(sm.cert + 8u * (uint32_t)(buf * W + w), pk(t0, t1));
     }
     // next checkpoint (consumed at the top of the next iteration)
-    if (k2 + 1 < nsd) ckpt_load_swapped<K>(ck + (size_t)(nsd - 2 - k2) * NL * G::CKF, wv, ew);
+    if (k2 + kRS < nsd) ckpt_load_swapped<K>(ck + (size_t)(nsd - 1 - kRS - k2) * NL * G::CKF, wv, ew);
     __syncwarp();
     if (lane == 0) {
       bar_arrive(sm.bars, kBarXFull + buf);
-      if (w < W - 1) bar_arrive(sm.bars, kBarRFull + (w + 1) * kRD + slot);
-      if (w > 0) bar_arrive(sm.bars, kBarREmpty + w * kRD + slot);
+      if (w < W - 1) bar_arrive(sm.bars, kBarRFull + rbar + (w + 1) * kRD + slot);
+      if (w > 0) bar_arrive(sm.bars, kBarREmpty + rbar + w * kRD + slot);
     }
     ptile_release(sm, cx, pr, 1);
+#pragma unroll
+    for (int r = 1; r < kRS; ++r) pr.next(cx.NB);   // the other sets' tiles
+    buf += kRS;
+    if (buf >= NAB) { buf -= NAB; rpar ^= 1u; }
   }
   PROF_MARK(0);
 #ifdef WFST_PROFILE
@@ -1440,10 +1448,11 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 384 ? 2 : 1))
 #endif
 
   // warp -> scheduler partition is warp % 4
+  constexpr int WR = W + kRS * W;
   if (warp < W) role_live<K, W>(a, sm, cx, warp);
-  else if (warp < 2 * W) role_rc<K, W>(a, sm, cx, warp - W);
-  else if (warp < 2 * W + 2) role_reduce<K, W>(a, sm, cx, warp - 2 * W);
-  else role_producer<W>(a, sm, cx, warp - 2 * W - 2);
+  else if (warp < WR) role_rc<K, W>(a, sm, cx, (warp - W) % W, (warp - W) / W);
+  else if (warp < WR + 2) role_reduce<K, W>(a, sm, cx, warp - WR);
+  else role_producer<W>(a, sm, cx, warp - WR - 2);
 }
 
 // ---- host side ----------------------------------------------------------------------
@@ -1531,6 +1540,14 @@ static bool pick_bufs_cfg(int idx, int C, int& NAB, int& NB, size_t& bytes) {
 }
 
 }  // namespace chaink
+
+// test / tuning hook: prefer configuration (K, W) for targets it can hold; (0, 0) = automatic
+int ctc_chain_force_config(int K, int W) {
+  chaink::read_forced();
+  chaink::g_force_k = K;
+  chaink::g_force_w = W;
+  return 0;
+}
 
 bool ctc_chain_eligible(int T, int C, int max_target_len) {
   if (T < 1 || C + 1 > 128) return false;

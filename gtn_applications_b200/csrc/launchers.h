@@ -54,6 +54,7 @@ int launch_ctc_pair(const float* E, const int* targets, const int* offsets, int 
 // chain-split scaled CTC (ctc_chain.cu): one utterance per block, both time directions packed
 // in FP32 pairs, the chain split over W warps skewed by one 8-frame step
 bool ctc_chain_eligible(int T, int C, int max_target_len);
+int ctc_chain_force_config(int K, int W);
 size_t ctc_chain_workspace_bytes(int B, int T, int max_target_len);
 int launch_ctc_chain(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                      int blank, int max_target_len, const float* grad_scale, float* z_out,

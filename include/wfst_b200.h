@@ -55,8 +55,13 @@ WFST_API int wfst_abi_version(void);
 /* test hook: 1 = run CTC on the log-semiring lattice kernel only (and ASG full-connect on the
  * generic lattice kernel), 2 = skip the paired scaled-probability kernel (use the
  * single-utterance one), 3 = dense ASG full-connect kernel with one warp per utterance only
- * (no two-warp split), 0 = default (returns the old value) */
+ * (no two-warp split), 4 = no chain-split CTC kernel, 5 = chain-split CTC kernel first
+ * (default: the paired kernel where it is eligible, the chain-split one otherwise),
+ * 0 = default (returns the old value) */
 WFST_API int wfst_debug_force_generic_ctc(int on);
+/* test / tuning hook: the chain-split CTC kernel (csrc/ctc_chain.cu) prefers the configuration
+ * (K slots per lane, W warps per chain) for targets it can hold; (0, 0) = automatic */
+WFST_API int wfst_debug_ctc_chain_config(int K, int W);
 /* test hook: 1 = the acceptor lattice entry points (CSR, ASG force-align, CTC fallback) use the
  * generic global-memory kernel even when the acceptor fits the shared-memory ("lean") kernels,
  * 2 = the single-block lean kernel only (no two-block cluster kernel), 3 = the two-block

@@ -22,6 +22,7 @@
 #include <deque>
 #include <unistd.h>
 #include <functional>
+#include <list>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -98,6 +99,14 @@ struct HostGraph {
   std::vector<AdjList> in, out;
   bool il_sorted = false, ol_sorted = false;
   bool calc_grad = false;
+  // identity for the alignment-graph cache: a process-wide serial number; frozen graphs are
+  // shared with that cache and must not be modified through a handle
+  uint64_t serial = next_serial();
+  bool frozen = false;
+  static uint64_t next_serial() {
+    static std::atomic<uint64_t> n{1};
+    return n.fetch_add(1);
+  }
   // provenance of a composed graph: arc k came from (a1[k], a2[k]) (-1 = epsilon move)
   std::vector<int32_t> prov1, prov2;
   // labels of the out-lists in list order, flattened (out_off[n] .. out_off[n+1]): built on
@@ -187,9 +196,20 @@ struct HostGraph {
 
 // ---- handle table ---------------------------------------------------------------
 std::mutex g_mu;
-std::vector<std::unique_ptr<HostGraph>> g_graphs;
+std::vector<std::shared_ptr<HostGraph>> g_graphs;   // shared: cached alignment graphs are also owned by the cache
 std::vector<int32_t> g_free;
 
+int32_t put_shared(std::shared_ptr<HostGraph> g) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_free.empty()) {
+    int32_t h = g_free.back();
+    g_free.pop_back();
+    g_graphs[h] = std::move(g);
+    return h;
+  }
+  g_graphs.push_back(std::move(g));
+  return (int32_t)g_graphs.size() - 1;
+}
 int32_t put(std::unique_ptr<HostGraph> g) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g_free.empty()) {
@@ -664,6 +684,76 @@ void parallel_for(int n, F&& fn) {
   WorkerPool::instance().run(n, job);
 }
 
+
+// ---- alignment-graph cache ---------------------------------------------------------
+// The alignment acceptor of an utterance depends on (token graph, lexicon graph, target) only,
+// and a training run meets the same targets again every epoch (the reference's
+// benchmarks/transducer_benchmark.py meets them again every iteration).  Building one costs
+// milliseconds of host time (two compositions), so finished graphs are kept, frozen, in an LRU
+// bounded by their total number of arcs; a hit hands out another handle to the same graph.
+struct AlignCache {
+  struct Entry {
+    uint64_t tk, lx;
+    int tk_arcs, lx_arcs;
+    std::vector<int32_t> target;
+    std::shared_ptr<HostGraph> graph;
+  };
+  std::mutex mu;
+  std::list<Entry> lru;   // front = most recent
+  std::unordered_multimap<uint64_t, std::list<Entry>::iterator> index;
+  size_t arcs = 0, cap = default_cap();
+  std::atomic<uint64_t> hits{0}, misses{0};
+  static size_t default_cap() {
+    const char* s = std::getenv("WFST_ALIGN_CACHE_ARCS");
+    return s ? (size_t)std::strtoull(s, nullptr, 10) : (size_t)16 << 20;
+  }
+  static uint64_t hash(uint64_t tk, uint64_t lx, const int32_t* t, int n) {
+    uint64_t h = 1469598103934665603ull ^ (tk * 0x9e3779b97f4a7c15ull) ^ (lx << 32);
+    for (int i = 0; i < n; ++i) { h ^= (uint32_t)t[i]; h *= 1099511628211ull; }
+    return h ^ (uint64_t)n;
+  }
+  std::shared_ptr<HostGraph> find(const HostGraph& tk, const HostGraph& lx, const int32_t* t, int n, uint64_t h) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto range = index.equal_range(h);
+    for (auto it = range.first; it != range.second; ++it) {
+      Entry& e = *it->second;
+      if (e.tk == tk.serial && e.lx == lx.serial && e.tk_arcs == tk.num_arcs() && e.lx_arcs == lx.num_arcs() &&
+          (int)e.target.size() == n && std::equal(e.target.begin(), e.target.end(), t)) {
+        lru.splice(lru.begin(), lru, it->second);
+        return e.graph;
+      }
+    }
+    return nullptr;
+  }
+  void insert(const HostGraph& tk, const HostGraph& lx, const int32_t* t, int n, uint64_t h, std::shared_ptr<HostGraph> g) {
+    std::lock_guard<std::mutex> lk(mu);
+    const size_t a = (size_t)g->num_arcs() + (size_t)g->num_nodes();
+    if (a > cap) return;
+    lru.push_front(Entry{tk.serial, lx.serial, tk.num_arcs(), lx.num_arcs(), std::vector<int32_t>(t, t + n), std::move(g)});
+    index.emplace(h, lru.begin());
+    arcs += a;
+    while (arcs > cap && !lru.empty()) {
+      auto last = std::prev(lru.end());
+      const uint64_t hl = hash(last->tk, last->lx, last->target.data(), (int)last->target.size());
+      auto range = index.equal_range(hl);
+      for (auto it = range.first; it != range.second; ++it)
+        if (it->second == last) { index.erase(it); break; }
+      arcs -= (size_t)last->graph->num_arcs() + (size_t)last->graph->num_nodes();
+      lru.erase(last);
+    }
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lk(mu);
+    index.clear();
+    lru.clear();
+    arcs = 0;
+  }
+};
+AlignCache& align_cache() {
+  static AlignCache* c = new AlignCache();   // never destroyed (no static-destruction order issues)
+  return *c;
+}
+
 }  // namespace
 }  // namespace wfst
 
@@ -694,7 +784,7 @@ int wfst_graph_destroy(int32_t h) {
 
 int wfst_graph_destroy_many(const int32_t* handles, int n) {
   if (n < 0 || (n > 0 && !handles)) { set_error("bad arguments"); return WFST_ERR_INVALID; }
-  std::vector<std::unique_ptr<HostGraph>> doomed(n);
+  std::vector<std::shared_ptr<HostGraph>> doomed(n);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     for (int k = 0; k < n; ++k) {
@@ -708,13 +798,21 @@ int wfst_graph_destroy_many(const int32_t* handles, int n) {
   return WFST_OK;
 }
 
+#define NOT_FROZEN(g)                                                                                   \
+  if ((g)->frozen) {                                                                                    \
+    set_error("this graph is shared with the alignment-graph cache and cannot be modified");           \
+    return WFST_ERR_INVALID;                                                                            \
+  }
+
 int wfst_graph_add_node(int32_t h, int start, int accept) {
   GRAPH_OR_FAIL(g, h);
+  NOT_FROZEN(g);
   return g->add_node(start != 0, accept != 0);
 }
 
 int wfst_graph_add_arc(int32_t h, int src, int dst, int ilabel, int olabel, float weight) {
   GRAPH_OR_FAIL(g, h);
+  NOT_FROZEN(g);
   if (src < 0 || dst < 0 || src >= g->num_nodes() || dst >= g->num_nodes()) {
     set_error("add_arc: node index out of range");
     return WFST_ERR_INVALID;
@@ -725,6 +823,7 @@ int wfst_graph_add_arc(int32_t h, int src, int dst, int ilabel, int olabel, floa
 int wfst_graph_add_arcs(int32_t h, int n, const int32_t* src, const int32_t* dst,
                         const int32_t* ilabel, const int32_t* olabel, const float* weight) {
   GRAPH_OR_FAIL(g, h);
+  NOT_FROZEN(g);
   for (int k = 0; k < n; ++k) {
     if (src[k] < 0 || dst[k] < 0 || src[k] >= g->num_nodes() || dst[k] >= g->num_nodes()) {
       set_error("add_arcs: node index out of range");
@@ -738,9 +837,16 @@ int wfst_graph_add_arcs(int32_t h, int n, const int32_t* src, const int32_t* dst
 int wfst_graph_num_nodes(int32_t h) { GRAPH_OR_FAIL(g, h); return g->num_nodes(); }
 int wfst_graph_num_arcs(int32_t h) { GRAPH_OR_FAIL(g, h); return g->num_arcs(); }
 
-int wfst_graph_arc_sort(int32_t h, int by_olabel) { GRAPH_OR_FAIL(g, h); g->arc_sort(by_olabel != 0); return WFST_OK; }
+int wfst_graph_arc_sort(int32_t h, int by_olabel) {
+  GRAPH_OR_FAIL(g, h);
+  if ((by_olabel && g->ol_sorted) || (!by_olabel && g->il_sorted)) return WFST_OK;
+  NOT_FROZEN(g);
+  g->arc_sort(by_olabel != 0);
+  return WFST_OK;
+}
 int wfst_graph_mark_arc_sorted(int32_t h, int by_olabel) {
   GRAPH_OR_FAIL(g, h);
+  NOT_FROZEN(g);
   if (by_olabel) g->ol_sorted = true; else g->il_sorted = true;
   return WFST_OK;
 }
@@ -750,6 +856,7 @@ int wfst_graph_set_calc_grad(int32_t h, int v) { GRAPH_OR_FAIL(g, h); g->calc_gr
 
 int wfst_graph_set_weights(int32_t h, const float* w) {
   GRAPH_OR_FAIL(g, h);
+  NOT_FROZEN(g);
   if (g->num_arcs()) std::memcpy(g->w.data(), w, sizeof(float) * g->num_arcs());
   return WFST_OK;
 }
@@ -1069,12 +1176,42 @@ int wfst_transducer_alignment_graphs(int32_t tokens, int32_t lexicon, const int3
   HostGraph* lx = get(lexicon);
   if (!tk || !lx) { set_error("invalid graph handle"); return WFST_ERR_INVALID; }
   tk->arc_sort(true);  // Transducer.forward: self.tokens.arc_sort(True) (transducer.py:188)
-  std::vector<std::unique_ptr<HostGraph>> built(B);
+  std::vector<std::shared_ptr<HostGraph>> built(B);
+  AlignCache& cache = align_cache();
+  const bool use_cache = cache.cap > 0;
   parallel_for(B, [&](int b) {
-    built[b] = alignment_graph(*tk, *lx, targets + target_offsets[b],
-                               target_offsets[b + 1] - target_offsets[b]);
+    const int32_t* t = targets + target_offsets[b];
+    const int n = target_offsets[b + 1] - target_offsets[b];
+    uint64_t h = 0;
+    if (use_cache) {
+      h = AlignCache::hash(tk->serial, lx->serial, t, n);
+      built[b] = cache.find(*tk, *lx, t, n, h);
+      if (built[b]) { cache.hits.fetch_add(1, std::memory_order_relaxed); return; }
+      cache.misses.fetch_add(1, std::memory_order_relaxed);
+    }
+    std::shared_ptr<HostGraph> g = alignment_graph(*tk, *lx, t, n);
+    if (use_cache) {
+      g->frozen = true;
+      cache.insert(*tk, *lx, t, n, h, g);
+    }
+    built[b] = std::move(g);
   });
-  for (int b = 0; b < B; ++b) out_handles[b] = put(std::move(built[b]));
+  for (int b = 0; b < B; ++b) out_handles[b] = put_shared(std::move(built[b]));
+  return WFST_OK;
+}
+
+// Capacity of the alignment-graph cache in arcs + nodes (0 disables it, < 0 keeps the current
+// value); always empties the cache.  hits / misses (may be null) receive the counters since the
+// last call.
+int wfst_transducer_alignment_cache(long long capacity, unsigned long long* hits, unsigned long long* misses) {
+  AlignCache& c = align_cache();
+  if (hits) *hits = c.hits.exchange(0);
+  if (misses) *misses = c.misses.exchange(0);
+  c.clear();
+  if (capacity >= 0) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.cap = (size_t)capacity;
+  }
   return WFST_OK;
 }
 

@@ -242,6 +242,14 @@ WFST_API int wfst_transducer_alignment_graphs(int32_t tokens, int32_t lexicon,
                                               const int32_t* targets,
                                               const int32_t* target_offsets, int B,
                                               int32_t* out_handles);
+/* The graphs above depend on (tokens, lexicon, target) only and are kept, frozen (handles to them
+ * reject modification), in an LRU bounded by `capacity` arcs + nodes (default 16 Mi, or
+ * $WFST_ALIGN_CACHE_ARCS): a target met again (next epoch; every iteration of the reference's
+ * benchmarks/transducer_benchmark.py) costs a lookup instead of two compositions.  This call
+ * empties the cache, sets its capacity (0 = off, < 0 = unchanged) and returns the hit / miss
+ * counters since the last call (pointers may be NULL). */
+WFST_API int wfst_transducer_alignment_cache(long long capacity, unsigned long long* hits,
+                                             unsigned long long* misses);
 
 /* Packs B host graphs into the arrays of wfst_acceptor_batch_t (HOST buffers sized from
  * wfst_graph_pack_sizes; the caller uploads them).  Arc lists keep their arc_sort order. */

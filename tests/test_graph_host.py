@@ -225,3 +225,42 @@ def test_batched_decode_matches_the_per_utterance_pipeline(blank, rep):
             chain.add_arc(i, i + 1, int(lab))
         want = G.remove(G.project_output(G.viterbi_path(G.compose(chain, tokens)))).labels_to_list()
         assert out[b, :counts[b]].tolist() == want
+
+
+def test_alignment_graph_cache_returns_the_same_graphs_and_freezes_them():
+    """wfst_transducer_alignment_cache: a target met again comes from the LRU (same arrays, bit
+    for bit, as a freshly built graph); cached graphs reject modification through a handle."""
+    import ctypes
+    from gtn_applications_b200 import _lib, graph as PG
+    from gtn_applications_b200.criterions.transducer import make_lexicon_graph, make_token_graph
+    L = _lib.lib()
+    tokens = ["a", "b", "ab", "ba", "aba", "bb"]
+    g2i = {"a": 0, "b": 1}
+    tk = make_token_graph(tokens, blank="optional", allow_repeats=False)
+    lx = make_lexicon_graph(tokens, g2i)
+    targets = [[0, 1, 0], [1, 1, 0, 0, 1], [0], [0, 1, 0]]
+    flat = np.array([t for y in targets for t in y], dtype=np.int32)
+    off = np.zeros(len(targets) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(y) for y in targets])
+    B = len(targets)
+
+    def build():
+        hs = (ctypes.c_int32 * B)()
+        _lib.check(L.wfst_transducer_alignment_graphs(tk._h, lx._h, flat.ctypes.data, off.ctypes.data, B, hs))
+        return [PG.Graph(_handle=h) for h in hs]
+
+    hits, misses = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    _lib.check(L.wfst_transducer_alignment_cache(0, None, None))          # off
+    plain = [g.arrays() for g in build()]
+    _lib.check(L.wfst_transducer_alignment_cache(1 << 20, None, None))    # on, empty
+    first = build()
+    second = build()
+    _lib.check(L.wfst_transducer_alignment_cache(-1, ctypes.byref(hits), ctypes.byref(misses)))
+    assert misses.value >= 3 and hits.value >= B          # utterances 0 and 3 share a target
+    for ref, a, b in zip(plain, first, second):
+        for k in ("start", "accept", "src", "dst", "ilabel", "olabel", "weight"):
+            assert np.array_equal(ref[k], a.arrays()[k]) and np.array_equal(ref[k], b.arrays()[k])
+    with pytest.raises(Exception):
+        second[0].add_node()
+    second[0].arc_sort()          # already ilabel-sorted: a no-op, allowed
+    _lib.check(L.wfst_transducer_alignment_cache(16 << 20, None, None))   # back to the default capacity

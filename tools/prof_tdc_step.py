@@ -2,11 +2,9 @@ import cProfile, os, pstats, random, sys, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gtn_applications_b200.criterions.transducer import Transducer
 random.seed(0)
-letters = "abcdefghijklmnopqrstuvwxyz"
-pieces = sorted({"".join(random.choice(letters) for _ in range(random.randint(1, 4))) for _ in range(1400)})[:1000]
-for ch in letters:
-    if ch not in pieces: pieces[random.randrange(len(pieces))] = ch
-pieces = sorted(set(pieces))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pieces = sorted([l.strip() for l in open(os.path.join(ROOT, "tests", "golden", "word_pieces_tokens_1000.txt"))])
+letters = sorted(set(c for t in pieces for c in t))
 g2i = {ch: i for i, ch in enumerate(letters)}
 B, T, NP = 64, 1000, 150
 crit = Transducer(pieces, g2i, blank="optional", allow_repeats=False, reduction="mean")
@@ -26,3 +24,11 @@ torch.cuda.synchronize()
 pr.disable()
 print("per step %.2f ms" % ((time.perf_counter() - t0) / 6 * 1e3))
 pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+# GPU time of one step
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); e0.record(); step(); e1.record(); torch.cuda.synchronize()
+print("one step, GPU events: %.2f ms" % e0.elapsed_time(e1))
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    step(); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=8))

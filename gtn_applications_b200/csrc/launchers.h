@@ -59,6 +59,14 @@ size_t ctc_chain_workspace_bytes(int B, int T, int max_target_len);
 int launch_ctc_chain(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                      int blank, int max_target_len, const float* grad_scale, float* z_out,
                      float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
+// solo-chain scaled CTC (ctc_solo.cu): as ctc_chain.cu, but every time direction has its own warps
+// and plain float arithmetic (shorter dependent chain per warp)
+bool ctc_solo_eligible(int T, int C, int max_target_len);
+int ctc_solo_force_config(int K, int W);
+size_t ctc_solo_workspace_bytes(int B, int T, int max_target_len);
+int launch_ctc_solo(const float* E, const int* targets, const int* offsets, int B, int T, int C,
+                    int blank, int max_target_len, const float* grad_scale, float* z_out,
+                    float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
 // float64 log-semiring CTC (ctc_exact.cu): recomputes the utterances the scaled kernels flag
 bool ctc_exact_eligible(int T, int C, int max_target_len);
 size_t ctc_exact_hist_bytes(int B, int T, int max_target_len);

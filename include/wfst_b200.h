@@ -57,6 +57,7 @@ WFST_API int wfst_abi_version(void);
  * single-utterance one), 3 = dense ASG full-connect kernel with one warp per utterance only
  * (no two-warp split), 4 = no chain-split CTC kernel, 5 = chain-split CTC kernel first
  * (default: the paired kernel where it is eligible, the chain-split one otherwise),
+ * 6 = solo-chain CTC kernel first (csrc/ctc_solo.cu; never selected by default),
  * 0 = default (returns the old value) */
 WFST_API int wfst_debug_force_generic_ctc(int on);
 /* test / tuning hook: the chain-split CTC kernel (csrc/ctc_chain.cu) prefers the configuration

@@ -1,5 +1,6 @@
-"""The chain-split scaled CTC kernel (csrc/ctc_chain.cu) through the C ABI, forced ahead of the
-paired kernel (wfst_debug_force_generic_ctc(5)), against the float64 DP: every (K, W)
+"""The chain-split scaled CTC kernels through the C ABI — csrc/ctc_chain.cu (both directions
+packed in f32x2; wfst_debug_force_generic_ctc(5)) and csrc/ctc_solo.cu (one direction per warp
+set, scalar; hook 6) — forced ahead of the paired kernel, against the float64 DP: every (K, W)
 configuration incl. more warps than the target needs (the warp-to-warp ring, the carry-in of the
 exponent scan, partial steps next to the meeting point), ragged / empty targets, T down to 1, the
 BASELINE shapes (cfg2 slice, cfg5 slice: the shape the paired layout cannot hold)."""
@@ -12,11 +13,11 @@ from _capi import ctc_capi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def chain_first():
+@pytest.fixture(params=[5, 6], ids=["packed", "solo"])
+def chain_first(request):
     from gtn_applications_b200 import _lib
     L = _lib.lib()
-    old = L.wfst_debug_force_generic_ctc(5)
+    old = L.wfst_debug_force_generic_ctc(request.param)
     yield L
     L.wfst_debug_ctc_chain_config(0, 0)
     L.wfst_debug_force_generic_ctc(old)

@@ -4,6 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from _capi import ctc_capi
 import dp_numpy
+from gtn_applications_b200 import _lib as _l
+_l.lib().wfst_debug_force_generic_ctc(int(os.environ.get('WFST_CTC_HOOK', '5')))
 def run(B, T, C, L, scale=1.0, ragged=False, nchk=4, seed=0):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, T, C, generator=g) * scale

@@ -13,6 +13,7 @@ flat, offsets, _, max_len = rt.pack_targets(tg, C, dev)
 gs = torch.full((B,), 1.0 / B, device=dev)
 out = torch.empty(B + 1, device=dev); grad = torch.empty_like(lps[0])
 Lb = _lib.lib()
+Lb.wfst_debug_force_generic_ctc(int(os.environ.get('WFST_CTC_HOOK', '0')))
 ws = rt.workspace(dev, Lb.wfst_ctc_workspace_bytes(B, T, C, max_len))
 def call(i):
     _lib.check(Lb.wfst_ctc_forward_backward(lps[i % 4].data_ptr(), flat.data_ptr(), offsets.data_ptr(), B, T, C, C - 1,

@@ -47,6 +47,25 @@ constexpr int kMaxW = 4;
 constexpr int kRingF = 12;            // floats per ring slot: 9 boundary values, the exponent, pad
 constexpr int kRegList = 16;          // entries of a class list the reduction keeps in registers
 
+#ifdef WFST_PROFILE
+#define PROF_DECL long long pf_t0 = clock64(), pf_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(i) do { long long pf_t1 = clock64(); pf_acc[i] += pf_t1 - pf_t0; pf_t0 = pf_t1; } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#endif
+
+// timing diagnosis only (results are wrong when set): bit 0 no shuffle, bit 1 no p loads,
+// bit 2 no ring traffic, bit 3 no renormalisation events
+#ifndef WFST_EXP
+#define WFST_EXP 0
+#endif
+#if WFST_EXP
+#define WFST_HAZ(ptr, bits) ((void)0)
+#else
+#define WFST_HAZ(ptr, bits) atomicOr(ptr, bits)
+#endif
+
 struct Args {
   const float* E;
   const int* targets;
@@ -124,6 +143,18 @@ __device__ __forceinline__ void bar_expect_tx(uint32_t bars, int idx, uint32_t b
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * idx), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bar_wait(uint32_t bars, int idx, uint32_t parity) {
+#if WFST_EXP & 512
+  // plain polling
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WFSTS_BW_%=:\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WFSTS_BD_%=;\n"
+      "bra WFSTS_BW_%=;\n"
+      "WFSTS_BD_%=:\n"
+      "}\n" ::"r"(bars + 8u * idx), "r"(parity) : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -133,6 +164,7 @@ __device__ __forceinline__ void bar_wait(uint32_t bars, int idx, uint32_t parity
       "bra WFSTS_BW_%=;\n"
       "WFSTS_BD_%=:\n"
       "}\n" ::"r"(bars + 8u * idx), "r"(parity), "r"(0x989680u) : "memory");
+#endif
 }
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -281,9 +313,15 @@ template <int K>
 __device__ __forceinline__ PRow<K> load_prow(const TileAddr<K>& t, int it) {
   PRow<K> p;
   const uint32_t o = 4u * (uint32_t)it;
+#if WFST_EXP & 2
+#pragma unroll
+  for (int q = 0; q < K / 2; ++q) p.pl[q] = __uint_as_float(0x3f000000u + t.la[q] + o);
+  p.pb = __uint_as_float(0x3f000000u + t.pba + o);
+#else
 #pragma unroll
   for (int q = 0; q < K / 2; ++q) p.pl[q] = lds(t.la[q] + o);
   p.pb = lds(t.pba + o);
+#endif
   return p;
 }
 
@@ -307,10 +345,26 @@ __device__ __forceinline__ void step(float (&v)[K], float (&abar)[K / 2], const 
   }
 }
 
+__device__ __forceinline__ float ring_ld(uint32_t a) {
+#if WFST_EXP & 4
+  return __uint_as_float(a & 0u);
+#else
+  return lds(a);
+#endif
+}
+__device__ __forceinline__ void ring_st(uint32_t a, float v, int lane) {
+#if !(WFST_EXP & 4)
+  if (lane == 31) sts(a, v);
+#endif
+}
 // the left neighbour's last slot: by shuffle; lane 0 takes the value the previous warp of the
 // chain left in the ring (zero for the first warp: its ring is never written)
 __device__ __forceinline__ float left_in(float last, float bv, int lane, float f) {
+#if WFST_EXP & 1
+  float left = last;
+#else
   float left = __shfl_up_sync(kFull, last, 1);
+#endif
   if (lane == 0) left = bv;
   return left * f;
 }
@@ -461,7 +515,10 @@ __device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, con
     // A row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface through the
     // certificate.
     float base[kSeg];
-    if (groups == 1) {
+    if (WFST_EXP & 64) {
+#pragma unroll
+      for (int r = 0; r < kSeg; ++r) base[r] = 0.f;
+    } else if (groups == 1) {
       const bool valid = lane < C;
       float x[kSeg];
 #pragma unroll
@@ -573,15 +630,23 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   const bool has_partial = nsd > cx.nfull;
 
   // start of global step g: take the left warp's ring entry, renormalise if due, open my own entry
+  PROF_DECL;
   auto step_begin = [&](int g, bool ev) {
     const int slot = g % kRD;
     rin = ring_in0 + 4u * (uint32_t)(slot * kRingF);
     rout = ring_out0 + 4u * (uint32_t)(slot * kRingF);
+    PROF_MARK(0);
     if (w > 0) bar_wait(sm.bars, kBarLFull + lbar + w * kRD + slot, (uint32_t)(g / kRD) & 1u);
+    PROF_MARK(1);
     if (ev) {
       const int Ein = w > 0 ? ldsi(rin + 36u) : kUndef;
+#if WFST_EXP & 8
+      if (g == 0) event1<K>(v, e, f, lane, Ein);
+#else
       event1<K>(v, e, f, lane, Ein);
+#endif
     }
+    PROF_MARK(2);
     if (w < W - 1) {
       if (g >= kRD) bar_wait(sm.bars, kBarLEmpty + lbar + (w + 1) * kRD + slot, (uint32_t)(g / kRD - 1) & 1u);
       if (lane == 31) {
@@ -589,6 +654,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
         stsi(rout + 36u, e);
       }
     }
+    PROF_MARK(3);
   };
   auto step_end = [&](int g) {
     const int slot = g % kRD;
@@ -618,25 +684,37 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     step_begin(g, g % kEventEvery == 0);
     ckpt_store<K, G::CKF>(ck + (size_t)g * NL * G::CKF, v, e);
     const bool partial = has_partial && g == cx.nfull;
+    PROF_MARK(4);
     const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, c, pr));
-    if (!partial) {
+    PROF_MARK(5);
+    if (WFST_EXP & 256) {
+    } else if (!partial) {
       PRow<K> nx = load_prow<K>(ta, 0);
-      float bvn = lds(rin);
+      float bvn = ring_ld(rin);
 #pragma unroll
       for (int it = 0; it < kSeg; ++it) {
         const PRow<K> cur = nx;
         const float bv = bvn;
-        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); bvn = lds(rin + 4u * (it + 1)); }
+        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); bvn = ring_ld(rin + 4u * (it + 1)); }
         const float in1 = left_in(v[K - 1], bv, lane, f);
         step<K, false>(v, abar, tp, cur, in1);
-        if (lane == 31) sts(rout + 4u * (it + 1), v[K - 1]);
+        ring_st(rout + 4u * (it + 1), v[K - 1], lane);
       }
     } else {
       slow_frames(ta, c == 0 ? cx.r0 : cx.r1, 0u, false);
     }
+    PROF_MARK(6);
     ptile_release(sm, cx, c, pr, 2);   // no recompute warp reads phase-1 tiles
     step_end(g);
+    PROF_MARK(7);
   }
+#ifdef WFST_PROFILE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("L%d.%d phase 1: misc %lld wait_ring %lld event %lld ring_empty+put %lld ckpt %lld wait_ptile %lld frames %lld release+end %lld\n", c, w,
+           pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3], pf_acc[4], pf_acc[5], pf_acc[6], pf_acc[7]);
+  for (int i = 0; i < 10; ++i) pf_acc[i] = 0;
+  pf_t0 = clock64();
+#endif
 
   // ------------------------------------------------------------------ meeting: Z
   // every live warp renormalises (consistent exponents for the successor sums below); the alpha
@@ -700,7 +778,13 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
       const int Ei = ldsi(sm.zx + 36u + 8u * (uint32_t)i);
       if (defined_exp(Ei)) tot += lds(sm.zx + 32u + 8u * (uint32_t)i) * pow2c(Ei - Emax);
     }
+#if WFST_EXP
+    const bool ok = true;
+    if (!(tot > 0.f && tot < 3.0e38f)) tot = 1.f;
+    if (!defined_exp(Emax)) Emax = 0;
+#else
     const bool ok = defined_exp(Emax) && tot > 0.f && tot < 3.0e38f;
+#endif
     int ex = 0;
     float Zm = 1.f;
     if (ok) {
@@ -712,7 +796,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     stsi(sm.zx + 4u, ok ? Emax + ex : 0);
     sts(sm.zx + 8u, ok ? 1.f : 0.f);
     // reason 2: infeasible or out of range -- the fallback kernel decides
-    if (!ok) atomicOr(&a.hazard[cx.b], 2);
+    if (!ok) WFST_HAZ(&a.hazard[cx.b], 2);
     bar_arrive(sm.bars, kBarZ);
   }
   bar_wait(sm.bars, kBarZ, 0u);
@@ -727,6 +811,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     const int g = nsd + 1 + k2;
     step_begin(g, g % kEventEvery == 0);
     if (k2 >= NAB) bar_wait(sm.bars, kBarAEmpty + c * kMaxAB + buf, rpar ^ 1u);
+    PROF_MARK(8);
     {
       stsi(lexpb + 4u * (uint32_t)(buf * NL + gl), e);
       // state at the step boundary: the recompute warps check Z against it (certificate)
@@ -736,30 +821,40 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     }
     // component c continues through the other direction's steps, last one (the partial one) first
     const bool partial = has_partial && k2 == 0;
+    PROF_MARK(4);
     const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, c, pr));
+    PROF_MARK(5);
     const uint32_t ar = abuf + (uint32_t)(buf * kSeg) * G::ROWB + myabar;
-    if (!partial) {
+    if (WFST_EXP & 256) {
+    } else if (!partial) {
       PRow<K> nx = load_prow<K>(ta, 0);
-      float bvn = lds(rin);
+      float bvn = ring_ld(rin);
 #pragma unroll
       for (int it = 0; it < kSeg; ++it) {
         const PRow<K> cur = nx;
         const float bv = bvn;
-        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); bvn = lds(rin + 4u * (it + 1)); }
+        if (it + 1 < kSeg) { nx = load_prow<K>(ta, it + 1); bvn = ring_ld(rin + 4u * (it + 1)); }
         const float in1 = left_in(v[K - 1], bv, lane, f);
         step<K, true>(v, abar, tp, cur, in1);
 #pragma unroll
         for (int q = 0; q < HL; ++q) sts(ar + (uint32_t)it * G::ROWB + 4u * q, abar[q]);
-        if (lane == 31) sts(rout + 4u * (it + 1), v[K - 1]);
+        ring_st(rout + 4u * (it + 1), v[K - 1], lane);
       }
     } else {
       slow_frames(ta, c == 0 ? cx.r1 : cx.r0, ar, true);
     }
+    PROF_MARK(6);
     __syncwarp();
     if (lane == 0) bar_arrive(sm.bars, kBarAFull + c * kMaxAB + buf);
     ptile_release(sm, cx, c, pr, 1);
     step_end(g);
+    PROF_MARK(7);
   }
+#ifdef WFST_PROFILE
+  if (blockIdx.x == 0 && lane == 0)
+    printf("L%d.%d phase 2: misc %lld wait_ring %lld event %lld ring_empty+put %lld bnd/lexp %lld wait_ptile %lld frames %lld release+end %lld wait_aempty %lld\n", c, w,
+           pf_acc[0], pf_acc[1], pf_acc[2], pf_acc[3], pf_acc[4], pf_acc[5], pf_acc[6], pf_acc[7], pf_acc[8]);
+#endif
   // certificate, last leg: the sweep must arrive with total mass Z on the two slots that end the
   // chain in this orientation (the recompute warps check every earlier step boundary)
   {
@@ -779,7 +874,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     if (c == 0) named_sync(3, 32 * W); else named_sync(4, 32 * W);
     if (w == 0 && lane == 0) {
       const float t0 = lds(sm.zx + 64u + 4u * c);
-      if (!(fabsf(t0 - Zm) <= 2e-5f * Zm)) atomicOr(&a.hazard[cx.b], 8);
+      if (!(fabsf(t0 - Zm) <= 2e-5f * Zm)) WFST_HAZ(&a.hazard[cx.b], 8);
     }
   }
 }
@@ -867,18 +962,19 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     }
     const TileAddr<K> ta = tile_addr<K>(tp, ptile_wait(sm, cx, c, pr));
     const uint32_t ar = abuf + (uint32_t)(buf * kSeg) * G::ROWB + pabar;
-    if (!partial) {
+    if (WFST_EXP & 128) {
+    } else if (!partial) {
       // against the live step order
       PRow<K> nx = load_prow<K>(ta, kSeg - 1);
-      float bvn = lds(rin);
+      float bvn = ring_ld(rin);
 #pragma unroll
       for (int it = kSeg - 1; it >= 0; --it) {
         const PRow<K> cur = nx;
         const float bv = bvn;
-        if (it > 0) { nx = load_prow<K>(ta, it - 1); bvn = lds(rin + 4u * (kSeg - it)); }
+        if (it > 0) { nx = load_prow<K>(ta, it - 1); bvn = ring_ld(rin + 4u * (kSeg - it)); }
         const float in1 = left_in(wv[K - 1], bv, lane, frs);
         rc_frame<K>(wv, tp, cur, in1, hsc, ar + (uint32_t)it * G::ROWB, G::EXTB);
-        if (lane == 31) sts(rout + 4u * (kSeg - it), wv[K - 1]);
+        ring_st(rout + 4u * (kSeg - it), wv[K - 1], lane);
       }
     } else {
 #pragma unroll 1
@@ -920,7 +1016,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     ptile_release(sm, cx, c, pr, 1);
   }
   bad = __reduce_or_sync(kFull, (unsigned)bad);
-  if (bad && lane == 0) atomicOr(&a.hazard[cx.b], bad);
+  if (bad && lane == 0) WFST_HAZ(&a.hazard[cx.b], bad);
 }
 
 // ---------------------------------------------------------------------------
@@ -1008,7 +1104,8 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
     float rs[kSeg];     // per-row sum of the label posteriors of this lane's classes
 #pragma unroll
     for (int j = 0; j < kSeg; ++j) rs[j] = 0.f;
-    if (reg_lists) {
+    if (WFST_EXP & 32) {
+    } else if (reg_lists) {
 #pragma unroll
       for (int i0 = 0; i0 < kRegList; i0 += 4) {
         if (i0 < nslots) {   // warp-uniform
@@ -1109,7 +1206,7 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
   }
   if (lane == 0) bulk_wait_all<0>();
   bad = __reduce_or_sync(kFull, (unsigned)bad);
-  if (bad && lane == 0) atomicOr(&a.hazard[cx.b], 8);
+  if (bad && lane == 0) WFST_HAZ(&a.hazard[cx.b], 8);
 }
 
 // ---------------------------------------------------------------------------
@@ -1238,7 +1335,7 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1))
       }
     }
   }
-  if (flag && threadIdx.x == 0) atomicOr(&a.hazard[cx.b], flag);
+  if (flag && threadIdx.x == 0) WFST_HAZ(&a.hazard[cx.b], flag);
   __syncthreads();
   if (flag) return;
 

@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/../gtn_applications_b200/csrc"
 mkdir -p /tmp/wfst_prof
-for f in capi lattice lattice_pair ctc_fast ctc_chain ctc_exact ctc_pair_cs0 ctc_pair_cs32 ctc_pair_cs64 ctc_pair_cs128 lsm asg_dense viterbi; do
+for f in capi lattice lattice_pair ctc_fast ctc_chain ctc_solo ctc_exact ctc_pair_cs0 ctc_pair_cs32 ctc_pair_cs64 ctc_pair_cs128 lsm asg_dense viterbi; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr -DWFST_PROFILE -c $f.cu -o /tmp/wfst_prof/$f.o &
 done
 wait

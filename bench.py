@@ -255,6 +255,31 @@ def other_configs(dev):
                                       "repeat as in the reference benchmark (alignment graphs from the LRU cache); "
                                       "cold_*: cache emptied before every step" % len(tokens)}
     del x
+    # ---- n-gram transducers (benchmarks/transducer_benchmark.py:56-119: N=81 tokens, T=250, L=44, ngram=2;
+    # there B=1 on CPU, here B=32): epsilon transition graph, composition + fold for the batch in the
+    # host library (wfst_fold_transitions_batch), lattice kernels with final weights
+    try:
+        Nn, Tn, Ln, Bn = 81, 250, 44, 32
+        toks = [(i,) for i in range(Nn)]
+        gi = {i: i for i in range(Nn)}
+        xn = torch.randn(Bn, Tn, Nn, generator=g).to(dev).requires_grad_(True)
+        tgn = [t.squeeze() for t in torch.randint(Nn, size=(Bn, Ln), generator=g).split(1)]
+        res = {}
+        for name, kw in (("ngram_ctc", dict(ngram=2, blank="optional", allow_repeats=False, reduction="mean")),
+                         ("ngram_asg", dict(ngram=2, reduction="mean"))):
+            cn = Transducer(toks, gi, **kw).to(dev)
+
+            def ng():
+                xn.grad = None
+                cn(xn, tgn).backward()
+
+            res[name + "_ms_per_step"] = timed(ng, 5, warm=2) * 1e3
+        res["what"] = ("Transducer(ngram=2) fwd+bwd through the module, B=32, T=250, 81 tokens, L=44 "
+                       "(the shapes of transducer_benchmark.py:56-119, which runs B=1 on CPU)")
+        out["transducer_ngram2"] = res
+        del xn
+    except Exception as exc:
+        out["transducer_ngram2"] = {"error": repr(exc)[:200]}
     # ---- configs[4], one GPU's shard
     B5, T5, C5, L5 = WORKLOADS["ctc_cfg5"]
     lp5, tg5 = synth("ctc_cfg5", dev, 7)

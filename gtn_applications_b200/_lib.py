@@ -87,6 +87,10 @@ SIGNATURES = {
     "wfst_graph_viterbi_path": (_I32, [_I32]),
     "wfst_graph_score": (_I, [_I32, _I, _P, _P]),
     "wfst_transducer_alignment_cache": (_I, [ctypes.c_longlong, _P, _P]),
+    "wfst_fold_transitions_batch": (_I32, [_I32, _P, _I, _P]),
+    "wfst_fold_sizes": (_I, [_I32, _P]),
+    "wfst_fold_fill": (_I, [_I32, _P, _P, _P, _P, _P]),
+    "wfst_fold_destroy": (_I, [_I32]),
     "wfst_lattice_viterbi_workspace_bytes": (_Z, [_I, _I, _I]),
     "wfst_lattice_viterbi": (_I, [_P, _I, _I, _I, ctypes.POINTER(AcceptorBatch), _I, _P, _P, _P, _P, _Z, _P]),
     "wfst_graph_pack_sizes": (_I, [_P, _I, _P, _P, _P, _P, _P]),

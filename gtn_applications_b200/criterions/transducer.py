@@ -139,16 +139,33 @@ def _graph_has_epsilon(g):
     return cached
 
 
+def _fold_batch(transitions, align_handles, B, dev):
+    """(packed, ties) of intersect(transitions, alignment_b) for the whole batch, epsilons folded: the
+    composition, the fold and the tie arrays come from the host library in one call on host threads
+    (wfst_fold_transitions_batch); align_handles = None folds the transition graph itself."""
+    import ctypes
+    from ..epsilon import FoldedBatch
+    L = _lib.lib()
+    out = (ctypes.c_int32 * B)()
+    fold = L.wfst_fold_transitions_batch(transitions._h, align_handles, B, out)
+    if fold < 0:
+        _lib.check(fold)
+    try:
+        ties = FoldedBatch.from_fold(fold, dev)
+        packed = G.pack_handles(out, B, dev)
+    finally:
+        L.wfst_fold_destroy(fold)
+        G.destroy_handles(out, B)
+    return packed, ties
+
+
 def _folded_shared(transitions, dev):
     """(packed, ties) of the epsilon-folded transition graph, cached on the Graph object
     (the topology does not change between steps; the weights are gathered per call)."""
-    from ..epsilon import FoldedAcceptor, FoldedBatch
-    from ..packing import PackedAcceptors
     key = "_folded_%s" % str(dev)
     hit = getattr(transitions, key, None)
     if hit is None:
-        f = FoldedAcceptor(transitions.arrays())
-        hit = (PackedAcceptors([f.graph_dict()], dev), FoldedBatch([f], dev))
+        hit = _fold_batch(transitions, None, 1, dev)
         try:
             setattr(transitions, key, hit)
         except AttributeError:
@@ -156,26 +173,17 @@ def _folded_shared(transitions, dev):
     return hit
 
 
-def _forward_with_epsilon_transitions(e, aligns, transitions, transition_params, sc, need_e, need_t):
+def _forward_with_epsilon_transitions(e, align_handles, transitions, transition_params, sc, need_e, need_t):
     """TransducerLossFunction.forward (transducer.py:279-309) when the transition graph has
     epsilon arcs (ngram > 1: the </s> arcs of make_transitions_graph :52-56; loaded back-off
     graphs).  intersect(transitions, alignments) is done by the host library with the
     epsilons in place, exactly as the reference does; then both the composed graphs and the
     transition graph itself are folded (epsilon.py) and scored by the lattice kernel with
     final weights.  Gradients return to `transition_params` through the fold's provenance."""
-    from ..epsilon import FoldedAcceptor, FoldedBatch
-    from ..packing import PackedAcceptors
     B = e.shape[0]
     dev = e.device
     tp = transition_params.detach().to(dev, torch.float32).contiguous()
-    folded, prov = [], []
-    for g in aligns:
-        c = G.intersect(transitions, g)
-        c.arc_sort()
-        folded.append(FoldedAcceptor(c.arrays()))
-        prov.append(np.asarray(c.provenance()[0], dtype=np.int64))     # composed arc -> transition arc
-    packed = PackedAcceptors([f.graph_dict() for f in folded], dev)
-    ties = FoldedBatch(folded, dev, orig_index=prov)
+    packed, ties = _fold_batch(transitions, align_handles, B, dev)
     w, fw, pw = ties.weights(tp)
     gs = -sc / B
     z_align, g_e, g_w, g_f = lattice_forward_backward(
@@ -216,54 +224,29 @@ class TransducerLossFunction(torch.autograd.Function):
             tokens._h, lexicon._h, flat.ctypes.data, offs.ctypes.data, B, handles))
         # without a transition graph the alignment graphs are only packed and freed: no Python
         # wrapper (and no per-graph destructor call) for them
-        aligns = [G.Graph(_handle=h) for h in handles] if transitions is not None else None
+        aligns = [G.Graph(_handle=h) for h in handles] if transitions is not None else None   # owners of the handles
         need_e = ctx.needs_input_grad[0]
         need_t = transitions is not None and ctx.needs_input_grad[4]
         with torch.cuda.device(dev):
             sc = torch.tensor(scales, dtype=torch.float32, device=dev)
-            tp = prov = None
-            if transitions is not None and _graph_has_epsilon(transitions):
+            if transitions is not None:
+                # alignments := intersect(transitions, alignments) (transducer.py:279-281), with or
+                # without epsilon arcs in the transition graph: composition, epsilon fold and the
+                # arrays that tie the composed arcs to transition_params for the whole batch in
+                # one call of the host library (an epsilon-free graph folds to itself)
                 loss, g_e, g_tp = _forward_with_epsilon_transitions(
-                    e, aligns, transitions, transition_params, sc, need_e, need_t)
+                    e, handles, transitions, transition_params, sc, need_e, need_t)
                 ctx.grads = (g_e if need_e else None, g_tp)
                 ctx.devices = (inputs.device, transition_params.device)
                 return loss if inputs.is_cuda else loss.cpu()
-            if transitions is not None:
-                # alignments := intersect(transitions, alignments) (transducer.py:279-281); the
-                # composed arc weights are the transition weights of their first parent
-                tp = transition_params.detach().to(dev, torch.float32).contiguous()
-                composed, prov = [], []
-                for g in aligns:
-                    c = G.intersect(transitions, g)
-                    c.arc_sort()
-                    composed.append(c)
-                    prov.append(c.provenance()[0])
-                aligns = composed
-            if aligns is None:
-                packed = G.pack_handles(handles, B, dev)
-                G.destroy_handles(handles, B)
-            else:
-                packed = G.pack_graphs(aligns, dev)
-            weights = None
-            if transitions is not None:
-                prov_idx = torch.from_numpy(np.concatenate(prov).astype(np.int64)).to(dev)
-                weights = tp[prov_idx] if prov_idx.numel() else torch.zeros(0, device=dev)
+            packed = G.pack_handles(handles, B, dev)
+            G.destroy_handles(handles, B)
             # loss_b = -(Z_align - Z_norm) * scale_b; mean over b (transducer.py:283-309)
             gs = -sc / B
             z_align, g_e, g_w = lattice_forward_backward(
-                e, packed, grad_scale=gs, want_grad_emissions=need_e, want_grad_weights=need_t,
-                weights=weights)
+                e, packed, grad_scale=gs, want_grad_emissions=need_e, want_grad_weights=False)
             score = z_align
             g_tp = None
-            if transitions is not None:
-                shared = G.pack_graphs([transitions], dev)
-                z_norm, _, g_wn = lattice_forward_backward(
-                    e, shared, grad_scale=-gs, want_grad_emissions=False, want_grad_weights=need_t,
-                    weights=tp, shared=True, accumulate_into=g_e if need_e else None)
-                score = z_align - z_norm
-                if need_t:
-                    g_tp = g_wn.clone()
-                    g_tp.index_add_(0, prov_idx, g_w)
             loss = (-score * sc).mean()
         ctx.grads = (g_e if need_e else None, g_tp)
         ctx.devices = (inputs.device, transition_params.device if transition_params is not None else None)
@@ -361,6 +344,18 @@ def make_kernel_graph(x, blank_idx, blank_optional, spike=False, calc_grad=False
     return g
 
 
+def _packed_kernel(k, dev):
+    key = "_packed_%s" % str(dev)
+    hit = getattr(k, key, None)
+    if hit is None:
+        hit = G.pack_graphs([k], dev)
+        try:
+            setattr(k, key, hit)
+        except AttributeError:
+            pass
+    return hit
+
+
 class ConvTransduce1DFunction(torch.autograd.Function):
     """criterions/transducer.py:461-556.  The reference scores every window of every
     utterance against every kernel graph with one GTN intersect + forward_score (or
@@ -385,7 +380,7 @@ class ConvTransduce1DFunction(torch.autograd.Function):
             win = e.unfold(1, kernel_size, stride)                    # [B, T', C, ks]
             Tp = win.shape[1]
             windows = win.permute(0, 1, 3, 2).reshape(B * Tp, kernel_size, C).contiguous()
-            packed = [G.pack_graphs([k], dev) for k in kernels]
+            packed = [_packed_kernel(k, dev) for k in kernels]     # packed once per kernel graph and device
             weights = [None] * len(kernels)
             if kernel_params is not None:
                 kp = kernel_params.detach().to(dev, torch.float32).contiguous()

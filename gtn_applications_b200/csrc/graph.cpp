@@ -685,6 +685,85 @@ void parallel_for(int n, F&& fn) {
 }
 
 
+// ---- epsilon folding ------------------------------------------------------------------
+// Epsilon-free view of an acceptor for the time-synchronous lattice kernels (the host side of
+// gtn_applications_b200/epsilon.py, which documents the construction): every path
+// u --eps*--> v --a--> x becomes one arc u --a--> x tied to the original arcs along it; every
+// path u --eps*--> v into an accept node gives u a final-weight term tied to the path's arcs.
+struct Folded {
+  std::unique_ptr<HostGraph> graph;          // folded arcs, accept = has a final path
+  std::vector<int64_t> arc_prov_ptr, arc_prov;   // original arc ids summed into folded arc k
+  std::vector<int64_t> fin_node, fin_prov_ptr, fin_prov;   // one entry per epsilon path into an accept node
+  bool ok = true;
+};
+
+Folded fold_epsilons(const HostGraph& g) {
+  Folded f;
+  const int N = g.num_nodes(), A = g.num_arcs();
+  std::vector<std::vector<int32_t>> eps_out(N), emit_out(N);
+  for (int a = 0; a < A; ++a) (g.il[a] == kEpsilon ? eps_out : emit_out)[g.src[a]].push_back(a);
+  // all epsilon paths from u: (node, arc ids), in depth-first order of the out-lists
+  struct Path { int32_t node; std::vector<int32_t> arcs; };
+  std::vector<std::vector<Path>> closures(N);
+  std::vector<uint8_t> state(N, 0);   // 0 new, 1 open, 2 done
+  std::function<bool(int)> closure = [&](int u) -> bool {
+    if (state[u] == 2) return true;
+    if (state[u] == 1) return false;   // epsilon cycle
+    state[u] = 1;
+    std::vector<Path> out;
+    out.push_back(Path{u, {}});
+    for (int32_t a : eps_out[u]) {
+      const int v = g.dst[a];
+      if (!closure(v)) return false;
+      for (const Path& p : closures[v]) {
+        Path q{p.node, {}};
+        q.arcs.reserve(p.arcs.size() + 1);
+        q.arcs.push_back(a);
+        q.arcs.insert(q.arcs.end(), p.arcs.begin(), p.arcs.end());
+        out.push_back(std::move(q));
+      }
+    }
+    closures[u] = std::move(out);
+    state[u] = 2;
+    return true;
+  };
+  f.graph = std::make_unique<HostGraph>();
+  f.arc_prov_ptr.push_back(0);
+  f.fin_prov_ptr.push_back(0);
+  std::vector<uint8_t> acc(N, 0);
+  struct NewArc { int32_t src, dst, lab; };
+  std::vector<NewArc> arcs;
+  for (int u = 0; u < N; ++u) {
+    if (!closure(u)) { f.ok = false; return f; }
+    for (const Path& p : closures[u]) {
+      for (int32_t a : emit_out[p.node]) {
+        arcs.push_back(NewArc{u, g.dst[a], g.il[a]});
+        for (int32_t e : p.arcs) f.arc_prov.push_back(e);
+        f.arc_prov.push_back(a);
+        f.arc_prov_ptr.push_back((int64_t)f.arc_prov.size());
+      }
+      if (g.flags[p.node] & 2) {
+        acc[u] = 1;
+        f.fin_node.push_back(u);
+        for (int32_t e : p.arcs) f.fin_prov.push_back(e);
+        f.fin_prov_ptr.push_back((int64_t)f.fin_prov.size());
+      }
+    }
+  }
+  for (int u = 0; u < N; ++u) f.graph->add_node((g.flags[u] & 1) != 0, acc[u] != 0);
+  for (const NewArc& a : arcs) f.graph->add_arc(a.src, a.dst, a.lab, a.lab, 0.f);
+  return f;
+}
+
+// a batch of folded acceptors with the index arrays that tie their arcs / final weights to ONE
+// vector of original parameters (epsilon.py, FoldedBatch)
+struct FoldBatch {
+  std::vector<int64_t> arc_seg, arc_src, fin_seg, fin_src, fin_node;
+  int64_t num_arcs = 0, num_paths = 0, num_nodes = 0;
+};
+std::mutex g_fold_mu;
+std::vector<std::unique_ptr<FoldBatch>> g_folds;
+
 // ---- alignment-graph cache ---------------------------------------------------------
 // The alignment acceptor of an utterance depends on (token graph, lexicon graph, target) only,
 // and a training run meets the same targets again every epoch (the reference's
@@ -1212,6 +1291,100 @@ int wfst_transducer_alignment_cache(long long capacity, unsigned long long* hits
     std::lock_guard<std::mutex> lk(c.mu);
     c.cap = (size_t)capacity;
   }
+  return WFST_OK;
+}
+
+// Transducer with an epsilon transition graph (criterions/transducer.py:279-281 with ngram > 1 or
+// a loaded back-off graph): for every utterance  intersect(transitions, aligns[b])  (epsilons in
+// place, as the reference), arc-sorted, then folded.  out_handles [B] receive the folded graphs
+// (pack them with wfst_graph_pack); the returned fold object holds the index arrays that tie
+// folded arcs and final weights to the TRANSITION graph's arcs (through the composition's
+// provenance).  aligns == NULL: fold the transition graph itself (B must be 1).
+int32_t wfst_fold_transitions_batch(int32_t transitions, const int32_t* aligns, int B, int32_t* out_handles) {
+  HostGraph* tr = get(transitions);
+  if (!tr || B < 1 || !out_handles) { set_error("bad arguments"); return WFST_ERR_INVALID; }
+  std::vector<HostGraph*> al(B, nullptr);
+  if (aligns) {
+    for (int b = 0; b < B; ++b) {
+      al[b] = get(aligns[b]);
+      if (!al[b]) { set_error("invalid graph handle %d", (int)aligns[b]); return WFST_ERR_INVALID; }
+    }
+  } else if (B != 1) {
+    set_error("folding the transition graph itself needs B == 1");
+    return WFST_ERR_INVALID;
+  }
+  std::vector<Folded> folded(B);
+  std::vector<std::vector<int32_t>> remap(B);
+  parallel_for(B, [&](int b) {
+    if (al[b]) {
+      auto c = compose_graphs(*tr, *al[b]);
+      c->arc_sort(false);
+      folded[b] = fold_epsilons(*c);
+      remap[b] = c->prov1;      // composed arc -> transition arc
+    } else {
+      folded[b] = fold_epsilons(*tr);
+    }
+  });
+  for (int b = 0; b < B; ++b)
+    if (!folded[b].ok) { set_error("epsilon cycle in acceptor"); return WFST_ERR_INVALID; }
+  auto fb = std::make_unique<FoldBatch>();
+  int64_t a0 = 0, p0 = 0, n0 = 0;
+  for (int b = 0; b < B; ++b) {
+    const Folded& f = folded[b];
+    const std::vector<int32_t>& m = remap[b];
+    auto orig = [&](int64_t x) { return m.empty() ? x : (int64_t)m[(size_t)x]; };
+    const int64_t na = (int64_t)f.arc_prov_ptr.size() - 1, np = (int64_t)f.fin_prov_ptr.size() - 1;
+    for (int64_t k = 0; k < na; ++k)
+      for (int64_t q = f.arc_prov_ptr[k]; q < f.arc_prov_ptr[k + 1]; ++q) {
+        fb->arc_seg.push_back(a0 + k);
+        fb->arc_src.push_back(orig(f.arc_prov[q]));
+      }
+    for (int64_t k = 0; k < np; ++k) {
+      fb->fin_node.push_back(n0 + f.fin_node[k]);
+      for (int64_t q = f.fin_prov_ptr[k]; q < f.fin_prov_ptr[k + 1]; ++q) {
+        fb->fin_seg.push_back(p0 + k);
+        fb->fin_src.push_back(orig(f.fin_prov[q]));
+      }
+    }
+    a0 += na; p0 += np; n0 += f.graph->num_nodes();
+  }
+  fb->num_arcs = a0; fb->num_paths = p0; fb->num_nodes = n0;
+  for (int b = 0; b < B; ++b) out_handles[b] = put(std::move(folded[b].graph));
+  std::lock_guard<std::mutex> lk(g_fold_mu);
+  for (size_t i = 0; i < g_folds.size(); ++i)
+    if (!g_folds[i]) { g_folds[i] = std::move(fb); return (int32_t)i; }
+  g_folds.push_back(std::move(fb));
+  return (int32_t)g_folds.size() - 1;
+}
+
+static FoldBatch* get_fold(int32_t h) {
+  std::lock_guard<std::mutex> lk(g_fold_mu);
+  if (h < 0 || h >= (int32_t)g_folds.size() || !g_folds[h]) return nullptr;
+  return g_folds[h].get();
+}
+
+// sizes: {folded arcs, final paths, nodes, arc tie entries, final tie entries}
+int wfst_fold_sizes(int32_t fold, int64_t* sizes) {
+  FoldBatch* f = get_fold(fold);
+  if (!f || !sizes) { set_error("invalid fold handle"); return WFST_ERR_INVALID; }
+  sizes[0] = f->num_arcs; sizes[1] = f->num_paths; sizes[2] = f->num_nodes;
+  sizes[3] = (int64_t)f->arc_seg.size(); sizes[4] = (int64_t)f->fin_seg.size();
+  return WFST_OK;
+}
+
+// copies the tie arrays (int64): arc_seg / arc_src [sizes[3]], fin_seg / fin_src [sizes[4]], fin_node [sizes[1]]
+int wfst_fold_fill(int32_t fold, int64_t* arc_seg, int64_t* arc_src, int64_t* fin_seg, int64_t* fin_src, int64_t* fin_node) {
+  FoldBatch* f = get_fold(fold);
+  if (!f) { set_error("invalid fold handle"); return WFST_ERR_INVALID; }
+  auto cp = [](int64_t* dst, const std::vector<int64_t>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), sizeof(int64_t) * v.size()); };
+  cp(arc_seg, f->arc_seg); cp(arc_src, f->arc_src); cp(fin_seg, f->fin_seg); cp(fin_src, f->fin_src); cp(fin_node, f->fin_node);
+  return WFST_OK;
+}
+
+int wfst_fold_destroy(int32_t fold) {
+  std::lock_guard<std::mutex> lk(g_fold_mu);
+  if (fold < 0 || fold >= (int32_t)g_folds.size() || !g_folds[fold]) return WFST_ERR_INVALID;
+  g_folds[fold].reset();
   return WFST_OK;
 }
 

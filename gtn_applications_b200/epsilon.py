@@ -114,6 +114,27 @@ class FoldedBatch:
         self.arc_seg, self.arc_src = cat(arc_seg), cat(arc_src)
         self.fin_seg, self.fin_src, self.fin_node = cat(fin_seg), cat(fin_src), cat(fin_node)
 
+    @classmethod
+    def from_fold(cls, fold, device):
+        """from a fold object of the host library (wfst_fold_transitions_batch: the composition with the
+        transition graph, the fold and these index arrays for the whole batch in C++ on host threads)"""
+        from . import _lib
+        L = _lib.lib()
+        sizes = np.zeros(5, dtype=np.int64)
+        _lib.check(L.wfst_fold_sizes(fold, sizes.ctypes.data))
+        na, npaths, nn, ea, ef = (int(x) for x in sizes)
+        arc_seg, arc_src = np.empty(ea, dtype=np.int64), np.empty(ea, dtype=np.int64)
+        fin_seg, fin_src = np.empty(ef, dtype=np.int64), np.empty(ef, dtype=np.int64)
+        fin_node = np.empty(npaths, dtype=np.int64)
+        _lib.check(L.wfst_fold_fill(fold, arc_seg.ctypes.data, arc_src.ctypes.data, fin_seg.ctypes.data,
+                                    fin_src.ctypes.data, fin_node.ctypes.data))
+        self = cls.__new__(cls)
+        self.num_arcs, self.num_paths, self.num_nodes = na, npaths, nn
+        up = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
+        self.arc_seg, self.arc_src = up(arc_seg), up(arc_src)
+        self.fin_seg, self.fin_src, self.fin_node = up(fin_seg), up(fin_src), up(fin_node)
+        return self
+
     def weights(self, params, tropical=False):
         """(folded arc weights [A'], final weights [N] (-inf where not accepting), path weights [P])"""
         dev = params.device

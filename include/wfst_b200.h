@@ -252,6 +252,23 @@ WFST_API int wfst_transducer_alignment_graphs(int32_t tokens, int32_t lexicon,
 WFST_API int wfst_transducer_alignment_cache(long long capacity, unsigned long long* hits,
                                              unsigned long long* misses);
 
+/* Transducer with a transition graph that has epsilon arcs (ngram > 1: the </s> arcs of
+ * make_transitions_graph, transducer.py:52-56; back-off graphs loaded with gtn.load): for every
+ * utterance intersect(transitions, aligns[b]) is formed with the epsilons in place (as
+ * transducer.py:279-281 does), arc-sorted and folded into an epsilon-free acceptor with final
+ * weights (gtn_applications_b200/epsilon.py describes the fold) on host threads.  out_handles [B]
+ * receive the folded graphs (pack them with wfst_graph_pack); the returned fold object holds the
+ * int64 index arrays that tie folded arcs / final-weight paths to the TRANSITION graph's arcs:
+ * wfst_fold_sizes -> {folded arcs, final paths, nodes, arc tie entries, final tie entries};
+ * wfst_fold_fill copies arc_seg / arc_src, fin_seg / fin_src, fin_node.  aligns == NULL (B = 1)
+ * folds the transition graph itself. */
+WFST_API int32_t wfst_fold_transitions_batch(int32_t transitions, const int32_t* aligns, int B,
+                                             int32_t* out_handles);
+WFST_API int wfst_fold_sizes(int32_t fold, int64_t* sizes);
+WFST_API int wfst_fold_fill(int32_t fold, int64_t* arc_seg, int64_t* arc_src, int64_t* fin_seg,
+                            int64_t* fin_src, int64_t* fin_node);
+WFST_API int wfst_fold_destroy(int32_t fold);
+
 /* Packs B host graphs into the arrays of wfst_acceptor_batch_t (HOST buffers sized from
  * wfst_graph_pack_sizes; the caller uploads them).  Arc lists keep their arc_sort order. */
 /* Alignment -> tokens for a batch of best alignments — the host part of Transducer.viterbi

@@ -369,7 +369,8 @@ static size_t asg_hist_fal_bytes(int B, int T, int C, int L) { return lattice_hi
 
 size_t wfst_asg_workspace_bytes(int B, int T, int C, int max_target_len) {
   return asg_hist_fcc_bytes(B, T, C) + asg_hist_fal_bytes(B, T, C, max_target_len) +
-         2 * align_up((size_t)B * sizeof(float), 256) + align_up((size_t)B * T * C * sizeof(float), 256);
+         2 * align_up((size_t)B * sizeof(float), 256) + align_up((size_t)B * T * C * sizeof(float), 256) +
+         (asg_fal_chain_eligible(T, C, max_target_len) ? asg_fal_chain_workspace_bytes(B, T, max_target_len) : 0);
 }
 
 int wfst_asg_forward_backward(const float* emissions, const float* transitions,
@@ -407,9 +408,24 @@ int wfst_asg_forward_backward(const float* emissions, const float* transitions,
   // of shared memory per block, and an SM that already runs the (static-shared-memory) dense
   // kernel keeps that kernel's small carveout until it drains — launched second, the lattice
   // blocks were confined to the SMs the dense kernel had left free (measured 0.77 -> 1.30 ms).
-  int rc2 = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
+  int rc2;
+  // (any lattice test hook selects the log-semiring lattice kernels for the force-align term)
+  if (asg_fal_chain_eligible(T, C, max_target_len) && !g_force_generic && lattice_forced_mode() == 0) {
+    // scaled-probability chain; the utterances it flags are redone by the log-semiring lattice
+    void* fal_ws = w + hb1 + hb2 + 2 * zb + align_up((size_t)B * T * C * sizeof(float), 256);
+    int* hz = nullptr;
+    rc2 = launch_asg_fal_chain(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
+                               grad_scale, -1.f, zfal, grad_emissions ? gfal : nullptr, grad_transitions, fal_ws,
+                               &hz, s2);
+    if (rc2 == WFST_OK)
+      rc2 = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
                            grad_scale, -1.f, zfal, grad_emissions ? gfal : nullptr, 0, grad_transitions,
-                           hist_fal, s2);
+                           hist_fal, s2, hz);
+  } else {
+    rc2 = launch_asg_fal(emissions, transitions, targets, target_offsets, B, T, C, max_target_len,
+                         grad_scale, -1.f, zfal, grad_emissions ? gfal : nullptr, 0, grad_transitions,
+                         hist_fal, s2);
+  }
   rc = (asg_fcc_dense_eligible(T, C) && !g_force_generic)
            ? launch_asg_fcc_dense(emissions, transitions, B, T, C, grad_scale, 1.f, zfcc, grad_emissions, 0,
                                   grad_transitions, hist_fcc, st)

@@ -148,6 +148,7 @@ static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, i
 }
 
 int lattice_force_generic(int on) { int old = g_force_generic_lattice; g_force_generic_lattice = on; return old; }
+int lattice_forced_mode() { return g_force_generic_lattice; }
 
 static size_t hist_bytes(int B, int T, int stride) {
   return align_up((size_t)B * (T + 1) * stride * sizeof(float), 256);
@@ -206,9 +207,10 @@ int launch_csr(const float* E, int T, int C, const wfst_acceptor_batch_t& g, int
 int launch_asg_fal(const float* E, const float* tr, const int* targets, const int* offsets, int B,
                    int T, int C, int max_target_len, const float* grad_scale, float sign,
                    float* scores, float* gradE, int accumulate, float* gradTr, float* hist,
-                   cudaStream_t st) {
+                   cudaStream_t st, const int* active) {
   LatticeArgs a = base_args(E, B, T, C, grad_scale, sign, scores, gradE, accumulate, hist,
                             max_target_len + 1, gradTr ? 2 * (C + 1) * C + 2 : 0);
+  a.active = active;
   AsgFalTopo::Params tp{targets, offsets, tr, gradTr, C};
   int rc;
   if (try_launch_lean<AsgFalLean>(a, tp, B, max_target_len + 1, 2 * (max_target_len + 1), gradTr ? 1 : 0, st, &rc))

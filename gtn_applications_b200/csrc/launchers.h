@@ -8,6 +8,7 @@ namespace wfst {
 size_t lattice_hist_bytes(int B, int T, int C, int max_nodes);
 // test hook: 1 = never use the shared-memory ("lean") lattice kernel; returns the old value
 int lattice_force_generic(int on);
+int lattice_forced_mode();
 int launch_ctc(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                int blank, int max_target_len, const float* grad_scale, float* scores,
                float* gradE, float* hist, const int* active, cudaStream_t st);
@@ -17,7 +18,15 @@ int launch_csr(const float* E, int T, int C, const wfst_acceptor_batch_t& g, int
 int launch_asg_fal(const float* E, const float* tr, const int* targets, const int* offsets, int B,
                    int T, int C, int max_target_len, const float* grad_scale, float sign,
                    float* scores, float* gradE, int accumulate, float* gradTr, float* hist,
-                   cudaStream_t st);
+                   cudaStream_t st, const int* active = nullptr);
+// scaled-probability force-align chain (asg_fal_chain.cu); utterances it flags in *hazard_out are
+// redone by launch_asg_fal(..., active = hazard)
+bool asg_fal_chain_eligible(int T, int C, int max_target_len);
+size_t asg_fal_chain_workspace_bytes(int B, int T, int max_target_len);
+int launch_asg_fal_chain(const float* E, const float* tr, const int* targets, const int* offsets, int B,
+                         int T, int C, int max_target_len, const float* grad_scale, float sign,
+                         float* scores, float* gradE, float* gradTr, void* workspace, int** hazard_out,
+                         cudaStream_t st);
 int launch_asg_fcc(const float* E, const float* tr, int B, int T, int C, const float* grad_scale,
                    float sign, float* scores, float* gradE, int accumulate, float* gradTr,
                    float* hist, cudaStream_t st);

@@ -89,3 +89,18 @@ def test_target_with_blank_label_goes_to_the_fallback(chain_first):
     Z, gZ = dp_numpy.ctc_dense_one(e[1].numpy().astype(np.float64), tg[1], C - 1)
     assert abs(losses[1] + Z) <= 1e-5 * abs(Z)
     np.testing.assert_allclose(grad[1], -gZ / B, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(256, 1000, 30, 176), (5, 100, 30, 40), (8, 1500, 80, 264)])
+def test_results_are_bit_identical_from_run_to_run(chain_first, shape):
+    """Every hand-off between the warps of a block goes through an mbarrier; a missed one would
+    show up as run-to-run differences (compute-sanitizer's racecheck cannot follow inline-PTX
+    mbarriers, profiles/r2_sanitizer.txt).  No float atomics anywhere in these kernels: three
+    runs of the same batch are bit-identical."""
+    B, T, C, L = shape
+    g = torch.Generator().manual_seed(11)
+    e = torch.log_softmax(torch.randn(B, T, C, generator=g), 2).cuda()
+    tg = torch.randint(C - 1, (B, L), generator=g).tolist()
+    runs = [ctc_capi(e, tg, C - 1) for _ in range(3)]
+    for r in runs[1:]:
+        assert np.array_equal(r[0], runs[0][0]) and np.array_equal(r[2], runs[0][2]) and np.array_equal(r[3], runs[0][3])

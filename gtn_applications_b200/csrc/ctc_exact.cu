@@ -20,7 +20,7 @@
 namespace wfst {
 namespace exactk {
 
-constexpr int kNT = 256;
+constexpr int kNT = 384;    // one state per thread up to S = 384 (cfg2: 353), two up to 768
 constexpr float kFix = 1073741824.f;   // 2^30
 
 struct Args {
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(kNT) ctc_exact_kernel(Args a) {
   double* buf0 = reinterpret_cast<double*>(smem_raw);
   double* buf1 = buf0 + S;
   int* lab = reinterpret_cast<int*>(buf1 + S);
-  unsigned* gt = reinterpret_cast<unsigned*>(lab + S);
-  unsigned char* skip = reinterpret_cast<unsigned char*>(gt + C);
+  unsigned* gt0 = reinterpret_cast<unsigned*>(lab + S);      // two tiles: one is cleared while the other is summed
+  unsigned char* skip = reinterpret_cast<unsigned char*>(gt0 + 2 * C);
   __shared__ double zsh;
   for (int s = tid; s < S; s += kNT) {
     int l = a.blank, sk = 0;
@@ -84,16 +84,45 @@ __global__ void __launch_bounds__(kNT) ctc_exact_kernel(Args a) {
     H[s] = v;
   }
   __syncthreads();
+  // one state per thread per round (S <= 2 kNT keeps the emissions of a thread's states in two
+  // registers, fetched one frame ahead so that the L2 latency hides behind the frame before)
+  const int s0 = tid, s1 = tid + kNT;
+  const bool two = S <= 2 * kNT;
+  float en0 = 0.f, en1 = 0.f;
+  if (two && T > 1) {
+    if (s0 < S) en0 = Eb[(size_t)C + lab[s0]];
+    if (s1 < S) en1 = Eb[(size_t)C + lab[s1]];
+  }
   for (int t = 1; t < T; ++t) {
     const float* Et = Eb + (size_t)t * C;
     double* Ht = H + (size_t)t * a.stride;
-    for (int s = tid; s < S; s += kNT) {
-      const double a0 = prev[s];
-      const double a1 = s >= 1 ? prev[s - 1] : -INFINITY;
-      const double a2 = (s >= 2 && skip[s]) ? prev[s - 2] : -INFINITY;
-      const double v = lse3(a0, a1, a2) + (double)Et[lab[s]];
-      cur[s] = v;
-      Ht[s] = v;
+    if (two) {
+      const float e0 = en0, e1 = en1;
+      if (t + 1 < T) {
+        if (s0 < S) en0 = Et[C + lab[s0]];
+        if (s1 < S) en1 = Et[C + lab[s1]];
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = r ? s1 : s0;
+        if (s < S) {
+          const double a0 = prev[s];
+          const double a1 = s >= 1 ? prev[s - 1] : -INFINITY;
+          const double a2 = (s >= 2 && skip[s]) ? prev[s - 2] : -INFINITY;
+          const double v = lse3(a0, a1, a2) + (double)(r ? e1 : e0);
+          cur[s] = v;
+          Ht[s] = v;
+        }
+      }
+    } else {
+      for (int s = tid; s < S; s += kNT) {
+        const double a0 = prev[s];
+        const double a1 = s >= 1 ? prev[s - 1] : -INFINITY;
+        const double a2 = (s >= 2 && skip[s]) ? prev[s - 2] : -INFINITY;
+        const double v = lse3(a0, a1, a2) + (double)Et[lab[s]];
+        cur[s] = v;
+        Ht[s] = v;
+      }
     }
     __syncthreads();
     double* tmp = prev; prev = cur; cur = tmp;
@@ -116,22 +145,56 @@ __global__ void __launch_bounds__(kNT) ctc_exact_kernel(Args a) {
   double* be = cur;
   for (int s = tid; s < S; s += kNT) beta[s] = (s >= S - 2) ? 0.0 : -INFINITY;
   __syncthreads();
+  float eb0 = 0.f, eb1 = 0.f;
+  double hb0 = -INFINITY, hb1 = -INFINITY;
+  if (two) {
+    const float* Et = Eb + (size_t)(T - 1) * C;
+    const double* Ht = H + (size_t)(T - 1) * a.stride;
+    if (s0 < S) { eb0 = Et[lab[s0]]; hb0 = Ht[s0]; }
+    if (s1 < S) { eb1 = Et[lab[s1]]; hb1 = Ht[s1]; }
+  }
+  for (int c = tid; c < 2 * C; c += kNT) gt0[c] = 0u;
+  __syncthreads();
   for (int t = T - 1; t >= 0; --t) {
     const float* Et = Eb + (size_t)t * C;
     const double* Ht = H + (size_t)t * a.stride;
-    for (int c = tid; c < C; c += kNT) gt[c] = 0u;
-    __syncthreads();
-    for (int s = tid; s < S; s += kNT) {
-      const double bs = beta[s];
-      const double g = Ht[s] + bs - Z;
-      if (g > -80.0) {
-        const float p = __expf((float)fmin(g, 0.0));
-        atomicAdd(&gt[lab[s]], (unsigned)(p * kFix + 0.5f));
+    unsigned* gt = gt0 + ((T - 1 - t) & 1) * C;
+    if (two) {
+      const float e0 = eb0, e1 = eb1;
+      const double h0 = hb0, h1 = hb1;
+      if (t > 0) {      // next frame's emissions and alpha row
+        if (s0 < S) { eb0 = Et[lab[s0] - C]; hb0 = Ht[s0 - a.stride]; }
+        if (s1 < S) { eb1 = Et[lab[s1] - C]; hb1 = Ht[s1 - a.stride]; }
       }
-      be[s] = bs + (double)Et[lab[s]];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = r ? s1 : s0;
+        if (s < S) {
+          const double bs = beta[s];
+          const double g = (r ? h1 : h0) + bs - Z;
+          if (g > -80.0) {
+            const float p = __expf((float)fmin(g, 0.0));
+            atomicAdd(&gt[lab[s]], (unsigned)(p * kFix + 0.5f));
+          }
+          be[s] = bs + (double)(r ? e1 : e0);
+        }
+      }
+    } else {
+      for (int s = tid; s < S; s += kNT) {
+        const double bs = beta[s];
+        const double g = Ht[s] + bs - Z;
+        if (g > -80.0) {
+          const float p = __expf((float)fmin(g, 0.0));
+          atomicAdd(&gt[lab[s]], (unsigned)(p * kFix + 0.5f));
+        }
+        be[s] = bs + (double)Et[lab[s]];
+      }
     }
     __syncthreads();
-    for (int c = tid; c < C; c += kNT) G[(size_t)t * C + c] = gsc * (float)gt[c];
+    for (int c = tid; c < C; c += kNT) {
+      G[(size_t)t * C + c] = gsc * (float)gt[c];
+      gt[c] = 0u;     // summed into again two frames from now, after two more barriers
+    }
     for (int s = tid; s < S; s += kNT) {
       const double b1 = s + 1 < S ? be[s + 1] : -INFINITY;
       const double b2 = (s + 2 < S && skip[s + 2]) ? be[s + 2] : -INFINITY;
@@ -141,7 +204,7 @@ __global__ void __launch_bounds__(kNT) ctc_exact_kernel(Args a) {
   }
 }
 
-static size_t smem_bytes(int S, int C) { return (size_t)S * (2 * sizeof(double) + sizeof(int) + 1) + (size_t)C * sizeof(unsigned) + 16; }
+static size_t smem_bytes(int S, int C) { return (size_t)S * (2 * sizeof(double) + sizeof(int) + 1) + (size_t)2 * C * sizeof(unsigned) + 16; }
 
 }  // namespace exactk
 

@@ -238,7 +238,9 @@ def other_configs(dev):
     # time_utils.py): alignment graphs come from the LRU after the first step ("warm").  "cold":
     # the cache is emptied before every step, i.e. every step builds its 64 alignment graphs.
     def tdc_cold():
+        from gtn_applications_b200.criterions import transducer as _tm
         _lib.check(L_.wfst_transducer_alignment_cache(-1, None, None))
+        _tm._PACKED_LRU.clear()
         tdc()
 
     s4c = timed(tdc_cold, 5, warm=2)
@@ -252,8 +254,8 @@ def other_configs(dev):
                                       "threads + lattice kernel), B=64 T=1000, the reference's %d word pieces "
                                       "(benchmarks/word_pieces_tokens_1000.txt), 150 pieces per utterance, blank "
                                       "optional, no repeats (transducer_benchmark.py:19-44); ms_per_step: targets "
-                                      "repeat as in the reference benchmark (alignment graphs from the LRU cache); "
-                                      "cold_*: cache emptied before every step" % len(tokens)}
+                                      "repeat as in the reference benchmark (alignment graphs and the packed device batch from the LRU caches); "
+                                      "cold_*: caches emptied before every step" % len(tokens)}
     del x
     # ---- n-gram transducers (benchmarks/transducer_benchmark.py:56-119: N=81 tokens, T=250, L=44, ngram=2;
     # there B=1 on CPU, here B=32): epsilon transition graph, composition + fold for the batch in the

@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwfst_b200.so")
+LIB_PATH = os.environ.get("WFST_B200_LIB") or os.path.join(_HERE, "lib", "libwfst_b200.so")
 
 c_float_p = ctypes.c_void_p
 c_int_p = ctypes.c_void_p

@@ -56,6 +56,8 @@ static int g_no_chain = 0;
 static int g_chain_first = 0;
 // test hook: 1 = skip the solo-chain kernel; 2 = solo-chain kernel first
 static int g_solo_mode = 0;
+// test hook: 1 = skip the tick-scheduled chain kernel; 2 = tick kernel first
+static int g_tick_mode = 0;
 
 }  // namespace wfst
 
@@ -77,6 +79,8 @@ int wfst_debug_force_generic_ctc(int on) {
   g_chain_first = (on == 5);
   // 6: solo-chain kernel first; 7: no solo-chain kernel (paired / chain-split as in round 2's first half)
   g_solo_mode = on == 6 ? 2 : ((on == 7 || on == 4 || on == 5 || on == 2) ? 1 : 0);
+  // 8: tick-scheduled chain kernel first; 9: no tick kernel
+  g_tick_mode = on == 8 ? 2 : ((on == 9 || on == 7 || on == 6 || on == 4 || on == 5 || on == 2) ? 1 : 0);
   g_asg_dense_single = (on == 3);
   return old;
 }
@@ -84,6 +88,7 @@ int wfst_debug_force_generic_lattice(int on) { return lattice_force_generic((on 
 unsigned long long wfst_launch_count(void) { return g_launches.load(); }
 int wfst_debug_ctc_chain_config(int K, int W) {
   ctc_solo_force_config(K, W);
+  ctc_tick_force_config(K, W);
   return ctc_chain_force_config(K, W);
 }
 
@@ -94,6 +99,7 @@ int wfst_debug_ctc_chain_config(int K, int W) {
 // paired layout cannot hold, e.g. cfg5), single (the rest), none (log-semiring kernels only)
 static int ctc_scaled_kind(int T, int C, int max_target_len) {
   if (g_force_generic) return 0;
+  if (g_tick_mode == 2 && ctc_tick_eligible(T, C, max_target_len)) return 5;
   if (g_solo_mode == 2 && ctc_solo_eligible(T, C, max_target_len)) return 4;
   if (g_chain_first && ctc_chain_eligible(T, C, max_target_len)) return 3;
   if (g_force_generic_kind != 2 && ctc_pair_eligible(T, C, max_target_len)) return 2;
@@ -115,6 +121,10 @@ static size_t ctc_scaled_workspace_bytes(int B, int T, int C, int max_target_len
   if (ctc_chain_eligible(T, C, max_target_len)) n = ctc_chain_workspace_bytes(B, T, max_target_len);
   if (ctc_solo_eligible(T, C, max_target_len)) {
     size_t m = ctc_solo_workspace_bytes(B, T, max_target_len);
+    if (m > n) n = m;
+  }
+  if (ctc_tick_eligible(T, C, max_target_len)) {
+    size_t m = ctc_tick_workspace_bytes(B, T, max_target_len);
     if (m > n) n = m;
   }
   if (ctc_pair_eligible(T, C, max_target_len)) {
@@ -159,7 +169,9 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
     // scaled-probability kernel; utterances it flags are redone by the log-semiring kernel
     int* hazard = nullptr;
     void* fws = (char*)workspace + hb + align_up((size_t)B * sizeof(float), 256);
-    rc = kind == 4 ? launch_ctc_solo(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+    rc = kind == 5 ? launch_ctc_tick(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
+                                     grad_scale, z, grad, fws, &hazard, st)
+         : kind == 4 ? launch_ctc_solo(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
                                      grad_scale, z, grad, fws, &hazard, st)
          : kind == 3 ? launch_ctc_chain(emissions, targets, target_offsets, B, T, C, blank, max_target_len,
                                       grad_scale, z, grad, fws, &hazard, st)
@@ -251,7 +263,8 @@ int wfst_debug_ctc_hazards(const void* workspace, int B, int T, int C, int max_t
   const int kind = ctc_scaled_kind(T, C, max_target_len);
   if (kind == 0) return WFST_OK;
   size_t hb = ctc_hist_bytes(B, T, C, max_target_len) + align_up((size_t)B * sizeof(float), 256);
-  size_t fb = kind == 4 ? ctc_solo_workspace_bytes(B, T, max_target_len)
+  size_t fb = kind == 5 ? ctc_tick_workspace_bytes(B, T, max_target_len)
+              : kind == 4 ? ctc_solo_workspace_bytes(B, T, max_target_len)
               : kind == 3 ? ctc_chain_workspace_bytes(B, T, max_target_len)
               : kind == 2 ? ctc_pair_workspace_bytes(B, T, max_target_len) : ctc_fast_workspace_bytes(B, T, max_target_len);
   const char* hz = (const char*)workspace + hb + fb - align_up((size_t)B * sizeof(int), 256);

@@ -76,6 +76,14 @@ size_t ctc_solo_workspace_bytes(int B, int T, int max_target_len);
 int launch_ctc_solo(const float* E, const int* targets, const int* offsets, int B, int T, int C,
                     int blank, int max_target_len, const float* grad_scale, float* z_out,
                     float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
+// tick-scheduled chain CTC (ctc_tick.cu): ctc_solo.cu's roles and numerics, every hand-off between
+// roles through one named barrier per 8-frame tick instead of per-resource mbarriers
+bool ctc_tick_eligible(int T, int C, int max_target_len);
+int ctc_tick_force_config(int K, int W);
+size_t ctc_tick_workspace_bytes(int B, int T, int max_target_len);
+int launch_ctc_tick(const float* E, const int* targets, const int* offsets, int B, int T, int C,
+                    int blank, int max_target_len, const float* grad_scale, float* z_out,
+                    float* gradE, void* workspace, int** hazard_out, cudaStream_t st);
 // float64 log-semiring CTC (ctc_exact.cu): recomputes the utterances the scaled kernels flag
 bool ctc_exact_eligible(int T, int C, int max_target_len);
 size_t ctc_exact_hist_bytes(int B, int T, int max_target_len);

@@ -13,7 +13,7 @@ from _capi import ctc_capi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[5, 6], ids=["packed", "solo"])
+@pytest.fixture(params=[5, 6, 8], ids=["packed", "solo", "tick"])
 def chain_first(request):
     from gtn_applications_b200 import _lib
     L = _lib.lib()

@@ -20,7 +20,8 @@
 //                      X[c]: step m - 2W
 //
 //   p tiles      ring of NB >= 2W+1 (written one tick ahead, last read by rc[W-1])
-//   step buffers ring of NAB >= 2W+1 (abar rows, boundary state, lane exponents, certificate)
+//   step buffers ring of NAB = 2W (abar rows, boundary state, lane exponents: live -> rc)
+//   tiles        ring of W+1 (integer gradient tile, certificate terms: rc -> X)
 //   chain rings  2 entries per warp boundary (written at tick t, read at tick t+1)
 //
 // The only mbarriers left are the producer's own TMA completion barriers.  Lanes are
@@ -44,10 +45,7 @@ constexpr int kNR = 3;                // raw (TMA) staging slots per producer wa
 constexpr int kRD = 2;                // entries per chain ring (step parity)
 constexpr int kMaxAB = 8;             // step buffers per component, at most
 constexpr int kMaxNB = 12;            // p tiles per component, at most
-constexpr int kMaxList = 48;          // reduction table: sum over class rounds of the longest list
-constexpr int kMaxW = 4;
 constexpr int kRingF = 12;            // floats per ring entry: 9 boundary values, the exponent, pad
-constexpr int kRegList = 16;          // entries of a class list the reduction keeps in registers
 
 #define WFST_HAZ(ptr, bits) atomicOr(ptr, bits)
 
@@ -200,12 +198,13 @@ struct Geo {
 
 // shared memory layout (in floats); every per-component region is [2][...]
 struct Layout {
-  size_t raw, out, abuf, bnd, lexp, cert, ptile, ringL, ringR, bars, zx, ytab, xtab, hist, prof, total;
-  size_t abuf_c, bnd_c, lexp_c, cert_c, ptile_c, ring_c;   // size of one component's part
+  size_t raw, out, abuf, bnd, lexp, cert, gacc, ptile, ringL, ringR, bars, zx, ytab, prof, total;
+  size_t abuf_c, bnd_c, lexp_c, cert_c, gacc_c, ptile_c, ring_c;   // size of one component's part
   size_t zero_end;
 };
 template <int K, int W>
 __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
+  const int NG = W + 1;   // tiles / certificate terms: written by rc, read by X
   using G = Geo<K, W>;
   Layout L;
   const size_t rawsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
@@ -219,8 +218,10 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
   L.bnd = p;    p += 2 * L.bnd_c;                                   // [c][buf][word]: live state at the step boundary
   L.lexp_c = (size_t)NAB * G::NL;
   L.lexp = p;   p += 2 * L.lexp_c;                                  // [c][buf][gl] (int)
-  L.cert_c = (size_t)NAB * W;
+  L.cert_c = (size_t)NG * G::NL;
   L.cert = p;   p += 2 * L.cert_c;                                  // [c][buf][w]
+  L.gacc_c = (size_t)NG * kSeg * CP;
+  L.gacc = p;   p += 2 * L.gacc_c;                                  // [c][buf][row][class] (int, 2^-29 units)
   L.ptile_c = (size_t)NB * CP * 9 + 8;
   L.ptile = p;  p += 2 * L.ptile_c;                                 // [c][buf][col][9]
   p = (p + 3) & ~(size_t)3;
@@ -233,8 +234,6 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
   p = (p + 3) & ~(size_t)3;
   L.zx = p;     p += 32;   // Zm, eZ, ok, -, msum(double), zpart[kMaxW]{contrib, Emax}, endacc[2]
   L.ytab = p;   p += (size_t)G::Sp / 2 + 4;                         // targets of the utterance
-  L.xtab = p;   p += (size_t)2 * kMaxList * 32 / 2;                 // [c][entry][lane] (u16 row offsets)
-  L.hist = p;   p += (size_t)C + 16;                                // per-class counts; then per-round {nmax, base}
   p = (p + 3) & ~(size_t)3;
   L.prof = p;
 #ifdef WFST_PROFILE
@@ -245,11 +244,9 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
 }
 
 struct Smem {
-  uint32_t raw, out, abuf, bnd, lexp, cert, ptile, ringL, ringR, bars, zx, xtab;
-  uint32_t abuf_c, bnd_c, lexp_c, cert_c, ptile_c, ring_c;   // bytes per component
+  uint32_t raw, out, abuf, bnd, lexp, cert, gacc, ptile, ringL, ringR, bars, zx;
+  uint32_t abuf_c, bnd_c, lexp_c, cert_c, gacc_c, ptile_c, ring_c;   // bytes per component
   int* ytab;
-  int* hist;
-  unsigned short* xtab_gen;
   float* out_gen;
   float* prof_gen;
 };
@@ -506,7 +503,26 @@ __device__ __forceinline__ void producer_convert(const Smem& sm, const Ctx& cx, 
   // A row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface through the
   // certificate.
   float base[kSeg];
-  if (groups == 1) {
+  if (groups == 1 && rows == kSeg) {
+    // the common case (full tile, C <= 32) without row predicates
+    const bool valid = lane < C;
+    const uint32_t e0 = valid ? er : raw0 + 4u * (uint32_t)slot * rawsz;   // idle lanes re-read class 0: the maximum is unchanged
+    float x[kSeg];
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) x[r] = lds(e0 + 4u * (uint32_t)(r * C));
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) {
+      const float mx = warp_max(x[r]);
+      base[r] = (mx == kNegInf) ? 0.f : mx;
+    }
+    if (valid) {
+      const uint32_t p0 = pt + (c == 0 ? 0u : 4u * (kSeg - 1));
+      const int32_t dp = c == 0 ? 4 : -4;
+#pragma unroll
+      for (int r = 0; r < kSeg; ++r)
+        sts(p0 + (uint32_t)(r * dp), ex2_fast((x[r] - base[r]) * 1.4426950408889634f));
+    }
+  } else if (groups == 1) {
     const bool valid = lane < C;
     float x[kSeg];
 #pragma unroll
@@ -775,8 +791,9 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     float Zm = 1.f;
     if (ok) {
       ex = (int)((__float_as_uint(tot) >> 23) & 0xffu) - 127;
-      ex = min(max(ex, -126), 126);
-      Zm = tot * pow2i(-ex);
+      ex = min(max(ex, -126), 125);
+      Zm = tot * pow2i(-ex) * 0.5f;   // in [0.5, 1): the fixed-point posteriors stay below 1
+      ex += 1;
     }
     sts(sm.zx, Zm);
     stsi(sm.zx + 4u, ok ? Emax + ex : 0);
@@ -863,9 +880,19 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
 // rows.  Before each step the lane is rescaled so that its effective exponent is
 // eZ - e_live(partner lane): products need no further factor.
 // ---------------------------------------------------------------------------
+// Fixed point in 2^-23 units without a conversion: for 0 <= x < 1 the float 1 + x has the
+// exponent of 1.0 and its mantissa field is round(x * 2^23); the integer difference to the bits
+// of 1.0 stays continuous at x = 1.  Zm is kept in [0.5, 1), so every posterior is below 1.
+constexpr float kFix = 8388608.f;
+__device__ __forceinline__ void red_add(uint32_t a, float w, float av) {
+  const int v = __float_as_int(fmaf(w, av, 1.f)) - 0x3f800000;
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// gt: this frame's row of the step's gradient tile; gofs[q]: byte offset of the class of my odd
+// slot 2q+1 in a tile row (the dump column for padding slots)
 template <int K>
 __device__ __forceinline__ void rc_frame(float (&w)[K], const Topo<K>& tp, const PRow<K>& cur, float in1, float h, uint32_t arow,
-                                         uint32_t extb) {
+                                         uint32_t extb, uint32_t gt, const uint32_t (&gofs)[K / 2]) {
   // partner of my odd slot i (<= K-3) is label slot (K-3-i)/2 of the partner block; of my slot
   // K-1, the last label slot of the block before it
   float av[K / 2], dummy[K / 2];
@@ -873,9 +900,11 @@ __device__ __forceinline__ void rc_frame(float (&w)[K], const Topo<K>& tp, const
   for (int q = 0; q < K / 2 - 1; ++q) av[q] = lds(arow + 4u * q);
   const float ext = lds(arow - extb);
   step<K, false>(w, dummy, tp, cur, in1);
+  // posteriors (times Zm) of my label states, summed by class with integer atomics: the sum does
+  // not depend on the order
 #pragma unroll
-  for (int q = 0; q < K / 2 - 1; ++q) sts(arow + 4u * q, w[K - 3 - 2 * q] * av[q]);
-  sts(arow - extb, (w[K - 1] * ext) * h);
+  for (int q = 0; q < K / 2 - 1; ++q) red_add(gt + gofs[(K - 3 - 2 * q) >> 1], w[K - 3 - 2 * q], av[q]);
+  red_add(gt + gofs[(K - 1) >> 1], w[K - 1] * h, ext);
 }
 
 template <int K, int W>
@@ -899,13 +928,18 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   const uint32_t ring_out0 = ring_in0 + 4u * (uint32_t)(kRD * kRingF);
   const uint32_t abuf = sm.abuf + (uint32_t)c * sm.abuf_c, bndb = sm.bnd + (uint32_t)c * sm.bnd_c,
                  lexpb = sm.lexp + (uint32_t)c * sm.lexp_c, certb = sm.cert + (uint32_t)c * sm.cert_c;
+  uint32_t gofs[K / 2];
+#pragma unroll
+  for (int q = 0; q < K / 2; ++q) gofs[q] = tp.labofs[q] / 9u;   // 36 col -> 4 col
+  const uint32_t gaccb = sm.gacc + (uint32_t)c * sm.gacc_c;
+  const uint32_t growb = 4u * (uint32_t)cx.CP;
   int bad = 0;   // reason 4: scale overflow when pairing live and recomputed values
   float wv[K], nv[K];
   int ew, ne;
   // the checkpoint of a step is fetched while the step before it runs
   ckpt_load<K, G::CKF>(ck + (size_t)(nsd - 1) * NL * G::CKF, nv, ne);
   const bool has_partial = nsd > cx.nfull;
-  int pbuf = nsd % cx.NB, buf = 0;
+  int pbuf = nsd % cx.NB, buf = 0, gbuf = 0;
   Prof pf;
   pf.setup(sm.prof_gen + 64, tick_mask<W>(c, 2));
   tick2<W>(c, pf);
@@ -945,6 +979,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
       const TileAddr<K> ta = tile_addr<K>(tp, ptile_addr(sm, cx, c, pbuf));
       if (++pbuf == cx.NB) pbuf = 0;
       const uint32_t ar = abuf + (uint32_t)(buf * kSeg) * G::ROWB + pabar;
+      const uint32_t gt0 = gaccb + (uint32_t)(gbuf * kSeg) * growb;
       if (!partial) {
         // against the live step order
         PRow<K> nx = load_prow<K>(ta, kSeg - 1);
@@ -955,7 +990,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
           const float bv = bvn;
           if (it > 0) { nx = load_prow<K>(ta, it - 1); bvn = ring_ld(rin + 4u * (kSeg - it)); }
           const float in1 = left_in(wv[K - 1], bv, lane, frs);
-          rc_frame<K>(wv, tp, cur, in1, hsc, ar + (uint32_t)it * G::ROWB, G::EXTB);
+          rc_frame<K>(wv, tp, cur, in1, hsc, ar + (uint32_t)it * G::ROWB, G::EXTB, gt0 + (uint32_t)it * growb, gofs);
           ring_st(rout + 4u * (kSeg - it), wv[K - 1], lane);
         }
       } else {
@@ -963,7 +998,7 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
         for (int it = rows - 1; it >= 0; --it) {
           const PRow<K> cur = load_prow<K>(ta, it);
           const float in1 = left_in(wv[K - 1], lds(rin + 4u * (uint32_t)(rows - 1 - it)), lane, frs);
-          rc_frame<K>(wv, tp, cur, in1, hsc, ar + (uint32_t)it * G::ROWB, G::EXTB);
+          rc_frame<K>(wv, tp, cur, in1, hsc, ar + (uint32_t)it * G::ROWB, G::EXTB, gt0 + (uint32_t)it * growb, gofs);
           if (lane == 31) sts(rout + 4u * (uint32_t)(rows - it), wv[K - 1]);
         }
       }
@@ -984,10 +1019,10 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
           if (i == K - 1) acc = fmaf(sx * hsc, lds(bb - 4u), acc);
           else acc = fmaf(sx, lds(bb + 4u * (K - 2 - i)), acc);
         }
-        const float t0 = warp_sum(acc);
-        if (lane == 0) sts(certb + 4u * (uint32_t)(buf * W + w), t0);
+        sts(certb + 4u * (uint32_t)(gbuf * NL + gl), acc);   // X sums the lanes' terms
       }
       if (++buf == NAB) buf = 0;
+      if (++gbuf == W + 1) gbuf = 0;
     }
     tick2<W>(c, pf);
   }
@@ -997,57 +1032,14 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
 }
 
 // ---------------------------------------------------------------------------
-// X[c]: per-label reduction of a step's posteriors of component c + gradient tile store.
-// Lane = class (classes beyond 32 in further rounds); entry i of a round holds, per lane, the
-// row offset of the i-th occurrence of the lane's class (or of a zero pad).
+// X[c]: turns a step's integer tile (label posteriors summed by class by the recompute warps)
+// into the [8, C] gradient tile and stores it.  Lane = class (classes beyond 32 in further
+// rounds).
 // ---------------------------------------------------------------------------
 template <int K, int W>
 __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const Ctx& cx, const int c) {
-  using G = Geo<K, W>;
   const int lane = cx.lane, nsd = cx.nsd, T = cx.T, C = cx.C, NAB = cx.NAB;
   const int rounds = (C + 31) >> 5;
-  const int* rinfo = sm.hist + C;   // per round {nmax, base}
-  // One round of classes: the lane's list of row offsets lives in registers, ordered (while
-  // phase 1 runs) so that, slot by slot, the lanes of the warp read distinct banks: every slot
-  // each lane proposes one of its next three entries, the lowest lane wins a contested bank.
-  bool reg_lists = rounds == 1;
-  uint32_t offs[kRegList];
-  int nslots = 0;
-  if (reg_lists) {
-    const uint32_t tb = sm.xtab + 2u * (uint32_t)(c * kMaxList * 32 + lane);   // entry k at tb + 64 k
-    const int n = lane < C ? sm.hist[lane] : 0;
-    int done = 0;
-#pragma unroll
-    for (int sl = 0; sl < kRegList; ++sl) {
-      uint32_t taken = 0u, mine = 0xffffu;
-#pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const int k = done + t;
-        const bool cand = mine == 0xffffu && k < n;
-        const uint32_t off = cand ? lds_u16(tb + 64u * (uint32_t)k) : 0u;
-        const uint32_t bank = (off >> 2) & 31u;
-        const bool okb = cand && !((taken >> bank) & 1u);
-        const unsigned peers = __match_any_sync(kFull, okb ? bank : 32u + (uint32_t)lane);
-        const bool win = okb && (__ffs(peers) - 1) == lane;
-        if (win) {
-          mine = off;
-          if (t > 0) {   // swap it with the first entry still to be placed: those stay contiguous, the table a permutation
-            const uint32_t first = lds_u16(tb + 64u * (uint32_t)done);
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(tb + 64u * (uint32_t)k), "h"((unsigned short)first) : "memory");
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(tb + 64u * (uint32_t)done), "h"((unsigned short)off) : "memory");
-          }
-        }
-        taken |= __reduce_or_sync(kFull, win ? (1u << bank) : 0u);
-      }
-      if (mine != 0xffffu) ++done;
-      offs[sl] = mine != 0xffffu ? mine : 0u;     // no entry: the zero word in front of the row
-      if (__any_sync(kFull, mine != 0xffffu)) nslots = sl + 1;
-    }
-    reg_lists = __all_sync(kFull, done == n);   // else: the table (a permutation of itself) is walked from shared memory
-  } else {
-#pragma unroll
-    for (int i = 0; i < kRegList; ++i) offs[i] = 0u;
-  }
   __syncthreads();   // meeting A
   __syncthreads();   // meeting B
   __syncthreads();   // meeting C: Z published
@@ -1057,7 +1049,8 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
   const float Zm = lds(sm.zx);
   const float kappa = -(a.grad_scale ? a.grad_scale[cx.b] : 1.f) / Zm;
   const bool has_partial = nsd > cx.nfull;
-  const uint32_t abuf = sm.abuf + (uint32_t)c * sm.abuf_c, certb = sm.cert + (uint32_t)c * sm.cert_c;
+  const uint32_t gaccb = sm.gacc + (uint32_t)c * sm.gacc_c, certb = sm.cert + (uint32_t)c * sm.cert_c;
+  const uint32_t growb = 4u * (uint32_t)cx.CP;
   int bad = 0;
   float* gE = a.gradE + (size_t)cx.b * T * C;
   int buf = 0;
@@ -1076,65 +1069,36 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
       {
         float tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < W; ++i) tot += lds(certb + 4u * (uint32_t)(buf * W + i));
+        for (int i = 0; i < W; ++i) tot += lds(certb + 4u * (uint32_t)(buf * 32 * W + 32 * i + lane));
+        tot = warp_sum(tot);
         if (!(fabsf(tot - Zm) <= 2e-5f * Zm)) bad = 8;
       }
       if (lane == 0) bulk_wait_read<1>();   // the store that last read this out buffer is done
       __syncwarp();
       pf.mark(0);
-      const uint32_t ab = abuf + (uint32_t)(buf * kSeg) * G::ROWB;
+      const uint32_t gt = gaccb + (uint32_t)(buf * kSeg) * growb;
       const uint32_t ot = sm.out + 4u * (uint32_t)((c * 2 + ob) * rawsz);
-      // buffer row j holds the frame of step j: frame row r = j (c = 0) or rows-1-j (c = 1)
+      // tile row j holds the frame of step j: frame row r = j (c = 0) or rows-1-j (c = 1)
       const int rsign = c == 0 ? 1 : -1, rbase = c == 0 ? 0 : rows - 1;
       float rs[kSeg];     // per-row sum of the label posteriors of this lane's classes
 #pragma unroll
       for (int j = 0; j < kSeg; ++j) rs[j] = 0.f;
-      if (reg_lists) {
+      for (int r = 0; r < rounds; ++r) {
+        const int cls = 32 * r + lane;
+        const bool mine = cls < C && cls != a.blank;
+        const uint32_t ga = gt + 4u * (uint32_t)(cls < C ? cls : C);
+        float acc[kSeg];
 #pragma unroll
-        for (int i0 = 0; i0 < kRegList; i0 += 4) {
-          if (i0 < nslots) {   // warp-uniform
-            float t[4][kSeg];
+        for (int j = 0; j < kSeg; ++j) acc[j] = (float)ldsi(ga + (uint32_t)j * growb) * (1.f / kFix);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t o = ab + offs[i0 + i];
-#pragma unroll
-              for (int j = 0; j < kSeg; ++j) t[i][j] = lds(o + (uint32_t)j * G::ROWB);   // rows >= `rows` hold finite stale data; never stored
-            }
-#pragma unroll
-            for (int j = 0; j < kSeg; ++j) rs[j] += (t[0][j] + t[1][j]) + (t[2][j] + t[3][j]);
-          }
-        }
-        if (lane < C && lane != a.blank) {
-          uint32_t dsto = ot + 4u * (uint32_t)(lane + rbase * C);
+        for (int j = 0; j < kSeg; ++j) stsi(ga + (uint32_t)j * growb, 0);   // the tile is clean for its next step
+        if (mine) {
+          uint32_t dsto = ot + 4u * (uint32_t)(cls + rbase * C);
           const int32_t dstep = 4 * rsign * C;
 #pragma unroll
           for (int j = 0; j < kSeg; ++j) {
-            if (j < rows) sts(dsto, rs[j] * kappa);
+            if (j < rows) sts(dsto, acc[j] * kappa);
             dsto += dstep;
-          }
-        }
-      } else {
-        for (int r = 0; r < rounds; ++r) {
-          const int nmax = rinfo[2 * r], base = rinfo[2 * r + 1];
-          const int cls = 32 * r + lane;
-          float acc[kSeg];
-#pragma unroll
-          for (int j = 0; j < kSeg; ++j) acc[j] = 0.f;
-          uint32_t xt = sm.xtab + 2u * (uint32_t)((c * kMaxList + base) * 32 + lane);
-#pragma unroll 2
-          for (int i = 0; i < nmax; ++i, xt += 64u) {
-            const uint32_t o = ab + lds_u16(xt);
-#pragma unroll
-            for (int j = 0; j < kSeg; ++j) acc[j] += lds(o + (uint32_t)j * G::ROWB);
-          }
-          if (cls < C && cls != a.blank) {
-            uint32_t dsto = ot + 4u * (uint32_t)(cls + rbase * C);
-            const int32_t dstep = 4 * rsign * C;
-#pragma unroll
-            for (int j = 0; j < kSeg; ++j) {
-              if (j < rows) sts(dsto, acc[j] * kappa);
-              dsto += dstep;
-            }
           }
 #pragma unroll
           for (int j = 0; j < kSeg; ++j) rs[j] += acc[j];
@@ -1189,7 +1153,7 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
       if (lane == 0) bulk_commit();   // one group per step (possibly empty)
       __syncwarp();
       pf.mark(3);
-      if (++buf == NAB) buf = 0;
+      if (++buf == W + 1) buf = 0;
     }
     tick2<W>(c, pf);
   }
@@ -1229,21 +1193,20 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1))
     sm.bnd = base + 4u * (uint32_t)lay.bnd;
     sm.lexp = base + 4u * (uint32_t)lay.lexp;
     sm.cert = base + 4u * (uint32_t)lay.cert;
+    sm.gacc = base + 4u * (uint32_t)lay.gacc;
     sm.ptile = base + 4u * (uint32_t)lay.ptile;
     sm.ringL = base + 4u * (uint32_t)lay.ringL;
     sm.ringR = base + 4u * (uint32_t)lay.ringR;
     sm.bars = base + 4u * (uint32_t)lay.bars;
     sm.zx = base + 4u * (uint32_t)lay.zx;
-    sm.xtab = base + 4u * (uint32_t)lay.xtab;
     sm.abuf_c = 4u * (uint32_t)lay.abuf_c;
     sm.bnd_c = 4u * (uint32_t)lay.bnd_c;
     sm.lexp_c = 4u * (uint32_t)lay.lexp_c;
     sm.cert_c = 4u * (uint32_t)lay.cert_c;
+    sm.gacc_c = 4u * (uint32_t)lay.gacc_c;
     sm.ptile_c = 4u * (uint32_t)lay.ptile_c;
     sm.ring_c = 4u * (uint32_t)lay.ring_c;
     sm.ytab = reinterpret_cast<int*>(smem_raw + lay.ytab);
-    sm.hist = reinterpret_cast<int*>(smem_raw + lay.hist);
-    sm.xtab_gen = reinterpret_cast<unsigned short*>(smem_raw + lay.xtab);
     sm.out_gen = smem_raw + lay.out;
     sm.prof_gen = smem_raw + lay.prof;
   }
@@ -1273,52 +1236,6 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1))
     // outside [0, C)
     if (__syncthreads_or(has_bad)) flag = 1;
     if (2 * cx.L + 1 > G::Sp - 1) flag = 1;
-  }
-  if (!flag) {
-    // per-class counts (integer atomics: order independent)
-    for (int cc = threadIdx.x; cc < C + 16; cc += NT) sm.hist[cc] = 0;
-    __syncthreads();
-    for (int n = threadIdx.x; n < cx.L; n += NT) atomicAdd(&sm.hist[sm.ytab[n]], 1);
-    __syncthreads();
-    const int rounds = (C + 31) >> 5;
-    if (warp == 0) {
-      int base = 0;
-      for (int r = 0; r < rounds; ++r) {
-        const int cc = 32 * r + cx.lane;
-        const int nm = __reduce_max_sync(kFull, cc < C ? sm.hist[cc] : 0);
-        if (cx.lane == 0) { sm.hist[C + 2 * r] = nm; sm.hist[C + 2 * r + 1] = base; }
-        base += nm;
-      }
-      if (cx.lane == 0) sm.hist[C + 2 * rounds] = base;
-    }
-    __syncthreads();
-    // tables the reduction cannot hold go to the fallback kernel (reason 16)
-    if (sm.hist[C + 2 * rounds] > kMaxList) flag = 16;
-    if (!flag) {
-      // position n becomes entry (number of earlier positions with the same label) of its class:
-      // a deterministic order, so the sums of the reduction do not depend on scheduling
-      for (int n = threadIdx.x; n < cx.L; n += NT) {
-        const int cc = sm.ytab[n];
-        int rank = 0;
-#pragma unroll 4
-        for (int m = 0; m < n; ++m) rank += (sm.ytab[m] == cc);
-        const int base = sm.hist[C + 2 * (cc >> 5) + 1], ln = cc & 31;
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          const int j = d == 0 ? 2 * n + 1 : G::Sp - 3 - 2 * n;
-          const int off = 4 * (G::PADA + (j / K) * G::SA + (j % K) / 2);
-          sm.xtab_gen[(d * kMaxList + base + rank) * 32 + ln] = (unsigned short)off;
-        }
-      }
-      for (int cc = threadIdx.x; cc < 32 * rounds; cc += NT) {
-        const int r = cc >> 5, ln = cc & 31;
-        const int nm = sm.hist[C + 2 * r], base = sm.hist[C + 2 * r + 1];
-        for (int i = cc < C ? sm.hist[cc] : 0; i < nm; ++i) {
-          sm.xtab_gen[(base + i) * 32 + ln] = 0;                 // word 0 of a row is always zero
-          sm.xtab_gen[(kMaxList + base + i) * 32 + ln] = 0;
-        }
-      }
-    }
   }
   if (flag && threadIdx.x == 0) WFST_HAZ(&a.hazard[cx.b], flag);
   __syncthreads();
@@ -1356,7 +1273,7 @@ static int pick_cfg(int max_target_len) {
 // later), a p tile from the tick before live[0]'s to rc[W-1]'s
 template <int K, int W>
 static bool pick_bufs(int C, int& NAB, int& NB, size_t& bytes) {
-  NAB = 2 * W + 1;
+  NAB = 2 * W;       // abar rows, boundary state, lane exponents: live -> rc
   NB = 2 * W + 1;
   if (NAB > kMaxAB || NB > kMaxNB) return false;
   bytes = make_layout<K, W>(C, NAB, NB).total * sizeof(float);

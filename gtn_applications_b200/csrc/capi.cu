@@ -93,15 +93,20 @@ int wfst_debug_ctc_chain_config(int K, int W) {
 }
 
 // --------------------------------------------------------------------- CTC
-// scaled-probability kernels, in order of preference: paired (two utterances per block: 4 %
-// faster at cfg2 than the chain-split one, 0.213 vs 0.221 ms in bench.py), chain-split (one
-// utterance per block, both time directions packed, chain split over warps: everything the
-// paired layout cannot hold, e.g. cfg5), single (the rest), none (log-semiring kernels only)
-static int ctc_scaled_kind(int T, int C, int max_target_len) {
+// scaled-probability kernels, in order of preference: tick-scheduled chain (one utterance per
+// block, one time direction per warp set, roles advance in lock step: 0.176 ms at cfg2) when two
+// of its blocks fit on an SM or the batch leaves one SM per utterance anyway; paired (two
+// utterances per block, 0.209 ms at cfg2; the kernel of the fused-logits entry); chain-split
+// (both time directions packed: what neither layout holds, e.g. cfg5); single (the rest); none
+// (log-semiring kernels only)
+static int ctc_scaled_kind(int B, int T, int C, int max_target_len) {
   if (g_force_generic) return 0;
   if (g_tick_mode == 2 && ctc_tick_eligible(T, C, max_target_len)) return 5;
   if (g_solo_mode == 2 && ctc_solo_eligible(T, C, max_target_len)) return 4;
   if (g_chain_first && ctc_chain_eligible(T, C, max_target_len)) return 3;
+  if (g_tick_mode == 0 && ctc_tick_eligible(T, C, max_target_len) &&
+      (ctc_tick_two_per_sm(T, C, max_target_len) || B <= 148))
+    return 5;
   if (g_force_generic_kind != 2 && ctc_pair_eligible(T, C, max_target_len)) return 2;
   if (!g_no_chain && ctc_chain_eligible(T, C, max_target_len)) return 3;
   if (ctc_fast_eligible(T, C, max_target_len)) return 1;
@@ -164,7 +169,7 @@ int wfst_ctc_forward_backward(const float* emissions, const int32_t* targets,
   size_t hb = ctc_hist_bytes(B, T, C, max_target_len);
   float* z = (float*)((char*)workspace + hb);
   int rc;
-  const int kind = ctc_scaled_kind(T, C, max_target_len);
+  const int kind = ctc_scaled_kind(B, T, C, max_target_len);
   if (kind != 0) {
     // scaled-probability kernel; utterances it flags are redone by the log-semiring kernel
     int* hazard = nullptr;
@@ -260,7 +265,7 @@ int wfst_debug_ctc_hazards(const void* workspace, int B, int T, int C, int max_t
                             int32_t* host_flags) {
   WFST_REQUIRE(workspace && host_flags, "null pointer argument");
   for (int b = 0; b < B; ++b) host_flags[b] = -1;
-  const int kind = ctc_scaled_kind(T, C, max_target_len);
+  const int kind = ctc_scaled_kind(B, T, C, max_target_len);
   if (kind == 0) return WFST_OK;
   size_t hb = ctc_hist_bytes(B, T, C, max_target_len) + align_up((size_t)B * sizeof(float), 256);
   size_t fb = kind == 5 ? ctc_tick_workspace_bytes(B, T, max_target_len)

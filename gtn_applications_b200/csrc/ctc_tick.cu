@@ -1325,6 +1325,18 @@ bool ctc_tick_eligible(int T, int C, int max_target_len) {
   return tickk::pick_bufs_cfg(idx, C, nab, nb, bytes);
 }
 
+// two blocks of the selected configuration fit on one SM (what makes this kernel the faster one
+// for batches beyond one block per SM)
+bool ctc_tick_two_per_sm(int T, int C, int max_target_len) {
+  if (T < 1 || C + 1 > 128) return false;
+  const int idx = tickk::pick_cfg(max_target_len);
+  if (idx < 0) return false;
+  int nab, nb;
+  size_t bytes;
+  if (!tickk::pick_bufs_cfg(idx, C, nab, nb, bytes)) return false;
+  return bytes + 1024 <= (size_t)(114 * 1024) && 32 * (4 * tickk::kCfgs[idx].W + 4) <= 512;
+}
+
 static int tick_nsd(int T) {
   const int a = T / 16, R = T - 16 * a;
   return a + (R > 0 ? 1 : 0);

@@ -79,6 +79,7 @@ int launch_ctc_solo(const float* E, const int* targets, const int* offsets, int 
 // tick-scheduled chain CTC (ctc_tick.cu): ctc_solo.cu's roles and numerics, every hand-off between
 // roles through one named barrier per 8-frame tick instead of per-resource mbarriers
 bool ctc_tick_eligible(int T, int C, int max_target_len);
+bool ctc_tick_two_per_sm(int T, int C, int max_target_len);
 int ctc_tick_force_config(int K, int W);
 size_t ctc_tick_workspace_bytes(int B, int T, int max_target_len);
 int launch_ctc_tick(const float* E, const int* targets, const int* offsets, int B, int T, int C,

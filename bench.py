@@ -770,8 +770,12 @@ def run_gpu(args):
                     "path": "CTCLoss(emissions, targets).backward() with both copied pinned host -> cuda on a copy stream every step (two steps in flight); every step's loss copied to pinned host memory and read by the host one step later"},
             "gpu_launches": int(launches),
             "fallback_rate": fallback_rate,
-            "kernel": "ctc_chain_kernel (csrc/ctc_chain.cu): one block per utterance, both time directions packed in "
-                      "FP32 pairs, chain split over warps; flagged utterances -> ctc_exact_kernel (float64)",
+            "kernel": ("ctc_chain_kernel (csrc/ctc_chain.cu): one block per utterance, both time directions packed in "
+                       "FP32 pairs, chain split over warps" if args.workload == "ctc_cfg5" else
+                       "ctc_tick_kernel<6,2> (csrc/ctc_tick.cu): one block per utterance, one time direction per warp "
+                       "set, chain split over 2 warps, roles (producer / live / recompute / reduce) advance one "
+                       "8-frame step per tick behind one named barrier") +
+                      "; flagged utterances -> ctc_exact_kernel (float64)",
             "function_path": {
                 "ms_per_step": fp_s * 1e3, "value": B * world / fp_s, "unit": "utterances/s", "iterations": fp_iters,
                 "what": "CTCLoss(inputs, list_of_lists, C-1).backward() exactly as benchmarks/ctc_benchmark.py:"

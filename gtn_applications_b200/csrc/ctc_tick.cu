@@ -41,7 +41,7 @@ constexpr int kSeg = 8;               // frames per step / tile
 constexpr int kEventEvery = 2;        // lanes are renormalised every kEventEvery ticks
 constexpr int kUndef = -(1 << 19);    // "no exponent": lane holds only zeros
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kNR = 3;                // raw (TMA) staging slots per producer warp
+constexpr int kNR = 3;                // raw (TMA) staging slots per producer warp, at most (Args::NR of them used)
 constexpr int kRD = 2;                // entries per chain ring (step parity)
 constexpr int kMaxAB = 8;             // step buffers per component, at most
 constexpr int kMaxNB = 12;            // p tiles per component, at most
@@ -63,7 +63,7 @@ struct Args {
   int nfull;        // full (8-frame) steps per direction
   int r0, r1;       // frames of the partial step of direction 0 / 1 (next to the meeting point)
   int Th;           // first frame of direction 1's half
-  int NAB, NB;
+  int NAB, NB, NR;
 };
 
 // ---- shared-state-space accesses on 32-bit addresses ------------------------------
@@ -203,14 +203,14 @@ struct Layout {
   size_t zero_end;
 };
 template <int K, int W>
-__host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
+__host__ __device__ inline Layout make_layout(int C, int NAB, int NB, int NR) {
   const int NG = W + 1;   // tiles / certificate terms: written by rc, read by X
   using G = Geo<K, W>;
   Layout L;
   const size_t rawsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
   const size_t CP = (size_t)C + 1;
   size_t p = 0;
-  L.raw = p;    p += 2 * (size_t)kNR * rawsz + 32;                  // [c][slot][8*C] (+ slack)
+  L.raw = p;    p += 2 * (size_t)NR * rawsz + 32;                  // [c][slot][8*C] (+ slack)
   L.out = p;    p += 2 * 2 * rawsz;                                 // [c][ob][8*C]
   L.abuf_c = (size_t)NAB * kSeg * G::ROWW;
   L.abuf = p;   p += 2 * L.abuf_c;                                  // [c][buf][row][word]
@@ -253,7 +253,7 @@ struct Smem {
 
 struct Ctx {
   int lane, T, C, CP, L, b;
-  int nsd, nfull, r0, r1, Th, NAB, NB;
+  int nsd, nfull, r0, r1, Th, NAB, NB, NR;
   bool want_grad;
   uint32_t rawsz;
 };
@@ -449,13 +449,13 @@ __device__ __forceinline__ void producer_fetch(const Args& a, const Smem& sm, co
                                                const int c, const int kt_end) {
   const int lane = cx.lane, T = cx.T, C = cx.C;
   const uint32_t rawsz = cx.rawsz;
-  const uint32_t raw0 = sm.raw + 4u * (uint32_t)(c * kNR) * rawsz;
-  const int tbar = kBarTma + c * kNR;
+  const uint32_t raw0 = sm.raw + 4u * (uint32_t)(c * cx.NR) * rawsz;
+  const int tbar = kBarTma + c * cx.NR;
   const float* Eb = a.E + (size_t)cx.b * T * C;
-  while (ps.fetched < kt_end && ps.fetched < ps.converted + kNR) {
+  while (ps.fetched < kt_end && ps.fetched < ps.converted + cx.NR) {
     int lo_, rows;
     comp_seg(cx, c, ps.fetched, lo_, rows);
-    const int slot = ps.fetched % kNR;
+    const int slot = ps.fetched % cx.NR;
     const uint32_t bytes = (uint32_t)rows * C * 4u;
     const float* src = Eb + (size_t)lo_ * C;
     const uint32_t dst = raw0 + 4u * (uint32_t)slot * rawsz;
@@ -484,10 +484,10 @@ __device__ __forceinline__ void producer_convert(const Smem& sm, const Ctx& cx, 
   pf.mark0();
   const int lane = cx.lane, C = cx.C;
   const uint32_t rawsz = cx.rawsz;
-  const uint32_t raw0 = sm.raw + 4u * (uint32_t)(c * kNR) * rawsz;
-  const int tbar = kBarTma + c * kNR;
+  const uint32_t raw0 = sm.raw + 4u * (uint32_t)(c * cx.NR) * rawsz;
+  const int tbar = kBarTma + c * cx.NR;
   const int groups = (C + 31) >> 5;
-  const int slot = ps.converted % kNR;
+  const int slot = ps.converted % cx.NR;
   int lo_, rows;
   comp_seg(cx, c, kt, lo_, rows);
   const int buf = ps.pbuf;
@@ -1177,13 +1177,13 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1))
   cx.lane = threadIdx.x & 31;
   cx.T = a.T; cx.C = C; cx.CP = C + 1;
   cx.nsd = a.nsd; cx.nfull = a.nfull; cx.r0 = a.r0; cx.r1 = a.r1; cx.Th = a.Th;
-  cx.NAB = a.NAB; cx.NB = a.NB;
+  cx.NAB = a.NAB; cx.NB = a.NB; cx.NR = a.NR;
   cx.b = blockIdx.x;
   cx.want_grad = a.gradE != nullptr;
   cx.rawsz = (uint32_t)((kSeg * C + 3) & ~3);
   const int* y = a.targets + a.offsets[cx.b];
   cx.L = a.offsets[cx.b + 1] - a.offsets[cx.b];
-  const Layout lay = make_layout<K, W>(C, a.NAB, a.NB);
+  const Layout lay = make_layout<K, W>(C, a.NAB, a.NB, a.NR);
   Smem sm;
   {
     const uint32_t base = smem_u32(smem_raw);
@@ -1272,12 +1272,15 @@ static int pick_cfg(int max_target_len) {
 // ring depths the tick schedule needs: a step buffer lives from live[0]'s tick to X's (2W ticks
 // later), a p tile from the tick before live[0]'s to rc[W-1]'s
 template <int K, int W>
-static bool pick_bufs(int C, int& NAB, int& NB, size_t& bytes) {
+static bool pick_bufs(int C, int& NAB, int& NB, int& NR, size_t& bytes) {
   NAB = 2 * W;       // abar rows, boundary state, lane exponents: live -> rc
   NB = 2 * W + 1;
   if (NAB > kMaxAB || NB > kMaxNB) return false;
-  bytes = make_layout<K, W>(C, NAB, NB).total * sizeof(float);
-  return bytes <= (size_t)(227 * 1024);
+  for (NR = kNR; NR >= 2; --NR) {   // raw tiles in flight: three where they fit
+    bytes = make_layout<K, W>(C, NAB, NB, NR).total * sizeof(float);
+    if (bytes <= (size_t)(227 * 1024)) return true;
+  }
+  return false;
 }
 
 template <int K, int W>
@@ -1301,9 +1304,9 @@ static int launch_kw(const Args& a, size_t smem, cudaStream_t st) {
     default: break;                               \
   }
 
-static bool pick_bufs_cfg(int idx, int C, int& NAB, int& NB, size_t& bytes) {
+static bool pick_bufs_cfg(int idx, int C, int& NAB, int& NB, int& NR, size_t& bytes) {
   bool ok = false;
-  WFST_TICK_DISPATCH(idx, ok = (pick_bufs<K, W>(C, NAB, NB, bytes)));
+  WFST_TICK_DISPATCH(idx, ok = (pick_bufs<K, W>(C, NAB, NB, NR, bytes)));
   return ok;
 }
 static int ckf_of(int idx) { return (kCfgs[idx].K + 2 + 3) & ~3; }
@@ -1320,9 +1323,9 @@ bool ctc_tick_eligible(int T, int C, int max_target_len) {
   if (T < 1 || C + 1 > 128) return false;
   const int idx = tickk::pick_cfg(max_target_len);
   if (idx < 0) return false;
-  int nab, nb;
+  int nab, nb, nr;
   size_t bytes;
-  return tickk::pick_bufs_cfg(idx, C, nab, nb, bytes);
+  return tickk::pick_bufs_cfg(idx, C, nab, nb, nr, bytes);
 }
 
 // two blocks of the selected configuration fit on one SM (what makes this kernel the faster one
@@ -1331,9 +1334,9 @@ bool ctc_tick_two_per_sm(int T, int C, int max_target_len) {
   if (T < 1 || C + 1 > 128) return false;
   const int idx = tickk::pick_cfg(max_target_len);
   if (idx < 0) return false;
-  int nab, nb;
+  int nab, nb, nr;
   size_t bytes;
-  if (!tickk::pick_bufs_cfg(idx, C, nab, nb, bytes)) return false;
+  if (!tickk::pick_bufs_cfg(idx, C, nab, nb, nr, bytes)) return false;
   return bytes + 1024 <= (size_t)(114 * 1024) && 32 * (4 * tickk::kCfgs[idx].W + 4) <= 512;
 }
 
@@ -1374,7 +1377,7 @@ int launch_ctc_tick(const float* E, const int* targets, const int* offsets, int 
   a.nsd = a.nfull + (R > 0 ? 1 : 0);
   a.Th = kSeg * a.nfull + a.r0;
   size_t smem = 0;
-  if (idx < 0 || !pick_bufs_cfg(idx, C, a.NAB, a.NB, smem)) {
+  if (idx < 0 || !pick_bufs_cfg(idx, C, a.NAB, a.NB, a.NR, smem)) {
     set_error("no tick-chain CTC configuration for C=%d L=%d", C, max_target_len);
     return WFST_ERR_UNSUPPORTED;
   }

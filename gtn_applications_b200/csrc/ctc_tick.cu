@@ -1166,8 +1166,9 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
+// W = 3 needs more than half an SM of shared memory: one block per SM, twice the registers
 template <int K, int W>
-__global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1)) ctc_tick_kernel(Args a) {
+__global__ void __launch_bounds__(Geo<K, W>::NT, (W <= 2 ? 2 : 1)) ctc_tick_kernel(Args a) {
   extern __shared__ __align__(16) float smem_raw[];
   using G = Geo<K, W>;
   constexpr int NT = G::NT;
@@ -1210,6 +1211,9 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1))
     sm.out_gen = smem_raw + lay.out;
     sm.prof_gen = smem_raw + lay.prof;
   }
+
+  // flags: cleared by the block that owns them (no memset node in front of the kernel)
+  if (threadIdx.x == 0) a.hazard[cx.b] = 0;
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
@@ -1384,7 +1388,6 @@ int launch_ctc_tick(const float* E, const int* targets, const int* offsets, int 
   a.ckpt = (float*)workspace;
   a.hazard = (int*)((char*)workspace + tick_ckpt_bytes(B, T, idx));
   *hazard_out = a.hazard;
-  WFST_CUDA_CHECK(cudaMemsetAsync(a.hazard, 0, (size_t)B * sizeof(int), st));
   int rc = WFST_ERR_UNSUPPORTED;
   WFST_TICK_DISPATCH(idx, rc = (launch_kw<K, W>(a, smem, st)));
   if (rc == WFST_ERR_UNSUPPORTED) set_error("no tick-chain CTC instantiation for configuration %d", idx);

@@ -12,7 +12,10 @@ def hazards(B, T, C, L):
     _lib.check(_lib.lib().wfst_debug_ctc_hazards(ws.data_ptr(), B, T, C, L, flags.ctypes.data))
     return flags
 
-B, T, C, L = 64, 1000, 30, 176
+B, T, C, L = int(os.environ.get("WFST_B", "64")), 1000, 30, 176
+_lib.lib().wfst_debug_force_generic_ctc(int(os.environ.get("WFST_CTC_HOOK", "0")))
+if os.environ.get("WFST_CHAIN_CFG"):
+    _lib.lib().wfst_debug_ctc_chain_config(*[int(v) for v in os.environ["WFST_CHAIN_CFG"].split(",")])
 torch.manual_seed(0)
 tg = torch.randint(C - 2, (B, L))
 for scale in (1, 2, 3, 4, 6, 8, 12):

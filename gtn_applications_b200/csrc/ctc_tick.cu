@@ -1086,12 +1086,15 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
       for (int r = 0; r < rounds; ++r) {
         const int cls = 32 * r + lane;
         const bool mine = cls < C && cls != a.blank;
+        // lane cls == C takes the padding column; the lanes beyond it have nothing to do
         const uint32_t ga = gt + 4u * (uint32_t)(cls < C ? cls : C);
         float acc[kSeg];
 #pragma unroll
-        for (int j = 0; j < kSeg; ++j) acc[j] = (float)ldsi(ga + (uint32_t)j * growb) * (1.f / kFix);
+        for (int j = 0; j < kSeg; ++j) acc[j] = cls <= C ? (float)ldsi(ga + (uint32_t)j * growb) * (1.f / kFix) : 0.f;
+        if (cls <= C) {
 #pragma unroll
-        for (int j = 0; j < kSeg; ++j) stsi(ga + (uint32_t)j * growb, 0);   // the tile is clean for its next step
+          for (int j = 0; j < kSeg; ++j) stsi(ga + (uint32_t)j * growb, 0);   // the tile is clean for its next step
+        }
         if (mine) {
           uint32_t dsto = ot + 4u * (uint32_t)(cls + rbase * C);
           const int32_t dstep = 4 * rsign * C;

@@ -63,7 +63,7 @@ struct Args {
   int nfull;        // full (8-frame) steps per direction
   int r0, r1;       // frames of the partial step of direction 0 / 1 (next to the meeting point)
   int Th;           // first frame of direction 1's half
-  int NAB, NB, NR;
+  int NAB, NB, NR, NO;
 };
 
 // ---- shared-state-space accesses on 32-bit addresses ------------------------------
@@ -203,7 +203,7 @@ struct Layout {
   size_t zero_end;
 };
 template <int K, int W>
-__host__ __device__ inline Layout make_layout(int C, int NAB, int NB, int NR) {
+__host__ __device__ inline Layout make_layout(int C, int NAB, int NB, int NR, int NO) {
   const int NG = W + 1;   // tiles / certificate terms: written by rc, read by X
   using G = Geo<K, W>;
   Layout L;
@@ -211,7 +211,7 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB, int NR) {
   const size_t CP = (size_t)C + 1;
   size_t p = 0;
   L.raw = p;    p += 2 * (size_t)NR * rawsz + 32;                  // [c][slot][8*C] (+ slack)
-  L.out = p;    p += 2 * 2 * rawsz;                                 // [c][ob][8*C]
+  L.out = p;    p += 2 * (size_t)NO * rawsz;                        // [c][ob][8*C]
   L.abuf_c = (size_t)NAB * kSeg * G::ROWW;
   L.abuf = p;   p += 2 * L.abuf_c;                                  // [c][buf][row][word]
   L.bnd_c = (size_t)NAB * G::BNDW;
@@ -253,7 +253,7 @@ struct Smem {
 
 struct Ctx {
   int lane, T, C, CP, L, b;
-  int nsd, nfull, r0, r1, Th, NAB, NB, NR;
+  int nsd, nfull, r0, r1, Th, NAB, NB, NR, NO;
   bool want_grad;
   uint32_t rawsz;
 };
@@ -1064,7 +1064,7 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
       const int kk = nsd - 1 - k2;
       const int rows = (has_partial && k2 == 0) ? (c == 0 ? cx.r1 : cx.r0) : kSeg;
       const int lo_ = seg_lo(cx, 1 - c, kk);
-      const int ob = k2 & 1;
+      const int ob = cx.NO == 2 ? (k2 & 1) : 0;
       pf.mark0();
       {
         float tot = 0.f;
@@ -1073,11 +1073,13 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
         tot = warp_sum(tot);
         if (!(fabsf(tot - Zm) <= 2e-5f * Zm)) bad = 8;
       }
-      if (lane == 0) bulk_wait_read<1>();   // the store that last read this out buffer is done
+      if (lane == 0) {   // the store that last read this out buffer is done
+        if (cx.NO == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+      }
       __syncwarp();
       pf.mark(0);
       const uint32_t gt = gaccb + (uint32_t)(buf * kSeg) * growb;
-      const uint32_t ot = sm.out + 4u * (uint32_t)((c * 2 + ob) * rawsz);
+      const uint32_t ot = sm.out + 4u * (uint32_t)((c * cx.NO + ob) * rawsz);
       // tile row j holds the frame of step j: frame row r = j (c = 0) or rows-1-j (c = 1)
       const int rsign = c == 0 ? 1 : -1, rbase = c == 0 ? 0 : rows - 1;
       float rs[kSeg];     // per-row sum of the label posteriors of this lane's classes
@@ -1149,7 +1151,7 @@ __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const
                          : "memory");
         } else {
           __syncwarp();
-          const float* src = sm.out_gen + (size_t)(c * 2 + ob) * rawsz;
+          const float* src = sm.out_gen + (size_t)(c * cx.NO + ob) * rawsz;
           for (int q = lane; q < n; q += 32) dst[q] = src[q];
         }
       }
@@ -1181,13 +1183,13 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (W <= 2 ? 2 : 1)) ctc_tick_kern
   cx.lane = threadIdx.x & 31;
   cx.T = a.T; cx.C = C; cx.CP = C + 1;
   cx.nsd = a.nsd; cx.nfull = a.nfull; cx.r0 = a.r0; cx.r1 = a.r1; cx.Th = a.Th;
-  cx.NAB = a.NAB; cx.NB = a.NB; cx.NR = a.NR;
+  cx.NAB = a.NAB; cx.NB = a.NB; cx.NR = a.NR; cx.NO = a.NO;
   cx.b = blockIdx.x;
   cx.want_grad = a.gradE != nullptr;
   cx.rawsz = (uint32_t)((kSeg * C + 3) & ~3);
   const int* y = a.targets + a.offsets[cx.b];
   cx.L = a.offsets[cx.b + 1] - a.offsets[cx.b];
-  const Layout lay = make_layout<K, W>(C, a.NAB, a.NB, a.NR);
+  const Layout lay = make_layout<K, W>(C, a.NAB, a.NB, a.NR, a.NO);
   Smem sm;
   {
     const uint32_t base = smem_u32(smem_raw);
@@ -1279,12 +1281,15 @@ static int pick_cfg(int max_target_len) {
 // ring depths the tick schedule needs: a step buffer lives from live[0]'s tick to X's (2W ticks
 // later), a p tile from the tick before live[0]'s to rc[W-1]'s
 template <int K, int W>
-static bool pick_bufs(int C, int& NAB, int& NB, int& NR, size_t& bytes) {
+static bool pick_bufs(int C, int& NAB, int& NB, int& NR, int& NO, size_t& bytes) {
   NAB = 2 * W;       // abar rows, boundary state, lane exponents: live -> rc
   NB = 2 * W + 1;
   if (NAB > kMaxAB || NB > kMaxNB) return false;
-  for (NR = kNR; NR >= 2; --NR) {   // raw tiles in flight: three where they fit
-    bytes = make_layout<K, W>(C, NAB, NB, NR).total * sizeof(float);
+  // raw tiles in flight / gradient staging tiles: 3 / 2 where they fit, then 2 / 2, then 2 / 1
+  static const int tries[3][2] = {{kNR, 2}, {2, 2}, {2, 1}};
+  for (int i = 0; i < 3; ++i) {
+    NR = tries[i][0]; NO = tries[i][1];
+    bytes = make_layout<K, W>(C, NAB, NB, NR, NO).total * sizeof(float);
     if (bytes <= (size_t)(227 * 1024)) return true;
   }
   return false;
@@ -1311,9 +1316,9 @@ static int launch_kw(const Args& a, size_t smem, cudaStream_t st) {
     default: break;                               \
   }
 
-static bool pick_bufs_cfg(int idx, int C, int& NAB, int& NB, int& NR, size_t& bytes) {
+static bool pick_bufs_cfg(int idx, int C, int& NAB, int& NB, int& NR, int& NO, size_t& bytes) {
   bool ok = false;
-  WFST_TICK_DISPATCH(idx, ok = (pick_bufs<K, W>(C, NAB, NB, NR, bytes)));
+  WFST_TICK_DISPATCH(idx, ok = (pick_bufs<K, W>(C, NAB, NB, NR, NO, bytes)));
   return ok;
 }
 static int ckf_of(int idx) { return (kCfgs[idx].K + 2 + 3) & ~3; }
@@ -1330,9 +1335,9 @@ bool ctc_tick_eligible(int T, int C, int max_target_len) {
   if (T < 1 || C + 1 > 128) return false;
   const int idx = tickk::pick_cfg(max_target_len);
   if (idx < 0) return false;
-  int nab, nb, nr;
+  int nab, nb, nr, no;
   size_t bytes;
-  return tickk::pick_bufs_cfg(idx, C, nab, nb, nr, bytes);
+  return tickk::pick_bufs_cfg(idx, C, nab, nb, nr, no, bytes);
 }
 
 // two blocks of the selected configuration fit on one SM (what makes this kernel the faster one
@@ -1341,9 +1346,9 @@ bool ctc_tick_two_per_sm(int T, int C, int max_target_len) {
   if (T < 1 || C + 1 > 128) return false;
   const int idx = tickk::pick_cfg(max_target_len);
   if (idx < 0) return false;
-  int nab, nb, nr;
+  int nab, nb, nr, no;
   size_t bytes;
-  if (!tickk::pick_bufs_cfg(idx, C, nab, nb, nr, bytes)) return false;
+  if (!tickk::pick_bufs_cfg(idx, C, nab, nb, nr, no, bytes)) return false;
   return bytes + 1024 <= (size_t)(114 * 1024) && 32 * (4 * tickk::kCfgs[idx].W + 4) <= 512;
 }
 
@@ -1384,7 +1389,7 @@ int launch_ctc_tick(const float* E, const int* targets, const int* offsets, int 
   a.nsd = a.nfull + (R > 0 ? 1 : 0);
   a.Th = kSeg * a.nfull + a.r0;
   size_t smem = 0;
-  if (idx < 0 || !pick_bufs_cfg(idx, C, a.NAB, a.NB, a.NR, smem)) {
+  if (idx < 0 || !pick_bufs_cfg(idx, C, a.NAB, a.NB, a.NR, a.NO, smem)) {
     set_error("no tick-chain CTC configuration for C=%d L=%d", C, max_target_len);
     return WFST_ERR_UNSUPPORTED;
   }

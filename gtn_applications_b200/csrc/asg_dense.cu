@@ -222,29 +222,48 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_kernel(
 }
 
 // ---------------------------------------------------------------------------------------
-// The same lattice on TWO warps per utterance that meet in the middle: the kernel above is a
-// chain of 2T dependent frame steps of one warp; here warp A owns the frames [0, Th) and warp
-// B the frames [Th, T):
-//   A: alpha up over its frames (stores a^_t, c_t)      | B: beta down over its frames (stores b^_t)
-//   exchange a^_{Th-1} and b^_{Th-1} through shared memory (one named barrier)
-//   A: beta down over its frames, posteriors with its    | B: alpha up over its frames, posteriors
-//      stored a^_t (the sweep of the kernel above)       |    with its stored b^_t (the mirror image)
-// Every posterior formula is self-normalised, so the beta normalisers are never needed:
-//   log Z = sum_t (base_t + log c_t) + log sum_i a^_{T-1}[i], the first half of the sum from A,
-//   the second from B's alpha sweep.
-__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// Gradient version, one block of SIX warps per utterance.
+//
+// Two recurrence warps meet in the middle: A runs alpha up over [0, Th) while B runs beta down
+// over [Th, T); they exchange a^_{Th-1} and b^_{Th-1} through shared memory (one named barrier);
+// then A runs beta down over its half against its stored alpha vectors and B runs alpha up over
+// its half against its stored beta vectors.  The kernel is a pure latency chain (a few warps
+// per SM), so in that second phase a recurrence warp does NOTHING but the recurrence: per
+// frame it leaves the vectors the gradient needs in a shared-memory ring (A: r_t = p_t b^_t and
+// b^_t; B: a^_{t-1}, a^_t and c_t), eight frames per chunk, and two helper warps per direction
+// take alternate frames of the previous chunk: posterior sum (five shuffle steps), gradient
+// row, the rank-one update of the transition-gradient accumulators (32 FMAs against a
+// broadcast vector).  Measured at cfg3: with that bookkeeping on the recurrence warp (the
+// previous two-warp kernel) 0.45 ms alone and 0.67 ms next to the force-align kernel; a timing
+// run with the bookkeeping deleted: 0.30 ms, ASG call 0.69 -> 0.45 ms.  One named barrier per
+// chunk and direction (recurrence warp + its two helpers), double-buffered chunks.
+// ---------------------------------------------------------------------------------------
+constexpr int kChunk = 8;                 // frames per ring chunk
+constexpr int kEnt = 2 * kCP;             // floats per ring entry: V0[kCP] (16-byte aligned, broadcast), V1[kCP]
+constexpr int kGradWarps = 6;             // A, B, helpers of A (2), helpers of B (2)
 
-__global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_split_kernel(
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// named barriers 1, 2: a recurrence warp and its two helpers (immediate ids: the block reserves 5 barriers, not 16)
+__device__ __forceinline__ void tick_bar(int role) {
+  if (role == 0) asm volatile("bar.sync 1, 96;" ::: "memory");
+  else asm volatile("bar.sync 2, 96;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(32 * kGradWarps, 3) asg_fcc_dense_split_kernel(
     const float* __restrict__ E, const float* __restrict__ tr, int B, int T, int C,
     const float* __restrict__ grad_scale, float sign, float* __restrict__ scores,
     float* __restrict__ gradE, int accumulate, float* __restrict__ gradTr, float* __restrict__ hist) {
-  __shared__ __align__(16) float bcast[kWarps][2][kCP];
-  __shared__ __align__(16) float xch[kWarps][kCP];
-  __shared__ double zpart[kWarps];
+  __shared__ __align__(16) float bcast[2][2][kCP];            // recurrence warps, phase 1
+  __shared__ __align__(16) float hb[4][kCP];                  // helpers' broadcast vectors
+  __shared__ __align__(16) float ring[2][2][kChunk][kEnt];    // [direction][chunk parity][frame][entry]
+  __shared__ __align__(16) float xch[2][kCP];
+  __shared__ double zpart[2];
   __shared__ float red[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int role = warp & 1, pair = warp >> 1;
-  const int b = blockIdx.x * (kWarps / 2) + pair;
+  const int role = warp < 2 ? warp : (warp - 2) >> 1;     // direction: 0 = A's half, 1 = B's half
+  const bool helper = warp >= 2;
+  const int hidx = (warp - 2) & 1;                          // which of the direction's two helpers
+  const int b = blockIdx.x;
   const bool valid = lane < C;
   if (threadIdx.x < 32) {
     float m = kNegInf, m0 = kNegInf;
@@ -257,35 +276,146 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_split_kernel(
       red[1] = (m0 == kNegInf) ? 0.f : m0;
     }
   }
-  for (int k = threadIdx.x; k < kWarps * 2 * kCP; k += blockDim.x) (&bcast[0][0][0])[k] = 0.f;
-  for (int k = threadIdx.x; k < kWarps * kCP; k += blockDim.x) (&xch[0][0])[k] = 0.f;
+  for (int k = threadIdx.x; k < 2 * 2 * kCP; k += blockDim.x) (&bcast[0][0][0])[k] = 0.f;
+  for (int k = threadIdx.x; k < 4 * kCP; k += blockDim.x) (&hb[0][0])[k] = 0.f;
+  for (int k = threadIdx.x; k < 2 * 2 * kChunk * kEnt; k += blockDim.x) (&ring[0][0][0][0])[k] = 0.f;
+  for (int k = threadIdx.x; k < 2 * kCP; k += blockDim.x) (&xch[0][0])[k] = 0.f;
   __syncthreads();
   const float wmax = red[0], w0max = red[1];
-  if (b >= B) return;                       // both warps of the pair
 
-  float Wr[kCP], Wc[kCP];
-#pragma unroll
-  for (int j = 0; j < kCP; ++j) {
-    Wr[j] = (valid && j < C) ? __expf(tr[C + lane * C + j] - wmax) : 0.f;
-    Wc[j] = (valid && j < C) ? __expf(tr[C + j * C + lane] - wmax) : 0.f;
-  }
-  const float w0 = valid ? __expf(tr[lane] - w0max) : 0.f;
   const float* Eb = E + (size_t)b * T * C;
   float* hV = hist + (size_t)b * T * (C + 1);   // [T][C]: a^_t for t < Th (A), b^_t for t >= Th (B)
   float* hC = hV + (size_t)T * C;               // [T] normalisers c_t of the alpha vectors
-  float* bc0 = bcast[warp][0];
-  float* bc1 = bcast[warp][1];
   const int Th = T / 2;                          // >= 1 (launcher: T >= 2)
   const float gs = sign * (grad_scale ? grad_scale[b] : 1.f);
   float* gEb = gradE ? gradE + (size_t)b * T * C : nullptr;
-  float acc[kCP];
+  // phase 2 of direction d walks nfr frames in chunks of kChunk: A descends from Th-1, B ascends from Th
+  const int nfr = role == 0 ? Th : T - Th;
+  const int nch = (nfr + kChunk - 1) / kChunk;
+
+  if (helper) {
+    // ================================================================ helper warps
+    float acc[kCP];
 #pragma unroll
-  for (int j = 0; j < kCP; ++j) acc[j] = 0.f;
+    for (int j = 0; j < kCP; ++j) acc[j] = 0.f;
+    float* mybc = hb[warp - 2];
+    constexpr int kH = kChunk / 2;              // frames of a chunk per helper
+    // what a frame needs from global memory, fetched one chunk ahead:
+    //   A's half: a^_t, a^_{t-1}, c_t;   B's half: b^_t, E_t (for p_t)
+    float g0[kH], g1[kH], g2[kH];
+    auto frame_of = [&](int n, int i) {         // i-th frame of this helper in chunk n (-1: none)
+      const int k = n * kChunk + 2 * i + hidx;
+      if (k >= nfr) return -1;
+      return role == 0 ? Th - 1 - k : Th + k;
+    };
+    auto prefetch = [&](int n) {
+#pragma unroll
+      for (int i = 0; i < kH; ++i) {
+        const int t = frame_of(n, i);
+        if (role == 0) {
+          g0[i] = (valid && t >= 0) ? hV[(size_t)t * C + lane] : 0.f;
+          g1[i] = (valid && t >= 1) ? hV[(size_t)(t - 1) * C + lane] : 0.f;
+          g2[i] = (t >= 0) ? hC[t] : 1.f;
+        } else {
+          g0[i] = (valid && t >= 0) ? hV[(size_t)t * C + lane] : 0.f;
+          g1[i] = (valid && t >= 0) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+          g2[i] = 0.f;
+        }
+      }
+    };
+    tick_bar(role);                     // the meeting is over: the stored vectors are visible
+    prefetch(0);
+    for (int n = 0; n < nch; ++n) {
+      tick_bar(role);                   // chunk n is complete
+      float c0[kH], c1[kH], c2[kH];
+#pragma unroll
+      for (int i = 0; i < kH; ++i) { c0[i] = g0[i]; c1[i] = g1[i]; c2[i] = g2[i]; }
+      if (n + 1 < nch) prefetch(n + 1);
+#pragma unroll
+      for (int i = 0; i < kH; ++i) {
+        const int t = frame_of(n, i);
+        if (t < 0) break;
+        const float* ent = ring[role][n & 1][2 * i + hidx];
+        float gq, rnum, cden;
+        const float* avec;                      // a^_{t-1}, broadcastable
+        if (role == 0) {
+          // V0 = r_t = p_t b^_t, V1 = b^_t
+          gq = c0[i] * ent[kCP + lane];
+          rnum = ent[lane];
+          cden = c2[i];
+          mybc[lane] = c1[i];
+          avec = mybc;
+        } else {
+          // V0 = a^_{t-1}, V1 = a^_t, V1[32] = c_t
+          const float m = warp_max(c1[i]);
+          const float base = (m == kNegInf) ? 0.f : m;
+          const float p = valid ? __expf(c1[i] - base) : 0.f;
+          gq = ent[kCP + lane] * c0[i];
+          rnum = p * c0[i];
+          cden = ent[kCP + 32];
+          avec = ent;
+        }
+        const float G = warp_sum(gq);
+        const float gamma = G > 0.f ? __fdividef(gq, G) : 0.f;
+        if (gEb && valid) {
+          float* dst = gEb + (size_t)t * C + lane;
+          *dst = accumulate ? *dst + gs * gamma : gs * gamma;
+        }
+        if (t == 0) {                           // only in A's half: the start arcs
+          if (gradTr && valid && gamma != 0.f) atomicAdd(&gradTr[lane], gs * gamma);
+          break;
+        }
+        const float nn = cden * G;
+        const float rn = nn > 0.f ? __fdividef(rnum, nn) : 0.f;
+        __syncwarp();
+        {
+          const float4* v = reinterpret_cast<const float4*>(avec);
+#pragma unroll
+          for (int q = 0; q < kCP / 4; ++q) {
+            const float4 a4 = v[q];
+            acc[4 * q + 0] = fmaf(a4.x, rn, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(a4.y, rn, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(a4.z, rn, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(a4.w, rn, acc[4 * q + 3]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (gradTr && valid) {
+#pragma unroll
+      for (int j = 0; j < kCP; ++j) {
+        if (j < C) {
+          const float v = gs * __expf(tr[C + lane * C + j] - wmax) * acc[j];
+          if (v != 0.f) atomicAdd(&gradTr[C + lane * C + j], v);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================================================== recurrence warps
+  // the lane's row of W for the alpha recursions, its column for the beta recursions: a warp
+  // needs one of them per phase, so ONE register array is refilled at the meeting (the block
+  // must leave registers for the force-align blocks that share the SM: 3 blocks per SM)
+  float Wx[kCP];
+  auto load_row = [&]() {
+#pragma unroll
+    for (int j = 0; j < kCP; ++j) Wx[j] = (valid && j < C) ? __expf(tr[C + lane * C + j] - wmax) : 0.f;
+  };
+  auto load_col = [&]() {
+#pragma unroll
+    for (int j = 0; j < kCP; ++j) Wx[j] = (valid && j < C) ? __expf(tr[C + j * C + lane] - wmax) : 0.f;
+  };
+  const float w0 = valid ? __expf(tr[lane] - w0max) : 0.f;
+  float* bc0 = bcast[warp][0];
+  float* bc1 = bcast[warp][1];
   double logz = 0.0;
 
   if (role == 0) {
     // ------------------------------------------------------------ A: alpha up over [0, Th)
     logz = (double)w0max + (double)(Th - 1) * (double)wmax;
+    load_row();
     float ahat = 0.f;
     float xn[kPF];
 #pragma unroll
@@ -311,7 +441,7 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_split_kernel(
         } else {
           bc0[lane] = ahat;
           __syncwarp();
-          av = p * dot_row(Wr, bc0);
+          av = p * dot_row(Wx, bc0);
           __syncwarp();
         }
         const float c = warp_max(av);
@@ -321,9 +451,9 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_split_kernel(
         if (lane == 0) hC[t] = c;
       }
     }
-    xch[warp][lane] = ahat;                      // a^_{Th-1} for B
-    pair_sync(1 + pair);
-    float bhat = xch[warp + 1][lane];            // b^_{Th-1} from B
+    xch[0][lane] = ahat;                         // a^_{Th-1} for B
+    asm volatile("bar.sync 3, 64;" ::: "memory");
+    float bhat = xch[1][lane];                   // b^_{Th-1} from B
     {
       __syncwarp();
       double lc = 0.0;
@@ -333,69 +463,47 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_split_kernel(
       logz += lc;
     }
     // ------------------------------------------------------------ A: beta down over [0, Th)
-    float acur = ahat;
-    float xq[kPF], aq[kPF], cq[kPF];
+    load_col();
+    tick_bar(role);                      // my stored vectors are visible to my helpers
+    float xq[kPF];
 #pragma unroll
     for (int k = 0; k < kPF; ++k) {
       const int t = Th - 1 - k;
       xq[k] = (valid && t >= 0) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
-      aq[k] = (valid && t >= 1) ? hV[(size_t)(t - 1) * C + lane] : 0.f;
-      cq[k] = (t >= 0) ? hC[t] : 1.f;
     }
-    for (int t0 = Th - 1; t0 >= 0; t0 -= kPF) {
-      float xc[kPF], ac[kPF], cc[kPF];
+    for (int n = 0; n < nch; ++n) {
 #pragma unroll
-      for (int k = 0; k < kPF; ++k) {
-        xc[k] = xq[k]; ac[k] = aq[k]; cc[k] = cq[k];
-        const int t = t0 - kPF - k;
-        xq[k] = (valid && t >= 0) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
-        aq[k] = (valid && t >= 1) ? hV[(size_t)(t - 1) * C + lane] : 0.f;
-        cq[k] = (t >= 0) ? hC[t] : 1.f;
+      for (int h = 0; h < kChunk / kPF; ++h) {
+        float xc[kPF];
+#pragma unroll
+        for (int k = 0; k < kPF; ++k) {
+          xc[k] = xq[k];
+          const int t = Th - 1 - (n * kChunk + h * kPF + kPF + k);
+          xq[k] = (valid && t >= 0) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
+        }
+#pragma unroll
+        for (int k = 0; k < kPF; ++k) {
+          const int t = Th - 1 - (n * kChunk + h * kPF + k);
+          if (t < 0) break;
+          float* ent = ring[0][n & 1][h * kPF + k];
+          const float m = warp_max(xc[k]);
+          const float base = (m == kNegInf) ? 0.f : m;
+          const float p = valid ? __expf(xc[k] - base) : 0.f;
+          const float r = p * bhat;
+          ent[lane] = r;
+          ent[kCP + lane] = bhat;
+          if (t == 0) break;
+          __syncwarp();
+          const float bn = dot_row(Wx, ent);
+          const float nb = warp_max(bn);
+          bhat = nb > 0.f ? __fdividef(bn, nb) : 0.f;
+        }
       }
-#pragma unroll
-      for (int k = 0; k < kPF; ++k) {
-        const int t = t0 - k;
-        if (t < 0) break;
-        const float m = warp_max(xc[k]);
-        const float base = (m == kNegInf) ? 0.f : m;
-        const float p = valid ? __expf(xc[k] - base) : 0.f;
-        const float gq = acur * bhat;
-        const float G = warp_sum(gq);
-        const float gamma = G > 0.f ? __fdividef(gq, G) : 0.f;
-        if (gEb && valid) {
-          float* dst = gEb + (size_t)t * C + lane;
-          *dst = accumulate ? *dst + gs * gamma : gs * gamma;
-        }
-        if (t == 0) {
-          if (gradTr && valid && gamma != 0.f) atomicAdd(&gradTr[lane], gs * gamma);
-          break;
-        }
-        const float r = p * bhat;
-        const float n = cc[k] * G;
-        const float rn = n > 0.f ? __fdividef(r, n) : 0.f;
-        bc0[lane] = ac[k];
-        bc1[lane] = r;
-        __syncwarp();
-        {
-          const float4* v = reinterpret_cast<const float4*>(bc0);
-#pragma unroll
-          for (int q = 0; q < kCP / 4; ++q) {
-            const float4 a4 = v[q];
-            acc[4 * q + 0] = fmaf(a4.x, rn, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(a4.y, rn, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(a4.z, rn, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(a4.w, rn, acc[4 * q + 3]);
-          }
-        }
-        const float bn = dot_row(Wc, bc1);
-        __syncwarp();
-        const float nb = warp_max(bn);
-        bhat = nb > 0.f ? __fdividef(bn, nb) : 0.f;
-        acur = ac[k];
-      }
+      tick_bar(role);                    // chunk n is complete
     }
   } else {
     // ------------------------------------------------------------ B: beta down over [Th, T)
+    load_col();
     float bhat = valid ? 1.f : 0.f;
     float xq[kPF];
 #pragma unroll
@@ -421,70 +529,58 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_split_kernel(
         if (valid) hV[(size_t)t * C + lane] = bhat;          // b^_t
         bc1[lane] = p * bhat;
         __syncwarp();
-        const float bn = dot_row(Wc, bc1);
+        const float bn = dot_row(Wx, bc1);
         __syncwarp();
         const float nb = warp_max(bn);
         bhat = nb > 0.f ? __fdividef(bn, nb) : 0.f;           // b^_{t-1}
       }
     }
-    xch[warp][lane] = bhat;                      // b^_{Th-1} for A
-    pair_sync(1 + pair);
-    float ahat = xch[warp - 1][lane];            // a^_{Th-1} from A
+    xch[1][lane] = bhat;                         // b^_{Th-1} for A
+    asm volatile("bar.sync 3, 64;" ::: "memory");
+    float ahat = xch[0][lane];                   // a^_{Th-1} from A
     // ------------------------------------------------------------ B: alpha up over [Th, T)
+    load_row();
+    tick_bar(role);                      // my stored vectors are visible to my helpers
     logz = (double)(T - Th) * (double)wmax;
-    float xn[kPF], bq[kPF];
+    float xn[kPF];
 #pragma unroll
     for (int k = 0; k < kPF; ++k) {
       const int t = Th + k;
       xn[k] = (valid && t < T) ? __ldg(Eb + (size_t)t * C + lane) : kNegInf;
-      bq[k] = (valid && t < T) ? hV[(size_t)t * C + lane] : 0.f;
     }
-    for (int t0 = Th; t0 < T; t0 += kPF) {
-      float xc[kPF], bcur[kPF];
+    for (int n = 0; n < nch; ++n) {
 #pragma unroll
-      for (int k = 0; k < kPF; ++k) {
-        xc[k] = xn[k]; bcur[k] = bq[k];
-        const int tn = t0 + kPF + k;
-        xn[k] = (valid && tn < T) ? __ldg(Eb + (size_t)tn * C + lane) : kNegInf;
-        bq[k] = (valid && tn < T) ? hV[(size_t)tn * C + lane] : 0.f;
-      }
+      for (int h = 0; h < kChunk / kPF; ++h) {
+        float xc[kPF];
 #pragma unroll
-      for (int k = 0; k < kPF; ++k) {
-        const int t = t0 + k;
-        if (t >= T) break;
-        const float m = warp_max(xc[k]);
-        const float base = (m == kNegInf) ? 0.f : m;
-        const float p = valid ? __expf(xc[k] - base) : 0.f;
-        bc0[lane] = ahat;                                   // a^_{t-1}
-        __syncwarp();
-        const float av = p * dot_row(Wr, bc0);
-        const float c = warp_max(av);
-        const float anew = c > 0.f ? __fdividef(av, c) : 0.f;
-        const float gq = anew * bcur[k];
-        const float G = warp_sum(gq);
-        const float gamma = G > 0.f ? __fdividef(gq, G) : 0.f;
-        if (gEb && valid) {
-          float* dst = gEb + (size_t)t * C + lane;
-          *dst = accumulate ? *dst + gs * gamma : gs * gamma;
+        for (int k = 0; k < kPF; ++k) {
+          xc[k] = xn[k];
+          const int tn = Th + n * kChunk + h * kPF + kPF + k;
+          xn[k] = (valid && tn < T) ? __ldg(Eb + (size_t)tn * C + lane) : kNegInf;
         }
-        const float n = c * G;
-        const float rn = n > 0.f ? __fdividef(p * bcur[k], n) : 0.f;
-        {
-          const float4* v = reinterpret_cast<const float4*>(bc0);
 #pragma unroll
-          for (int q = 0; q < kCP / 4; ++q) {
-            const float4 a4 = v[q];
-            acc[4 * q + 0] = fmaf(a4.x, rn, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(a4.y, rn, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(a4.z, rn, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(a4.w, rn, acc[4 * q + 3]);
+        for (int k = 0; k < kPF; ++k) {
+          const int t = Th + n * kChunk + h * kPF + k;
+          if (t >= T) break;
+          float* ent = ring[1][n & 1][h * kPF + k];
+          const float m = warp_max(xc[k]);
+          const float base = (m == kNegInf) ? 0.f : m;
+          const float p = valid ? __expf(xc[k] - base) : 0.f;
+          ent[lane] = ahat;                                  // a^_{t-1}
+          __syncwarp();
+          const float av = p * dot_row(Wx, ent);
+          const float c = warp_max(av);
+          const float anew = c > 0.f ? __fdividef(av, c) : 0.f;
+          ent[kCP + lane] = anew;
+          if (lane == 0) {
+            ent[kCP + 32] = c;
+            hC[t] = c;
           }
+          ahat = anew;
+          logz += (double)base;
         }
-        __syncwarp();
-        ahat = anew;
-        logz += (double)base;
-        if (lane == 0) hC[t] = c;
       }
+      tick_bar(role);                    // chunk n is complete
     }
     {
       __syncwarp();
@@ -496,18 +592,9 @@ __global__ void __launch_bounds__(32 * kWarps) asg_fcc_dense_split_kernel(
       logz += lc + (double)logf(tail);
     }
   }
-  if (lane == 0) zpart[warp] = logz;
-  pair_sync(1 + pair);
-  if (role == 0 && lane == 0) scores[b] = (float)(zpart[warp] + zpart[warp + 1]);
-  if (gradTr && valid) {
-#pragma unroll
-    for (int j = 0; j < kCP; ++j) {
-      if (j < C) {
-        const float v = gs * Wr[j] * acc[j];
-        if (v != 0.f) atomicAdd(&gradTr[C + lane * C + j], v);
-      }
-    }
-  }
+  if (lane == 0) zpart[role] = logz;
+  asm volatile("bar.sync 4, 64;" ::: "memory");
+  if (role == 0 && lane == 0) scores[b] = (float)(zpart[0] + zpart[1]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -623,9 +710,9 @@ int launch_asg_fcc_dense(const float* E, const float* tr, int B, int T, int C, c
     cudaFuncSetAttribute(asg_fcc_dense_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     carveout_set.fetch_or(bit);
   }
-  // two warps per utterance that meet in the middle when gradients are wanted and T allows
+  // six warps per utterance (two that meet in the middle + their helpers) when gradients are wanted and T allows
   if (T >= 8 && (gradE || gradTr) && !g_asg_dense_single)
-    asg_fcc_dense_split_kernel<<<(B + kWarps / 2 - 1) / (kWarps / 2), 32 * kWarps, 0, st>>>(
+    asg_fcc_dense_split_kernel<<<B, 32 * kGradWarps, 0, st>>>(
         E, tr, B, T, C, grad_scale, sign, scores, gradE, accumulate, gradTr, hist);
   else
     asg_fcc_dense_kernel<<<(B + kWarps - 1) / kWarps, 32 * kWarps, 0, st>>>(

@@ -1,4 +1,7 @@
-// Scaled-probability ASG force-align lattice: forward_score + backward of
+// Scaled-probability ASG force-align lattice on the TICK schedule of ctc_tick.cu (read its header
+// for the schedule: one named barrier per 8-frame step and component instead of per-resource
+// mbarriers, rings sized by writer-reader distance, node posteriors summed by class with
+// fixed-point shared-memory atomics in the recompute warps): forward_score + backward of
 //   intersect(intersect(g_fal, g_transitions), g_emissions)      (criterions/asg.py:53-81,103-115,158)
 // as a chain recursion, on the machinery of ctc_solo.cu (read that header first): one block per
 // utterance, one warp set per time direction, meet in the middle, recompute from checkpoints,
@@ -33,13 +36,10 @@ constexpr int kEventEvery = 1;        // lanes are renormalised every step: labe
 constexpr int kUndef = -(1 << 19);    // "no exponent": lane holds only zeros
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNR = 3;                // raw (TMA) staging slots per producer warp
-constexpr int kRD = 4;                // depth of the warp-to-warp chain rings
+constexpr int kRD = 2;                // entries per chain ring (step parity)
 constexpr int kMaxAB = 8;             // step buffers per component, at most
 constexpr int kMaxNB = 12;            // p tiles per component, at most
-constexpr int kMaxList = 48;          // reduction table: sum over class rounds of the longest list
-constexpr int kMaxW = 4;
 constexpr int kRingF = 12;            // floats per ring slot: 9 boundary values, the exponent, pad
-constexpr int kRegList = 16;          // entries of a class list the reduction keeps in registers
 
 #ifdef WFST_FAL_DEBUG
 #define WFST_HAZ(ptr, bits) do { if (blockIdx.x < 3) printf("hazard b=%d bits=%d line %d warp %d\n", (int)blockIdx.x, (int)(bits), __LINE__, (int)(threadIdx.x >> 5)); atomicOr(ptr, bits); } while (0)
@@ -103,25 +103,12 @@ __device__ __forceinline__ float pow2i(int d) {  // 2^d for d in [-126, 127]
 // 2^d clamped: 0 below the normal range, 2^126 above it (callers bound d from above)
 __device__ __forceinline__ float pow2c(int d) { return (d < -126) ? 0.f : pow2i(min(d, 126)); }
 
-// ---- mbarriers (per component: index = base + c * stride) --------------------------
-constexpr int kBarPFull = 0;                              // [2][kMaxNB]        p tile ready (P[c] -> live[c], rc[c])
-constexpr int kBarPEmpty = kBarPFull + 2 * kMaxNB;        // [2][kMaxNB]        p tile released (count 2W)
-constexpr int kBarTma = kBarPEmpty + 2 * kMaxNB;          // [2][kNR]           raw tiles landed
-constexpr int kBarLFull = kBarTma + 2 * kNR;              // [2][kMaxW][kRD]    live chain ring entry written (w-1 -> w)
-constexpr int kBarLEmpty = kBarLFull + 2 * kMaxW * kRD;   //                    ... consumed
-constexpr int kBarRFull = kBarLEmpty + 2 * kMaxW * kRD;   // [2][kMaxW][kRD]    recompute chain ring
-constexpr int kBarREmpty = kBarRFull + 2 * kMaxW * kRD;
-constexpr int kBarAFull = kBarREmpty + 2 * kMaxW * kRD;   // [2][kMaxAB]        abar rows of a step stored (count W; live -> rc)
-constexpr int kBarXFull = kBarAFull + 2 * kMaxAB;         // [2][kMaxAB]        products ready (count W; rc -> X)
-constexpr int kBarAEmpty = kBarXFull + 2 * kMaxAB;        // [2][kMaxAB]        step buffer free (count 1; X -> live)
-constexpr int kBarZ = kBarAEmpty + 2 * kMaxAB;            // Z published
-constexpr int kNumBars = kBarZ + 1;
+// ---- mbarriers: the producers' TMA completion barriers only ------------------------
+constexpr int kBarTma = 0;            // [2][kNR] raw tiles landed
+constexpr int kNumBars = 2 * kNR;
 
 __device__ __forceinline__ void bar_init(uint32_t bars, int idx, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * idx), "r"(count));
-}
-__device__ __forceinline__ void bar_arrive(uint32_t bars, int idx, uint32_t count = 1) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * idx), "r"(count) : "memory");
 }
 __device__ __forceinline__ void bar_expect_tx(uint32_t bars, int idx, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8u * idx), "r"(bytes) : "memory");
@@ -130,16 +117,66 @@ __device__ __forceinline__ void bar_wait(uint32_t bars, int idx, uint32_t parity
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WFSTF_BW_%=:\n"
+      "WFSTT_BW_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra WFSTF_BD_%=;\n"
-      "bra WFSTF_BW_%=;\n"
-      "WFSTF_BD_%=:\n"
+      "@p bra WFSTT_BD_%=;\n"
+      "bra WFSTT_BW_%=;\n"
+      "WFSTT_BD_%=:\n"
       "}\n" ::"r"(bars + 8u * idx), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// ---- ticks: one named barrier per component and phase ------------------------------
+// phase 1: live[c][0..W) + P[c]; phase 2: live[c], rc[c], X[c], P[c]
+// WFST_PROFILE: per-role cycles spent working / idle per tick (block 0 prints).  Clocks are
+// read BEFORE the barrier only (a clock read after BAR.SYNC.DEFER_BLOCKING does not wait for
+// the barrier): every warp posts its arrival time, the release time of a tick is the latest
+// arrival among the component's warps.
+struct Prof {
+#ifdef WFST_PROFILE
+  long long work, idle, wmax, prev_rel, mine;
+  volatile long long* tab;   // [2][16] in shared memory
+  unsigned mask;
+  int warp, par;
+  __device__ __forceinline__ Prof() : work(0), idle(0), wmax(0), tab(nullptr), mask(0), warp(0), par(0) { prev_rel = clock64(); mine = prev_rel; }
+  __device__ __forceinline__ void setup(float* smem_prof, unsigned m) { tab = reinterpret_cast<volatile long long*>(smem_prof); mask = m; warp = threadIdx.x >> 5; prev_rel = clock64(); }
+  long long acc[6] = {0, 0, 0, 0, 0, 0}, tm = 0;
+  __device__ __forceinline__ void mark0() { tm = clock64(); }
+  __device__ __forceinline__ void mark(int i) { const long long t = clock64(); acc[i] += t - tm; tm = t; }
+  __device__ __forceinline__ void before() { mine = clock64(); tab[par * 16 + warp] = mine; }
+  __device__ __forceinline__ void after() {
+    long long rel = 0;
+    for (int i = 0; i < 16; ++i) if ((mask >> i) & 1u) { const long long t = tab[par * 16 + i]; rel = t > rel ? t : rel; }
+    const long long d = mine - prev_rel;
+    work += d; if (d > wmax) wmax = d;
+    idle += rel - mine;
+    prev_rel = rel; par ^= 1;
+  }
+  __device__ __forceinline__ void report(const char* role, int c, int w, int phase, int lane) {
+    if (blockIdx.x == 0 && lane == 0) printf("%s[%d][%d] phase %d: work %lld idle %lld longest %lld marks %lld %lld %lld %lld %lld %lld\n", role, c, w, phase, work, idle, wmax, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5]);
+    work = 0; idle = 0; wmax = 0; prev_rel = clock64();
+    for (int i = 0; i < 6; ++i) acc[i] = 0;
+  }
+#else
+  __device__ __forceinline__ void setup(float*, unsigned) {}
+  __device__ __forceinline__ void mark0() {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void before() {}
+  __device__ __forceinline__ void after() {}
+  __device__ __forceinline__ void report(const char*, int, int, int, int) {}
+#endif
+};
+template <int W>
+__device__ __forceinline__ unsigned tick_mask(int c, int phase) {
+  unsigned m = (((1u << W) - 1u) << (c * W)) | (1u << (4 * W + 2 + c));
+  if (phase == 2) m |= (((1u << W) - 1u) << (2 * W + c * W)) | (1u << (4 * W + c));
+  return m;
+}
+template <int W>
+__device__ __forceinline__ void tick1(int c, Prof& pf) { pf.before(); named_sync(8 + c, 32 * (W + 1)); pf.after(); }
+template <int W>
+__device__ __forceinline__ void tick2(int c, Prof& pf) { pf.before(); named_sync(10 + c, 32 * (2 * W + 2)); pf.after(); }
 
 // ---- geometry ------------------------------------------------------------------------
 template <int K, int W>
@@ -159,13 +196,14 @@ struct Geo {
 
 // shared memory layout (in floats); every per-component region is [2][...]
 struct Layout {
-  size_t raw, out, abuf, bnd, lexp, cert, ptile, ringL, ringR, bars, zx, ytab, xtab, hist, total;
-  size_t abuf_c, bnd_c, lexp_c, cert_c, ptile_c, ring_c;   // size of one component's part
+  size_t raw, out, abuf, bnd, lexp, cert, gacc, ptile, ringL, ringR, bars, zx, ytab, prof, total;
+  size_t abuf_c, bnd_c, lexp_c, cert_c, gacc_c, ptile_c, ring_c;   // size of one component's part
   size_t zero_end;
 };
 template <int K, int W>
 __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
   using G = Geo<K, W>;
+  const int NG = W + 1;   // tiles / certificate terms: written by rc, read by X
   Layout L;
   const size_t rawsz = ((size_t)kSeg * C + 3) & ~(size_t)3;
   const size_t CP = (size_t)C + 1;
@@ -178,8 +216,10 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
   L.bnd = p;    p += 2 * L.bnd_c;                                   // [c][buf][word]: live state at the step boundary
   L.lexp_c = (size_t)NAB * G::NL;
   L.lexp = p;   p += 2 * L.lexp_c;                                  // [c][buf][gl] (int)
-  L.cert_c = (size_t)NAB * W;
-  L.cert = p;   p += 2 * L.cert_c;                                  // [c][buf][w]
+  L.cert_c = (size_t)NG * G::NL;
+  L.cert = p;   p += 2 * L.cert_c;                                  // [c][buf][gl]: the lanes' certificate terms
+  L.gacc_c = (size_t)NG * kSeg * CP;
+  L.gacc = p;   p += 2 * L.gacc_c;                                  // [c][buf][row][class] (int, 2^-23 units)
   L.ptile_c = (size_t)NB * CP * 9 + 8;
   L.ptile = p;  p += 2 * L.ptile_c;                                 // [c][buf][col][9]
   p = (p + 3) & ~(size_t)3;
@@ -192,24 +232,26 @@ __host__ __device__ inline Layout make_layout(int C, int NAB, int NB) {
   p = (p + 3) & ~(size_t)3;
   L.zx = p;     p += 32;   // Zm, eZ, ok, trmax, msum(double), zpart[kMaxW]{contrib, Emax}, endacc[2], bad flag
   L.ytab = p;   p += (size_t)G::Sp + 4;                             // targets of the utterance
-  L.xtab = p;   p += (size_t)2 * kMaxList * 32 / 2;                 // [c][entry][lane] (u16 row offsets)
-  L.hist = p;   p += (size_t)C + 16;                                // per-class counts; then per-round {nmax, base}
+  p = (p + 3) & ~(size_t)3;
+  L.prof = p;
+#ifdef WFST_PROFILE
+  p += 2 * 2 * 16 * 2;
+#endif
   L.total = p + 4;
   return L;
 }
 
 struct Smem {
-  uint32_t raw, out, abuf, bnd, lexp, cert, ptile, ringL, ringR, bars, zx, xtab;
-  uint32_t abuf_c, bnd_c, lexp_c, cert_c, ptile_c, ring_c;   // bytes per component
+  uint32_t raw, out, abuf, bnd, lexp, cert, gacc, ptile, ringL, ringR, bars, zx;
+  uint32_t abuf_c, bnd_c, lexp_c, cert_c, gacc_c, ptile_c, ring_c;   // bytes per component
   int* ytab;
-  int* hist;
-  unsigned short* xtab_gen;
   float* out_gen;
+  float* prof_gen;
 };
 
 struct Ctx {
   int lane, T, C, CP, L, b;
-  int nsd, nfull, r0, r1, Th, NAB, NB;
+  int nsd, nfull, r0, r1, Th, NAB, NB, NR, NO;
   bool want_grad;
   uint32_t rawsz;
   float trmax;
@@ -376,49 +418,35 @@ __device__ __forceinline__ void ckpt_load(const float* base, float (&v)[K], int&
   e = __float_as_int(t[K]);
 }
 
-// p-tile ring of one component, as seen by a consumer warp that takes every tile from `first` on
-struct PRing {
-  int buf;
-  uint32_t par;
-  __device__ __forceinline__ void init(int first, int NB) { buf = first % NB; par = (uint32_t)(first / NB) & 1u; }
-  __device__ __forceinline__ void next(int NB) {
-    if (++buf == NB) { buf = 0; par ^= 1u; }
-  }
-};
-__device__ __forceinline__ uint32_t ptile_wait(const Smem& sm, const Ctx& cx, int c, const PRing& r) {
-  bar_wait(sm.bars, kBarPFull + c * kMaxNB + r.buf, r.par);
-  return sm.ptile + (uint32_t)c * sm.ptile_c + 4u * (uint32_t)(r.buf * cx.CP * 9);
-}
-__device__ __forceinline__ void ptile_release(const Smem& sm, const Ctx& cx, int c, PRing& r, uint32_t count) {
-  __syncwarp();
-  if (cx.lane == 0) bar_arrive(sm.bars, kBarPEmpty + c * kMaxNB + r.buf, count);
-  r.next(cx.NB);
+// p tile buffer `buf` of component c
+__device__ __forceinline__ uint32_t ptile_addr(const Smem& sm, const Ctx& cx, int c, int buf) {
+  return sm.ptile + (uint32_t)c * sm.ptile_c + 4u * (uint32_t)(buf * cx.CP * 9);
 }
 
 // ---------------------------------------------------------------------------
-// P[c]: producer of component c's p tiles: phase-1 tiles first; the phase-2 tiles only once Z
-// is known to be usable.  Lane = class (classes beyond 32 in further groups): a row maximum is
-// one warp reduction, the transposed tile is written with conflict-free stores.
+// P[c]: producer of component c's p tiles, one tick ahead of live[c][0]: phase-1 tiles first;
+// the phase-2 tiles only once Z is known to be usable.  Lane = class (classes beyond 32 in
+// further groups): a row maximum is one warp reduction, the transposed tile is written with
+// conflict-free stores.  Raw tiles arrive by TMA, up to kNR in flight (the only mbarriers).
 // ---------------------------------------------------------------------------
 struct ProducerState {
   int fetched, converted;
   uint32_t tma_phase, tma_used;
   int pbuf;            // p-tile buffer of the next tile
-  uint32_t ppar;       // parity of its "empty" barrier
   double msum;
 };
 
-__device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, const Ctx& cx, ProducerState& ps,
-                                              const int c, const int kbeg, const int kcnt, const bool phase1) {
+// raw tiles of [.., kt_end) in flight, at most kNR beyond the last converted one
+__device__ __forceinline__ void producer_fetch(const Args& a, const Smem& sm, const Ctx& cx, ProducerState& ps,
+                                               const int c, const int kt_end) {
   const int lane = cx.lane, T = cx.T, C = cx.C;
   const uint32_t rawsz = cx.rawsz;
   const uint32_t raw0 = sm.raw + 4u * (uint32_t)(c * kNR) * rawsz;
   const int tbar = kBarTma + c * kNR;
   const float* Eb = a.E + (size_t)cx.b * T * C;
-  const int groups = (C + 31) >> 5;
-  auto issue_raw = [&](int kt) {
+  while (ps.fetched < kt_end && ps.fetched < ps.converted + kNR) {
     int lo_, rows;
-    comp_seg(cx, c, kt, lo_, rows);
+    comp_seg(cx, c, ps.fetched, lo_, rows);
     const int slot = ps.fetched % kNR;
     const uint32_t bytes = (uint32_t)rows * C * 4u;
     const float* src = Eb + (size_t)lo_ * C;
@@ -439,96 +467,136 @@ __device__ __forceinline__ void produce_range(const Args& a, const Smem& sm, con
       __syncwarp();
     }
     ++ps.fetched;
-  };
-  int kf = 0;   // next entry to fetch (relative)
-  for (int i = 0; i < kcnt; ++i) {
-    while (kf < kcnt && ps.fetched < ps.converted + kNR) issue_raw(kbeg + kf++);
-    const int kt = kbeg + i;
-    const int slot = ps.converted % kNR;
-    int lo_, rows;
-    comp_seg(cx, c, kt, lo_, rows);
-    const int buf = ps.pbuf;
-    if (kt >= cx.NB) bar_wait(sm.bars, kBarPEmpty + c * kMaxNB + buf, ps.ppar);   // consumers have released this buffer
-    if (++ps.pbuf == cx.NB) { ps.pbuf = 0; if (kt >= cx.NB) ps.ppar ^= 1u; }
-    if ((ps.tma_used >> slot) & 1u) {
-      bar_wait(sm.bars, tbar + slot, (ps.tma_phase >> slot) & 1u);
-      ps.tma_phase ^= 1u << slot;
+  }
+}
+
+// tile kt (== ps.converted) from its raw slot into its p-tile buffer
+__device__ __forceinline__ void producer_convert(const Smem& sm, const Ctx& cx, ProducerState& ps, const int c,
+                                                 const int kt, const bool phase1, Prof& pf) {
+  pf.mark0();
+  const int lane = cx.lane, C = cx.C;
+  const uint32_t rawsz = cx.rawsz;
+  const uint32_t raw0 = sm.raw + 4u * (uint32_t)(c * kNR) * rawsz;
+  const int tbar = kBarTma + c * kNR;
+  const int groups = (C + 31) >> 5;
+  const int slot = ps.converted % kNR;
+  int lo_, rows;
+  comp_seg(cx, c, kt, lo_, rows);
+  const int buf = ps.pbuf;
+  if (++ps.pbuf == cx.NB) ps.pbuf = 0;
+  if ((ps.tma_used >> slot) & 1u) {
+    bar_wait(sm.bars, tbar + slot, (ps.tma_phase >> slot) & 1u);
+    ps.tma_phase ^= 1u << slot;
+  }
+  pf.mark(0);
+  const uint32_t er = raw0 + 4u * (uint32_t)slot * rawsz + 4u * (uint32_t)lane;
+  const uint32_t pt = ptile_addr(sm, cx, c, buf) + 36u * (uint32_t)lane;
+  // tile row = the step at which component c consumes the frame (c = 0 ascends, c = 1 descends).
+  // A row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface through the
+  // certificate.
+  float base[kSeg];
+  if (groups == 1 && rows == kSeg) {
+    // the common case (full tile, C <= 32) without row predicates
+    const bool valid = lane < C;
+    const uint32_t e0 = valid ? er : raw0 + 4u * (uint32_t)slot * rawsz;   // idle lanes re-read class 0: the maximum is unchanged
+    float x[kSeg];
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) x[r] = lds(e0 + 4u * (uint32_t)(r * C));
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) {
+      const float mx = warp_max(x[r]);
+      base[r] = (mx == kNegInf) ? 0.f : mx;
     }
-    const uint32_t er = raw0 + 4u * (uint32_t)slot * rawsz + 4u * (uint32_t)lane;
-    const uint32_t pt = sm.ptile + (uint32_t)c * sm.ptile_c + 4u * (uint32_t)(buf * cx.CP * 9) + 36u * (uint32_t)lane;
-    // tile row = the step at which component c consumes the frame (c = 0 ascends, c = 1 descends).
-    // A row that is entirely -inf keeps p = 0 (dead frame); +inf / NaN rows surface through the
-    // certificate.
-    float base[kSeg];
-    if (groups == 1) {
-      const bool valid = lane < C;
-      float x[kSeg];
+    if (valid) {
+      const uint32_t p0 = pt + (c == 0 ? 0u : 4u * (kSeg - 1));
+      const int32_t dp = c == 0 ? 4 : -4;
 #pragma unroll
-      for (int r = 0; r < kSeg; ++r) x[r] = (valid && r < rows) ? lds(er + 4u * (uint32_t)(r * C)) : kNegInf;
+      for (int r = 0; r < kSeg; ++r)
+        sts(p0 + (uint32_t)(r * dp), ex2_fast((x[r] - base[r]) * 1.4426950408889634f));
+    }
+  } else if (groups == 1) {
+    const bool valid = lane < C;
+    float x[kSeg];
 #pragma unroll
-      for (int r = 0; r < kSeg; ++r) {
-        const float mx = warp_max(x[r]);
-        base[r] = (mx == kNegInf) ? 0.f : mx;
+    for (int r = 0; r < kSeg; ++r) x[r] = (valid && r < rows) ? lds(er + 4u * (uint32_t)(r * C)) : kNegInf;
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) {
+      const float mx = warp_max(x[r]);
+      base[r] = (mx == kNegInf) ? 0.f : mx;
+    }
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) {
+      if (valid && r < rows) {
+        const int trow = c == 0 ? r : rows - 1 - r;
+        sts(pt + 4u * (uint32_t)trow, ex2_fast(fmaf(x[r], 1.4426950408889634f, -base[r] * 1.4426950408889634f)));
       }
+    }
+  } else {
+    float mx[kSeg];
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) mx[r] = kNegInf;
+    for (int g = 0; g < groups; ++g) {
+      const bool valid = 32 * g + lane < C;
+#pragma unroll
+      for (int r = 0; r < kSeg; ++r)
+        if (valid && r < rows) mx[r] = fmaxf(mx[r], lds(er + 4u * (uint32_t)(r * C + 32 * g)));
+    }
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) {
+      const float m = warp_max(mx[r]);
+      base[r] = (m == kNegInf) ? 0.f : m;
+    }
+    for (int g = 0; g < groups; ++g) {
+      const bool valid = 32 * g + lane < C;
 #pragma unroll
       for (int r = 0; r < kSeg; ++r) {
         if (valid && r < rows) {
           const int trow = c == 0 ? r : rows - 1 - r;
-          sts(pt + 4u * (uint32_t)trow, ex2_fast(fmaf(x[r], 1.4426950408889634f, -base[r] * 1.4426950408889634f)));
-        }
-      }
-    } else {
-      float mx[kSeg];
-#pragma unroll
-      for (int r = 0; r < kSeg; ++r) mx[r] = kNegInf;
-      for (int g = 0; g < groups; ++g) {
-        const bool valid = 32 * g + lane < C;
-#pragma unroll
-        for (int r = 0; r < kSeg; ++r)
-          if (valid && r < rows) mx[r] = fmaxf(mx[r], lds(er + 4u * (uint32_t)(r * C + 32 * g)));
-      }
-#pragma unroll
-      for (int r = 0; r < kSeg; ++r) {
-        const float m = warp_max(mx[r]);
-        base[r] = (m == kNegInf) ? 0.f : m;
-      }
-      for (int g = 0; g < groups; ++g) {
-        const bool valid = 32 * g + lane < C;
-#pragma unroll
-        for (int r = 0; r < kSeg; ++r) {
-          if (valid && r < rows) {
-            const int trow = c == 0 ? r : rows - 1 - r;
-            const float x = lds(er + 4u * (uint32_t)(r * C + 32 * g));
-            sts(pt + 36u * (uint32_t)(32 * g) + 4u * (uint32_t)trow, ex2_fast(fmaf(x, 1.4426950408889634f, -base[r] * 1.4426950408889634f)));
-          }
+          const float x = lds(er + 4u * (uint32_t)(r * C + 32 * g));
+          sts(pt + 36u * (uint32_t)(32 * g) + 4u * (uint32_t)trow, ex2_fast(fmaf(x, 1.4426950408889634f, -base[r] * 1.4426950408889634f)));
         }
       }
     }
-    if (phase1) {
-      float s = 0.f;
-#pragma unroll
-      for (int r = 0; r < kSeg; ++r) s += r < rows ? base[r] : 0.f;
-      ps.msum += (double)s;
-    }
-    __syncwarp();
-    if (lane == 0) bar_arrive(sm.bars, kBarPFull + c * kMaxNB + buf);
-    ++ps.converted;
   }
+  if (phase1) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < kSeg; ++r) s += r < rows ? base[r] : 0.f;
+    ps.msum += (double)s;
+  }
+  pf.mark(1);
+  ++ps.converted;
 }
 
+template <int W>
 __device__ __forceinline__ void role_producer(const Args& a, const Smem& sm, const Ctx& cx, const int c) {
   const int lane = cx.lane, nsd = cx.nsd;
+  Prof pf;
+  pf.setup(sm.prof_gen, tick_mask<W>(c, 1));
   ProducerState ps;
   ps.fetched = 0; ps.converted = 0; ps.tma_phase = 0u; ps.tma_used = 0u;
-  ps.pbuf = 0; ps.ppar = 0u;
+  ps.pbuf = 0;
   ps.msum = 0.0;
-  produce_range(a, sm, cx, ps, c, 0, nsd, true);
+  producer_fetch(a, sm, cx, ps, c, nsd);
+  producer_convert(sm, cx, ps, c, 0, true, pf);
+  producer_fetch(a, sm, cx, ps, c, nsd);
+  tick1<W>(c, pf);
+  for (int n = 0; n < nsd + W; ++n) {
+    if (n + 1 < nsd) {
+      producer_convert(sm, cx, ps, c, n + 1, true, pf);
+      producer_fetch(a, sm, cx, ps, c, nsd);
+      pf.mark(2);
+    }
+    tick1<W>(c, pf);
+  }
+  pf.report("P", c, 0, 1, lane);
   // loss: log Z = log(Zm) + eZ ln2 + sum_t max_t; the two producers each hold the row maxima
   // of their phase-1 half (every lane holds the same sum)
   double* msh = reinterpret_cast<double*>(__cvta_shared_to_generic(sm.zx + 16u));
   if (c == 0 && lane == 0) msh[0] = ps.msum;
-  named_sync(2, 64);
-  bar_wait(sm.bars, kBarZ, 0u);
+  __syncthreads();   // meeting A
+  __syncthreads();   // meeting B
+  __syncthreads();   // meeting C: Z published
   const float Zm = lds(sm.zx);
   const int eZ = ldsi(sm.zx + 4u);
   const bool ok = lds(sm.zx + 8u) != 0.f;
@@ -537,9 +605,21 @@ __device__ __forceinline__ void role_producer(const Args& a, const Smem& sm, con
                                  (double)cx.T * (double)cx.trmax)   // every path takes T arcs scaled by exp(-max tr)
                            : kNegInf;
   if (!cx.want_grad || !ok) return;
-  produce_range(a, sm, cx, ps, c, nsd, nsd, false);
+  pf.setup(sm.prof_gen + 64, tick_mask<W>(c, 2));
+  producer_fetch(a, sm, cx, ps, c, 2 * nsd);
+  producer_convert(sm, cx, ps, c, nsd, false, pf);
+  producer_fetch(a, sm, cx, ps, c, 2 * nsd);
+  tick2<W>(c, pf);
+  for (int m = 0; m < nsd + 2 * W; ++m) {
+    if (m + 1 < nsd) {
+      producer_convert(sm, cx, ps, c, nsd + m + 1, false, pf);
+      producer_fetch(a, sm, cx, ps, c, 2 * nsd);
+      pf.mark(2);
+    }
+    tick2<W>(c, pf);
+  }
+  pf.report("P", c, 0, 2, lane);
 }
-
 
 // ---------------------------------------------------------------------------
 // live[c][w]: warp w of component c's chain
@@ -568,36 +648,20 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
   }
   const uint32_t ring_in0 = sm.ringL + (uint32_t)c * sm.ring_c + 4u * (uint32_t)(w * kRD * kRingF);
   const uint32_t ring_out0 = ring_in0 + 4u * (uint32_t)(kRD * kRingF);
-  const int lbar = c * kMaxW * kRD;
   uint32_t rin = ring_in0, rout = ring_out0;
-  PRing pr;
-  pr.init(0, cx.NB);
   const bool has_partial = nsd > cx.nfull;
 
-  // start of global step g: take the left warp's ring entry, renormalise if due, open my own entry
-  auto step_begin = [&](int g, bool ev) {
-    const int slot = g % kRD;
+  // start of global step g: the left warp's ring entry of this step was written one tick ago;
+  // renormalise (every step here), open my own entry
+  auto step_begin = [&](int g) {
+    const int slot = g & 1;
     rin = ring_in0 + 4u * (uint32_t)(slot * kRingF);
     rout = ring_out0 + 4u * (uint32_t)(slot * kRingF);
-    if (w > 0) bar_wait(sm.bars, kBarLFull + lbar + w * kRD + slot, (uint32_t)(g / kRD) & 1u);
-    if (ev) {
-      const int Ein = w > 0 ? ldsi(rin + 36u) : kUndef;
-      event1<K>(v, e, f, lane, Ein);
-    }
-    if (w < W - 1) {
-      if (g >= kRD) bar_wait(sm.bars, kBarLEmpty + lbar + (w + 1) * kRD + slot, (uint32_t)(g / kRD - 1) & 1u);
-      if (lane == 31) {
-        sts(rout, v[K - 1]);
-        stsi(rout + 36u, e);
-      }
-    }
-  };
-  auto step_end = [&](int g) {
-    const int slot = g % kRD;
-    __syncwarp();
-    if (lane == 0) {
-      if (w < W - 1) bar_arrive(sm.bars, kBarLFull + lbar + (w + 1) * kRD + slot);
-      if (w > 0) bar_arrive(sm.bars, kBarLEmpty + lbar + w * kRD + slot);
+    const int Ein = w > 0 ? ldsi(rin + 36u) : kUndef;
+    event1<K>(v, e, f, lane, Ein);
+    if (w < W - 1 && lane == 31) {
+      sts(rout, v[K - 1]);
+      stsi(rout + 36u, e);
     }
   };
   // frames of a partial step
@@ -618,45 +682,54 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     }
   };
 
-  // ------------------------------------------------------------------ phase 1
-  for (int g = 0; g < nsd; ++g) {
-    step_begin(g, g % kEventEvery == 0);
-    ckpt_store<K, G::CKF>(ck + (size_t)g * NL * G::CKF, v, e);
-    const bool partial = has_partial && g == cx.nfull;
-    const TileAddr<K> tad = tile_addr<K>(tp, ptile_wait(sm, cx, c, pr));
-    if (!partial) {
-      PRow<K> nx = load_prow<K>(tad, 0);
-      float bvn = lds(rin);
-#pragma unroll
-      for (int it = 0; it < kSeg; ++it) {
-        const PRow<K> cur = nx;
-        const float bv = bvn;
-        if (it + 1 < kSeg) { nx = load_prow<K>(tad, it + 1); bvn = lds(rin + 4u * (it + 1)); }
-        const float in1 = left_in(v[K - 1], bv, lane, f);
-        step<K, false>(v, ts, ta, tp, cur, in1);
-        if (lane == 31) sts(rout + 4u * (it + 1), v[K - 1]);
-      }
-    } else {
-      slow_frames(tad, c == 0 ? cx.r0 : cx.r1, 0u, false);
-    }
-    ptile_release(sm, cx, c, pr, 2);   // no recompute warp reads phase-1 tiles
-    step_end(g);
-  }
-
-  // ------------------------------------------------------------------ meeting: Z
-  // every live warp renormalises (consistent exponents for the successor sums below); the alpha
-  // warps publish their state in the layout of a boundary row (their buffer 0); the beta warps
-  // form   Z = sum over their slots of (successor sum of beta~)(slot) * alpha(partner slot).
-  step_begin(nsd, true);
   const uint32_t mybnd = 4u * (uint32_t)(4 + gl * K);       // my slots in a boundary row
   const uint32_t myrow = 4u * (uint32_t)(G::PADA + gl * G::SA);
-  if (c == 0) {
+
+  // ------------------------------------------------------------------ phase 1
+  Prof pf;
+  pf.setup(sm.prof_gen, tick_mask<W>(c, 1));
+  int pbuf = 0;
+  tick1<W>(c, pf);   // tile 0 is there
+  for (int n = 0; n < nsd + W; ++n) {
+    const int g = n - w;
+    if (g >= 0 && g < nsd) {
+      step_begin(g);
+      ckpt_store<K, G::CKF>(ck + (size_t)g * NL * G::CKF, v, e);
+      const bool partial = has_partial && g == cx.nfull;
+      const TileAddr<K> tad = tile_addr<K>(tp, ptile_addr(sm, cx, c, pbuf));
+      if (++pbuf == cx.NB) pbuf = 0;
+      if (!partial) {
+        PRow<K> nx = load_prow<K>(tad, 0);
+        float bvn = lds(rin);
 #pragma unroll
-    for (int i = 0; i < K; ++i) sts(sm.bnd + mybnd + 4u * i, v[i]);
-    stsi(sm.lexp + 4u * (uint32_t)gl, e);
+        for (int it = 0; it < kSeg; ++it) {
+          const PRow<K> cur = nx;
+          const float bv = bvn;
+          if (it + 1 < kSeg) { nx = load_prow<K>(tad, it + 1); bvn = lds(rin + 4u * (it + 1)); }
+          const float in1 = left_in(v[K - 1], bv, lane, f);
+          step<K, false>(v, ts, ta, tp, cur, in1);
+          if (lane == 31) sts(rout + 4u * (it + 1), v[K - 1]);
+        }
+      } else {
+        slow_frames(tad, c == 0 ? cx.r0 : cx.r1, 0u, false);
+      }
+    } else if (g == nsd) {
+      // meeting: every live warp renormalises (consistent exponents for the successor sums
+      // below); the alpha warps publish their state in the layout of a boundary row (buffer 0)
+      step_begin(nsd);
+      if (c == 0) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) sts(sm.bnd + mybnd + 4u * i, v[i]);
+        stsi(sm.lexp + 4u * (uint32_t)gl, e);
+      }
+    }
+    tick1<W>(c, pf);
   }
-  step_end(nsd);
-  named_sync(1, 64 * W);
+  pf.report("live", c, w, 1, lane);
+
+  // ------------------------------------------------------------------ meeting: Z
+  // the beta warps form   Z = sum over their slots of (successor sum of beta~)(slot) * alpha(partner slot).
+  __syncthreads();   // A: both chains have arrived, the alpha state is published
   if (c == 1) {
     // partner of my slot i is slot K-1-i of lane NL-1-gl
     const int pl = NL - 1 - gl;
@@ -682,7 +755,7 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
       stsi(sm.zx + 36u + 8u * (uint32_t)w, Emax);
     }
   }
-  named_sync(1, 64 * W);
+  __syncthreads();   // B
   if (c == 1 && w == 0 && lane == 0) {
     int Emax = kUndef;
     for (int i = 0; i < W; ++i) Emax = max(Emax, ldsi(sm.zx + 36u + 8u * (uint32_t)i));
@@ -696,8 +769,9 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
     float Zm = 1.f;
     if (ok) {
       ex = (int)((__float_as_uint(tot) >> 23) & 0xffu) - 127;
-      ex = min(max(ex, -126), 126);
-      Zm = tot * pow2i(-ex);
+      ex = min(max(ex, -126), 125);
+      Zm = tot * pow2i(-ex) * 0.5f;   // in [0.5, 1): the fixed-point posteriors stay below 1
+      ex += 1;
     }
     sts(sm.zx, Zm);
     stsi(sm.zx + 4u, ok ? Emax + ex : 0);
@@ -707,56 +781,59 @@ __device__ __forceinline__ void role_live(const Args& a, const Smem& sm, const C
 #endif
     // reason 2: infeasible or out of range -- the log-semiring kernel decides
     if (!ok) { WFST_HAZ(&a.hazard[cx.b], 2); stsi(sm.zx + 72u, 1); }
-    bar_arrive(sm.bars, kBarZ);
   }
-  bar_wait(sm.bars, kBarZ, 0u);
+  __syncthreads();   // C: Z published
   const bool okz = lds(sm.zx + 8u) != 0.f;
   if (!cx.want_grad || !okz) return;
 
   // ------------------------------------------------------------------ phase 2
   const uint32_t abuf = sm.abuf + (uint32_t)c * sm.abuf_c, bndb = sm.bnd + (uint32_t)c * sm.bnd_c,
                  lexpb = sm.lexp + (uint32_t)c * sm.lexp_c;
-  uint32_t rpar = 0u;   // (k2 / NAB) & 1
-  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, rpar ^= (buf + 1 == NAB), buf = (buf + 1 == NAB) ? 0 : buf + 1) {
-    const int g = nsd + 1 + k2;
-    step_begin(g, g % kEventEvery == 0);
-    if (k2 >= NAB) bar_wait(sm.bars, kBarAEmpty + c * kMaxAB + buf, rpar ^ 1u);
-    {
-      stsi(lexpb + 4u * (uint32_t)(buf * NL + gl), e);
-      // state at the step boundary: the recompute warps check Z against it (certificate)
-      const uint32_t bb = bndb + (uint32_t)buf * G::BNDB + mybnd;
+  pbuf = nsd % cx.NB;
+  int buf = 0;
+  pf.setup(sm.prof_gen + 64, tick_mask<W>(c, 2));
+  tick2<W>(c, pf);   // the first phase-2 tile is there
+  for (int m = 0; m < nsd + 2 * W; ++m) {
+    const int k2 = m - w;
+    if (k2 >= 0 && k2 < nsd) {
+      step_begin(nsd + 1 + k2);
+      {
+        stsi(lexpb + 4u * (uint32_t)(buf * NL + gl), e);
+        // state at the step boundary: the recompute warps check Z against it (certificate)
+        const uint32_t bb = bndb + (uint32_t)buf * G::BNDB + mybnd;
 #pragma unroll
-      for (int i = 0; i < K; ++i) sts(bb + 4u * i, v[i]);
-    }
-    // component c continues through the other direction's steps, last one (the partial one) first
-    const bool partial = has_partial && k2 == 0;
-    const TileAddr<K> tad = tile_addr<K>(tp, ptile_wait(sm, cx, c, pr));
-    const uint32_t ar = abuf + (uint32_t)(buf * kSeg) * G::ROWB + myrow;
-    if (!partial) {
-      PRow<K> nx = load_prow<K>(tad, 0);
-      float bvn = lds(rin);
-#pragma unroll
-      for (int it = 0; it < kSeg; ++it) {
-        const PRow<K> cur = nx;
-        const float bv = bvn;
-        if (it + 1 < kSeg) { nx = load_prow<K>(tad, it + 1); bvn = lds(rin + 4u * (it + 1)); }
-        const float in1 = left_in(v[K - 1], bv, lane, f);
-        step<K, true>(v, ts, ta, tp, cur, in1);
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-          sts(ar + (uint32_t)it * G::ROWB + 8u * i, ts[i]);
-          sts(ar + (uint32_t)it * G::ROWB + 8u * i + 4u, ta[i]);
-        }
-        if (lane == 31) sts(rout + 4u * (it + 1), v[K - 1]);
+        for (int i = 0; i < K; ++i) sts(bb + 4u * i, v[i]);
       }
-    } else {
-      slow_frames(tad, c == 0 ? cx.r1 : cx.r0, ar, true);
+      // component c continues through the other direction's steps, last one (the partial one) first
+      const bool partial = has_partial && k2 == 0;
+      const TileAddr<K> tad = tile_addr<K>(tp, ptile_addr(sm, cx, c, pbuf));
+      if (++pbuf == cx.NB) pbuf = 0;
+      const uint32_t ar = abuf + (uint32_t)(buf * kSeg) * G::ROWB + myrow;
+      if (!partial) {
+        PRow<K> nx = load_prow<K>(tad, 0);
+        float bvn = lds(rin);
+#pragma unroll
+        for (int it = 0; it < kSeg; ++it) {
+          const PRow<K> cur = nx;
+          const float bv = bvn;
+          if (it + 1 < kSeg) { nx = load_prow<K>(tad, it + 1); bvn = lds(rin + 4u * (it + 1)); }
+          const float in1 = left_in(v[K - 1], bv, lane, f);
+          step<K, true>(v, ts, ta, tp, cur, in1);
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            sts(ar + (uint32_t)it * G::ROWB + 8u * i, ts[i]);
+            sts(ar + (uint32_t)it * G::ROWB + 8u * i + 4u, ta[i]);
+          }
+          if (lane == 31) sts(rout + 4u * (it + 1), v[K - 1]);
+        }
+      } else {
+        slow_frames(tad, c == 0 ? cx.r1 : cx.r0, ar, true);
+      }
+      if (++buf == NAB) buf = 0;
     }
-    __syncwarp();
-    if (lane == 0) bar_arrive(sm.bars, kBarAFull + c * kMaxAB + buf);
-    ptile_release(sm, cx, c, pr, 1);
-    step_end(g);
+    tick2<W>(c, pf);
   }
+  pf.report("live", c, w, 2, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -774,7 +851,9 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
 #pragma unroll
   for (int i = 0; i < K; ++i) { gself[i] = 0.f; gadv[i] = 0.f; }
   ran = false;
-  bar_wait(sm.bars, kBarZ, 0u);      // phase 1 (and every checkpoint) is complete
+  __syncthreads();   // meeting A
+  __syncthreads();   // meeting B
+  __syncthreads();   // meeting C: phase 1 (and every checkpoint) is complete, Z published
   const bool ok = lds(sm.zx + 8u) != 0.f;
   if (!cx.want_grad || !ok) return;
   ran = true;
@@ -787,24 +866,35 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
   const uint32_t pbnd = 4u * (uint32_t)(4 + pl * K);              // partner block in a boundary row
   const uint32_t ring_in0 = sm.ringR + (uint32_t)c * sm.ring_c + 4u * (uint32_t)(w * kRD * kRingF);
   const uint32_t ring_out0 = ring_in0 + 4u * (uint32_t)(kRD * kRingF);
-  const int rbar = c * kMaxW * kRD;
   const uint32_t abuf = sm.abuf + (uint32_t)c * sm.abuf_c, bndb = sm.bnd + (uint32_t)c * sm.bnd_c,
                  lexpb = sm.lexp + (uint32_t)c * sm.lexp_c, certb = sm.cert + (uint32_t)c * sm.cert_c;
   int bad = 0;   // reason 4: scale overflow when pairing live and recomputed values
-  float wv[K], dts[K], dta[K];
-  int ew;
-  ckpt_load<K, G::CKF>(ck + (size_t)(nsd - 1) * NL * G::CKF, wv, ew);
-  PRing pr;
-  pr.init(nsd, cx.NB);
+  uint32_t gofs[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) gofs[i] = tp.labofs[i] / 9u;   // 36 col -> 4 col (the padding column for nodes without a label)
+  const uint32_t gaccb = sm.gacc + (uint32_t)c * sm.gacc_c;
+  const uint32_t growb = 4u * (uint32_t)cx.CP;
+  float wv[K], nv[K], dts[K], dta[K];
+  int ew, ne;
+  // the checkpoint of a step is fetched while the step before it runs
+  ckpt_load<K, G::CKF>(ck + (size_t)(nsd - 1) * NL * G::CKF, nv, ne);
   const bool has_partial = nsd > cx.nfull;
-  uint32_t rpar = 0u;   // (k2 / NAB) & 1
-  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, rpar ^= (buf + 1 == NAB), buf = (buf + 1 == NAB) ? 0 : buf + 1) {
-    const int slot = k2 % kRD;
+  int pbuf = nsd % cx.NB, buf = 0, gbuf = 0;
+  Prof pf;
+  pf.setup(sm.prof_gen + 64, tick_mask<W>(c, 2));
+  tick2<W>(c, pf);
+  for (int m = 0; m < nsd + 2 * W; ++m) {
+    const int k2 = m - W - w;
+    if (k2 >= 0 && k2 < nsd) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) wv[i] = nv[i];
+    ew = ne;
+    if (k2 + 1 < nsd) ckpt_load<K, G::CKF>(ck + (size_t)(nsd - 2 - k2) * NL * G::CKF, nv, ne);
+    const int slot = k2 & 1;
     const uint32_t rin = ring_in0 + 4u * (uint32_t)(slot * kRingF);
     const uint32_t rout = ring_out0 + 4u * (uint32_t)(slot * kRingF);
     const bool partial = has_partial && k2 == 0;
     const int rows = partial ? (c == 0 ? cx.r1 : cx.r0) : kSeg;
-    bar_wait(sm.bars, kBarAFull + c * kMaxAB + buf, rpar);
     // scales
     float gsc = 0.f, frs = 0.f;
     {
@@ -826,14 +916,12 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
     }
 #pragma unroll
     for (int i = 0; i < K; ++i) wv[i] *= gsc;
-    // chain ring: my left neighbour's entry of this step; open my own
-    if (w > 0) bar_wait(sm.bars, kBarRFull + rbar + w * kRD + slot, (uint32_t)(k2 / kRD) & 1u);
-    if (w < W - 1) {
-      if (k2 >= kRD) bar_wait(sm.bars, kBarREmpty + rbar + (w + 1) * kRD + slot, (uint32_t)(k2 / kRD - 1) & 1u);
-      if (lane == 31) sts(rout, wv[K - 1]);
-    }
-    const TileAddr<K> tad = tile_addr<K>(tp, ptile_wait(sm, cx, c, pr));
+    // chain ring: my left neighbour wrote its entry of this step one tick ago; open my own
+    if (w < W - 1 && lane == 31) sts(rout, wv[K - 1]);
+    const TileAddr<K> tad = tile_addr<K>(tp, ptile_addr(sm, cx, c, pbuf));
+    if (++pbuf == cx.NB) pbuf = 0;
     const uint32_t ar = abuf + (uint32_t)(buf * kSeg) * G::ROWB + prow;
+    const uint32_t gt0 = gaccb + (uint32_t)(gbuf * kSeg) * growb;
     // In the lower half (c = 1) a stored term at frame t belongs to an arc taken at frame t+1; the
     // arcs into frame Th are already counted by the upper half: the first row of the first step
     // contributes node posteriors only.
@@ -847,11 +935,15 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
       }
       const float in1 = left_in(wv[K - 1], bv, lane, frs);
       step<K, false>(wv, dts, dta, tp, cur, in1);
+      // node posteriors (times Zm < 1) summed by class with integer atomics in 2^-23 units: the
+      // float 1 + x has the exponent of 1.0 and round(x 2^23) as its mantissa field
+      const uint32_t gt = gt0 + (uint32_t)it * growb;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         const float ps = tsv[i] * wv[i], pa = tav[i] * wv[i];
         if (count_arcs) { gself[i] += ps; gadv[i] += pa; }
-        sts(arow + 8u * (K - 1 - i), ps + pa);
+        const int q = __float_as_int((ps + pa) + 1.f) - 0x3f800000;
+        asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(gt + gofs[i]), "r"(q) : "memory");
       }
     };
     if (!partial) {
@@ -886,177 +978,108 @@ __device__ __forceinline__ void role_rc(const Args& a, const Smem& sm, const Ctx
         const float sx = fmaf(wv[i], tp.selfc[i], a1 * tp.advc[i]);
         acc = fmaf(sx, lds(bb + 4u * (K - 1 - i)), acc);
       }
-      const float t0 = warp_sum(acc);
-      if (lane == 0) sts(certb + 4u * (uint32_t)(buf * W + w), t0);
+      sts(certb + 4u * (uint32_t)(gbuf * NL + gl), acc);   // X sums the lanes' terms
     }
-    // next checkpoint (consumed at the top of the next iteration)
-    if (k2 + 1 < nsd) ckpt_load<K, G::CKF>(ck + (size_t)(nsd - 2 - k2) * NL * G::CKF, wv, ew);
-    __syncwarp();
-    if (lane == 0) {
-      bar_arrive(sm.bars, kBarXFull + c * kMaxAB + buf);
-      if (w < W - 1) bar_arrive(sm.bars, kBarRFull + rbar + (w + 1) * kRD + slot);
-      if (w > 0) bar_arrive(sm.bars, kBarREmpty + rbar + w * kRD + slot);
+    if (++buf == NAB) buf = 0;
+    if (++gbuf == W + 1) gbuf = 0;
     }
-    ptile_release(sm, cx, c, pr, 1);
+    tick2<W>(c, pf);
   }
+  pf.report("rc", c, w, 2, lane);
   bad = __reduce_or_sync(kFull, (unsigned)bad);
   if (bad && lane == 0) { WFST_HAZ(&a.hazard[cx.b], bad); stsi(sm.zx + 72u, 1); }
 }
 // ---------------------------------------------------------------------------
-// X[c]: per-label reduction of a step's node posteriors of component c + gradient tile store.
-// Lane = class (classes beyond 32 in further rounds); entry i of a round holds, per lane, the
-// row offset of the i-th occurrence of the lane's class (or of a zero pad).
+// X[c]: turns a step's integer tile (node posteriors summed by class by the recompute warps) into
+// the [8, C] gradient tile and stores it.  Lane = class (classes beyond 32 in further rounds).
 // ---------------------------------------------------------------------------
 template <int K, int W>
 __device__ __forceinline__ void role_reduce(const Args& a, const Smem& sm, const Ctx& cx, const int c) {
-  using G = Geo<K, W>;
-  const int lane = cx.lane, nsd = cx.nsd, T = cx.T, C = cx.C, NAB = cx.NAB;
+  const int lane = cx.lane, nsd = cx.nsd, T = cx.T, C = cx.C;
   const int rounds = (C + 31) >> 5;
-  const int* rinfo = sm.hist + C;   // per round {nmax, base}
-  // One round of classes: the lane's list of row offsets lives in registers, ordered (while
-  // phase 1 runs) so that, slot by slot, the lanes of the warp read distinct banks: every slot
-  // each lane proposes one of its next three entries, the lowest lane wins a contested bank.
-  bool reg_lists = rounds == 1;
-  uint32_t offs[kRegList];
-  int nslots = 0;
-  if (reg_lists) {
-    const uint32_t tb = sm.xtab + 2u * (uint32_t)(c * kMaxList * 32 + lane);   // entry k at tb + 64 k
-    const int n = lane < C ? sm.hist[lane] : 0;
-    int done = 0;
-#pragma unroll
-    for (int sl = 0; sl < kRegList; ++sl) {
-      uint32_t taken = 0u, mine = 0xffffu;
-#pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const int k = done + t;
-        const bool cand = mine == 0xffffu && k < n;
-        const uint32_t off = cand ? lds_u16(tb + 64u * (uint32_t)k) : 0u;
-        const uint32_t bank = (off >> 2) & 31u;
-        const bool okb = cand && !((taken >> bank) & 1u);
-        const unsigned peers = __match_any_sync(kFull, okb ? bank : 32u + (uint32_t)lane);
-        const bool win = okb && (__ffs(peers) - 1) == lane;
-        if (win) {
-          mine = off;
-          if (t > 0) {   // swap it with the first entry still to be placed: those stay contiguous, the table a permutation
-            const uint32_t first = lds_u16(tb + 64u * (uint32_t)done);
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(tb + 64u * (uint32_t)k), "h"((unsigned short)first) : "memory");
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(tb + 64u * (uint32_t)done), "h"((unsigned short)off) : "memory");
-          }
-        }
-        taken |= __reduce_or_sync(kFull, win ? (1u << bank) : 0u);
-      }
-      if (mine != 0xffffu) ++done;
-      offs[sl] = mine != 0xffffu ? mine : 0u;     // no entry: the zero word in front of the row
-      if (__any_sync(kFull, mine != 0xffffu)) nslots = sl + 1;
-    }
-    reg_lists = __all_sync(kFull, done == n);   // else: the table (a permutation of itself) is walked from shared memory
-  } else {
-#pragma unroll
-    for (int i = 0; i < kRegList; ++i) offs[i] = 0u;
-  }
-  bar_wait(sm.bars, kBarZ, 0u);
+  __syncthreads();   // meeting A
+  __syncthreads();   // meeting B
+  __syncthreads();   // meeting C: Z published
   const bool ok = lds(sm.zx + 8u) != 0.f;
   if (!cx.want_grad || !ok) return;
   const uint32_t rawsz = cx.rawsz;
   const float Zm = lds(sm.zx);
-  const float kappa = a.sign * (a.grad_scale ? a.grad_scale[cx.b] : 1.f) / Zm;
+  const float kappa = a.sign * (a.grad_scale ? a.grad_scale[cx.b] : 1.f) / Zm * (1.f / 8388608.f);
   const bool has_partial = nsd > cx.nfull;
-  const uint32_t abuf = sm.abuf + (uint32_t)c * sm.abuf_c, certb = sm.cert + (uint32_t)c * sm.cert_c;
+  const uint32_t gaccb = sm.gacc + (uint32_t)c * sm.gacc_c, certb = sm.cert + (uint32_t)c * sm.cert_c;
+  const uint32_t growb = 4u * (uint32_t)cx.CP;
   int bad = 0;
   float* gE = a.gradE + (size_t)cx.b * T * C;
-  uint32_t rpar = 0u;
-  for (int k2 = 0, buf = 0; k2 < nsd; ++k2, rpar ^= (buf + 1 == NAB), buf = (buf + 1 == NAB) ? 0 : buf + 1) {
-    // component c works through the other direction's steps, the partial one first
-    const int kk = nsd - 1 - k2;
-    const int rows = (has_partial && k2 == 0) ? (c == 0 ? cx.r1 : cx.r0) : kSeg;
-    const int lo_ = seg_lo(cx, 1 - c, kk);
-    const int ob = k2 & 1;
-    bar_wait(sm.bars, kBarXFull + c * kMaxAB + buf, rpar);
-    {
-      float tot = 0.f;
+  int buf = 0;
+  Prof pf;
+  pf.setup(sm.prof_gen + 64, tick_mask<W>(c, 2));
+  tick2<W>(c, pf);
+  for (int m = 0; m < nsd + 2 * W; ++m) {
+    const int k2 = m - 2 * W;
+    if (k2 >= 0) {
+      // component c works through the other direction's steps, the partial one first
+      const int kk = nsd - 1 - k2;
+      const int rows = (has_partial && k2 == 0) ? (c == 0 ? cx.r1 : cx.r0) : kSeg;
+      const int lo_ = seg_lo(cx, 1 - c, kk);
+      const int ob = k2 & 1;
+      {
+        float tot = 0.f;
 #pragma unroll
-      for (int i = 0; i < W; ++i) tot += lds(certb + 4u * (uint32_t)(buf * W + i));
-      if (!(fabsf(tot - Zm) <= 2e-5f * Zm)) bad = 8;
-    }
-    if (lane == 0) bulk_wait_read<1>();   // the store that last read this out buffer is done
-    __syncwarp();
-    const uint32_t ab = abuf + (uint32_t)(buf * kSeg) * G::ROWB;
-    const uint32_t ot = sm.out + 4u * (uint32_t)((c * 2 + ob) * rawsz);
-    // buffer row j holds the frame of step j: frame row r = j (c = 0) or rows-1-j (c = 1)
-    const int rsign = c == 0 ? 1 : -1, rbase = c == 0 ? 0 : rows - 1;
-    float rs[kSeg];     // per-row sum of the node posteriors of this lane's class
-#pragma unroll
-    for (int j = 0; j < kSeg; ++j) rs[j] = 0.f;
-    if (reg_lists) {
-#pragma unroll
-      for (int i0 = 0; i0 < kRegList; i0 += 4) {
-        if (i0 < nslots) {   // warp-uniform
-          float t[4][kSeg];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t o = ab + offs[i0 + i];
-#pragma unroll
-            for (int j = 0; j < kSeg; ++j) t[i][j] = lds(o + (uint32_t)j * G::ROWB);   // rows >= `rows` hold finite stale data; never stored
-          }
-#pragma unroll
-          for (int j = 0; j < kSeg; ++j) rs[j] += (t[0][j] + t[1][j]) + (t[2][j] + t[3][j]);
-        }
+        for (int i = 0; i < W; ++i) tot += lds(certb + 4u * (uint32_t)(buf * 32 * W + 32 * i + lane));
+        tot = warp_sum(tot);
+        if (!(fabsf(tot - Zm) <= 2e-5f * Zm)) bad = 8;
       }
-      if (lane < C) {
-        uint32_t dsto = ot + 4u * (uint32_t)(lane + rbase * C);
-        const int32_t dstep = 4 * rsign * C;
-#pragma unroll
-        for (int j = 0; j < kSeg; ++j) {
-          if (j < rows) sts(dsto, rs[j] * kappa);
-          dsto += dstep;
-        }
-      }
-    } else {
+      if (lane == 0) bulk_wait_read<1>();   // the store that last read this out buffer is done
+      __syncwarp();
+      const uint32_t gt = gaccb + (uint32_t)(buf * kSeg) * growb;
+      const uint32_t ot = sm.out + 4u * (uint32_t)((c * 2 + ob) * rawsz);
+      // tile row j holds the frame of step j: frame row r = j (c = 0) or rows-1-j (c = 1)
+      const int rsign = c == 0 ? 1 : -1, rbase = c == 0 ? 0 : rows - 1;
       for (int r = 0; r < rounds; ++r) {
-        const int nmax = rinfo[2 * r], base = rinfo[2 * r + 1];
         const int cls = 32 * r + lane;
-        float acc[kSeg];
+        // lane cls == C takes the padding column; the lanes beyond it have nothing to do
+        if (cls <= C) {
+          const uint32_t ga = gt + 4u * (uint32_t)cls;
+          int acc[kSeg];
 #pragma unroll
-        for (int j = 0; j < kSeg; ++j) acc[j] = 0.f;
-        uint32_t xt = sm.xtab + 2u * (uint32_t)((c * kMaxList + base) * 32 + lane);
-#pragma unroll 2
-        for (int i = 0; i < nmax; ++i, xt += 64u) {
-          const uint32_t o = ab + lds_u16(xt);
+          for (int j = 0; j < kSeg; ++j) acc[j] = ldsi(ga + (uint32_t)j * growb);
 #pragma unroll
-          for (int j = 0; j < kSeg; ++j) acc[j] += lds(o + (uint32_t)j * G::ROWB);
-        }
-        if (cls < C) {
-          uint32_t dsto = ot + 4u * (uint32_t)(cls + rbase * C);
-          const int32_t dstep = 4 * rsign * C;
+          for (int j = 0; j < kSeg; ++j) stsi(ga + (uint32_t)j * growb, 0);   // the tile is clean for its next step
+          if (cls < C) {
+            uint32_t dsto = ot + 4u * (uint32_t)(cls + rbase * C);
+            const int32_t dstep = 4 * rsign * C;
 #pragma unroll
-          for (int j = 0; j < kSeg; ++j) {
-            if (j < rows) sts(dsto, acc[j] * kappa);
-            dsto += dstep;
+            for (int j = 0; j < kSeg; ++j) {
+              if (j < rows) sts(dsto, (float)acc[j] * kappa);
+              dsto += dstep;
+            }
           }
         }
       }
-    }
-    __syncwarp();
-    if (lane == 0) bar_arrive(sm.bars, kBarAEmpty + c * kMaxAB + buf);   // products consumed
-    if (rows > 0) {
-      const int n = rows * C;
-      float* dst = gE + (size_t)lo_ * C;
-      const bool tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
-      if (tma) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0)
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ot),
-                       "r"((uint32_t)n * 4u)
-                       : "memory");
-      } else {
-        const float* src = sm.out_gen + (size_t)(c * 2 + ob) * rawsz;
-        for (int q = lane; q < n; q += 32) dst[q] = src[q];
+      if (rows > 0) {
+        const int n = rows * C;
+        float* dst = gE + (size_t)lo_ * C;
+        const bool tma = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0);
+        if (tma) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ot),
+                         "r"((uint32_t)n * 4u)
+                         : "memory");
+        } else {
+          __syncwarp();
+          const float* src = sm.out_gen + (size_t)(c * 2 + ob) * rawsz;
+          for (int q = lane; q < n; q += 32) dst[q] = src[q];
+        }
       }
+      if (lane == 0) bulk_commit();   // one group per step (possibly empty)
+      __syncwarp();
+      if (++buf == W + 1) buf = 0;
     }
-    if (lane == 0) bulk_commit();   // one group per step (possibly empty)
-    __syncwarp();
+    tick2<W>(c, pf);
   }
+  pf.report("X", c, 0, 2, lane);
   if (lane == 0) bulk_wait_all<0>();
   bad = __reduce_or_sync(kFull, (unsigned)bad);
   if (bad && lane == 0) { WFST_HAZ(&a.hazard[cx.b], 8); stsi(sm.zx + 72u, 1); }
@@ -1092,33 +1115,30 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1))
     sm.bnd = base + 4u * (uint32_t)lay.bnd;
     sm.lexp = base + 4u * (uint32_t)lay.lexp;
     sm.cert = base + 4u * (uint32_t)lay.cert;
+    sm.gacc = base + 4u * (uint32_t)lay.gacc;
     sm.ptile = base + 4u * (uint32_t)lay.ptile;
     sm.ringL = base + 4u * (uint32_t)lay.ringL;
     sm.ringR = base + 4u * (uint32_t)lay.ringR;
     sm.bars = base + 4u * (uint32_t)lay.bars;
     sm.zx = base + 4u * (uint32_t)lay.zx;
-    sm.xtab = base + 4u * (uint32_t)lay.xtab;
     sm.abuf_c = 4u * (uint32_t)lay.abuf_c;
     sm.bnd_c = 4u * (uint32_t)lay.bnd_c;
     sm.lexp_c = 4u * (uint32_t)lay.lexp_c;
     sm.cert_c = 4u * (uint32_t)lay.cert_c;
+    sm.gacc_c = 4u * (uint32_t)lay.gacc_c;
     sm.ptile_c = 4u * (uint32_t)lay.ptile_c;
     sm.ring_c = 4u * (uint32_t)lay.ring_c;
     sm.ytab = reinterpret_cast<int*>(smem_raw + lay.ytab);
-    sm.hist = reinterpret_cast<int*>(smem_raw + lay.hist);
-    sm.xtab_gen = reinterpret_cast<unsigned short*>(smem_raw + lay.xtab);
     sm.out_gen = smem_raw + lay.out;
+    sm.prof_gen = smem_raw + lay.prof;
   }
+
+  // flags: cleared by the block that owns them (no memset node in front of the kernel)
+  if (threadIdx.x == 0) a.hazard[cx.b] = 0;
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumBars; ++i) {
-      uint32_t cnt = 1u;
-      if (i >= kBarPEmpty && i < kBarPEmpty + 2 * kMaxNB) cnt = 2u * W;
-      else if (i >= kBarAFull && i < kBarAFull + 2 * kMaxAB) cnt = W;
-      else if (i >= kBarXFull && i < kBarXFull + 2 * kMaxAB) cnt = W;
-      bar_init(sm.bars, i, cnt);
-    }
+    for (int i = 0; i < kNumBars; ++i) bar_init(sm.bars, i, 1u);
     fence_barrier_init();
   }
   // zero everything up to the barriers: p-tile padding columns, row pads, rings of the first
@@ -1152,52 +1172,6 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1))
     if (__syncthreads_or(has_bad)) flag = 1;
     if (cx.L < 1 || cx.L + 2 > G::Sp) flag = 1;
   }
-  if (!flag) {
-    // per-class counts (integer atomics: order independent)
-    for (int cc = threadIdx.x; cc < C + 16; cc += NT) sm.hist[cc] = 0;
-    __syncthreads();
-    for (int n = threadIdx.x; n < cx.L; n += NT) atomicAdd(&sm.hist[sm.ytab[n]], 1);
-    __syncthreads();
-    const int rounds = (C + 31) >> 5;
-    if (warp == 0) {
-      int base = 0;
-      for (int r = 0; r < rounds; ++r) {
-        const int cc = 32 * r + cx.lane;
-        const int nm = __reduce_max_sync(kFull, cc < C ? sm.hist[cc] : 0);
-        if (cx.lane == 0) { sm.hist[C + 2 * r] = nm; sm.hist[C + 2 * r + 1] = base; }
-        base += nm;
-      }
-      if (cx.lane == 0) sm.hist[C + 2 * rounds] = base;
-    }
-    __syncthreads();
-    // tables the reduction cannot hold go to the log-semiring kernel (reason 16)
-    if (sm.hist[C + 2 * rounds] > kMaxList) flag = 16;
-    if (!flag) {
-      // position n becomes entry (number of earlier positions with the same label) of its class:
-      // a deterministic order, so the sums of the reduction do not depend on scheduling
-      for (int n = threadIdx.x; n < cx.L; n += NT) {
-        const int cc = sm.ytab[n];
-        int rank = 0;
-#pragma unroll 4
-        for (int m = 0; m < n; ++m) rank += (sm.ytab[m] == cc);
-        const int base = sm.hist[C + 2 * (cc >> 5) + 1], ln = cc & 31;
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          const int j = d == 0 ? n + 1 : G::Sp - 2 - n;     // node n+1 in orientation d
-          const int off = 4 * (G::PADA + (j / K) * G::SA + 2 * (j % K));
-          sm.xtab_gen[(d * kMaxList + base + rank) * 32 + ln] = (unsigned short)off;
-        }
-      }
-      for (int cc = threadIdx.x; cc < 32 * rounds; cc += NT) {
-        const int r = cc >> 5, ln = cc & 31;
-        const int nm = sm.hist[C + 2 * r], base = sm.hist[C + 2 * r + 1];
-        for (int i = cc < C ? sm.hist[cc] : 0; i < nm; ++i) {
-          sm.xtab_gen[(base + i) * 32 + ln] = 0;                 // word 0 of a row is always zero
-          sm.xtab_gen[(kMaxList + base + i) * 32 + ln] = 0;
-        }
-      }
-    }
-  }
   if (flag && threadIdx.x == 0) WFST_HAZ(&a.hazard[cx.b], flag);
   __syncthreads();
   if (flag) return;
@@ -1210,7 +1184,7 @@ __global__ void __launch_bounds__(Geo<K, W>::NT, (Geo<K, W>::NT <= 512 ? 2 : 1))
   if (warp < 2 * W) role_live<K, W>(a, sm, cx, warp / W, warp % W);
   else if (is_rc) role_rc<K, W>(a, sm, cx, rc_c, rc_w, gself, gadv, rc_ran);
   else if (warp < 4 * W + 2) role_reduce<K, W>(a, sm, cx, warp - 4 * W);
-  else role_producer(a, sm, cx, warp - 4 * W - 2);
+  else role_producer<W>(a, sm, cx, warp - 4 * W - 2);
   // ---- transition gradient: arc posteriors summed over time, one atomic per node and arc kind;
   // nothing from an utterance that was flagged (the log-semiring kernel redoes it)
   __syncthreads();
@@ -1249,21 +1223,14 @@ static int pick_w(int max_target_len) {
   return 0;
 }
 
+// ring depths the tick schedule needs (ctc_tick.cu): step buffers live -> rc, p tiles P -> rc[W-1]
 template <int K, int W>
 static bool pick_bufs(int C, int& NAB, int& NB, size_t& bytes) {
-  const int nab_want = min(2 * W + 1, kMaxAB), nb_want = min(2 * W + 3, kMaxNB);
-  const size_t two = (size_t)(113 * 1024), one = (size_t)(227 * 1024);
-  for (int pass = 0; pass < 2; ++pass) {
-    const size_t lim = pass == 0 ? two : one;
-    const int nab_min = pass == 0 ? max(nab_want - 1, 3) : 3, nb_min = pass == 0 ? max(nb_want - 2, 4) : 4;
-    for (int nab = nab_want; nab >= nab_min; --nab) {
-      for (int nb = nb_want; nb >= nb_min; --nb) {
-        const size_t b = make_layout<K, W>(C, nab, nb).total * sizeof(float);
-        if (b <= lim) { NAB = nab; NB = nb; bytes = b; return true; }
-      }
-    }
-  }
-  return false;
+  NAB = 2 * W;
+  NB = 2 * W + 1;
+  if (NAB > kMaxAB || NB > kMaxNB) return false;
+  bytes = make_layout<K, W>(C, NAB, NB).total * sizeof(float);
+  return bytes <= (size_t)(227 * 1024);
 }
 static bool pick_bufs_w(int W, int C, int& NAB, int& NB, size_t& bytes) {
   return W == 1 ? pick_bufs<kK, 1>(C, NAB, NB, bytes) : pick_bufs<kK, 2>(C, NAB, NB, bytes);
@@ -1331,7 +1298,6 @@ int launch_asg_fal_chain(const float* E, const float* tr, const int* targets, co
   a.ckpt = (float*)workspace;
   a.hazard = (int*)((char*)workspace + fal_ckpt_bytes(B, T, W));
   *hazard_out = a.hazard;
-  WFST_CUDA_CHECK(cudaMemsetAsync(a.hazard, 0, (size_t)B * sizeof(int), st));
   return W == 1 ? launch_kw<kK, 1>(a, smem, st) : launch_kw<kK, 2>(a, smem, st);
 }
 

@@ -110,7 +110,7 @@ template <class Builder>
 static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, int max_nodes, int aslots,
                             int want_gw, cudaStream_t st, int* rc) {
   if (g_force_generic_lattice == 1) return false;
-  if (max_nodes < 1 || max_nodes > 16 * 1024 || aslots > 65535 || a.C > 65535) return false;
+  if (max_nodes < 1 || max_nodes > 16 * 1024 || aslots > 65535 || a.C >= 16 * 1024) return false;
   int npt = (max_nodes + 1023) / 1024;
   npt = npt <= 4 ? npt : (npt <= 8 ? 8 : 16);
   int nt = ((max_nodes + npt - 1) / npt + 31) / 32 * 32;
@@ -126,7 +126,7 @@ static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, i
   if (lay.total > 227u * 1024u) return false;
   a.Kt = kt;
   a.renorm_every = (16 + kt - 1) / kt;
-  lean::Args g{a, aslots, want_gw};
+  lean::Args g{a, aslots, want_gw, lay};
   // two blocks per utterance that meet in the middle (half the dependent frame steps each) when
   // there are tiles to split and the single-block launch would leave the SMs short of warps
   // (measured: B=64 x 22 warps 5.4 -> 2.9 ms; B=256 x 12 warps, already issue-bound, 1.9 -> 2.1 ms)

@@ -4,8 +4,9 @@
 // materialised ONCE into shared memory as packed arc records, and the per-frame loops
 // run on 32-bit shared-memory addresses only.
 //
-//   in-arc  record (8 B): { src  | label << 16, weight }      grouped by destination
-//   out-arc record (8 B): { dst  | label << 16, weight }      grouped by source
+//   in-arc  record (8 B): { 4 src | 4 label << 16, weight }   grouped by destination
+//   out-arc record (8 B): { 4 dst | 4 label << 16, weight }   grouped by source
+//   (both fields are byte offsets into the alpha row / the emission row: no shift per use)
 //   node record   (4 B) : { first slot | end slot << 16 }     one for in-, one for out-arcs
 //
 // What replaces what: forward_score(intersect(emissions, A_b)) + gtn.backward of
@@ -20,7 +21,7 @@
 // hundreds of same-address shared-memory atomics per frame.
 //
 // Limits (the launcher falls back to the generic kernel beyond them): nodes, arc slots and
-// classes < 65536, nodes <= 16 * 1024, everything must fit 227 KB of shared memory.
+// < 65536, nodes and classes < 16 * 1024, everything must fit 227 KB of shared memory.
 #pragma once
 
 #include "lattice.cuh"
@@ -98,6 +99,8 @@ struct Args {
   LatticeArgs a;     // E, T, C, grad_scale, sign, scores, gradE, accumulate, hist, offs, Kt, npad, active
   int aslots;        // arc slots reserved per direction
   int want_gw;       // arc-weight gradients wanted
+  Layout lay;        // make_layout(Kt, C, npad, aslots, want_gw), computed by the launcher: the kernels
+                     // read the offsets from the constant bank instead of recomputing them in the loops
 };
 
 // what a builder sees while it materialises the acceptor
@@ -113,11 +116,11 @@ struct Build {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(nflags + (uint32_t)v), "r"((uint32_t)f) : "memory");
   }
   __device__ __forceinline__ void in_arc(uint32_t slot, int src, int label, float w, int gidx) const {
-    sts_u2(in_pack + 8u * slot, (uint32_t)src | ((uint32_t)label << 16), __float_as_uint(w));
+    sts_u2(in_pack + 8u * slot, ((uint32_t)src << 2) | ((uint32_t)label << 18), __float_as_uint(w));
     if (want_gw) sts_u(in_gidx + 4u * slot, (uint32_t)gidx);
   }
   __device__ __forceinline__ void out_arc(uint32_t slot, int dst, int label, float w, int gidx) const {
-    sts_u2(out_pack + 8u * slot, (uint32_t)dst | ((uint32_t)label << 16), __float_as_uint(w));
+    sts_u2(out_pack + 8u * slot, ((uint32_t)dst << 2) | ((uint32_t)label << 18), __float_as_uint(w));
     if (want_gw) sts_u(out_gidx + 4u * slot, (uint32_t)gidx);
   }
 };
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
   const int b = blockIdx.x;
   if (a.active && a.active[b] == 0) return;
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-  const Layout L = make_layout(a.Kt, a.C, a.npad, g.aslots, g.want_gw);
+  const Layout& L = g.lay;
   const uint32_t sb = smem_u32(smem_lean);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lean + L.bars);
   float* red = reinterpret_cast<float*>(smem_lean + L.red);
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
     __syncthreads();
     for (int v = tid; v < N; v += NT) {
       const uint32_t be = lds_u(s_node_out + 4u * v);
-      for (uint32_t k = be & 0xffffu; k < (be >> 16); ++k) red_add_u(s_gt + 4u * (lds_u(s_out + 8u * k) >> 16), 1u);
+      for (uint32_t k = be & 0xffffu; k < (be >> 16); ++k) red_add_u(s_gt + (lds_u(s_out + 8u * k) >> 16), 1u);
     }
     __syncthreads();
     uint32_t best = 0;
@@ -272,6 +275,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
     best = __reduce_max_sync(0xffffffffu, best);
     cstar = 0xffffu - (best & 0xffffu);
     if (cstar >= (uint32_t)C) cstar = 0;
+    cstar <<= 2;     // byte offset, like the label field of the arc records
     __syncthreads();
   }
 
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
           float x[DEG];
 #pragma unroll
           for (int d = 0; d < DEG; ++d) {
-            const float av = lds_f(cur + 4u * (rec[d].x & 0xffffu)), ev = lds_f(Et + 4u * (rec[d].x >> 16));
+            const float av = lds_f(cur + (rec[d].x & 0xffffu)), ev = lds_f(Et + (rec[d].x >> 16));
             x[d] = (k0 + d < ke) ? av + ev + __uint_as_float(rec[d].y) : kNegInf;
           }
           float m = x[0];
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
           for (int d = 1; d < DEG; ++d) m = fmaxf(m, x[d]);
           auto eval = [&](uint32_t k) {
             const uint2 r = lds_u2(s_in + 8u * k);
-            return lds_f(cur + 4u * (r.x & 0xffffu)) + lds_f(Et + 4u * (r.x >> 16)) + __uint_as_float(r.y);
+            return lds_f(cur + (r.x & 0xffffu)) + lds_f(Et + (r.x >> 16)) + __uint_as_float(r.y);
           };
           if (TAIL)
             for (uint32_t k = k0 + DEG; k < ke; ++k) m = fmaxf(m, eval(k));
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
           const uint32_t lab = rx >> 16;
           qtot += q;
           if (lab == cstar) qstar += q;
-          else if (q != 0u) red_add_u(grow + 4u * lab, q);
+          else if (q != 0u) red_add_u(grow + lab, q);
         }
         if (want_gW && p != 0.f) sts_f(s_gw + 4u * k, lds_f(s_gw + 4u * k) + p);
       };
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
           float x[DEG];
 #pragma unroll
           for (int d = 0; d < DEG; ++d) {
-            const float bv = lds_f(nxt + 4u * (rec[d].x & 0xffffu)), ev = lds_f(Et + 4u * (rec[d].x >> 16));
+            const float bv = lds_f(nxt + (rec[d].x & 0xffffu)), ev = lds_f(Et + (rec[d].x >> 16));
             x[d] = (k0 + d < ke) ? ev + __uint_as_float(rec[d].y) + bv : kNegInf;
           }
           float m = x[0];
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
           auto eval = [&](uint32_t k, uint32_t& rx) {
             const uint2 r = lds_u2(s_out + 8u * k);
             rx = r.x;
-            return lds_f(Et + 4u * (r.x >> 16)) + __uint_as_float(r.y) + lds_f(nxt + 4u * (r.x & 0xffffu));
+            return lds_f(Et + (r.x >> 16)) + __uint_as_float(r.y) + lds_f(nxt + (r.x & 0xffffu));
           };
           if (TAIL)
             for (uint32_t k = k0 + DEG; k < ke; ++k) m = fmaxf(m, eval(k, rr));
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
         qstar = __reduce_add_sync(0xffffffffu, qstar);
         qtot = __reduce_add_sync(0xffffffffu, qtot);
         if (lane == 0) {
-          if (qstar) red_add_u(grow + 4u * cstar, qstar);
+          if (qstar) red_add_u(grow + cstar, qstar);
           if (qtot) red_add_u(s_rowsum + 4u * (uint32_t)tt, qtot);
         }
       }
@@ -567,7 +571,7 @@ __device__ __forceinline__ void st_peer_u2(uint32_t addr, uint32_t x, uint32_t y
   asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
 
-template <class Builder, int NPT>
+template <class Builder, int NPT, bool GW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(1024, 1)
 lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
   constexpr int DEG = Builder::kDeg;
@@ -578,7 +582,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
   const uint32_t role = cluster_rank();
   if (a.active && a.active[b] == 0) return;        // both blocks of the pair
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-  const Layout L = make_layout(a.Kt, a.C, a.npad, g.aslots, g.want_gw);
+  const Layout& L = g.lay;
   const uint32_t sb = smem_u32(smem_lean);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lean + L.bars);
   float* red = reinterpret_cast<float*>(smem_lean + L.red);
@@ -695,6 +699,10 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
     for (int j = 0; j < NPT; ++j) vnode[j] = (tid + j * NT < N) ? tid + j * NT : -1;
   }
   auto slot_of = [&](int j) { return (Builder::kSort && (j & 1)) ? j * NT + NT - 1 - tid : j * NT + tid; };
+  uint32_t hslot[NPT];     // history rows are addressed by 32-bit element offsets (row * stride + slot)
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) hslot[j] = (uint32_t)slot_of(j);
+  const uint32_t hstride = (uint32_t)a.hist_stride;
 
   // label carried by most arcs of the secondary direction
   uint32_t cstar = 0;
@@ -703,7 +711,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
     __syncthreads();
     for (int v = tid; v < N; v += NT) {
       const uint32_t be = lds_u(s_snode + 4u * v);
-      for (uint32_t k = be & 0xffffu; k < (be >> 16); ++k) red_add_u(s_gt + 4u * (lds_u(s_spack + 8u * k) >> 16), 1u);
+      for (uint32_t k = be & 0xffffu; k < (be >> 16); ++k) red_add_u(s_gt + (lds_u(s_spack + 8u * k) >> 16), 1u);
     }
     __syncthreads();
     uint32_t best = 0;
@@ -719,6 +727,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
     best = __reduce_max_sync(0xffffffffu, best);
     cstar = 0xffffu - (best & 0xffffu);
     if (cstar >= (uint32_t)C) cstar = 0;
+    cstar <<= 2;     // byte offset, like the label field of the arc records
     __syncthreads();
   }
   cluster_sync_all();     // the peer block runs: its shared memory may be written from here on
@@ -733,7 +742,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
   for (int v = tid; v < N; v += NT) sts_f(cur + 4u * v, init_val(v));
 #pragma unroll
   for (int j = 0; j < NPT; ++j)
-    if (vnode[j] >= 0) hist[slot_of(j)] = init_val(vnode[j]);
+    if (vnode[j] >= 0) hist[hslot[j]] = init_val(vnode[j]);
   issue_tile(gtile_of(0), 0);
   uint32_t be_p[NPT];
 #pragma unroll
@@ -759,7 +768,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
       const int tt = role ? rows - 1 - r : r;
       const int s = sbase + r;
       const uint32_t Et = s_tile(buf) + 4u * (uint32_t)(tt * C);
-      float* hrow = hist + (size_t)(s + 1) * a.hist_stride;
+      const uint32_t hrow = (uint32_t)(s + 1) * hstride;
       const bool keep = s + 1 < S;                   // R_S goes to the peer, not to the history
 #pragma unroll
       for (int j = 0; j < NPT; ++j) {
@@ -772,7 +781,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           float x[DEG];
 #pragma unroll
           for (int d = 0; d < DEG; ++d) {
-            const float av = lds_f(cur + 4u * (rec[d].x & 0xffffu)), ev = lds_f(Et + 4u * (rec[d].x >> 16));
+            const float av = lds_f(cur + (rec[d].x & 0xffffu)), ev = lds_f(Et + (rec[d].x >> 16));
             x[d] = (k0 + d < ke) ? av + ev + __uint_as_float(rec[d].y) : kNegInf;
           }
           float m = x[0];
@@ -780,7 +789,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           for (int d = 1; d < DEG; ++d) m = fmaxf(m, x[d]);
           auto eval = [&](uint32_t k) {
             const uint2 rr = lds_u2(s_ppack + 8u * k);
-            return lds_f(cur + 4u * (rr.x & 0xffffu)) + lds_f(Et + 4u * (rr.x >> 16)) + __uint_as_float(rr.y);
+            return lds_f(cur + (rr.x & 0xffffu)) + lds_f(Et + (rr.x >> 16)) + __uint_as_float(rr.y);
           };
           if (TAIL)
             for (uint32_t k = k0 + DEG; k < ke; ++k) m = fmaxf(m, eval(k));
@@ -794,7 +803,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
             rv = m + __logf(sum);
           }
           sts_f(nxt + 4u * v, rv);
-          if (keep) hrow[slot_of(j)] = rv;
+          if (keep) hist[hrow + hslot[j]] = rv;
         }
       }
       __syncthreads();
@@ -824,7 +833,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
   const float Z = (float)Zd;
   if (tid == 0 && role == 0) a.scores[b] = Z;
   const bool want_gE = a.gradE != nullptr;
-  const bool want_gW = g.want_gw != 0;
+  constexpr bool want_gW = GW;     // == (g.want_gw != 0), launcher
   if (!want_gE && !want_gW) return;
   const float gs = a.sign * (a.grad_scale ? a.grad_scale[b] : 1.f);
   float* gEb = want_gE ? a.gradE + (size_t)b * T * C : nullptr;
@@ -845,7 +854,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
   uint32_t be_s[NPT];
 #pragma unroll
   for (int j = 0; j < NPT; ++j) {
-    pr_next[j] = (vnode[j] >= 0) ? hist[(size_t)(S - 1) * a.hist_stride + slot_of(j)] : kNegInf;
+    pr_next[j] = (vnode[j] >= 0) ? hist[(uint32_t)(S - 1) * hstride + hslot[j]] : kNegInf;
     be_s[j] = (vnode[j] >= 0) ? lds_u(s_snode + 4u * vnode[j]) : 0u;
   }
   __syncthreads();
@@ -882,7 +891,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
 #pragma unroll
       for (int j = 0; j < NPT; ++j) {
         pr[j] = pr_next[j];
-        pr_next[j] = (vnode[j] >= 0 && s > 0) ? hist[(size_t)(s - 1) * a.hist_stride + slot_of(j)] : kNegInf;
+        pr_next[j] = (vnode[j] >= 0 && s > 0) ? hist[(uint32_t)(s - 1) * hstride + hslot[j]] : kNegInf;
       }
       uint32_t qstar = 0, qtot = 0;
       auto post = [&](float xv, uint32_t rx, uint32_t k, float off) {
@@ -892,7 +901,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           const uint32_t lab = rx >> 16;
           qtot += q;
           if (lab == cstar) qstar += q;
-          else if (q != 0u) red_add_u(grow + 4u * lab, q);
+          else if (q != 0u) red_add_u(grow + lab, q);
         }
         if (want_gW && p != 0.f) sts_f(s_gw + 4u * k, lds_f(s_gw + 4u * k) + p);
       };
@@ -907,7 +916,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           float x[DEG];
 #pragma unroll
           for (int d = 0; d < DEG; ++d) {
-            const float bv = lds_f(nxt + 4u * (rec[d].x & 0xffffu)), ev = lds_f(Et + 4u * (rec[d].x >> 16));
+            const float bv = lds_f(nxt + (rec[d].x & 0xffffu)), ev = lds_f(Et + (rec[d].x >> 16));
             x[d] = (k0 + d < ke) ? ev + __uint_as_float(rec[d].y) + bv : kNegInf;
           }
           float m = x[0];
@@ -917,7 +926,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           auto eval = [&](uint32_t k, uint32_t& rx) {
             const uint2 q = lds_u2(s_spack + 8u * k);
             rx = q.x;
-            return lds_f(Et + 4u * (q.x >> 16)) + __uint_as_float(q.y) + lds_f(nxt + 4u * (q.x & 0xffffu));
+            return lds_f(Et + (q.x >> 16)) + __uint_as_float(q.y) + lds_f(nxt + (q.x & 0xffffu));
           };
           if (TAIL)
             for (uint32_t k = k0 + DEG; k < ke; ++k) m = fmaxf(m, eval(k, rr));
@@ -949,7 +958,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
         qstar = __reduce_add_sync(0xffffffffu, qstar);
         qtot = __reduce_add_sync(0xffffffffu, qtot);
         if (lane == 0) {
-          if (qstar) red_add_u(grow + 4u * cstar, qstar);
+          if (qstar) red_add_u(grow + cstar, qstar);
           if (qtot) red_add_u(s_rowsum + 4u * (uint32_t)tt, qtot);
         }
       }

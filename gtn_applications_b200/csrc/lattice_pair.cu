@@ -4,15 +4,24 @@
 
 namespace wfst {
 
-template <class Builder, int NPT>
-static int launch_lean_pair_npt(const lean::Args& g, typename Builder::Params bp, int B, int nt, size_t smem,
-                                cudaStream_t st) {
-  auto kern = lean::lattice_lean_pair_kernel<Builder, NPT>;
+template <class Builder, int NPT, bool GW>
+static int launch_lean_pair_gw(const lean::Args& g, typename Builder::Params bp, int B, int nt, size_t smem,
+                               cudaStream_t st) {
+  auto kern = lean::lattice_lean_pair_kernel<Builder, NPT, GW>;
   WFST_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<2 * B, nt, smem, st>>>(g, bp);      // clusters of two blocks (compile-time cluster dims)
   g_launches++;
   WFST_CUDA_CHECK(cudaGetLastError());
   return WFST_OK;
+}
+
+// arc-weight gradients are a compile-time switch of the kernel (the per-arc test in the posterior
+// loop cost 3 % of the instructions of a launch that does not want them)
+template <class Builder, int NPT>
+static int launch_lean_pair_npt(const lean::Args& g, typename Builder::Params bp, int B, int nt, size_t smem,
+                                cudaStream_t st) {
+  return g.want_gw ? launch_lean_pair_gw<Builder, NPT, true>(g, bp, B, nt, smem, st)
+                   : launch_lean_pair_gw<Builder, NPT, false>(g, bp, B, nt, smem, st);
 }
 
 template <class Builder>

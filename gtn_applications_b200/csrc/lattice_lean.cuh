@@ -58,6 +58,13 @@ __device__ __forceinline__ void red_add_u(uint32_t a, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // byte offsets of the regions inside dynamic shared memory
 struct Layout {
   uint32_t bars, red, rowsum, tile0, tile1, gtile, alpha0, alpha1, node_in, node_out, nflags, fw, perm,
@@ -678,7 +685,10 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
     __syncthreads();
     auto key_of = [&](int v) {
       const uint32_t bi = lds_u(s_node_in + 4u * v), bo = lds_u(s_node_out + 4u * v);
-      const uint32_t d = max((bi >> 16) - (bi & 0xffffu), (bo >> 16) - (bo & 0xffffu));
+      // nodes with at most DEG arcs cost the same (the register path evaluates DEG slots): one
+      // bucket, in which they keep the order of their ids -- neighbouring nodes gather from
+      // neighbouring alpha rows, i.e. from different banks
+      const uint32_t d = max(max((bi >> 16) - (bi & 0xffffu), (bo >> 16) - (bo & 0xffffu)), (uint32_t)DEG);
       return 31u - min(d, 31u);
     };
     for (int v = tid; v < N; v += NT) atomicAdd(&cnt[key_of(v) + 1], 1u);
@@ -796,10 +806,11 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           float rv = kNegInf;
           if (m != kNegInf) {
             float sum = 0.f;
+            const float ml = -m * kLog2e;
 #pragma unroll
-            for (int d = 0; d < DEG; ++d) sum += __expf(x[d] - m);
+            for (int d = 0; d < DEG; ++d) sum += ex2_approx(fmaf(x[d], kLog2e, ml));
             if (TAIL)
-              for (uint32_t k = k0 + DEG; k < ke; ++k) sum += __expf(eval(k) - m);
+              for (uint32_t k = k0 + DEG; k < ke; ++k) sum += ex2_approx(fmaf(eval(k), kLog2e, ml));
             rv = m + __logf(sum);
           }
           sts_f(nxt + 4u * v, rv);
@@ -894,10 +905,13 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
         pr_next[j] = (vnode[j] >= 0 && s > 0) ? hist[(uint32_t)(s - 1) * hstride + hslot[j]] : kNegInf;
       }
       uint32_t qstar = 0, qtot = 0;
-      auto post = [&](float xv, uint32_t rx, uint32_t k, float off) {
-        const float p = __expf(xv + off);
+      // off2 = (offset of the posterior) * log2(e) + 30: exp2 gives the posterior in the fixed-point
+      // unit of the tile (kFixOne = 2^30) directly; an arc at -inf (padding slot included) gives 0
+      auto post = [&](float xv, uint32_t rx, uint32_t k, float off2) {
+        const float pf = ex2_approx(fmaf(xv, kLog2e, off2));
+        const float p = pf * (1.f / kFixOne);      // used by the weight gradient only
         if (want_gE) {
-          const uint32_t q = __float2uint_rn(p * kFixOne);
+          const uint32_t q = __float2uint_rn(pf);
           const uint32_t lab = rx >> 16;
           qtot += q;
           if (lab == cstar) qstar += q;
@@ -933,20 +947,20 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           float rv = kNegInf;
           if (m != kNegInf) {
             float sum = 0.f;
+            const float ml = -m * kLog2e;
 #pragma unroll
-            for (int d = 0; d < DEG; ++d) sum += __expf(x[d] - m);
+            for (int d = 0; d < DEG; ++d) sum += ex2_approx(fmaf(x[d], kLog2e, ml));
             if (TAIL)
-              for (uint32_t k = k0 + DEG; k < ke; ++k) sum += __expf(eval(k, rr) - m);
+              for (uint32_t k = k0 + DEG; k < ke; ++k) sum += ex2_approx(fmaf(eval(k, rr), kLog2e, ml));
             rv = m + __logf(sum);
             if (pr[j] != kNegInf) {
-              const float off = pr[j] + dlt;
+              const float off = fmaf(pr[j] + dlt, kLog2e, 30.f);
 #pragma unroll
-              for (int d = 0; d < DEG; ++d)
-                if (x[d] != kNegInf) post(x[d], rec[d].x, k0 + d, off);
+              for (int d = 0; d < DEG; ++d) post(x[d], rec[d].x, k0 + d, off);
               if (TAIL)
                 for (uint32_t k = k0 + DEG; k < ke; ++k) {
                   const float xv = eval(k, rr);
-                  if (xv != kNegInf) post(xv, rr, k, off);
+                  post(xv, rr, k, off);
                 }
             }
           }

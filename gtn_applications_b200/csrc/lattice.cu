@@ -1,6 +1,7 @@
 // Acceptor policies for the generic lattice kernel (lattice.cuh) and the C ABI
 // entry points built on it.  See include/wfst_b200.h for the contract of each
 // entry point and the reference call sites it replaces.
+#include <cstdlib>
 #include "lattice_builders.cuh"
 
 #include <cstring>
@@ -93,7 +94,7 @@ static int launch_lattice(LatticeArgs a, typename Topo::Params tp, int B, int ma
 
 
 // Lean kernel when the acceptor fits its limits (lattice_lean.cuh); returns false otherwise.
-static int g_force_generic_lattice = 0;   // test hook: 1 = never use the lean kernels, 2 = no pair (cluster) kernel, 3 = pair kernel whenever T allows
+static int g_force_generic_lattice = 0;   // test hook: 1 = never use the lean kernels, 2 = no pair (cluster) kernel, 3 = pair kernel whenever T allows, 4 = like 3 without the wide-register variant
 
 template <class Builder, int NPT>
 static int launch_lean_npt(const lean::Args& g, typename Builder::Params bp, int B, int nt, size_t smem,
@@ -113,6 +114,10 @@ static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, i
   if (max_nodes < 1 || max_nodes > 16 * 1024 || aslots > 65535 || a.C >= 16 * 1024) return false;
   int npt = (max_nodes + 1023) / 1024;
   npt = npt <= 4 ? npt : (npt <= 8 ? 8 : 16);
+  // degree-sorted (CSR) acceptors of 1025..2048 nodes that take the cluster kernel: four nodes per
+  // thread on 512 threads with 128 registers (lattice_lean_wide.cuh); test hook 4 switches it off
+  const bool wide = Builder::kSort && max_nodes > 1024 && max_nodes <= 2048 && g_force_generic_lattice != 4;
+  if (wide) npt = 4;
   int nt = ((max_nodes + npt - 1) / npt + 31) / 32 * 32;
   if (nt < 64) nt = 64;
   a.npad = (max_nodes + 3) & ~3;
@@ -132,9 +137,19 @@ static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, i
   // (measured: B=64 x 22 warps 5.4 -> 2.9 ms; B=256 x 12 warps, already issue-bound, 1.9 -> 2.1 ms)
   const int ntiles = (a.T + kt - 1) / kt;
   const bool starved = (long long)B * (nt / 32) <= 148LL * 16;
-  if (g_force_generic_lattice != 2 && ntiles >= 2 && (starved || g_force_generic_lattice == 3)) {
+  if (g_force_generic_lattice != 2 && ntiles >= 2 && (starved || g_force_generic_lattice >= 3)) {
+    if constexpr (Builder::kSort) {
+      if (wide) {
+        *rc = launch_lean_wide(g, bp, B, nt, lay.total, st);
+        return true;
+      }
+    }
     *rc = launch_lean_pair<Builder>(g, bp, B, nt, lay.total, npt, st);
     return true;
+  }
+  if (wide) {      // single-block launch: back to the usual split
+    npt = (max_nodes + 1023) / 1024;
+    nt = ((max_nodes + npt - 1) / npt + 31) / 32 * 32;
   }
   switch (npt) {
     case 1: *rc = launch_lean_npt<Builder, 1>(g, bp, B, nt, lay.total, st); break;

@@ -67,7 +67,9 @@ WFST_API int wfst_debug_ctc_chain_config(int K, int W);
  * generic global-memory kernel even when the acceptor fits the shared-memory ("lean") kernels,
  * 2 = the single-block lean kernel only (no two-block cluster kernel), 3 = the two-block
  * cluster kernel whenever T allows (by default only when the single-block launch would leave the
- * SMs short of warps), 0 = default (returns the old value) */
+ * SMs short of warps), 4 = like 3 but without the wide-register variant of the cluster kernel
+ * (packed CSR acceptors of 1025..2048 nodes, csrc/lattice_lean_wide.cuh), 0 = default (returns
+ * the old value) */
 WFST_API int wfst_debug_force_generic_lattice(int on);
 /* test hook: copies the per-utterance fallback flags of the last CTC call that used
  * `workspace` to the host (1 = recomputed by the log-semiring kernel, -1 = fast path not used) */

@@ -40,12 +40,13 @@ def gtn64():
     return gtn64
 
 
-@pytest.fixture(params=["lean-pair", "lean-single", "generic"])
+@pytest.fixture(params=["lean-pair", "lean-pair-narrow", "lean-single", "generic"])
 def lattice_kernel(request):
     """Runs a GPU test on each lattice kernel through the C-ABI test hook: the shared-memory
     "lean" kernel as a cluster of two blocks that meet in the middle (whenever T allows), the
-    single-block lean kernel, and the generic global-memory kernel."""
+    same without its wide-register variant for CSR acceptors of 1025..2048 nodes, the single-block
+    lean kernel, and the generic global-memory kernel."""
     from gtn_applications_b200 import _lib
-    old = _lib.lib().wfst_debug_force_generic_lattice({"lean-pair": 3, "lean-single": 2, "generic": 1}[request.param])
+    old = _lib.lib().wfst_debug_force_generic_lattice({"lean-pair": 3, "lean-pair-narrow": 4, "lean-single": 2, "generic": 1}[request.param])
     yield request.param
     _lib.lib().wfst_debug_force_generic_lattice(old)

@@ -22,7 +22,10 @@ def random_acceptor(rng, N, A, C, weights=True):
 
 @pytest.mark.parametrize("B,T,C,N,A", [(3, 9, 5, 6, 20), (4, 33, 17, 40, 160), (2, 70, 1001, 300, 900),
                                        (5, 16, 8, 1, 3), (2, 21, 40, 2300, 7000), (2, 40, 6, 3, 40),
-                                       (3, 300, 6, 40, 150), (2, 531, 17, 25, 90), (2, 129, 9, 12, 30)])
+                                       (3, 300, 6, 40, 150), (2, 531, 17, 25, 90), (2, 129, 9, 12, 30),
+                                       # 1025..2048 nodes: the wide-register cluster kernel (register slots
+                                       # + tail arcs: random degrees reach 10 and more), several tiles
+                                       (2, 150, 30, 1500, 5200), (2, 40, 1001, 1100, 3600), (2, 23, 300, 2048, 9000)])
 def test_random_acceptors(B, T, C, N, A, lattice_kernel):
     from gtn_applications_b200.packing import PackedAcceptors
     from gtn_applications_b200.lattice import lattice_forward_backward
@@ -88,7 +91,7 @@ def test_shared_graph_accumulates_weight_gradient(lattice_kernel, T):
     assert_close(gW.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("B,T,C,N,A", [(3, 150, 6, 30, 110), (2, 300, 1001, 200, 700)])
+@pytest.mark.parametrize("B,T,C,N,A", [(3, 150, 6, 30, 110), (2, 300, 1001, 200, 700), (2, 150, 30, 1300, 4500)])
 def test_final_weights_and_weight_gradients_agree_across_kernels(B, T, C, N, A):
     """Final weights (ABI 2) over many tiles: the two-block cluster kernel and the single-block
     shared-memory kernel against the generic kernel (itself checked against the reference's
@@ -104,7 +107,7 @@ def test_final_weights_and_weight_gradients_agree_across_kernels(B, T, C, N, A):
     fw = torch.tensor(rng.standard_normal(packed.num_nodes).astype(np.float32), device="cuda")
     gs = torch.tensor(rng.uniform(0.5, 2.0, B).astype(np.float32), device="cuda")
     out = {}
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 4):
         old = _lib.lib().wfst_debug_force_generic_lattice(mode)
         try:
             out[mode] = [x.cpu().numpy() for x in lattice_forward_backward(
@@ -112,7 +115,7 @@ def test_final_weights_and_weight_gradients_agree_across_kernels(B, T, C, N, A):
         finally:
             _lib.lib().wfst_debug_force_generic_lattice(old)
     assert np.isfinite(out[1][0]).any()
-    for mode in (2, 3):
+    for mode in (2, 3, 4):
         for ref, got in zip(out[1], out[mode]):
             fin = np.isfinite(ref)
             assert np.array_equal(fin, np.isfinite(got))

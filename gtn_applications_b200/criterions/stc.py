@@ -137,7 +137,7 @@ class STC(torch.nn.Module):
             # keep only the tokens that occur in this batch (stc.py:204-214)
             present = [STC_BLANK_IDX] + list(set(t for tgt in targets for t in tgt))
             remap = {t: i for i, t in enumerate(present)}
-            idx = torch.tensor(present, dtype=torch.long, device=log_probs.device)
+            idx = rt.host_values_to_device(present, log_probs.device, torch.long)
             sel = log_probs.index_select(2, idx)
             targets = [[remap[t] for t in tgt] for tgt in targets]
             # <star>\token for every present token, then [tokens, <star>, <star>\tokens]

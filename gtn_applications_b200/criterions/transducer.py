@@ -255,7 +255,7 @@ class TransducerLossFunction(torch.autograd.Function):
         need_e = ctx.needs_input_grad[0]
         need_t = transitions is not None and ctx.needs_input_grad[4]
         with torch.cuda.device(dev):
-            sc = torch.tensor(scales, dtype=torch.float32, device=dev)
+            sc = rt.host_values_to_device(scales, dev)
             if transitions is not None:
                 # alignments := intersect(transitions, alignments) (transducer.py:279-281), with or
                 # without epsilon arcs in the transition graph: composition, epsilon fold and the

@@ -905,10 +905,9 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
         pr_next[j] = (vnode[j] >= 0 && s > 0) ? hist[(uint32_t)(s - 1) * hstride + hslot[j]] : kNegInf;
       }
       uint32_t qstar = 0, qtot = 0;
-      // off2 = (offset of the posterior) * log2(e) + 30: exp2 gives the posterior in the fixed-point
-      // unit of the tile (kFixOne = 2^30) directly; an arc at -inf (padding slot included) gives 0
-      auto post = [&](float xv, uint32_t rx, uint32_t k, float off2) {
-        const float pf = ex2_approx(fmaf(xv, kLog2e, off2));
+      // pf: the posterior of the arc in the fixed-point unit of the tile (kFixOne = 2^30); an arc
+      // at -inf (padding slot included) gives 0
+      auto post = [&](float pf, uint32_t rx, uint32_t k) {
         const float p = pf * (1.f / kFixOne);      // used by the weight gradient only
         if (want_gE) {
           const uint32_t q = __float2uint_rn(pf);
@@ -949,18 +948,23 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
             float sum = 0.f;
             const float ml = -m * kLog2e;
 #pragma unroll
-            for (int d = 0; d < DEG; ++d) sum += ex2_approx(fmaf(x[d], kLog2e, ml));
+            for (int d = 0; d < DEG; ++d) {
+              x[d] = ex2_approx(fmaf(x[d], kLog2e, ml));     // exp(x - m): reused by the posterior below
+              sum += x[d];
+            }
             if (TAIL)
               for (uint32_t k = k0 + DEG; k < ke; ++k) sum += ex2_approx(fmaf(eval(k, rr), kLog2e, ml));
             rv = m + __logf(sum);
             if (pr[j] != kNegInf) {
-              const float off = fmaf(pr[j] + dlt, kLog2e, 30.f);
+              // posterior * 2^30 = exp(x - m) * exp2((alpha + offsets - Z) * log2(e) + 30 + m * log2(e)):
+              // one exp2 per node instead of one per arc
+              const float scale = ex2_approx(fmaf(pr[j] + dlt, kLog2e, 30.f) - ml);
 #pragma unroll
-              for (int d = 0; d < DEG; ++d) post(x[d], rec[d].x, k0 + d, off);
+              for (int d = 0; d < DEG; ++d) post(x[d] * scale, rec[d].x, k0 + d);
               if (TAIL)
                 for (uint32_t k = k0 + DEG; k < ke; ++k) {
                   const float xv = eval(k, rr);
-                  post(xv, rr, k, off);
+                  post(ex2_approx(fmaf(xv, kLog2e, ml)) * scale, rr, k);
                 }
             }
           }

@@ -424,7 +424,11 @@ lattice_lean_wide_kernel(Args g, typename Builder::Params bp) {
         sum[j] = 0.f;
 #pragma unroll
         for (int d = 0; d < D0; ++d)
-          if (d < sc_of(j)) sum[j] += ex2_approx(fmaf(x[sb_of(j) + d], kLog2e, ml[j]));
+          if (d < sc_of(j)) {
+            // x becomes exp(x - m): the posterior below is this times one factor per node
+            x[sb_of(j) + d] = ex2_approx(fmaf(x[sb_of(j) + d], kLog2e, ml[j]));
+            sum[j] += x[sb_of(j) + d];
+          }
       }
       if (tail_any) {
 #pragma unroll
@@ -434,12 +438,13 @@ lattice_lean_wide_kernel(Args g, typename Builder::Params bp) {
           for (uint32_t k = kb; k < ke; ++k) sum[j] += ex2_approx(fmaf(eval(k, rr), kLog2e, ml[j]));
         }
       }
-      // posteriors: off2 = (alpha + offsets - Z) * log2(e) + 30, so that exp2 gives the posterior in
-      // the fixed-point unit of the tile (kFixOne = 2^30); an arc at -inf (padding slots, nodes
-      // alpha has not reached: off2 = -inf) gives 0
+      // posteriors in the fixed-point unit of the tile (kFixOne = 2^30):
+      //   exp(x + alpha + offsets - Z) * 2^30 = exp(x - m) * exp2((alpha + offsets - Z) * log2(e) + 30 + m * log2(e)),
+      // the first factor is already there from the sum, the second is one exp2 per NODE instead
+      // of one per arc; an arc at -inf (padding slots) has exp(x - m) = 0, a node alpha has not
+      // reached has the factor exp2(-inf) = 0
       uint32_t qstar = 0, qtot = 0;
-      auto post = [&](float xv, uint32_t lab, uint32_t k, float off2) {
-        const float pf = ex2_approx(fmaf(xv, kLog2e, off2));
+      auto post = [&](float pf, uint32_t lab, uint32_t k) {
         if (want_gE) {
           const uint32_t q = __float2uint_rn(pf);
           qtot += q;
@@ -448,13 +453,13 @@ lattice_lean_wide_kernel(Args g, typename Builder::Params bp) {
         }
         if (want_gW && pf != 0.f) sts_f(s_gw + 4u * k, lds_f(s_gw + 4u * k) + pf * (1.f / kFixOne));
       };
-      float off2[NPT];
+      float scale[NPT];
 #pragma unroll
       for (int j = 0; j < NPT; ++j) {
-        off2[j] = fmaf(pr[j] + dlt, kLog2e, 30.f);
+        scale[j] = ex2_approx(fmaf(pr[j] + dlt, kLog2e, 30.f) - ml[j]);
 #pragma unroll
         for (int d = 0; d < D0; ++d)
-          if (d < sc_of(j)) post(x[sb_of(j) + d], rl[sb_of(j) + d], k0r[j] + d, off2[j]);
+          if (d < sc_of(j)) post(x[sb_of(j) + d] * scale[j], rl[sb_of(j) + d], k0r[j] + d);
       }
       if (tail_any) {
 #pragma unroll
@@ -463,7 +468,7 @@ lattice_lean_wide_kernel(Args g, typename Builder::Params bp) {
           tail_of(j, s_snode, kb, ke);
           for (uint32_t k = kb; k < ke; ++k) {
             const float xv = eval(k, rr);
-            post(xv, rr >> 16, k, off2[j]);
+            post(ex2_approx(fmaf(xv, kLog2e, ml[j])) * scale[j], rr >> 16, k);
           }
         }
       }

@@ -382,13 +382,55 @@ def _packed_kernel(k, dev):
     return hit
 
 
+def _score_all_kernels(windows, packed, weights, grad_scale=None, grad_emissions=None, grad_weights=None,
+                       narcs=None):
+    """scores [K, B'] of every window against every kernel graph (wfst_lattice_forward_backward_many);
+    with grad_scale [K, B']: window gradients are added to `grad_emissions`, arc-weight gradients
+    written to the slices of the flat buffer `grad_weights` (narcs: arcs per kernel graph)."""
+    import ctypes
+    Bw, ks, C = windows.shape
+    K = len(packed)
+    dev = windows.device
+    L = _lib.lib()
+    scores = torch.empty(K, Bw, dtype=torch.float32, device=dev)
+    if K == 0:
+        return scores
+    # the K structs of a set of kernel graphs are built once and kept on the first packed graph
+    # (the packed graphs themselves are cached on the kernel graphs); only the weight pointers
+    # change from call to call
+    hit = getattr(packed[0], "_many_structs", None)
+    if hit is None or hit[0] != [id(pk) for pk in packed]:
+        hit = ([id(pk) for pk in packed], (_lib.AcceptorBatch * K)(*[pk.struct() for pk in packed]),
+               [pk.t["weights"].data_ptr() for pk in packed])
+        packed[0]._many_structs = hit
+    structs = hit[1]
+    for i in range(K):
+        structs[i].weights = weights[i].data_ptr() if weights[i] is not None else hit[2][i]
+    gw_ptrs = None
+    if grad_weights is not None:
+        gw_ptrs = (ctypes.c_void_p * K)()
+        pos = 0
+        for i in range(K):
+            gw_ptrs[i] = grad_weights.data_ptr() + 4 * pos
+            pos += narcs[i]
+    with torch.cuda.device(dev):
+        ws = rt.workspace(dev, L.wfst_lattice_workspace_bytes(Bw, ks, C, 0, max(pk.max_nodes for pk in packed)))
+        _lib.check(L.wfst_lattice_forward_backward_many(
+            windows.data_ptr(), Bw, ks, C, structs, K,
+            grad_scale.data_ptr() if grad_scale is not None else None, scores.data_ptr(),
+            grad_emissions.data_ptr() if grad_emissions is not None else None, gw_ptrs,
+            ws.data_ptr(), ws.numel(), rt.stream_ptr(dev)))
+    return scores
+
+
 class ConvTransduce1DFunction(torch.autograd.Function):
     """criterions/transducer.py:461-556.  The reference scores every window of every
     utterance against every kernel graph with one GTN intersect + forward_score (or
     viterbi_score) on CPU threads and keeps all graphs alive in a module-level global for
     the backward pass.  Here the windows become one batch [B*T', kernel_size, C] on the
-    device and each kernel graph is one launch of the lattice kernel in shared-graph mode;
-    backward re-runs the launch with grad_scale = the incoming output gradient, which
+    device and each kernel graph is one launch of the lattice kernel in shared-graph mode, all
+    of them issued by one call of the library (wfst_lattice_forward_backward_many);
+    backward re-runs the launches with grad_scale = the incoming output gradient, which
     yields the window gradients (overlap-added into the input gradient) and, summed over
     windows, the kernel weight gradients.  Nothing is kept between calls but the windows."""
 
@@ -414,16 +456,17 @@ class ConvTransduce1DFunction(torch.autograd.Function):
                 for i, k in enumerate(kernels):
                     weights[i] = kp[pos:pos + k.num_arcs()]
                     pos += k.num_arcs()
-            out = torch.empty(B * Tp, len(kernels), dtype=torch.float32, device=dev)
             paths = []
-            for i, pk in enumerate(packed):
-                if viterbi:
+            if viterbi:
+                out = torch.empty(B * Tp, len(kernels), dtype=torch.float32, device=dev)
+                for i, pk in enumerate(packed):
                     sc, labels, arcs = lattice_viterbi(windows, pk, shared=True, weights=weights[i])
                     paths.append((labels, arcs))
-                else:
-                    sc, _, _ = lattice_forward_backward(windows, pk, want_grad_emissions=False, shared=True,
-                                                        weights=weights[i])
-                out[:, i] = sc
+                    out[:, i] = sc
+            else:
+                # every kernel graph against every window in ONE call of the library (the launches
+                # are issued back to back from C: no Python work per lexicon entry)
+                out = _score_all_kernels(windows, packed, weights).t().contiguous()
         ctx.saved = (windows, packed, weights, paths, [k.num_arcs() for k in kernels])
         ctx.meta = (B, T, C, Tp, kernel_size, stride, viterbi, inputs.device,
                     kernel_params.device if kernel_params is not None else None)
@@ -441,28 +484,29 @@ class ConvTransduce1DFunction(torch.autograd.Function):
             deltas = grad_output.detach().to(dev, torch.float32).reshape(B * Tp, len(packed))
             gwin = torch.zeros_like(windows)
             kgrads = []
-            for i, pk in enumerate(packed):
+            for i, pk in enumerate(packed if viterbi else []):
                 gs = deltas[:, i].contiguous()
-                if viterbi:
-                    # d viterbi_score / d weights = indicator of the best path's arcs
-                    # (a window with no accepting path has score -inf and labels / arcs of -1:
-                    # it contributes nothing — the indices are clamped and the values masked)
-                    labels, arcs = paths[i]
-                    valid = (labels >= 0).to(torch.float32)                 # [B*T', ks]
-                    vals = gs.view(-1, 1) * valid
-                    if need_in:
-                        gwin.scatter_add_(2, labels.clamp_min(0).long().unsqueeze(2), vals.unsqueeze(2).contiguous())
-                    if need_k:
-                        kg = torch.zeros(narcs[i], dtype=torch.float32, device=dev)
-                        if narcs[i] > 0:
-                            kg.index_add_(0, arcs.clamp_min(0).long().reshape(-1), vals.reshape(-1))
-                        kgrads.append(kg)
-                else:
-                    _, _, g_w = lattice_forward_backward(
-                        windows, pk, grad_scale=gs, want_grad_emissions=need_in, want_grad_weights=need_k,
-                        weights=weights[i], shared=True, accumulate_into=gwin if need_in else None)
-                    if need_k:
-                        kgrads.append(g_w)
+                # d viterbi_score / d weights = indicator of the best path's arcs
+                # (a window with no accepting path has score -inf and labels / arcs of -1:
+                # it contributes nothing — the indices are clamped and the values masked)
+                labels, arcs = paths[i]
+                valid = (labels >= 0).to(torch.float32)                 # [B*T', ks]
+                vals = gs.view(-1, 1) * valid
+                if need_in:
+                    gwin.scatter_add_(2, labels.clamp_min(0).long().unsqueeze(2), vals.unsqueeze(2).contiguous())
+                if need_k:
+                    kg = torch.zeros(narcs[i], dtype=torch.float32, device=dev)
+                    if narcs[i] > 0:
+                        kg.index_add_(0, arcs.clamp_min(0).long().reshape(-1), vals.reshape(-1))
+                    kgrads.append(kg)
+            if not viterbi and len(packed):
+                # one call for all kernel graphs: window gradients accumulate in gwin, the weight
+                # gradients of kernel graph i land in their slice of one flat buffer
+                flat = torch.empty(sum(narcs), dtype=torch.float32, device=dev) if need_k else None
+                _score_all_kernels(windows, packed, weights, grad_scale=deltas.t().contiguous(),
+                                   grad_emissions=gwin if need_in else None, grad_weights=flat, narcs=narcs)
+                if need_k:
+                    kgrads = [flat]
             g_in = None
             if need_in:
                 g_in = torch.zeros(B, T, C, dtype=torch.float32, device=dev)

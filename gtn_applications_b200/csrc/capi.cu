@@ -357,6 +357,36 @@ int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
                     accumulate, grad_weights, (float*)workspace, st);
 }
 
+int wfst_lattice_forward_backward_many(const float* emissions, int B, int T, int C,
+                                       const wfst_acceptor_batch_t* graphs, int K,
+                                       const float* grad_scale, float* scores, float* grad_emissions,
+                                       float* const* grad_weights, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  WFST_REQUIRE(emissions && graphs && scores && workspace, "null pointer argument");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0 && K >= 0, "bad shape B=%d T=%d C=%d K=%d", B, T, C, K);
+  for (int k = 0; k < K; ++k) {
+    WFST_REQUIRE(graphs[k].B == 1, "acceptor %d is a batch of %d, not a shared acceptor", k, graphs[k].B);
+    WFST_REQUIRE(graphs[k].max_nodes > 0, "acceptor %d is empty", k);
+    if (workspace_bytes < lattice_hist_bytes(B, T, C, graphs[k].max_nodes)) {
+      set_error("workspace too small");
+      return WFST_ERR_WORKSPACE;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int k = 0; k < K; ++k) {
+    wfst_acceptor_batch_t g = graphs[k];
+    g.B = B;
+    float* gw = grad_weights ? grad_weights[k] : nullptr;
+    if (gw) WFST_CUDA_CHECK(cudaMemsetAsync(gw, 0, (size_t)graphs[k].max_arcs * 4, st));
+    if (graphs[k].grad_final_weights)
+      WFST_CUDA_CHECK(cudaMemsetAsync(graphs[k].grad_final_weights, 0, (size_t)graphs[k].max_nodes * 4, st));
+    const int rc = launch_csr(emissions, T, C, g, 1, grad_scale ? grad_scale + (size_t)k * B : nullptr, 1.f,
+                              scores + (size_t)k * B, grad_emissions, 1, gw, (float*)workspace, st);
+    if (rc != WFST_OK) return rc;
+  }
+  return WFST_OK;
+}
+
 // --------------------------------------------------------------------- ASG
 // The full-connect and the force-align lattices of one batch are independent until their
 // gradients meet; each is a latency-bound kernel that fills a fraction of the GPU (one warp /

@@ -179,6 +179,22 @@ WFST_API int wfst_lattice_forward_backward(const float* emissions, int B, int T,
                                   int accumulate, float* grad_weights, void* workspace,
                                   size_t workspace_bytes, void* stream);
 
+/* The same emissions against K shared acceptors, one after the other on `stream` — replaces the
+ * loops over lexicon entries and windows of ConvTransduce1DFunction.forward / .backward
+ * (criterions/transducer.py:487-509, 529-556), which score every window against every kernel graph.
+ *   graphs        K acceptor batches with B == 1 each (acceptor k is shared by all B items)
+ *   grad_scale    [K, B] or NULL (= 1)
+ *   scores        [K, B] out
+ *   grad_emissions[B, T, C] or NULL: sum over k of grad_scale[k, b] * dZ_kb/dE[b] is ADDED to what
+ *                 the buffer holds (the caller clears it)
+ *   grad_weights  K pointers ([arcs of acceptor k] out, summed over b) or NULL
+ *   workspace     >= wfst_lattice_workspace_bytes(B, T, C, 0, max over k of graphs[k].max_nodes) */
+WFST_API int wfst_lattice_forward_backward_many(const float* emissions, int B, int T, int C,
+                                  const wfst_acceptor_batch_t* graphs, int K,
+                                  const float* grad_scale, float* scores, float* grad_emissions,
+                                  float* const* grad_weights, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------
  * ASG — replaces ASGLossFunction.forward + .backward (criterions/asg.py:83-185):
  *   loss_b = Z(E_b o transitions) - Z((force_align(y_b) o transitions) o E_b)

@@ -120,3 +120,46 @@ def test_final_weights_and_weight_gradients_agree_across_kernels(B, T, C, N, A):
             fin = np.isfinite(ref)
             assert np.array_equal(fin, np.isfinite(got))
             assert_close(got[fin], ref[fin])
+
+
+def test_many_shared_acceptors_in_one_call_match_one_call_each(lattice_kernel):
+    """wfst_lattice_forward_backward_many (every window against every kernel graph of
+    ConvTransduce1D in one call) against one shared-graph call per acceptor: scores, the
+    emission gradient summed over the acceptors, the arc-weight gradients of each."""
+    import ctypes
+    from gtn_applications_b200 import _lib, _runtime as rt
+    from gtn_applications_b200.packing import PackedAcceptors
+    from gtn_applications_b200.lattice import lattice_forward_backward
+    rng = np.random.default_rng(3)
+    B, T, C, K = 7, 20, 9, 4
+    graphs = [random_acceptor(rng, 5 + 3 * k, 18 + 7 * k, C) for k in range(K)]
+    E = torch.tensor(rng.standard_normal((B, T, C)).astype(np.float32), device="cuda")
+    gs = torch.tensor(rng.uniform(0.5, 2.0, (K, B)).astype(np.float32), device="cuda")
+    packed = [PackedAcceptors([g], "cuda") for g in graphs]
+    want_s, want_w = [], []
+    want_e = torch.zeros_like(E)
+    for k, pk in enumerate(packed):
+        s, _, w = lattice_forward_backward(E, pk, grad_scale=gs[k].contiguous(), want_grad_weights=True,
+                                           shared=True, accumulate_into=want_e)
+        want_s.append(s)
+        want_w.append(w)
+    L = _lib.lib()
+    structs = (_lib.AcceptorBatch * K)(*[pk.struct() for pk in packed])
+    narcs = [pk.num_arcs for pk in packed]
+    flat = torch.empty(sum(narcs), dtype=torch.float32, device="cuda")
+    ptrs = (ctypes.c_void_p * K)()
+    pos = 0
+    for k in range(K):
+        ptrs[k] = flat.data_ptr() + 4 * pos
+        pos += narcs[k]
+    scores = torch.empty(K, B, dtype=torch.float32, device="cuda")
+    got_e = torch.zeros_like(E)
+    ws = rt.workspace(E.device, L.wfst_lattice_workspace_bytes(B, T, C, 0, max(pk.max_nodes for pk in packed)))
+    _lib.check(L.wfst_lattice_forward_backward_many(
+        E.data_ptr(), B, T, C, structs, K, gs.data_ptr(), scores.data_ptr(), got_e.data_ptr(), ptrs,
+        ws.data_ptr(), ws.numel(), rt.stream_ptr(E.device)))
+    torch.cuda.synchronize()
+    assert torch.equal(scores, torch.stack(want_s))
+    assert torch.equal(got_e, want_e)
+    # summed over the items with float atomics: the order of the additions is not fixed
+    assert_close(flat.cpu().numpy(), torch.cat(want_w).cpu().numpy())

@@ -123,16 +123,18 @@ class FoldedBatch:
         sizes = np.zeros(5, dtype=np.int64)
         _lib.check(L.wfst_fold_sizes(fold, sizes.ctypes.data))
         na, npaths, nn, ea, ef = (int(x) for x in sizes)
-        arc_seg, arc_src = np.empty(ea, dtype=np.int64), np.empty(ea, dtype=np.int64)
-        fin_seg, fin_src = np.empty(ef, dtype=np.int64), np.empty(ef, dtype=np.int64)
-        fin_node = np.empty(npaths, dtype=np.int64)
-        _lib.check(L.wfst_fold_fill(fold, arc_seg.ctypes.data, arc_src.ctypes.data, fin_seg.ctypes.data,
-                                    fin_src.ctypes.data, fin_node.ctypes.data))
+        # the five index arrays are filled into ONE pinned staging tensor and travel in one
+        # asynchronous copy (five synchronous copies from pageable memory made the host wait for
+        # the previous step's kernels: 1.9 ms per step of the n-gram transducers)
+        cuts = np.cumsum([0, ea, ea, ef, ef, npaths])
+        host = torch.empty(int(cuts[-1]), dtype=torch.int64, pin_memory=torch.cuda.is_available())
+        base = host.data_ptr()
+        _lib.check(L.wfst_fold_fill(fold, *(base + 8 * int(c) for c in cuts[:5])))
+        dev = host.to(device, non_blocking=True)
         self = cls.__new__(cls)
         self.num_arcs, self.num_paths, self.num_nodes = na, npaths, nn
-        up = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
-        self.arc_seg, self.arc_src = up(arc_seg), up(arc_src)
-        self.fin_seg, self.fin_src, self.fin_node = up(fin_seg), up(fin_src), up(fin_node)
+        self.arc_seg, self.arc_src, self.fin_seg, self.fin_src, self.fin_node = (
+            dev[int(cuts[i]):int(cuts[i + 1])] for i in range(5))
         return self
 
     def weights(self, params, tropical=False):

@@ -137,6 +137,19 @@ static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, i
   // (measured: B=64 x 22 warps 5.4 -> 2.9 ms; B=256 x 12 warps, already issue-bound, 1.9 -> 2.1 ms)
   const int ntiles = (a.T + kt - 1) / kt;
   const bool starved = (long long)B * (nt / 32) <= 148LL * 16;
+  if constexpr (Builder::kSort) {
+    // small dense acceptors (n-gram transition graphs: 84 nodes x 81 arcs): a warp per node in the
+    // cluster kernel instead of a thread per node, whatever the batch size (test hooks 2 and 4:
+    // off)
+    const bool dense = max_nodes <= 32 * 16 && (long long)aslots >= 16LL * max_nodes;
+    if (dense && ntiles >= 2 && g_force_generic_lattice != 2 && g_force_generic_lattice != 4) {
+      const int ng = max_nodes < 32 ? max_nodes : 32;          // warps = node groups
+      int np = (max_nodes + ng - 1) / ng;
+      np = np <= 4 ? np : (np <= 8 ? 8 : 16);
+      *rc = launch_lean_pair_wpn(g, bp, B, 32 * (ng < 2 ? 2 : ng), lay.total, np, st);
+      return true;
+    }
+  }
   if (g_force_generic_lattice != 2 && ntiles >= 2 && (starved || g_force_generic_lattice >= 3)) {
     if constexpr (Builder::kSort) {
       if (wide) {

@@ -384,6 +384,9 @@ template <class Builder>
 int launch_lean_pair(const lean::Args& g, typename Builder::Params bp, int B, int nt, size_t smem, int npt,
                      cudaStream_t st);
 
+// cluster kernel with a warp per node for small dense packed CSR acceptors (lattice_pair_wpn.cu)
+int launch_lean_pair_wpn(const lean::Args& g, CsrLean::Params bp, int B, int nt, size_t smem, int npt, cudaStream_t st);
+
 // wide-register cluster kernel for degree-sorted acceptors of at most 2048 nodes (lattice_wide.cu)
 int launch_lean_wide(const lean::Args& g, CsrLean::Params bp, int B, int nt, size_t smem, cudaStream_t st);
 

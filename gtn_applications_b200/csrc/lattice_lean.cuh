@@ -578,7 +578,12 @@ __device__ __forceinline__ void st_peer_u2(uint32_t addr, uint32_t x, uint32_t y
   asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
 
-template <class Builder, int NPT, bool GW>
+// TPN: threads per node.  1: a thread walks its nodes' arc lists alone (NPT nodes per thread).
+// 32: a WARP per node (NPT nodes per warp) -- lane l takes arcs l, l + 32, ... of the list, the
+// maximum and the sum are combined with shuffles, lane 0 stores the node's value.  For small
+// dense acceptors (the n-gram transition graph of the transducer: 84 nodes x 81 arcs), where a
+// thread per node leaves 84 threads walking 81 arcs each, three times per frame step.
+template <class Builder, int NPT, bool GW, int TPN = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(1024, 1)
 lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
   constexpr int DEG = Builder::kDeg;
@@ -589,6 +594,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
   const uint32_t role = cluster_rank();
   if (a.active && a.active[b] == 0) return;        // both blocks of the pair
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const int gid = tid / TPN, NG = NT / TPN, gl = tid % TPN;     // node group of this thread, lane in it
   const Layout& L = g.lay;
   const uint32_t sb = smem_u32(smem_lean);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lean + L.bars);
@@ -700,15 +706,15 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
-      const int q = j * NT + ((j & 1) ? NT - 1 - tid : tid);
+      const int q = j * NG + ((j & 1) ? NG - 1 - gid : gid);
       vnode[j] = (q < N) ? (int)lds_u(s_perm + 4u * q) : -1;
     }
     __syncthreads();
   } else {
 #pragma unroll
-    for (int j = 0; j < NPT; ++j) vnode[j] = (tid + j * NT < N) ? tid + j * NT : -1;
+    for (int j = 0; j < NPT; ++j) vnode[j] = (gid + j * NG < N) ? gid + j * NG : -1;
   }
-  auto slot_of = [&](int j) { return (Builder::kSort && (j & 1)) ? j * NT + NT - 1 - tid : j * NT + tid; };
+  auto slot_of = [&](int j) { return (Builder::kSort && (j & 1)) ? j * NG + NG - 1 - gid : j * NG + gid; };
   uint32_t hslot[NPT];     // history rows are addressed by 32-bit element offsets (row * stride + slot)
 #pragma unroll
   for (int j = 0; j < NPT; ++j) hslot[j] = (uint32_t)slot_of(j);
@@ -752,7 +758,7 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
   for (int v = tid; v < N; v += NT) sts_f(cur + 4u * v, init_val(v));
 #pragma unroll
   for (int j = 0; j < NPT; ++j)
-    if (vnode[j] >= 0) hist[hslot[j]] = init_val(vnode[j]);
+    if (vnode[j] >= 0 && gl == 0) hist[hslot[j]] = init_val(vnode[j]);
   issue_tile(gtile_of(0), 0);
   uint32_t be_p[NPT];
 #pragma unroll
@@ -787,12 +793,16 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           const uint32_t k0 = be_p[j] & 0xffffu, ke = be_p[j] >> 16;
           uint2 rec[DEG];
 #pragma unroll
-          for (int d = 0; d < DEG; ++d) rec[d] = lds_u2(s_ppack + 8u * (k0 + d));
+          for (int d = 0; d < DEG; ++d) {
+            // TPN == 1 reads up to DEG - 1 records past the list (padding slots of the layout)
+            const uint32_t kk = k0 + gl + d * TPN;
+            rec[d] = (TPN == 1 || kk < ke) ? lds_u2(s_ppack + 8u * kk) : make_uint2(0u, 0u);
+          }
           float x[DEG];
 #pragma unroll
           for (int d = 0; d < DEG; ++d) {
             const float av = lds_f(cur + (rec[d].x & 0xffffu)), ev = lds_f(Et + (rec[d].x >> 16));
-            x[d] = (k0 + d < ke) ? av + ev + __uint_as_float(rec[d].y) : kNegInf;
+            x[d] = (k0 + gl + d * TPN < ke) ? av + ev + __uint_as_float(rec[d].y) : kNegInf;
           }
           float m = x[0];
 #pragma unroll
@@ -802,7 +812,11 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
             return lds_f(cur + (rr.x & 0xffffu)) + lds_f(Et + (rr.x >> 16)) + __uint_as_float(rr.y);
           };
           if (TAIL)
-            for (uint32_t k = k0 + DEG; k < ke; ++k) m = fmaxf(m, eval(k));
+            for (uint32_t k = k0 + gl + DEG * TPN; k < ke; k += TPN) m = fmaxf(m, eval(k));
+          if (TPN > 1) {
+#pragma unroll
+            for (int o = TPN / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          }
           float rv = kNegInf;
           if (m != kNegInf) {
             float sum = 0.f;
@@ -810,11 +824,17 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
 #pragma unroll
             for (int d = 0; d < DEG; ++d) sum += ex2_approx(fmaf(x[d], kLog2e, ml));
             if (TAIL)
-              for (uint32_t k = k0 + DEG; k < ke; ++k) sum += ex2_approx(fmaf(eval(k), kLog2e, ml));
+              for (uint32_t k = k0 + gl + DEG * TPN; k < ke; k += TPN) sum += ex2_approx(fmaf(eval(k), kLog2e, ml));
+            if (TPN > 1) {
+#pragma unroll
+              for (int o = TPN / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            }
             rv = m + __logf(sum);
           }
-          sts_f(nxt + 4u * v, rv);
-          if (keep) hist[hrow + hslot[j]] = rv;
+          if (gl == 0) {
+            sts_f(nxt + 4u * v, rv);
+            if (keep) hist[hrow + hslot[j]] = rv;
+          }
         }
       }
       __syncthreads();
@@ -925,12 +945,15 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
           const uint32_t k0 = be_s[j] & 0xffffu, ke = be_s[j] >> 16;
           uint2 rec[DEG];
 #pragma unroll
-          for (int d = 0; d < DEG; ++d) rec[d] = lds_u2(s_spack + 8u * (k0 + d));
+          for (int d = 0; d < DEG; ++d) {
+            const uint32_t kk = k0 + gl + d * TPN;
+            rec[d] = (TPN == 1 || kk < ke) ? lds_u2(s_spack + 8u * kk) : make_uint2(0u, 0u);
+          }
           float x[DEG];
 #pragma unroll
           for (int d = 0; d < DEG; ++d) {
             const float bv = lds_f(nxt + (rec[d].x & 0xffffu)), ev = lds_f(Et + (rec[d].x >> 16));
-            x[d] = (k0 + d < ke) ? ev + __uint_as_float(rec[d].y) + bv : kNegInf;
+            x[d] = (k0 + gl + d * TPN < ke) ? ev + __uint_as_float(rec[d].y) + bv : kNegInf;
           }
           float m = x[0];
 #pragma unroll
@@ -942,7 +965,11 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
             return lds_f(Et + (q.x >> 16)) + __uint_as_float(q.y) + lds_f(nxt + (q.x & 0xffffu));
           };
           if (TAIL)
-            for (uint32_t k = k0 + DEG; k < ke; ++k) m = fmaxf(m, eval(k, rr));
+            for (uint32_t k = k0 + gl + DEG * TPN; k < ke; k += TPN) m = fmaxf(m, eval(k, rr));
+          if (TPN > 1) {
+#pragma unroll
+            for (int o = TPN / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          }
           float rv = kNegInf;
           if (m != kNegInf) {
             float sum = 0.f;
@@ -953,22 +980,26 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
               sum += x[d];
             }
             if (TAIL)
-              for (uint32_t k = k0 + DEG; k < ke; ++k) sum += ex2_approx(fmaf(eval(k, rr), kLog2e, ml));
+              for (uint32_t k = k0 + gl + DEG * TPN; k < ke; k += TPN) sum += ex2_approx(fmaf(eval(k, rr), kLog2e, ml));
+            if (TPN > 1) {
+#pragma unroll
+              for (int o = TPN / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            }
             rv = m + __logf(sum);
             if (pr[j] != kNegInf) {
               // posterior * 2^30 = exp(x - m) * exp2((alpha + offsets - Z) * log2(e) + 30 + m * log2(e)):
               // one exp2 per node instead of one per arc
               const float scale = ex2_approx(fmaf(pr[j] + dlt, kLog2e, 30.f) - ml);
 #pragma unroll
-              for (int d = 0; d < DEG; ++d) post(x[d] * scale, rec[d].x, k0 + d);
+              for (int d = 0; d < DEG; ++d) post(x[d] * scale, rec[d].x, k0 + gl + d * TPN);
               if (TAIL)
-                for (uint32_t k = k0 + DEG; k < ke; ++k) {
+                for (uint32_t k = k0 + gl + DEG * TPN; k < ke; k += TPN) {
                   const float xv = eval(k, rr);
                   post(ex2_approx(fmaf(xv, kLog2e, ml)) * scale, rr, k);
                 }
             }
           }
-          sts_f(cur + 4u * u, rv);
+          if (gl == 0) sts_f(cur + 4u * u, rv);
         }
       }
       if (want_gE) {

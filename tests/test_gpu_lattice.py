@@ -25,7 +25,11 @@ def random_acceptor(rng, N, A, C, weights=True):
                                        (3, 300, 6, 40, 150), (2, 531, 17, 25, 90), (2, 129, 9, 12, 30),
                                        # 1025..2048 nodes: the wide-register cluster kernel (register slots
                                        # + tail arcs: random degrees reach 10 and more), several tiles
-                                       (2, 150, 30, 1500, 5200), (2, 40, 1001, 1100, 3600), (2, 23, 300, 2048, 9000)])
+                                       (2, 150, 30, 1500, 5200), (2, 40, 1001, 1100, 3600), (2, 23, 300, 2048, 9000),
+                                       # small dense acceptors (n-gram transition graphs): a warp per node in the
+                                       # cluster kernel -- 1, 3 and 16 nodes per warp, lists longer than 32 x 4 arcs
+                                       (2, 150, 30, 84, 6800), (3, 130, 12, 20, 500), (2, 70, 50, 300, 6000),
+                                       (2, 150, 9, 12, 2400)])
 def test_random_acceptors(B, T, C, N, A, lattice_kernel):
     from gtn_applications_b200.packing import PackedAcceptors
     from gtn_applications_b200.lattice import lattice_forward_backward

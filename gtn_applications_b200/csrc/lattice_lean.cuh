@@ -927,14 +927,38 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
       uint32_t qstar = 0, qtot = 0;
       // pf: the posterior of the arc in the fixed-point unit of the tile (kFixOne = 2^30); an arc
       // at -inf (padding slot included) gives 0
-      auto post = [&](float pf, uint32_t rx, uint32_t k) {
+      // warp_call: all 32 lanes are here together (TPN == 32, register slots).  The in-arcs of a
+      // node of an n-gram transition graph all carry the node's own label: 32 atomics on one
+      // address would serialise, so a warp whose non-zero posteriors share a label adds their
+      // sum once
+      auto post = [&](float pf, uint32_t rx, uint32_t k, bool warp_call) {
         const float p = pf * (1.f / kFixOne);      // used by the weight gradient only
         if (want_gE) {
           const uint32_t q = __float2uint_rn(pf);
           const uint32_t lab = rx >> 16;
           qtot += q;
-          if (lab == cstar) qstar += q;
-          else if (q != 0u) red_add_u(grow + lab, q);
+          bool done = false;
+          if (TPN == 32 && warp_call) {
+            const uint32_t act = __ballot_sync(0xffffffffu, q != 0u);
+            if (act == 0u) {
+              done = true;
+            } else {
+              const int src = __ffs(act) - 1;
+              const uint32_t lab0 = __shfl_sync(0xffffffffu, lab, src);
+              if (__all_sync(0xffffffffu, q == 0u || lab == lab0)) {
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, q);    // posteriors of one frame: <= 2^30 in all
+                if (lane == src) {
+                  if (lab0 == cstar) qstar += tot;
+                  else red_add_u(grow + lab0, tot);
+                }
+                done = true;
+              }
+            }
+          }
+          if (!done) {
+            if (lab == cstar) qstar += q;
+            else if (q != 0u) red_add_u(grow + lab, q);
+          }
         }
         if (want_gW && p != 0.f) sts_f(s_gw + 4u * k, lds_f(s_gw + 4u * k) + p);
       };
@@ -991,11 +1015,11 @@ lattice_lean_pair_kernel(Args g, typename Builder::Params bp) {
               // one exp2 per node instead of one per arc
               const float scale = ex2_approx(fmaf(pr[j] + dlt, kLog2e, 30.f) - ml);
 #pragma unroll
-              for (int d = 0; d < DEG; ++d) post(x[d] * scale, rec[d].x, k0 + gl + d * TPN);
+              for (int d = 0; d < DEG; ++d) post(x[d] * scale, rec[d].x, k0 + gl + d * TPN, true);
               if (TAIL)
                 for (uint32_t k = k0 + gl + DEG * TPN; k < ke; k += TPN) {
                   const float xv = eval(k, rr);
-                  post(ex2_approx(fmaf(xv, kLog2e, ml)) * scale, rr, k);
+                  post(ex2_approx(fmaf(xv, kLog2e, ml)) * scale, rr, k, false);
                 }
             }
           }

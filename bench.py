@@ -282,6 +282,26 @@ def other_configs(dev):
         del xn
     except Exception as exc:
         out["transducer_ngram2"] = {"error": repr(exc)[:200]}
+    # ---- ConvTransduce1D: 500 lexicon entries of 1-4 letters against every window
+    try:
+        from gtn_applications_b200.criterions.transducer import ConvTransduce1D
+        rl = random.Random(1)
+        lex = [[rl.randrange(26) for _ in range(rl.randint(1, 4))] for _ in range(500)]
+        conv = ConvTransduce1D(lex, kernel_size=9, stride=4, blank_idx=26).to(dev)
+        xc = torch.randn(8, 200, 27, generator=g).to(dev).requires_grad_(True)
+
+        def cv():
+            xc.grad = None
+            conv(torch.log_softmax(xc, 2)).sum().backward()
+
+        out["conv_transduce1d"] = {
+            "ms_per_step": timed(cv, 5, warm=2) * 1e3,
+            "what": "ConvTransduce1D(500 lexicon entries of 1-4 letters, kernel_size=9, stride=4) fwd+bwd, B=8, "
+                    "T=200, C=27 (384 windows x 500 kernel graphs; one call of wfst_lattice_forward_backward_many "
+                    "per direction, one launch per kernel graph)"}
+        del xc, conv
+    except Exception as exc:
+        out["conv_transduce1d"] = {"error": repr(exc)[:200]}
     # ---- configs[4], one GPU's shard
     B5, T5, C5, L5 = WORKLOADS["ctc_cfg5"]
     lp5, tg5 = synth("ctc_cfg5", dev, 7)

@@ -302,6 +302,27 @@ def other_configs(dev):
         del xc, conv
     except Exception as exc:
         out["conv_transduce1d"] = {"error": repr(exc)[:200]}
+    # ---- STC: the module on [T, B, C] log-probabilities, acceptors of the batch from
+    # the host library (wfst_stc_graphs), lattice kernel
+    try:
+        from gtn_applications_b200.criterions.stc import STC
+        rs = random.Random(2)
+        Bs, Ts, Cs, Ls = 32, 500, 30, 60
+        stc = STC(0, 0.1, 0.9, 10000, "mean")
+        xs = torch.randn(Ts, Bs, Cs, generator=g).to(dev).requires_grad_(True)
+        tgs = [[rs.randrange(1, Cs) for _ in range(Ls)] for _ in range(Bs)]
+
+        def st():
+            xs.grad = None
+            stc(torch.log_softmax(xs, 2), tgs).backward()
+
+        out["stc"] = {"ms_per_step": timed(st, 10, warm=3) * 1e3,
+                      "what": "STC(blank 0, p0 0.1, plast 0.9) fwd+bwd through the module, B=32, T=500, C=30, L=60 "
+                              "(log_softmax + <star> features + STC acceptors of the batch built in the host library "
+                              "+ lattice kernel)"}
+        del xs
+    except Exception as exc:
+        out["stc"] = {"error": repr(exc)[:200]}
     # ---- configs[4], one GPU's shard
     B5, T5, C5, L5 = WORKLOADS["ctc_cfg5"]
     lp5, tg5 = synth("ctc_cfg5", dev, 7)

@@ -83,6 +83,7 @@ SIGNATURES = {
     "wfst_graph_savetxt": (_I, [_I32, ctypes.c_char_p]),
     "wfst_graph_load": (_I32, [ctypes.c_char_p]),
     "wfst_graph_save": (_I, [_I32, ctypes.c_char_p]),
+    "wfst_stc_graphs": (_I, [_P, _P, _I, _I, ctypes.c_float, _I, _P]),
     "wfst_transducer_alignment_graphs": (_I, [_I32, _I32, _P, _P, _I, _P]),
     "wfst_transducer_decode_paths": (_I, [_I32, _P, _I, _I, _P, _P]),
     "wfst_graph_viterbi_path": (_I32, [_I32]),

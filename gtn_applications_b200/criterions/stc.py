@@ -10,7 +10,8 @@ import math
 import torch
 
 from .. import _runtime as rt
-from ..graph import Graph, pack_graphs
+from .. import _lib
+from ..graph import Graph, pack_graphs, pack_handles, destroy_handles
 from ..lattice import lattice_forward_backward
 
 # blank idx is REQUIRED to be zero, as in the reference (stc.py:12)
@@ -65,15 +66,20 @@ class STCLossFunction(torch.autograd.Function):
         star = Cstar // 2
         e = rt.to_device(inputs.detach())
         dev = e.device
-        graphs = []
-        for tgt in targets:
-            if any(t < 0 or t >= star for t in tgt):
-                raise ValueError("target label outside [0, %d)" % star)
-            g = STCLossFunction.create_stc_graph(list(tgt), star, prob)
-            g.arc_sort(False)
-            graphs.append(g)
+        # the acceptors of the whole batch from the host library (wfst_stc_graphs: create_stc_graph
+        # below, same node and arc order, on host threads — no Python work per arc), packed once
+        import ctypes
+        if len(targets) != B:
+            raise ValueError("%d targets for a batch of %d" % (len(targets), B))
+        flat, offs = rt.flatten_targets_host([t if torch.is_tensor(t) else list(t) for t in targets])
+        handles = (ctypes.c_int32 * B)()
+        _lib.check(_lib.lib().wfst_stc_graphs(flat.ctypes.data, offs.ctypes.data, B, star, math.log(prob),
+                                              STC_BLANK_IDX, handles))
         with torch.cuda.device(dev):
-            packed = pack_graphs(graphs, dev)
+            try:
+                packed = pack_handles(handles, B, dev)
+            finally:
+                destroy_handles(handles, B)
             gscale = torch.full((B,), -scale / B, dtype=torch.float32, device=dev)
             scores, grad, _ = lattice_forward_backward(
                 e, packed, grad_scale=gscale, want_grad_emissions=inputs.requires_grad)

@@ -1279,6 +1279,53 @@ int wfst_transducer_alignment_graphs(int32_t tokens, int32_t lexicon, const int3
   return WFST_OK;
 }
 
+// STC acceptors of a whole batch (criterions/stc.py:22-64, create_stc_graph), built on host
+// threads with the node and arc order of the reference's builder, then ilabel-sorted: a CTC-like
+// chain (self loops on blank states only, unconditional skips) plus one <star> node per gap whose
+// entering / looping arcs carry log(prob).  Labels must lie in [0, star_idx).  out_handles [B].
+int wfst_stc_graphs(const int32_t* targets, const int32_t* target_offsets, int B, int star_idx,
+                    float log_prob, int blank_idx, int32_t* out_handles) {
+  if (!target_offsets || !out_handles || B < 0 || (!targets && B > 0 && target_offsets[B] > 0)) {
+    set_error("stc graphs: null pointer argument");
+    return WFST_ERR_INVALID;
+  }
+  for (int b = 0; b < B; ++b)
+    for (int k = target_offsets[b]; k < target_offsets[b + 1]; ++k)
+      if (targets[k] < 0 || targets[k] >= star_idx) {
+        set_error("target label outside [0, %d)", star_idx);
+        return WFST_ERR_INVALID;
+      }
+  std::vector<std::unique_ptr<HostGraph>> built(B);
+  parallel_for(B, [&](int b) {
+    const int32_t* y = targets + target_offsets[b];
+    const int L = target_offsets[b + 1] - target_offsets[b];
+    auto g = std::make_unique<HostGraph>();
+    g->calc_grad = false;
+    const int n_states = 2 * L + 1;
+    for (int s = 0; s < n_states; ++s) {
+      g->add_node(s == 0, s >= n_states - 2);
+      const int lab = (s % 2) ? y[(s - 1) / 2] : blank_idx;
+      if (lab == blank_idx) g->add_arc(s, s, lab, lab, 0.f);
+      if (s > 0) g->add_arc(s - 1, s, lab, lab, 0.f);
+      if ((s % 2) && s > 1) g->add_arc(s - 2, s, lab, lab, 0.f);
+    }
+    for (int k = 0; k <= L; ++k) {
+      const int prev_tok = 2 * k - 1, prev_blank = 2 * k;
+      const int c = g->add_node(false, k == L);
+      const int idx = (k == L) ? star_idx : star_idx + y[k];
+      if (prev_tok >= 0) g->add_arc(prev_tok, c, idx, idx, log_prob);
+      g->add_arc(prev_blank, c, idx, idx, log_prob);
+      g->add_arc(c, c, idx, idx, log_prob);
+      if (k < L) g->add_arc(c, 2 * k + 1, y[k], y[k], 0.f);
+      g->add_arc(c, prev_blank, blank_idx, blank_idx, 0.f);
+    }
+    g->arc_sort(false);
+    built[b] = std::move(g);
+  });
+  for (int b = 0; b < B; ++b) out_handles[b] = put(std::move(built[b]));
+  return WFST_OK;
+}
+
 // Capacity of the alignment-graph cache in arcs + nodes (0 disables it, < 0 keeps the current
 // value); always empties the cache.  hits / misses (may be null) receive the counters since the
 // last call.

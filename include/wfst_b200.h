@@ -254,6 +254,12 @@ WFST_API int wfst_graph_savetxt(int32_t graph, const char* path);
 WFST_API int32_t wfst_graph_load(const char* path);
 WFST_API int wfst_graph_save(int32_t graph, const char* path);
 
+/* STC acceptors of a whole batch — replaces STCLossFunction.create_stc_graph (criterions/stc.py:22-64)
+ * called once per utterance: same node and arc order, then arc-sorted by input label.  targets are
+ * token indices in [0, star_idx), concatenated; the <star> arcs weigh log_prob; out_handles [B]. */
+WFST_API int wfst_stc_graphs(const int32_t* targets, const int32_t* target_offsets, int B, int star_idx,
+                             float log_prob, int blank_idx, int32_t* out_handles);
+
 /* Alignment acceptors of a whole batch (transducer.py:260-276), built on host threads:
  * project_input(remove(compose(tokens, remove(project_output(compose(chain(y_b), lexicon)))))).
  * targets are grapheme indices, concatenated; out_handles [B]. */

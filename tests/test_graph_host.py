@@ -264,3 +264,35 @@ def test_alignment_graph_cache_returns_the_same_graphs_and_freezes_them():
         second[0].add_node()
     second[0].arc_sort()          # already ilabel-sorted: a no-op, allowed
     _lib.check(L.wfst_transducer_alignment_cache(16 << 20, None, None))   # back to the default capacity
+
+
+def test_stc_graphs_of_a_batch_equal_the_per_utterance_builder():
+    """wfst_stc_graphs (the whole batch in the host library) against STCLossFunction.create_stc_graph
+    (criterions/stc.py:22-64, itself checked against the oracle) + arc_sort: arrays bit-exact,
+    incl. an empty target, repeated labels and a single label; labels out of range are refused."""
+    import ctypes
+    import math
+    from gtn_applications_b200 import _lib, graph as G
+    from gtn_applications_b200.criterions.stc import STCLossFunction, STC_BLANK_IDX
+    L = _lib.lib()
+    star, prob = 7, 0.37
+    targets = [[1, 2, 2, 5, 1], [], [3], [6, 6, 6, 6], [1, 2, 3, 4, 5, 6, 1, 2, 3]]
+    flat = np.array([t for y in targets for t in y], dtype=np.int32)
+    offs = np.zeros(len(targets) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(y) for y in targets])
+    hs = (ctypes.c_int32 * len(targets))()
+    _lib.check(L.wfst_stc_graphs(flat.ctypes.data, offs.ctypes.data, len(targets), star, math.log(prob),
+                                 STC_BLANK_IDX, hs))
+    for h, y in zip(hs, targets):
+        got = G.Graph(_handle=h)
+        want = STCLossFunction.create_stc_graph(y, star, prob)
+        want.arc_sort(False)
+        ga, wa = got.arrays(), want.arrays()
+        for k in wa:
+            assert np.array_equal(ga[k], wa[k]), k
+        assert np.array_equal(got.arc_order(False), want.arc_order(False))
+        assert np.array_equal(got.arc_order(True), want.arc_order(True))
+    bad = np.array([1, 7], dtype=np.int32)
+    with pytest.raises(ValueError):
+        _lib.check(L.wfst_stc_graphs(bad.ctypes.data, np.array([0, 2], dtype=np.int32).ctypes.data, 1, star,
+                                     math.log(prob), STC_BLANK_IDX, hs))

@@ -43,6 +43,22 @@ def test_stc_function_fixtures_and_oracle(gtn64, case, lattice_kernel):
     assert_close(x.grad.cpu().numpy(), ref["grad"])
 
 
+def test_stc_function_at_a_training_shape_against_the_float64_oracle(gtn64, lattice_kernel):
+    """B=4, T=300, 15 tokens (C* = 32 with the <star> columns), L up to 40 -- several emission tiles,
+    acceptors of ~200 nodes from wfst_stc_graphs -- loss and gradient against the gtn64 oracle."""
+    from gtn_applications_b200.criterions.stc import STCLoss
+    rng = np.random.default_rng(21)
+    B, T, star = 4, 300, 16
+    tg = [rng.integers(1, star, size=n).tolist() for n in (40, 1, 23, 31)]
+    em = np.log(rng.dirichlet(np.ones(2 * star), size=(B, T))).astype(np.float32)
+    x = torch.tensor(em, device="cuda", requires_grad=True)
+    loss = STCLoss(x, tg, 0.3, "mean")
+    loss.backward()
+    ref = rc.stc(gtn64, em, tg, 0.3, "mean")
+    assert abs(loss.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert_close(x.grad.cpu().numpy(), ref["grad"])
+
+
 def test_stc_module_fixture():
     from gtn_applications_b200.criterions.stc import STC
     z = G.load("stc")

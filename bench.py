@@ -297,8 +297,8 @@ def other_configs(dev):
         out["conv_transduce1d"] = {
             "ms_per_step": timed(cv, 5, warm=2) * 1e3,
             "what": "ConvTransduce1D(500 lexicon entries of 1-4 letters, kernel_size=9, stride=4) fwd+bwd, B=8, "
-                    "T=200, C=27 (384 windows x 500 kernel graphs; one call of wfst_lattice_forward_backward_many "
-                    "per direction, one launch per kernel graph)"}
+                    "T=200, C=27 (384 windows x 500 kernel graphs; one launch per direction, "
+                    "wfst_lattice_forward_backward_cross)"}
         del xc, conv
     except Exception as exc:
         out["conv_transduce1d"] = {"error": repr(exc)[:200]}

@@ -51,6 +51,7 @@ SIGNATURES = {
     "wfst_lattice_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "wfst_lattice_forward_backward": (_I, [_P, _I, _I, _I, ctypes.POINTER(AcceptorBatch), _I, _P, _P,
                                            _P, _I, _P, _P, _Z, _P]),
+    "wfst_lattice_forward_backward_cross": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "wfst_lattice_forward_backward_many": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "wfst_asg_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "wfst_asg_forward_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),

@@ -408,8 +408,24 @@ def _packed_kernel(k, dev):
     return hit
 
 
+def _packed_all_kernels(kernels, dev):
+    """all kernel graphs as ONE packed batch (for the single-launch entry), cached on the first graph"""
+    if not kernels:
+        return None
+    key = "_packed_all_%s" % str(dev)
+    hit = getattr(kernels[0], key, None)
+    ids = [id(k) for k in kernels]
+    if hit is None or hit[0] != ids:
+        hit = (ids, G.pack_graphs(list(kernels), dev))
+        try:
+            setattr(kernels[0], key, hit)
+        except AttributeError:
+            pass
+    return hit[1]
+
+
 def _score_all_kernels(windows, packed, weights, grad_scale=None, grad_emissions=None, grad_weights=None,
-                       narcs=None):
+                       narcs=None, packed_all=None, flat_weights=None):
     """scores [K, B'] of every window against every kernel graph (wfst_lattice_forward_backward_many);
     with grad_scale [K, B']: window gradients are added to `grad_emissions`, arc-weight gradients
     written to the slices of the flat buffer `grad_weights` (narcs: arcs per kernel graph)."""
@@ -421,6 +437,22 @@ def _score_all_kernels(windows, packed, weights, grad_scale=None, grad_emissions
     scores = torch.empty(K, Bw, dtype=torch.float32, device=dev)
     if K == 0:
         return scores
+    if packed_all is not None and (flat_weights is not None or all(w is None for w in weights)):
+        # one launch: item (k, w) = kernel graph k against window w (wfst_lattice_forward_backward_cross);
+        # the library refuses (and launches nothing) when the graphs do not fit the shared-memory kernel
+        s = packed_all.struct(flat_weights)
+        with torch.cuda.device(dev):
+            ws = rt.workspace(dev, L.wfst_lattice_workspace_bytes(K * Bw, ks, C, 0, packed_all.max_nodes))
+            rc = L.wfst_lattice_forward_backward_cross(
+                windows.data_ptr(), Bw, ks, C, ctypes.byref(s),
+                grad_scale.data_ptr() if grad_scale is not None else None, scores.data_ptr(),
+                grad_emissions.data_ptr() if grad_emissions is not None else None,
+                grad_weights.data_ptr() if grad_weights is not None else None,
+                ws.data_ptr(), ws.numel(), rt.stream_ptr(dev))
+        if rc == 0:
+            return scores
+        if rc != -3:
+            _lib.check(rc)
     # the K structs of a set of kernel graphs are built once and kept on the first packed graph
     # (the packed graphs themselves are cached on the kernel graphs); only the weight pointers
     # change from call to call
@@ -476,6 +508,8 @@ class ConvTransduce1DFunction(torch.autograd.Function):
             windows = win.permute(0, 1, 3, 2).reshape(B * Tp, kernel_size, C).contiguous()
             packed = [_packed_kernel(k, dev) for k in kernels]     # packed once per kernel graph and device
             weights = [None] * len(kernels)
+            kp = None
+            packed_all = _packed_all_kernels(kernels, dev) if not viterbi else None
             if kernel_params is not None:
                 kp = kernel_params.detach().to(dev, torch.float32).contiguous()
                 pos = 0
@@ -492,8 +526,9 @@ class ConvTransduce1DFunction(torch.autograd.Function):
             else:
                 # every kernel graph against every window in ONE call of the library (the launches
                 # are issued back to back from C: no Python work per lexicon entry)
-                out = _score_all_kernels(windows, packed, weights).t().contiguous()
-        ctx.saved = (windows, packed, weights, paths, [k.num_arcs() for k in kernels])
+                out = _score_all_kernels(windows, packed, weights, packed_all=packed_all,
+                                         flat_weights=kp).t().contiguous()
+        ctx.saved = (windows, packed, weights, paths, [k.num_arcs() for k in kernels], packed_all, kp)
         ctx.meta = (B, T, C, Tp, kernel_size, stride, viterbi, inputs.device,
                     kernel_params.device if kernel_params is not None else None)
         out = out.view(B, Tp, len(kernels))
@@ -501,7 +536,7 @@ class ConvTransduce1DFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
-        windows, packed, weights, paths, narcs = ctx.saved
+        windows, packed, weights, paths, narcs, packed_all, kp = ctx.saved
         B, T, C, Tp, ks, stride, viterbi, in_dev, kp_dev = ctx.meta
         ctx.saved = None
         dev = windows.device
@@ -528,9 +563,10 @@ class ConvTransduce1DFunction(torch.autograd.Function):
             if not viterbi and len(packed):
                 # one call for all kernel graphs: window gradients accumulate in gwin, the weight
                 # gradients of kernel graph i land in their slice of one flat buffer
-                flat = torch.empty(sum(narcs), dtype=torch.float32, device=dev) if need_k else None
+                flat = torch.zeros(sum(narcs), dtype=torch.float32, device=dev) if need_k else None
                 _score_all_kernels(windows, packed, weights, grad_scale=deltas.t().contiguous(),
-                                   grad_emissions=gwin if need_in else None, grad_weights=flat, narcs=narcs)
+                                   grad_emissions=gwin if need_in else None, grad_weights=flat, narcs=narcs,
+                                   packed_all=packed_all, flat_weights=kp)
                 if need_k:
                     kgrads = [flat]
             g_in = None

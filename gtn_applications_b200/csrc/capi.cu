@@ -357,6 +357,24 @@ int wfst_lattice_forward_backward(const float* emissions, int B, int T, int C,
                     accumulate, grad_weights, (float*)workspace, st);
 }
 
+int wfst_lattice_forward_backward_cross(const float* emissions, int B, int T, int C,
+                                        const wfst_acceptor_batch_t* graphs, const float* grad_scale,
+                                        float* scores, float* grad_emissions, float* grad_weights,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  WFST_REQUIRE(emissions && graphs && scores && workspace, "null pointer argument");
+  WFST_REQUIRE(B > 0 && T >= 0 && C > 0 && graphs->B > 0, "bad shape B=%d T=%d C=%d K=%d", B, T, C, graphs->B);
+  WFST_REQUIRE(graphs->max_nodes > 0, "empty acceptor");
+  WFST_REQUIRE(!graphs->final_weights && !graphs->grad_final_weights, "final weights are not supported here");
+  const long long items = (long long)graphs->B * B;
+  if (items > 0x7fffffffLL) return WFST_ERR_UNSUPPORTED;
+  if (workspace_bytes < lattice_hist_bytes((int)items, T, C, graphs->max_nodes)) {
+    set_error("workspace too small");
+    return WFST_ERR_WORKSPACE;
+  }
+  return launch_csr_cross(emissions, B, T, C, *graphs, grad_scale, scores, grad_emissions, grad_weights,
+                          (float*)workspace, (cudaStream_t)stream);
+}
+
 int wfst_lattice_forward_backward_many(const float* emissions, int B, int T, int C,
                                        const wfst_acceptor_batch_t* graphs, int K,
                                        const float* grad_scale, float* scores, float* grad_emissions,

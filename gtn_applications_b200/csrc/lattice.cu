@@ -109,7 +109,7 @@ static int launch_lean_npt(const lean::Args& g, typename Builder::Params bp, int
 
 template <class Builder>
 static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, int max_nodes, int aslots,
-                            int want_gw, cudaStream_t st, int* rc) {
+                            int want_gw, cudaStream_t st, int* rc, bool single_only = false) {
   if (g_force_generic_lattice == 1) return false;
   if (max_nodes < 1 || max_nodes > 16 * 1024 || aslots > 65535 || a.C >= 16 * 1024) return false;
   int npt = (max_nodes + 1023) / 1024;
@@ -141,7 +141,7 @@ static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, i
     // small dense acceptors (n-gram transition graphs: 84 nodes x 81 arcs): a warp per node in the
     // cluster kernel instead of a thread per node, whatever the batch size (test hooks 2 and 4:
     // off)
-    const bool dense = max_nodes <= 32 * 16 && (long long)aslots >= 16LL * max_nodes;
+    const bool dense = !single_only && max_nodes <= 32 * 16 && (long long)aslots >= 16LL * max_nodes;
     if (dense && ntiles >= 2 && g_force_generic_lattice != 2 && g_force_generic_lattice != 4) {
       const int ng = max_nodes < 32 ? max_nodes : 32;          // warps = node groups
       int np = (max_nodes + ng - 1) / ng;
@@ -150,7 +150,7 @@ static bool try_launch_lean(LatticeArgs a, typename Builder::Params bp, int B, i
       return true;
     }
   }
-  if (g_force_generic_lattice != 2 && ntiles >= 2 && (starved || g_force_generic_lattice >= 3)) {
+  if (!single_only && g_force_generic_lattice != 2 && ntiles >= 2 && (starved || g_force_generic_lattice >= 3)) {
     if constexpr (Builder::kSort) {
       if (wide) {
         *rc = launch_lean_wide(g, bp, B, nt, lay.total, st);
@@ -230,6 +230,27 @@ int launch_csr(const float* E, int T, int C, const wfst_acceptor_batch_t& g, int
   int rc;
   if (try_launch_lean<CsrLean>(a, tp, g.B, g.max_nodes, g.max_arcs, gradW ? 1 : 0, st, &rc)) return rc;
   return launch_lattice<CsrTopo>(a, tp, g.B, g.max_nodes, st);
+}
+
+// Every emission item against every graph of a packed batch in ONE launch of the single-block lean
+// kernel: item k * Bw + w scores graph k against emission item w (scores, grad_scale [K, Bw]); the
+// emission gradients of all graphs are ADDED into gradE [Bw, T, C] atomically, the arc-weight
+// gradients into gradW [arcs of the batch] (both cleared by the caller).  WFST_ERR_UNSUPPORTED when
+// the acceptors do not fit the lean kernel (the caller then launches graph by graph).
+int launch_csr_cross(const float* E, int Bw, int T, int C, const wfst_acceptor_batch_t& g,
+                     const float* grad_scale, float* scores, float* gradE, float* gradW, float* hist,
+                     cudaStream_t st) {
+  const int K = g.B;
+  const long long items = (long long)K * Bw;
+  if (items > 0x7fffffffLL) return WFST_ERR_UNSUPPORTED;
+  LatticeArgs a = base_args(E, (int)items, T, C, grad_scale, 1.f, scores, gradE, 1, hist,
+                            g.max_nodes, gradW ? g.max_arcs : 0);
+  a.e_mod = Bw;
+  CsrTopo::Params tp{g, gradW, 0, Bw};
+  int rc;
+  if (try_launch_lean<CsrLean>(a, tp, (int)items, g.max_nodes, g.max_arcs, gradW ? 1 : 0, st, &rc, true))
+    return rc;
+  return WFST_ERR_UNSUPPORTED;
 }
 
 int launch_asg_fal(const float* E, const float* tr, const int* targets, const int* offsets, int B,

@@ -41,6 +41,8 @@ struct LatticeArgs {
   int npad;              // smem floats reserved per alpha buffer
   int extra_floats;      // policy-owned smem floats (after the fixed regions)
   const int* active;     // optional [B]: blocks with active[b] == 0 return at once
+  int e_mod;             // > 0 ("cross" launch of the single-block lean kernel): item b reads emission
+                         // item b % e_mod and ADDS its gradient there atomically (several items share it)
 };
 
 // shared memory carve-up (all float-sized slots; base is 16B aligned)

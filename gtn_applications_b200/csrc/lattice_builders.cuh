@@ -19,6 +19,8 @@ struct CsrTopo {
     wfst_acceptor_batch_t g;
     float* gradW;   // [arcs] or null
     int shared;     // all utterances use graph 0; gradW accumulated atomically
+    int graph_div;  // > 0 ("cross" launch, CsrLean only): item b uses graph b / graph_div, several items
+                    // share a graph: gradW accumulated atomically, cleared by the host
   };
   const int* in_ptr; const int* in_src; const int* in_label; const int* in_arc;
   const int* out_ptr; const int* out_dst; const int* out_label; const int* out_arc;
@@ -245,7 +247,7 @@ struct CsrLean {
   const uint8_t* flags; const float* w; float* gradW; const float* fw; float* gradF;
   int N, A, shared;
   __device__ void init(const Params& p, int b) {
-    int gb = p.shared ? 0 : b;
+    int gb = p.graph_div > 0 ? b / p.graph_div : (p.shared ? 0 : b);
     int nb = p.g.node_offsets[gb], ab = p.g.arc_offsets[gb];
     N = p.g.node_offsets[gb + 1] - nb;
     A = p.g.arc_offsets[gb + 1] - ab;
@@ -257,7 +259,7 @@ struct CsrLean {
     gradW = p.gradW ? p.gradW + ab : nullptr;
     fw = p.g.final_weights ? p.g.final_weights + nb : nullptr;
     gradF = p.g.grad_final_weights ? p.g.grad_final_weights + nb : nullptr;
-    shared = p.shared;
+    shared = p.shared || p.graph_div > 0;
   }
   __device__ int num_nodes() const { return N; }
   __device__ int num_slots() const { return A; }

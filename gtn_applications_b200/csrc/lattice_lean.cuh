@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
       for (int k = tid; k < A; k += NT) sts_f(s_gw + 4u * k, 0.f);
   }
   const int T = a.T, C = a.C, Kt = a.Kt;
-  const float* Eb = a.E + (size_t)b * T * C;
+  const int eb = a.e_mod > 0 ? b % a.e_mod : b;      // emission item of this block
+  const float* Eb = a.E + (size_t)eb * T * C;
   float* hist = a.hist + (size_t)b * (T + 1) * a.hist_stride;
   double* offA = a.offs + (size_t)b * a.offs_stride;
   const int ntiles = (T + Kt - 1) / Kt;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
   const bool want_gW = g.want_gw != 0;
   if (!want_gE && !want_gW) return;
   const float gs = a.sign * (a.grad_scale ? a.grad_scale[b] : 1.f);
-  float* gEb = want_gE ? a.gradE + (size_t)b * T * C : nullptr;
+  float* gEb = want_gE ? a.gradE + (size_t)eb * T * C : nullptr;
   const bool feasible = (Z != kNegInf) && (Z == Z) && (Z != -kNegInf);
   if (!feasible) {
     if (want_gE && !a.accumulate)
@@ -526,7 +527,11 @@ __global__ void __launch_bounds__(1024, 1) lattice_lean_kernel(Args g, typename 
         }
       } else {
         __syncthreads();
-        if (a.accumulate) {
+        if (a.e_mod > 0) {
+          // cross launch: other blocks (other graphs against the same emission item) add here too
+          for (int k = tid; k < n; k += NT)
+            if (gt[k] != 0.f) atomicAdd(&dst[k], gt[k]);
+        } else if (a.accumulate) {
           for (int k = tid; k < n; k += NT) dst[k] += gt[k];
         } else {
           for (int k = tid; k < n; k += NT) dst[k] = gt[k];

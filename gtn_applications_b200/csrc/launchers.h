@@ -15,6 +15,9 @@ int launch_ctc(const float* E, const int* targets, const int* offsets, int B, in
 int launch_csr(const float* E, int T, int C, const wfst_acceptor_batch_t& g, int shared,
                const float* grad_scale, float sign, float* scores, float* gradE, int accumulate,
                float* gradW, float* hist, cudaStream_t st);
+int launch_csr_cross(const float* E, int Bw, int T, int C, const wfst_acceptor_batch_t& g,
+                     const float* grad_scale, float* scores, float* gradE, float* gradW, float* hist,
+                     cudaStream_t st);
 int launch_asg_fal(const float* E, const float* tr, const int* targets, const int* offsets, int B,
                    int T, int C, int max_target_len, const float* grad_scale, float sign,
                    float* scores, float* gradE, int accumulate, float* gradTr, float* hist,

@@ -189,6 +189,19 @@ WFST_API int wfst_lattice_forward_backward(const float* emissions, int B, int T,
  *                 the buffer holds (the caller clears it)
  *   grad_weights  K pointers ([arcs of acceptor k] out, summed over b) or NULL
  *   workspace     >= wfst_lattice_workspace_bytes(B, T, C, 0, max over k of graphs[k].max_nodes) */
+/* The same, in ONE launch: every emission item against every acceptor of a packed batch of K.
+ *   graphs        one batch of K acceptors (no final weights)
+ *   grad_scale    [K, B] or NULL (= 1);  scores [K, B] out
+ *   grad_emissions[B, T, C] or NULL: ADDED to (float atomics; the caller clears it)
+ *   grad_weights  [arcs of the batch] or NULL: ADDED to, summed over the B items (the caller clears it)
+ *   workspace     >= wfst_lattice_workspace_bytes(K * B, T, C, 0, graphs->max_nodes)
+ * Returns WFST_ERR_UNSUPPORTED (and launches nothing) when the acceptors do not fit the
+ * shared-memory kernel; wfst_lattice_forward_backward_many takes any acceptor. */
+WFST_API int wfst_lattice_forward_backward_cross(const float* emissions, int B, int T, int C,
+                                  const wfst_acceptor_batch_t* graphs, const float* grad_scale,
+                                  float* scores, float* grad_emissions, float* grad_weights,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 WFST_API int wfst_lattice_forward_backward_many(const float* emissions, int B, int T, int C,
                                   const wfst_acceptor_batch_t* graphs, int K,
                                   const float* grad_scale, float* scores, float* grad_emissions,

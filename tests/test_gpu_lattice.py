@@ -167,3 +167,47 @@ def test_many_shared_acceptors_in_one_call_match_one_call_each(lattice_kernel):
     assert torch.equal(got_e, want_e)
     # summed over the items with float atomics: the order of the additions is not fixed
     assert_close(flat.cpu().numpy(), torch.cat(want_w).cpu().numpy())
+
+
+def test_cross_launch_matches_one_call_per_acceptor():
+    """wfst_lattice_forward_backward_cross (every emission item against every acceptor of a packed
+    batch in ONE launch, emission and weight gradients added atomically) against one shared-graph
+    call per acceptor; with the lean kernels switched off the entry refuses and launches nothing."""
+    import ctypes
+    from gtn_applications_b200 import _lib, _runtime as rt
+    from gtn_applications_b200.packing import PackedAcceptors
+    from gtn_applications_b200.lattice import lattice_forward_backward
+    rng = np.random.default_rng(4)
+    B, T, C, K = 9, 11, 9, 5
+    graphs = [random_acceptor(rng, 4 + 2 * k, 12 + 6 * k, C) for k in range(K)]
+    E = torch.tensor(rng.standard_normal((B, T, C)).astype(np.float32), device="cuda")
+    gs = torch.tensor(rng.uniform(0.5, 2.0, (K, B)).astype(np.float32), device="cuda")
+    want_s, want_w = [], []
+    want_e = torch.zeros_like(E)
+    for k, g in enumerate(graphs):
+        s, _, w = lattice_forward_backward(E, PackedAcceptors([g], "cuda"), grad_scale=gs[k].contiguous(),
+                                           want_grad_weights=True, shared=True, accumulate_into=want_e)
+        want_s.append(s)
+        want_w.append(w)
+    L = _lib.lib()
+    packed = PackedAcceptors(graphs, "cuda")
+    st = packed.struct()
+    scores = torch.empty(K, B, dtype=torch.float32, device="cuda")
+    got_e = torch.zeros_like(E)
+    got_w = torch.zeros(packed.num_arcs, dtype=torch.float32, device="cuda")
+    ws = rt.workspace(E.device, L.wfst_lattice_workspace_bytes(K * B, T, C, 0, packed.max_nodes))
+    args = (E.data_ptr(), B, T, C, ctypes.byref(st), gs.data_ptr(), scores.data_ptr(), got_e.data_ptr(),
+            got_w.data_ptr(), ws.data_ptr(), ws.numel(), rt.stream_ptr(E.device))
+    _lib.check(L.wfst_lattice_forward_backward_cross(*args))
+    torch.cuda.synchronize()
+    ws_, gs_ = torch.stack(want_s).cpu().numpy(), scores.cpu().numpy()
+    fin = np.isfinite(ws_)
+    assert np.array_equal(fin, np.isfinite(gs_)) and fin.any()
+    assert_close(gs_[fin], ws_[fin])
+    assert_close(got_e.cpu().numpy(), want_e.cpu().numpy())
+    assert_close(got_w.cpu().numpy(), torch.cat(want_w).cpu().numpy())
+    old = L.wfst_debug_force_generic_lattice(1)
+    try:
+        assert L.wfst_lattice_forward_backward_cross(*args) == -3
+    finally:
+        L.wfst_debug_force_generic_lattice(old)
